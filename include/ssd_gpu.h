@@ -1,0 +1,245 @@
+/*
+ * ssd_gpu.h -- C ABI of the B200-native per-frame geometry hot path of stair-step-detector.
+ *
+ * The reference has no FFI layer; its boundary for this path is the C++ class surface in namespace
+ * `stairs` (reference files, relative to the upstream repo root):
+ *   Pointcloud::process(const Camera::DepthFrame&)            pointcloud.h:35-36, pointcloud.cpp:608-626
+ *   Transformation_<Dim>, CameraToWorld, ToExternalWorld,
+ *   GeometricTransformation                                    transformation.h:42-126
+ *   Segmentation::detectOutline / detectFrontEdge             segmentation.h:32-58
+ *   QuadrilateralTest                                          quadrilateralTest.h:32-36
+ *   Stairs, Stairs::StairStep, Stairs::serialize              stairs.h:30-39
+ * Every entry point below names the reference interface it replaces. The C++ host classes in
+ * stair_step_detector_b200/csrc/host/ keep the reference's names on top of these functions.
+ *
+ * Conventions: plain pointers and sizes only; every function returns SSD_OK (0) or a negative
+ * SSD_E_* code and never throws; ssd_gpu_last_error() gives the text. One ctx per (device, host
+ * thread); calls on one ctx are serialised by the caller. There is NO CPU fallback: without a CUDA
+ * device ssd_gpu_create() fails with SSD_E_CUDA.
+ */
+#ifndef SSD_GPU_H_
+#define SSD_GPU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSD_GPU_ABI_VERSION 1
+
+/* ---- limits ---- */
+#define SSD_GPU_MAX_BINS 253      /* height-histogram bins; bin codes are u8, 253..255 reserved */
+#define SSD_GPU_MAX_PLATEAUS 32   /* histogram peaks kept per frame */
+#define SSD_GPU_MAX_STEPS 32      /* = MAX_PLATEAUS (ground + every valid plateau) */
+
+/* ---- per-point segment label codes (u8), SURVEY.md section 8(d) ---- */
+#define SSD_LABEL_REMAINDER 253u    /* inside the measuring range, in no plateau band (pointcloud.cpp:285-291) */
+#define SSD_LABEL_OUT_OF_RANGE 254u /* z > 0 but outside the measuring range (pointcloud.cpp:150-165) */
+#define SSD_LABEL_INVALID 255u      /* vertex.z <= 0 (pointcloud.cpp:143-146) */
+/* 0 .. n_plateaus-1 : index of the plateau (ascending histogram peak) the point belongs to */
+
+/* ---- error codes ---- */
+#define SSD_OK 0
+#define SSD_E_INVALID_ARG (-1)
+#define SSD_E_CUDA (-2)
+#define SSD_E_NOMEM (-3)
+#define SSD_E_RANGE (-4)
+#define SSD_E_STATE (-5)
+
+/* ---- per-frame status bits ---- */
+#define SSD_STATUS_NO_STEPS 0x1u             /* no valid plateau: Stairs has zero steps */
+#define SSD_STATUS_DEGENERATE_QUAD 0x2u      /* QuadrilateralTest ctor would throw (quadrilateralTest.cpp:287-372);
+                                                the reference terminates; here the step is dropped */
+#define SSD_STATUS_INVALID_FRONT_EDGE 0x4u   /* ground front edge invalid: all-zero ground step emitted (pointcloud.cpp:546) */
+#define SSD_STATUS_EMPTY_MEAN 0x8u           /* a step has no point inside its quadrilateral: height is NaN (pointcloud.cpp:580) */
+#define SSD_STATUS_TOO_MANY_PLATEAUS 0x10u   /* more than SSD_GPU_MAX_PLATEAUS peaks; the extra ones were dropped */
+#define SSD_STATUS_BEV_OOB 0x20u             /* a BEV pixel fell past the image end (pointcloud.cpp:81,468 has no bounds check) */
+#define SSD_STATUS_HMIN_WRAP 0x40u           /* uint16 wrap of heightMin-1 (pointcloud.cpp:324): plateaus came out empty */
+
+/*
+ * Replaces struct Configuration (configuration.h:27-52) + ProcessingConfiguration (pointcloud.cpp:99-106).
+ * Defaults (ssd_gpu_default_config) are the reference's values except width/height, which are parameters.
+ */
+typedef struct ssd_gpu_config
+{
+  int32_t width, height;          /* streams.depth width x height; also the BEV image size (pointcloud.cpp:71) */
+  double x_min, x_max;            /* measuringRange.x  (-0.6, 0.6) */
+  double y_min, y_max;            /* measuringRange.y  ( 0.1, 1.3) */
+  double z_min, z_max;            /* measuringRange.z  (-0.1, 1.1) */
+  double height_interval;         /* 0.01 */
+  double min_height_above_ground; /* 0.05 */
+  double min_step_depth;          /* 0.1 */
+  uint32_t min_peak_points;       /* 2000 (pointcloud.cpp:251) */
+  uint32_t reserved;
+} ssd_gpu_config;
+
+/*
+ * The doubles a GeometricTransformation holds (transformation.h:102-126):
+ *   a, b        CameraToWorld:  w = a * p + b, row-major 3x3      (transformation.h:59-64)
+ *   ext_a/b/z   ToExternalWorld: (x,y) -> ext_a*(x,y)+ext_b, z -> ext_z + z (transformation.cpp:190-194)
+ */
+typedef struct ssd_gpu_transform
+{
+  double a[9];
+  double b[3];
+  double ext_a[4];
+  double ext_b[2];
+  double ext_z;
+} ssd_gpu_transform;
+
+/* Replaces Stairs::StairStep (stairs.h:32-36): external-world height and corners
+ * [frontLeft, frontRight, backLeft, backRight] (segmentation.h:44-53). */
+typedef struct ssd_gpu_step
+{
+  double height;
+  double quad[4][2];
+} ssd_gpu_step;
+
+/* Per-plateau intermediate record (struct Plateau, pointcloud.cpp:259-265) for parity checks. */
+typedef struct ssd_gpu_plateau
+{
+  int32_t height;      /* histogram peak bin */
+  int32_t hmin, hmax;  /* height band [hmin,hmax] (pointcloud.cpp:302-316) */
+  uint32_t n_points;   /* plateauPoints.size() */
+  int32_t valid;       /* Plateau::valid after detectStairSteps */
+  int32_t outlined;    /* 1 if detectOutline ran on this plateau (height >= minHeight) */
+  uint32_t n_in_quad;  /* points inside quadriWorld2D (getPointsInQuadrilateral) */
+  int32_t quad_status; /* 0 ok, 1 QuadrilateralTest ctor would throw, -1 not evaluated */
+  double quad_world[4][2]; /* Plateau::quadriWorld2D */
+  double mean_z;       /* calcAverageZ over the points in the quadrilateral */
+} ssd_gpu_plateau;
+
+/* Per-frame summary. */
+typedef struct ssd_gpu_frame_info
+{
+  uint32_t status;            /* SSD_STATUS_* */
+  int32_t n_bins;
+  int32_t n_plateaus;         /* K = filtered peaks */
+  int32_t ground_index;       /* groundInd, -1 if none (pointcloud.cpp:403-418) */
+  int32_t first_valid_index;  /* firstValidInd, -1 if none */
+  int32_t n_steps;            /* Stairs::stairSteps.size() */
+  uint32_t n_nonzero;         /* vertices with z > 0 */
+  uint32_t n_in_range;        /* points inside the measuring range */
+} ssd_gpu_frame_info;
+
+typedef struct ssd_gpu_ctx ssd_gpu_ctx;
+
+/* Timing of the last ssd_gpu_process_* call, CUDA events on the ctx stream (milliseconds). */
+typedef struct ssd_gpu_timing
+{
+  float total_ms;    /* first kernel to results resident in pinned host memory */
+  float h2d_ms;      /* host->device upload (process_host only) */
+  float kernels_ms;  /* all kernels of the chain */
+  float label_ms;    /* the dominant transform/histogram/label stage alone */
+  int32_t n_launches;/* kernels launched by the call */
+  int32_t reserved;
+} ssd_gpu_timing;
+
+/* ---- configuration / lifetime ---- */
+void ssd_gpu_default_config(ssd_gpu_config *cfg, int32_t width, int32_t height);
+int ssd_gpu_abi_version(void);
+int ssd_gpu_device_count(void);
+
+/* Replaces Pointcloud::Pointcloud(const Window&, const GeometricTransformation&) (pointcloud.cpp:602-606):
+ * binds the constant transform and configuration, allocates device buffers for up to max_frames frames. */
+int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int device, int max_frames, ssd_gpu_ctx **out);
+void ssd_gpu_destroy(ssd_gpu_ctx *ctx);
+const char *ssd_gpu_last_error(const ssd_gpu_ctx *ctx); /* ctx may be NULL: last create() error */
+
+/* ---- the hot path: replaces Pointcloud::process (pointcloud.cpp:608-626), batched ---- */
+/* xyz: n_frames * width*height packed {float x,y,z} vertices (rs2::vertex layout, qvmTraits.h:70-90),
+ * row-major pixel order, invalid pixel = (0,0,0). Results stay in the ctx until the next call. */
+int ssd_gpu_process_host(ssd_gpu_ctx *ctx, const float *xyz_host, int n_frames);
+int ssd_gpu_process_device(ssd_gpu_ctx *ctx, const float *xyz_dev, int n_frames);
+/* Same, but skips the per-point label store (labels are still computed; results identical). */
+#define SSD_FLAG_NO_LABELS 0x1
+int ssd_gpu_process_device_ex(ssd_gpu_ctx *ctx, const float *xyz_dev, int n_frames, int flags);
+
+/* ---- results of the last process call ---- */
+/* Stairs of one frame: out[0..*n) ; replaces the value printed at pointcloud.cpp:624-625. */
+int ssd_gpu_get_steps(ssd_gpu_ctx *ctx, int frame, ssd_gpu_step *out, int cap, int *n, uint32_t *status);
+int ssd_gpu_get_frame_info(ssd_gpu_ctx *ctx, int frame, ssd_gpu_frame_info *out);
+int ssd_gpu_get_plateaus(ssd_gpu_ctx *ctx, int frame, ssd_gpu_plateau *out, int cap, int *n);
+/* Per-pixel segment labels (device -> host copy of width*height bytes). */
+int ssd_gpu_get_labels(ssd_gpu_ctx *ctx, int frame, uint8_t *out_host);
+/* Height histogram, HeightsHistogram::calcHist (pointcloud.cpp:194-204). */
+int ssd_gpu_get_histogram(ssd_gpu_ctx *ctx, int frame, uint32_t *out, int cap, int *n_bins);
+int ssd_gpu_get_timing(ssd_gpu_ctx *ctx, ssd_gpu_timing *out);
+/* Device pointer to the label array of the last call (n_frames * width*height bytes). */
+int ssd_gpu_labels_device_ptr(ssd_gpu_ctx *ctx, const uint8_t **out);
+
+/* Stairs::serialize (stairs.cpp:55-70): writes the NUL-terminated line into buf; returns the length
+ * needed (excluding NUL) or a negative error. Host only. */
+int ssd_stairs_serialize(const ssd_gpu_step *steps, int n, char *buf, size_t cap);
+
+/* ---- single-stage entry points (same kernels, one image / one quadrilateral) ---- */
+/* Segmentation::detectOutline (segmentation.cpp:919-971): image is width*height u8 (non-zero = set).
+ * quad_px: 4 x (x,y) image points, valid: isConvex. */
+int ssd_gpu_detect_outline(ssd_gpu_ctx *ctx, const uint8_t *image_host, int min_img_y_extent, double xy_ratio,
+                           double quad_px[8], int *valid);
+/* Segmentation::detectFrontEdge (segmentation.cpp:879-917). */
+int ssd_gpu_detect_front_edge(ssd_gpu_ctx *ctx, const uint8_t *image_host, double left_px[2], double right_px[2], int *valid);
+/* QuadrilateralTest ctor + isPointWithin (quadrilateralTest.cpp:275-451) over n host points (x,y pairs).
+ * *ctor_status = 0 ok, 1 the reference ctor would throw (then inside[] is all 0). */
+int ssd_gpu_points_in_quad(ssd_gpu_ctx *ctx, const double quad[8], const double *xy_host, int n, uint8_t *inside_host,
+                           int *ctor_status);
+/* CameraToWorld over n host vertices -> n x 3 doubles (transformation.h:59-64). */
+int ssd_gpu_camera_to_world(ssd_gpu_ctx *ctx, const float *xyz_host, int n, double *world_host);
+
+/* ---- host-side transformation builders (transformation.cpp), no GPU needed ---- */
+/* GeometricTransformation(worldPoints, cameraPoints) (transformation.cpp:196-215): 3 points each, xyz. */
+int ssd_make_transform(const double world_pts[9], const double camera_pts[9], ssd_gpu_transform *out);
+
+/* ---- synthetic input source (stands in for the stubbed RealSense capture) ---- */
+typedef struct ssd_scene
+{
+  int32_t width, height;
+  float fx, fy, ppx, ppy;      /* pin-hole intrinsics */
+  float depth_unit;            /* metres per z16 count (L515: 0.00025) */
+  float cam_height;            /* camera height above the calibration plane (m) */
+  float cam_pitch_deg;         /* optical axis below horizontal */
+  float cam_roll_deg;
+  float cam_yaw_deg;
+  float cam_x, cam_y;          /* camera foot point in scene coordinates */
+  float ground_z;              /* ground plane height */
+  int32_t n_steps;
+  float riser, tread, width_m; /* step geometry (m) */
+  float first_riser_y;         /* y of the first riser */
+  float x_center;              /* lateral centre of the flight */
+  float top_landing;           /* extra depth of the top tread (m) */
+  float noise_sigma;           /* N(0,sigma) along the ray (m) */
+  float dropout;               /* probability of a zero-depth pixel */
+  int32_t n_holes;             /* rectangular zero-depth holes */
+  int32_t n_occluders;         /* boxes floating between camera and stairs */
+  int32_t rotate180;           /* camera mounted upside down (README "descending stairs") */
+  uint64_t seed;
+} ssd_scene;
+
+void ssd_scene_default(ssd_scene *s, int32_t width, int32_t height);
+/* Randomise the geometry of frame `index` of a batch (SURVEY.md 8(d) config 3/4/5 distributions). */
+void ssd_scene_randomize(ssd_scene *s, const ssd_scene *base, uint64_t base_seed, int64_t index, int min_steps, int max_steps);
+/* Three ground points seen by the scene's camera, for ssd_make_transform / the reference ctor. */
+void ssd_scene_calibration_points(const ssd_scene *s, double world_pts[9], double camera_pts[9]);
+/* z16 depth image of one scene, host. */
+int ssd_synth_depth_host(const ssd_scene *s, uint16_t *depth_out);
+/* z16 -> vertices (the stubbed rs2::pointcloud::calculate, pointcloud.cpp:138), host. */
+int ssd_deproject_host(const ssd_scene *s, const uint16_t *depth, float *xyz_out);
+/* Device versions: generate n_frames randomised scenes straight into HBM (xyz_dev: n_frames*W*H*3 floats).
+ * depth_dev may be NULL. */
+int ssd_gpu_synth_frames(ssd_gpu_ctx *ctx, const ssd_scene *base, uint64_t base_seed, int64_t first_index, int n_frames,
+                         int min_steps, int max_steps, float *xyz_dev, uint16_t *depth_dev);
+
+/* ---- raw device memory helpers for callers without a CUDA runtime binding ---- */
+int ssd_gpu_malloc(ssd_gpu_ctx *ctx, size_t bytes, void **dev_ptr);
+int ssd_gpu_free(ssd_gpu_ctx *ctx, void *dev_ptr);
+int ssd_gpu_memcpy_h2d(ssd_gpu_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+int ssd_gpu_memcpy_d2h(ssd_gpu_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+int ssd_gpu_malloc_host(size_t bytes, void **host_ptr); /* pinned */
+int ssd_gpu_free_host(void *host_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSD_GPU_H_ */

@@ -1,0 +1,107 @@
+// ssd_host.cpp -- host-only entry points of the C ABI (no GPU needed): default configuration,
+// transformation builder, synthetic scene generator (host leg).
+#include "../../include/ssd_gpu.h"
+#include "host/transformation.h"
+#include "scene_model.h"
+#include <exception>
+
+extern "C"
+{
+
+int ssd_gpu_abi_version(void)
+{
+  return SSD_GPU_ABI_VERSION;
+}
+
+// Configuration (reference configuration.h:27-52) with the stream size as a parameter
+void ssd_gpu_default_config(ssd_gpu_config *c, int32_t width, int32_t height)
+{
+  c->width = width;
+  c->height = height;
+  c->x_min = -0.6;
+  c->x_max = 0.6;
+  c->y_min = 0.1;
+  c->y_max = 1.3;
+  c->z_min = -0.1;
+  c->z_max = 1.1;
+  c->height_interval = 0.01;
+  c->min_height_above_ground = 0.05;
+  c->min_step_depth = 0.1;
+  c->min_peak_points = 2000;
+  c->reserved = 0;
+}
+
+int ssd_make_transform(const double world_pts[9], const double camera_pts[9], ssd_gpu_transform *out)
+{
+  if(!world_pts || !camera_pts || !out)
+    return SSD_E_INVALID_ARG;
+  try
+  {
+    stairs::GeometricTransformation::RefPoints w, c;
+    for(int i = 0; i < 3; i++)
+    {
+      w[i] = stairs::Point3(world_pts[i * 3], world_pts[i * 3 + 1], world_pts[i * 3 + 2]);
+      c[i] = stairs::Point3(camera_pts[i * 3], camera_pts[i * 3 + 1], camera_pts[i * 3 + 2]);
+    }
+    const stairs::GeometricTransformation t(w, c);
+    *out = t.abi();
+    return SSD_OK;
+  }
+  catch(const std::exception &)
+  {
+    return SSD_E_INVALID_ARG;
+  }
+}
+
+void ssd_scene_default(ssd_scene *s, int32_t width, int32_t height)
+{
+  ssd_scene_default_hd(s, width, height);
+}
+
+void ssd_scene_randomize(ssd_scene *s, const ssd_scene *base, uint64_t base_seed, int64_t index, int min_steps, int max_steps)
+{
+  ssd_scene_randomize_hd(s, base, base_seed, index, min_steps, max_steps);
+}
+
+// Three marks on the calibration plane (z = 0 in scene coordinates), laid out like the reference's
+// calibration-triangle file (top-left, top-right, bottom), and where the scene's camera sees them.
+void ssd_scene_calibration_points(const ssd_scene *s, double world_pts[9], double camera_pts[9])
+{
+  ssd_scene_rt rt;
+  ssd_scene_prepare(s, &rt);
+  const double marks[3][3] = { { s->cam_x - 0.45, s->cam_y + 1.25, 0.0 }, { s->cam_x + 0.45, s->cam_y + 1.25, 0.0 },
+                               { s->cam_x + 0.30, s->cam_y + 0.35, 0.0 } };
+  for(int i = 0; i < 3; i++)
+  {
+    for(int j = 0; j < 3; j++)
+      world_pts[i * 3 + j] = marks[i][j];
+    ssd_scene_to_camera(&rt, marks[i], camera_pts + i * 3);
+  }
+}
+
+int ssd_synth_depth_host(const ssd_scene *s, uint16_t *depth_out)
+{
+  if(!s || !depth_out || s->width <= 0 || s->height <= 0)
+    return SSD_E_INVALID_ARG;
+  ssd_scene_rt rt;
+  ssd_scene_prepare(s, &rt);
+  for(int v = 0; v < s->height; v++)
+    for(int u = 0; u < s->width; u++)
+      depth_out[size_t(v) * s->width + u] = ssd_scene_depth(s, &rt, u, v);
+  return SSD_OK;
+}
+
+int ssd_deproject_host(const ssd_scene *s, const uint16_t *depth, float *xyz_out)
+{
+  if(!s || !depth || !xyz_out)
+    return SSD_E_INVALID_ARG;
+  for(int v = 0; v < s->height; v++)
+    for(int u = 0; u < s->width; u++)
+    {
+      const size_t i = size_t(v) * s->width + u;
+      ssd_deproject_pixel(s, u, v, depth[i], xyz_out + i * 3);
+    }
+  return SSD_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,229 @@
+"""Test infrastructure: loaders for the oracle (C restatement), the compiled reference (oracle/_ref)
+and scene helpers. Only tests/, bench.py's CPU legs and __graft_entry__.smoke() use this."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from stair_step_detector_b200 import _abi as A  # noqa: E402
+
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+REF_SRC = "/root/reference"
+_vp = C.c_void_p
+_P = C.POINTER
+
+
+class Derived(C.Structure):
+    _fields_ = [("height_interval_reciprocal", C.c_double), ("min_height", C.c_int32), ("min_img_y_extent", C.c_int32),
+                ("x_to_image", C.c_double), ("y_to_image", C.c_double), ("x_to_world", C.c_double), ("y_to_world", C.c_double),
+                ("xy_ratio", C.c_double), ("n_bins", C.c_int32), ("pad", C.c_int32)]
+
+
+def ref_tag(cfg):
+    return f"{cfg.width}x{cfg.height}_y{cfg.y_max:g}_z{cfg.z_max:g}"
+
+
+def build_oracle():
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR, "oracle"], check=True)
+    return os.path.join(ORACLE_DIR, "libssd_oracle.so")
+
+
+def load_oracle():
+    lib = C.CDLL(build_oracle())
+    lib.ssd_oracle_derive.argtypes = [_P(A.Config), _P(Derived)]
+    lib.ssd_oracle_process.argtypes = [_P(A.Config), _P(A.Transform), _vp, _vp, _vp, C.c_int, _P(A.FrameInfo), _P(A.Plateau), _P(A.Step)]
+    lib.ssd_oracle_process_batch.argtypes = [_P(A.Config), _P(A.Transform), _vp, C.c_int, _vp]
+    lib.ssd_oracle_detect_outline.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_double, _P(C.c_double), _P(C.c_int)]
+    lib.ssd_oracle_detect_front_edge.argtypes = [_vp, C.c_int, C.c_int, _P(C.c_double), _P(C.c_double), _P(C.c_int)]
+    lib.ssd_oracle_close.argtypes = [_vp, C.c_int, C.c_int]
+    lib.ssd_oracle_points_in_quad.argtypes = [_P(C.c_double), _vp, C.c_int, _vp, _P(C.c_int)]
+    lib.ssd_oracle_camera_to_world.argtypes = [_P(A.Transform), _vp, C.c_int, _vp]
+    lib.ssd_oracle_make_transform.argtypes = [_P(C.c_double), _P(C.c_double), _P(A.Transform)]
+    lib.ssd_oracle_serialize.argtypes = [_P(A.Step), C.c_int, C.c_char_p, C.c_size_t]
+    return lib
+
+
+def ref_available():
+    return os.path.isdir(REF_SRC)
+
+
+def ref_path(cfg):
+    return os.path.join(ORACLE_DIR, "_ref", f"libssd_ref_{ref_tag(cfg)}.so")
+
+
+def build_ref(cfg):
+    """Compile the reference TUs by path for this configuration (needs /root/reference)."""
+    path = ref_path(cfg)
+    if ref_available():
+        subprocess.run(["make", "-s", "-C", ORACLE_DIR, "ref", f"W={cfg.width}", f"H={cfg.height}",
+                        f"XMIN={cfg.x_min:g}", f"XMAX={cfg.x_max:g}", f"YMIN={cfg.y_min:g}", f"YMAX={cfg.y_max:g}",
+                        f"ZMIN={cfg.z_min:g}", f"ZMAX={cfg.z_max:g}", f"TAG={ref_tag(cfg)}"], check=True)
+    return path if os.path.exists(path) else None
+
+
+def load_ref(cfg):
+    path = build_ref(cfg)
+    if path is None:
+        return None
+    lib = C.CDLL(path)
+    lib.ssd_ref_last_error.restype = C.c_char_p
+    lib.ssd_ref_config.argtypes = [_P(A.Config)]
+    lib.ssd_ref_derived.argtypes = [_P(C.c_int), _P(C.c_int), _P(C.c_double), _P(C.c_double), _P(C.c_int)]
+    lib.ssd_ref_world_to_image.argtypes = [_vp, C.c_int, _vp]
+    lib.ssd_ref_image_to_world.argtypes = [_vp, C.c_int, _vp]
+    lib.ssd_ref_make_transform.argtypes = [_P(C.c_double), _P(C.c_double), _P(A.Transform)]
+    lib.ssd_ref_process.argtypes = [_P(A.Transform), _vp, _vp, _vp, C.c_int, _P(A.FrameInfo), _P(A.Plateau), _P(A.Step), C.c_char_p, C.c_size_t]
+    lib.ssd_ref_process_timed.argtypes = [_P(A.Transform), _vp, C.c_int, C.c_int, C.c_int, _P(C.c_double), _P(C.c_int)]
+    lib.ssd_ref_detect_outline.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_double, _P(C.c_double), _P(C.c_int)]
+    lib.ssd_ref_detect_front_edge.argtypes = [_vp, C.c_int, C.c_int, _P(C.c_double), _P(C.c_double), _P(C.c_int)]
+    lib.ssd_ref_close.argtypes = [_vp, C.c_int, C.c_int]
+    lib.ssd_ref_points_in_quad.argtypes = [_P(C.c_double), _vp, C.c_int, _vp, _P(C.c_int)]
+    lib.ssd_ref_camera_to_world.argtypes = [_P(A.Transform), _vp, C.c_int, _vp]
+    lib.ssd_ref_serialize.argtypes = [_P(A.Step), C.c_int, C.c_char_p, C.c_size_t]
+    got = A.Config()
+    lib.ssd_ref_config(C.byref(got))
+    for f, _ in A.Config._fields_:
+        if f != "reserved" and getattr(got, f) != getattr(cfg, f):
+            raise RuntimeError(f"reference build config mismatch on {f}: {getattr(got, f)} != {getattr(cfg, f)}")
+    return lib
+
+
+def ptr(a):
+    return a.ctypes.data_as(_vp)
+
+
+class FrameResult:
+    """Everything one frame produces, in numpy/python form, from any of the three implementations."""
+
+    def __init__(self, labels, hist, info, plats, steps, line=None):
+        self.labels, self.hist, self.info, self.plateaus, self.steps, self.line = labels, hist, info, plats, steps, line
+
+
+def _collect(labels, hist, info, plats, steps, line=None):
+    K = info.n_plateaus
+    P = [dict(height=p.height, hmin=p.hmin, hmax=p.hmax, n_points=p.n_points, valid=p.valid, outlined=p.outlined,
+              n_in_quad=p.n_in_quad, quad_status=p.quad_status,
+              quad_world=np.array([[p.quad_world[c][0], p.quad_world[c][1]] for c in range(4)]), mean_z=p.mean_z)
+         for p in plats[:K]]
+    S = [dict(height=s.height, quad=np.array([[s.quad[c][0], s.quad[c][1]] for c in range(4)])) for s in steps[:info.n_steps]]
+    I = {f: getattr(info, f) for f, _ in A.FrameInfo._fields_}
+    return FrameResult(labels, hist[:info.n_bins].copy(), I, P, S, line)
+
+
+def oracle_process(lib, cfg, xf, xyz):
+    N = cfg.width * cfg.height
+    labels = np.empty(N, np.uint8)
+    hist = np.zeros(A.MAX_BINS, np.uint32)
+    info = A.FrameInfo()
+    plats = (A.Plateau * A.MAX_PLATEAUS)()
+    steps = (A.Step * A.MAX_STEPS)()
+    xyz = np.ascontiguousarray(xyz, np.float32)
+    rc = lib.ssd_oracle_process(C.byref(cfg), C.byref(xf), ptr(xyz), ptr(labels), ptr(hist), A.MAX_BINS, C.byref(info), plats, steps)
+    assert rc == 0, rc
+    return _collect(labels, hist, info, plats, steps)
+
+
+def ref_process(lib, cfg, xf, xyz):
+    N = cfg.width * cfg.height
+    labels = np.empty(N, np.uint8)
+    hist = np.zeros(A.MAX_BINS, np.uint32)
+    info = A.FrameInfo()
+    plats = (A.Plateau * A.MAX_PLATEAUS)()
+    steps = (A.Step * A.MAX_STEPS)()
+    line = C.create_string_buffer(1 << 14)
+    xyz = np.ascontiguousarray(xyz, np.float32)
+    rc = lib.ssd_ref_process(C.byref(xf), ptr(xyz), ptr(labels), ptr(hist), A.MAX_BINS, C.byref(info), plats, steps, line, len(line))
+    assert rc == 0, (rc, lib.ssd_ref_last_error())
+    return _collect(labels, hist, info, plats, steps, line.value.decode())
+
+
+def make_config(hostlib, width, height, **kw):
+    cfg = A.Config()
+    hostlib.ssd_gpu_default_config(C.byref(cfg), width, height)
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def make_scene(hostlib, width, height, **kw):
+    s = A.Scene()
+    hostlib.ssd_scene_default(C.byref(s), width, height)
+    for k, v in kw.items():
+        setattr(s, k, v)
+    return s
+
+
+def scene_transform(hostlib, scene):
+    w = (C.c_double * 9)()
+    c = (C.c_double * 9)()
+    hostlib.ssd_scene_calibration_points(C.byref(scene), w, c)
+    xf = A.Transform()
+    rc = hostlib.ssd_make_transform(w, c, C.byref(xf))
+    assert rc == 0
+    return xf, np.array(w[:]).reshape(3, 3), np.array(c[:]).reshape(3, 3)
+
+
+def scene_depth(hostlib, scene):
+    d = np.empty((scene.height, scene.width), np.uint16)
+    assert hostlib.ssd_synth_depth_host(C.byref(scene), ptr(d)) == 0
+    return d
+
+
+def deproject_np(scene, depth):
+    """numpy restatement of ssd_deproject_pixel: single f32 operations in the same order."""
+    H, W = depth.shape
+    u = np.arange(W, dtype=np.float32)[None, :]
+    v = np.arange(H, dtype=np.float32)[:, None]
+    xn = (u - np.float32(scene.ppx)) / np.float32(scene.fx)
+    yn = (v - np.float32(scene.ppy)) / np.float32(scene.fy)
+    z = depth.astype(np.float32) * np.float32(scene.depth_unit)
+    out = np.empty((H, W, 3), np.float32)
+    out[..., 0] = z * xn
+    out[..., 1] = z * yn
+    out[..., 2] = z
+    return out
+
+
+def scene_xyz(hostlib, scene, depth=None):
+    if depth is None:
+        depth = scene_depth(hostlib, scene)
+    xyz = np.empty((scene.height, scene.width, 3), np.float32)
+    assert hostlib.ssd_deproject_host(C.byref(scene), ptr(depth), ptr(xyz)) == 0
+    return xyz
+
+
+def compare_results(a, b, tol=1e-4, check_labels=True):
+    """a, b: FrameResult. Labels/histogram/peaks exact; step heights and corners within tol metres
+    (0.1 mm, BASELINE.json north_star). Returns a list of mismatch strings."""
+    bad = []
+    if not np.array_equal(a.hist, b.hist):
+        bad.append("histogram differs")
+    if check_labels and a.labels is not None and b.labels is not None:
+        n = int((a.labels != b.labels).sum())
+        if n:
+            bad.append(f"{n} labels differ")
+    for k in ("n_bins", "n_plateaus", "ground_index", "first_valid_index", "n_steps", "n_nonzero", "n_in_range"):
+        if a.info[k] != b.info[k]:
+            bad.append(f"info.{k}: {a.info[k]} != {b.info[k]}")
+    for i, (p, q) in enumerate(zip(a.plateaus, b.plateaus)):
+        for k in ("height", "hmin", "hmax", "n_points", "valid", "outlined"):
+            if p[k] != q[k]:
+                bad.append(f"plateau {i}.{k}: {p[k]} != {q[k]}")
+        if p["valid"] and q["valid"]:
+            if not np.allclose(p["quad_world"], q["quad_world"], rtol=0, atol=tol):
+                bad.append(f"plateau {i}.quad_world differs by {np.abs(p['quad_world'] - q['quad_world']).max():.3g}")
+            if p["quad_status"] == 0 and q["quad_status"] == 0:
+                if p["n_in_quad"] != q["n_in_quad"]:
+                    bad.append(f"plateau {i}.n_in_quad: {p['n_in_quad']} != {q['n_in_quad']}")
+                if not np.isclose(p["mean_z"], q["mean_z"], rtol=0, atol=tol, equal_nan=True):
+                    bad.append(f"plateau {i}.mean_z: {p['mean_z']} != {q['mean_z']}")
+    for i, (s, t) in enumerate(zip(a.steps, b.steps)):
+        if not np.isclose(s["height"], t["height"], rtol=0, atol=tol, equal_nan=True):
+            bad.append(f"step {i}.height: {s['height']} != {t['height']}")
+        if not np.allclose(s["quad"], t["quad"], rtol=0, atol=tol, equal_nan=True):
+            bad.append(f"step {i}.quad differs by {np.abs(s['quad'] - t['quad']).max():.3g}")
+    return bad
