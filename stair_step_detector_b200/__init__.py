@@ -1,0 +1,272 @@
+"""stair_step_detector_b200 -- B200-native per-frame geometry hot path of stair-step-detector.
+
+Python is only the thin ctypes binding over the C ABI (include/ssd_gpu.h) used by tests and bench.py;
+the product is the CUDA library in csrc/ (kernels for sm_100a) and the C++ host classes in csrc/host/
+that keep the reference's Pointcloud / Transformation / Segmentation / Stairs surface.
+
+There is no CPU fallback: the shared library must have been built (``__graft_entry__.build()``) and
+``Detector`` needs a CUDA device.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi as A
+from ._abi import Config, FrameInfo, Plateau, Scene, Step, Timing, Transform  # noqa: F401
+
+_lib = None
+
+
+def lib():
+    """The loaded libssd_gpu.so (raises ImportError if it has not been built)."""
+    global _lib
+    if _lib is None:
+        _lib = A.load()
+    return _lib
+
+
+class SsdError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def default_config(width, height, **overrides):
+    cfg = Config()
+    lib().ssd_gpu_default_config(C.byref(cfg), width, height)
+    for k, v in overrides.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def make_transform(world_pts, camera_pts):
+    """GeometricTransformation(worldPoints, cameraPoints) -> Transform (reference transformation.cpp:196-215)."""
+    w = (C.c_double * 9)(*np.asarray(world_pts, np.float64).ravel())
+    c = (C.c_double * 9)(*np.asarray(camera_pts, np.float64).ravel())
+    xf = Transform()
+    rc = lib().ssd_make_transform(w, c, C.byref(xf))
+    if rc:
+        raise SsdError(f"ssd_make_transform failed ({rc})")
+    return xf
+
+
+def default_scene(width, height, **overrides):
+    s = Scene()
+    lib().ssd_scene_default(C.byref(s), width, height)
+    for k, v in overrides.items():
+        setattr(s, k, v)
+    return s
+
+
+def scene_transform(scene):
+    w = (C.c_double * 9)()
+    c = (C.c_double * 9)()
+    lib().ssd_scene_calibration_points(C.byref(scene), w, c)
+    xf = Transform()
+    rc = lib().ssd_make_transform(w, c, C.byref(xf))
+    if rc:
+        raise SsdError(f"ssd_make_transform failed ({rc})")
+    return xf
+
+
+def randomize_scene(base, base_seed, index, min_steps, max_steps):
+    s = Scene()
+    lib().ssd_scene_randomize(C.byref(s), C.byref(base), base_seed, index, min_steps, max_steps)
+    return s
+
+
+def synth_depth_host(scene):
+    d = np.empty((scene.height, scene.width), np.uint16)
+    rc = lib().ssd_synth_depth_host(C.byref(scene), _ptr(d))
+    if rc:
+        raise SsdError(f"ssd_synth_depth_host failed ({rc})")
+    return d
+
+
+def deproject_host(scene, depth):
+    depth = np.ascontiguousarray(depth, np.uint16)
+    xyz = np.empty((scene.height, scene.width, 3), np.float32)
+    rc = lib().ssd_deproject_host(C.byref(scene), _ptr(depth), _ptr(xyz))
+    if rc:
+        raise SsdError(f"ssd_deproject_host failed ({rc})")
+    return xyz
+
+
+def serialize(steps):
+    """Stairs::serialize (reference stairs.cpp:55-70) of a list of (height, 4x2 quad)."""
+    arr = (Step * max(1, len(steps)))()
+    for i, (h, q) in enumerate(steps):
+        arr[i].height = h
+        for c in range(4):
+            arr[i].quad[c][0] = q[c][0]
+            arr[i].quad[c][1] = q[c][1]
+    n = lib().ssd_stairs_serialize(arr, len(steps), None, 0)
+    buf = C.create_string_buffer(n + 1)
+    lib().ssd_stairs_serialize(arr, len(steps), buf, n + 1)
+    return buf.value.decode()
+
+
+class Detector:
+    """One GPU context: the constant transform + configuration bound to device buffers
+    (replaces Pointcloud's constructor, reference pointcloud.cpp:602-606)."""
+
+    def __init__(self, cfg, xf, device=0, max_frames=1):
+        self._l = lib()
+        self.cfg, self.xf, self.device, self.max_frames = cfg, xf, device, max_frames
+        self.n_points = cfg.width * cfg.height
+        h = C.c_void_p()
+        rc = self._l.ssd_gpu_create(C.byref(cfg), C.byref(xf), device, max_frames, C.byref(h))
+        if rc:
+            raise SsdError(f"ssd_gpu_create failed ({rc}): {self._l.ssd_gpu_last_error(None).decode()}")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._l.ssd_gpu_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc, what):
+        if rc:
+            raise SsdError(f"{what} failed ({rc}): {self._l.ssd_gpu_last_error(self._h).decode()}")
+
+    # ---- the hot path ----
+    def process_host(self, xyz):
+        """xyz: (n_frames, H, W, 3) or (n_frames, N, 3) float32 host array (pinned or pageable)."""
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        n = xyz.size // (self.n_points * 3)
+        self._ck(self._l.ssd_gpu_process_host(self._h, _ptr(xyz), n), "ssd_gpu_process_host")
+        return n
+
+    def process_host_ptr(self, ptr, n_frames):
+        self._ck(self._l.ssd_gpu_process_host(self._h, ptr, n_frames), "ssd_gpu_process_host")
+
+    def process_device(self, dev_ptr, n_frames, flags=0):
+        self._ck(self._l.ssd_gpu_process_device_ex(self._h, dev_ptr, n_frames, flags), "ssd_gpu_process_device")
+
+    # ---- results ----
+    def steps(self, frame):
+        out = (Step * A.MAX_STEPS)()
+        n = C.c_int()
+        st = C.c_uint32()
+        self._ck(self._l.ssd_gpu_get_steps(self._h, frame, out, A.MAX_STEPS, C.byref(n), C.byref(st)), "ssd_gpu_get_steps")
+        return [(s.height, np.array([[s.quad[c][0], s.quad[c][1]] for c in range(4)])) for s in out[:n.value]], st.value
+
+    def n_steps_all(self, n_frames):
+        out = np.empty(n_frames, np.int32)
+        n = C.c_int()
+        for f in range(n_frames):
+            self._ck(self._l.ssd_gpu_get_steps(self._h, f, None, 0, C.byref(n), None), "ssd_gpu_get_steps")
+            out[f] = n.value
+        return out
+
+    def frame_info(self, frame):
+        info = FrameInfo()
+        self._ck(self._l.ssd_gpu_get_frame_info(self._h, frame, C.byref(info)), "ssd_gpu_get_frame_info")
+        return info
+
+    def plateaus(self, frame):
+        out = (Plateau * A.MAX_PLATEAUS)()
+        n = C.c_int()
+        self._ck(self._l.ssd_gpu_get_plateaus(self._h, frame, out, A.MAX_PLATEAUS, C.byref(n)), "ssd_gpu_get_plateaus")
+        return out, n.value
+
+    def labels(self, frame):
+        out = np.empty(self.n_points, np.uint8)
+        self._ck(self._l.ssd_gpu_get_labels(self._h, frame, _ptr(out)), "ssd_gpu_get_labels")
+        return out
+
+    def histogram(self, frame):
+        out = np.zeros(A.MAX_BINS, np.uint32)
+        n = C.c_int()
+        self._ck(self._l.ssd_gpu_get_histogram(self._h, frame, out.ctypes.data_as(C.POINTER(C.c_uint32)), A.MAX_BINS, C.byref(n)),
+                 "ssd_gpu_get_histogram")
+        return out[:n.value]
+
+    def timing(self):
+        t = Timing()
+        self._ck(self._l.ssd_gpu_get_timing(self._h, C.byref(t)), "ssd_gpu_get_timing")
+        return t
+
+    def line(self, frame):
+        """The result line the reference prints for this frame (pointcloud.cpp:625)."""
+        s, _ = self.steps(frame)
+        return serialize(s)
+
+    # ---- single-stage entry points ----
+    def detect_outline(self, image, min_img_y_extent, xy_ratio):
+        image = np.ascontiguousarray(image, np.uint8)
+        q = (C.c_double * 8)()
+        v = C.c_int()
+        self._ck(self._l.ssd_gpu_detect_outline(self._h, _ptr(image), min_img_y_extent, xy_ratio, q, C.byref(v)), "ssd_gpu_detect_outline")
+        return np.array(q[:]).reshape(4, 2), v.value
+
+    def detect_front_edge(self, image):
+        image = np.ascontiguousarray(image, np.uint8)
+        l = (C.c_double * 2)()
+        r = (C.c_double * 2)()
+        v = C.c_int()
+        self._ck(self._l.ssd_gpu_detect_front_edge(self._h, _ptr(image), l, r, C.byref(v)), "ssd_gpu_detect_front_edge")
+        return np.array(l[:]), np.array(r[:]), v.value
+
+    def points_in_quad(self, quad, xy):
+        xy = np.ascontiguousarray(xy, np.float64)
+        n = xy.size // 2
+        q = (C.c_double * 8)(*np.asarray(quad, np.float64).ravel())
+        inside = np.empty(n, np.uint8)
+        st = C.c_int()
+        self._ck(self._l.ssd_gpu_points_in_quad(self._h, q, _ptr(xy), n, _ptr(inside), C.byref(st)), "ssd_gpu_points_in_quad")
+        return inside, st.value
+
+    def camera_to_world(self, xyz):
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        n = xyz.size // 3
+        out = np.empty((n, 3), np.float64)
+        self._ck(self._l.ssd_gpu_camera_to_world(self._h, _ptr(xyz), n, _ptr(out)), "ssd_gpu_camera_to_world")
+        return out
+
+    # ---- device memory + synthetic frames ----
+    def malloc(self, nbytes):
+        p = C.c_void_p()
+        self._ck(self._l.ssd_gpu_malloc(self._h, nbytes, C.byref(p)), "ssd_gpu_malloc")
+        return p
+
+    def free(self, p):
+        self._ck(self._l.ssd_gpu_free(self._h, p), "ssd_gpu_free")
+
+    def h2d(self, dst, src):
+        src = np.ascontiguousarray(src)
+        self._ck(self._l.ssd_gpu_memcpy_h2d(self._h, dst, _ptr(src), src.nbytes), "ssd_gpu_memcpy_h2d")
+
+    def d2h(self, dst, src, nbytes=None):
+        self._ck(self._l.ssd_gpu_memcpy_d2h(self._h, _ptr(dst), src, dst.nbytes if nbytes is None else nbytes), "ssd_gpu_memcpy_d2h")
+
+    def synth_frames(self, base_scene, base_seed, first_index, n_frames, min_steps, max_steps, xyz_dev, depth_dev=None):
+        self._ck(self._l.ssd_gpu_synth_frames(self._h, C.byref(base_scene), base_seed, first_index, n_frames, min_steps, max_steps,
+                                              xyz_dev, depth_dev), "ssd_gpu_synth_frames")
+
+
+def pinned_empty(shape, dtype):
+    """numpy array over pinned host memory (cudaMallocHost); keep the returned handle alive."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p()
+    rc = lib().ssd_gpu_malloc_host(n, C.byref(p))
+    if rc:
+        raise SsdError("ssd_gpu_malloc_host failed")
+    buf = (C.c_char * n).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    return arr, p
+
+
+def free_pinned(p):
+    lib().ssd_gpu_free_host(p)

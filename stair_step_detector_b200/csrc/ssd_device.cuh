@@ -1,0 +1,485 @@
+// ssd_device.cuh -- device-side data layout and exact geometry primitives of the hot path.
+//
+// This translation unit is compiled with -fmad=false: the reference build never contracts a*b+c
+// (CMakeLists.txt:23-28 sets no -march / -ffast-math), and bit-exact labels need the same roundings.
+// Every formula cites the reference file:line whose arithmetic (operation order) it reproduces.
+#pragma once
+#include "../../include/ssd_gpu.h"
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define SSD_BINS_PAD 256            // histogram slots: bins 0..252, 254 = out of range, 255 = invalid
+#define SSD_CODE_OUT_OF_RANGE 254u
+#define SSD_CODE_INVALID 255u
+#define SSD_MAX_LINE_PTS 192        // points per edge list (W/25 + 2 scans split in overlapping halves)
+#define SSD_MAX_SCANS 384
+#define SSD_MAX_VPTS 512            // vertical-edge probe rows (H/10 + 1)
+#define SSD_FIX_SHIFT 36            // fixed-point fraction bits of the per-step z accumulator
+
+// Constant per-context parameters, passed to every kernel by value (__grid_constant__).
+struct DevParams
+{
+  int W, H, N;             // image size, points per frame
+  int wpr;                 // 32-bit words per BEV bitmap row
+  int n_bins;              // HeightsHistogram size (pointcloud.cpp:196)
+  int min_height;          // ProcessingConfiguration::minHeight (pointcloud.cpp:102)
+  int min_img_y_extent;    // (pointcloud.cpp:103)
+  unsigned min_peak_points;
+  int bev_slots;           // BEV bitmaps per frame
+  int tiles_per_frame;
+  int pad0, pad1;
+  double a[9], b[3];       // CameraToWorld
+  double ext_a[4], ext_b[2], ext_z;
+  double x_min, x_max, y_min, y_max, z_min, z_max;
+  double hir;              // heightIntervalReciprocal (pointcloud.cpp:101)
+  double x_to_image, y_to_image, x_to_world, y_to_world, xy_ratio; // Projection2D (pointcloud.cpp:73-76,95)
+};
+
+struct SegmentDev
+{
+  double lo_x, hi_x, lo_y, hi_y; // bounding box
+  double k, c;                   // flat: x*k + y + c ; steep: x + y*k + c
+  int steep, left_is_pos;
+};
+
+// QuadrilateralTest flattened into data (quadrilateralTest.cpp:275-443): <=3 rows x <=3 cells,
+// each cell a constant or 1-2 half-plane tests.
+struct QuadTestDev
+{
+  double tb_lo_x, tb_hi_x, tb_lo_y, tb_hi_y;
+  SegmentDev seg[4];
+  double row_upper_y[3];
+  double cell_upper_x[3][3];
+  int nrow;
+  int ncell[3];
+  signed char cell_nseg[3][3]; // 0,1,2 segments; for 0: cell_seg[.][.][0] holds the constant result
+  signed char cell_seg[3][3][2];
+  int inside_is_left;
+  int status; // 0 ok, 1 the reference ctor would throw
+};
+
+struct PlateauDev
+{
+  int height, hmin, hmax;
+  unsigned n_points;
+  int valid, outlined;
+  unsigned n_in_quad;
+  int quad_status;
+  double quad_px[4][2];
+  double quad_world[4][2];
+  double mean_z;
+  unsigned long long sum_fix; // sum of z in 2^-36 m units (two's complement)
+  int row_min, row_max;       // BEV rows touched by this plateau's bitmap
+  int front_valid;
+  int pad;
+  QuadTestDev qt;
+};
+
+struct FrameDev
+{
+  unsigned hist[SSD_BINS_PAD];
+  unsigned char lut[SSD_BINS_PAD]; // bin code -> segment label
+  unsigned status;
+  int n_plateaus;
+  int ground_index, first_outlined, first_valid;
+  int n_steps;
+  unsigned n_nonzero, n_in_range;
+  PlateauDev plat[SSD_GPU_MAX_PLATEAUS];
+};
+
+// compact per-frame result copied to the host after every call
+struct FrameOut
+{
+  ssd_gpu_frame_info info;
+  ssd_gpu_step steps[SSD_GPU_MAX_STEPS];
+};
+
+struct P2d
+{
+  double x, y;
+};
+struct P2id
+{
+  int x, y;
+};
+struct LineDd
+{
+  double a, b, c;
+};
+struct LineId
+{
+  int a, b, c;
+};
+
+// ---- CameraToWorld: ((a_i0*x + a_i1*y) + a_i2*z) + b_i  (transformation.h:59-64, Boost.QVM mat*vec, vec+vec) ----
+__device__ __forceinline__ void camera_to_world(const DevParams &p, float fx, float fy, float fz, double &wx, double &wy, double &wz)
+{
+  const double x = fx, y = fy, z = fz;
+  wx = ((p.a[0] * x + p.a[1] * y) + p.a[2] * z) + p.b[0];
+  wy = ((p.a[3] * x + p.a[4] * y) + p.a[5] * z) + p.b[1];
+  wz = ((p.a[6] * x + p.a[7] * y) + p.a[8] * z) + p.b[2];
+}
+
+// z>0 (pointcloud.cpp:143-146), range (pointcloud.cpp:155-163), height index (pointcloud.cpp:175)
+__device__ __forceinline__ unsigned point_code(const DevParams &p, float fx, float fy, float fz)
+{
+  if(!(fz > 0.f))
+    return SSD_CODE_INVALID;
+  double wx, wy, wz;
+  camera_to_world(p, fx, fy, fz, wx, wy, wz);
+  const bool in = wx > p.x_min && wx < p.x_max && wy > p.y_min && wy < p.y_max && wz > p.z_min && wz < p.z_max;
+  if(!in)
+    return SSD_CODE_OUT_OF_RANGE;
+  return (unsigned)(unsigned short)((wz - p.z_min) * p.hir);
+}
+
+// Projection2D::worldToImage (pointcloud.cpp:79-83)
+__device__ __forceinline__ void world_to_image(const DevParams &p, double wx, double wy, int &ix, int &iy)
+{
+  ix = (int)((wx - p.x_min) * p.x_to_image);
+  iy = (int)((p.y_max - wy) * p.y_to_image);
+}
+
+// Projection2D::imageToWorld (pointcloud.cpp:84-88)
+__device__ __forceinline__ P2d image_to_world(const DevParams &p, P2d px)
+{
+  P2d w;
+  w.x = p.x_min + px.x * p.x_to_world;
+  w.y = p.y_max - px.y * p.y_to_world;
+  return w;
+}
+
+// Correctly rounded hypot for the magnitudes that occur here (no overflow/underflow handling needed):
+// x^2+y^2 in double-double via exact FMA residuals, one Newton correction of the square root.
+// Stands in for std::hypot (segmentation.cpp:346-349); tests/test_hypot.py checks it against glibc.
+__device__ __forceinline__ double hypot_cr(double x, double y)
+{
+  const double xx = x * x, yy = y * y;
+  const double ex = __fma_rn(x, x, -xx), ey = __fma_rn(y, y, -yy);
+  const double s = xx + yy;
+  const double bb = s - xx;
+  const double es = (xx - (s - bb)) + (yy - bb); // TwoSum error
+  const double lo = es + (ex + ey);
+  if(s == 0.0)
+    return 0.0;
+  const double h = sqrt(s);
+  const double r = __fma_rn(-h, h, s) + lo;
+  return h + r / (2.0 * h);
+}
+
+// ---- lines (types.h:117-163, segmentation.cpp:321-401) ----
+__device__ __forceinline__ LineId linei_from(P2id p, P2id q)
+{
+  LineId l;
+  l.a = q.y - p.y;
+  l.b = p.x - q.x;
+  l.c = q.x * p.y - p.x * q.y;
+  return l;
+}
+__device__ __forceinline__ LineDd lined_from_pts(P2d p, P2d q)
+{
+  LineDd l;
+  l.a = q.y - p.y;
+  l.b = p.x - q.x;
+  l.c = q.x * p.y - p.x * q.y;
+  return l;
+}
+__device__ __forceinline__ LineDd lined_from_i(LineId l)
+{
+  LineDd d;
+  d.a = l.a;
+  d.b = l.b;
+  d.c = l.c;
+  return d;
+}
+__device__ __forceinline__ LineDd lined_normalized(LineDd l) // segmentation.cpp:381-385
+{
+  const double h = hypot_cr(l.a, l.b);
+  LineDd r;
+  r.a = l.a / h;
+  r.b = l.b / h;
+  r.c = l.c / h;
+  return r;
+}
+__device__ __forceinline__ LineDd bisector(LineDd n, LineDd o) // :386-394, operands already normalized
+{
+  LineDd r;
+  r.a = n.a + o.a;
+  r.b = n.b + o.b;
+  r.c = n.c + o.c;
+  return r;
+}
+// Line::intersection with the 60 degree gate (segmentation.cpp:350-362)
+__device__ __forceinline__ bool lined_intersection(LineDd t, LineDd o, P2d &out)
+{
+  const double tan60 = 1.7320508075688772935274463415059;
+  const double numerator = t.a * o.b - o.a * t.b;
+  const double denominator = t.a * o.a + t.b * o.b;
+  if(fabs(numerator) > fabs(denominator) * tan60)
+  {
+    out.x = (t.b * o.c - o.b * t.c) / numerator;
+    out.y = (o.a * t.c - t.a * o.c) / numerator;
+    return true;
+  }
+  return false;
+}
+// nested Line::intersection without gate (pointcloud.cpp:514-526)
+__device__ __forceinline__ P2d line_intersection_plain(LineDd t, LineDd o)
+{
+  const double d = t.a * o.b - o.a * t.b;
+  P2d r;
+  r.x = (t.b * o.c - o.b * t.c) / d;
+  r.y = (o.a * t.c - t.a * o.c) / d;
+  return r;
+}
+
+// Quadrilateral::isConvex (segmentation.cpp:755-787)
+__device__ __forceinline__ bool quad_is_convex(const P2d q[4])
+{
+  const double vx[4] = { q[1].x - q[0].x, q[3].x - q[1].x, q[2].x - q[3].x, q[0].x - q[2].x };
+  const double vy[4] = { q[1].y - q[0].y, q[3].y - q[1].y, q[2].y - q[3].y, q[0].y - q[2].y };
+  const bool p01 = vx[0] * vy[1] - vx[1] * vy[0] > 0;
+  const bool p12 = vx[1] * vy[2] - vx[2] * vy[1] > 0;
+  const bool p23 = vx[2] * vy[3] - vx[3] * vy[2] > 0;
+  const bool p30 = vx[3] * vy[0] - vx[0] * vy[3] > 0;
+  return p01 == p12 && p01 == p23 && p01 == p30;
+}
+
+// ---- QuadrilateralTest (quadrilateralTest.cpp) ----
+struct SectorD
+{
+  double lo, hi;
+};
+__device__ __forceinline__ SectorD sector_make(double a, double b) // :29-41
+{
+  SectorD s;
+  s.lo = a;
+  s.hi = a;
+  if(s.lo > b)
+    s.lo = b;
+  else if(s.hi < b)
+    s.hi = b;
+  return s;
+}
+__device__ __forceinline__ void sector_expand(SectorD &s, double c)
+{
+  if(s.lo > c)
+    s.lo = c;
+  else if(s.hi < c)
+    s.hi = c;
+}
+__device__ __forceinline__ bool sector_overlaps(SectorD a, SectorD b) { return a.lo < b.hi && a.hi > b.lo; }
+__device__ __forceinline__ bool sector_is_above(SectorD a, SectorD b) { return (a.lo + a.hi) / 2 < b.lo; }
+__device__ __forceinline__ bool sector_is_below(SectorD a, SectorD b) { return (a.lo + a.hi) / 2 > b.hi; }
+
+__device__ __forceinline__ SegmentDev segment_create(P2d p, P2d q) // :240-259 with the line classes :133-231
+{
+  SegmentDev s;
+  SectorD sx = sector_make(p.x, q.x), sy = sector_make(p.y, q.y);
+  s.lo_x = sx.lo;
+  s.hi_x = sx.hi;
+  s.lo_y = sy.lo;
+  s.hi_y = sy.hi;
+  const double dx = q.x - p.x, dy = q.y - p.y;
+  const LineDd l = lined_from_pts(p, q);
+  if(fabs(dx) < fabs(dy))
+  {
+    s.steep = 1;
+    s.k = l.b / l.a;
+    s.c = l.c / l.a;
+    s.left_is_pos = !(dy > 0);
+  }
+  else
+  {
+    s.steep = 0;
+    s.k = l.a / l.b;
+    s.c = l.c / l.b;
+    s.left_is_pos = dx > 0;
+  }
+  return s;
+}
+__device__ __forceinline__ bool segment_is_left(const SegmentDev &s, double x, double y)
+{
+  const bool pos = s.steep ? (x + y * s.k + s.c > 0) : (x * s.k + y + s.c > 0);
+  return s.left_is_pos ? pos : !pos;
+}
+
+// ctor (quadrilateralTest.cpp:275-443). status 1 where the reference throws std::invalid_argument.
+__device__ inline void quadtest_init(QuadTestDev &t, const P2d q[4])
+{
+  t.status = 0;
+  SectorD tx = sector_make(q[0].x, q[1].x), ty = sector_make(q[0].y, q[1].y);
+  sector_expand(tx, q[2].x);
+  sector_expand(ty, q[2].y);
+  sector_expand(tx, q[3].x);
+  sector_expand(ty, q[3].y);
+  t.tb_lo_x = tx.lo;
+  t.tb_hi_x = tx.hi;
+  t.tb_lo_y = ty.lo;
+  t.tb_hi_y = ty.hi;
+  t.seg[0] = segment_create(q[0], q[1]);
+  t.seg[1] = segment_create(q[1], q[3]);
+  t.seg[2] = segment_create(q[3], q[2]);
+  t.seg[3] = segment_create(q[2], q[0]);
+  t.inside_is_left = segment_is_left(t.seg[0], q[3].x, q[3].y);
+  t.nrow = 0;
+  if(t.inside_is_left != (int)segment_is_left(t.seg[1], q[2].x, q[2].y) || t.inside_is_left != (int)segment_is_left(t.seg[2], q[0].x, q[0].y) ||
+     t.inside_is_left != (int)segment_is_left(t.seg[3], q[1].x, q[1].y))
+  {
+    t.status = 1;
+    return;
+  }
+  double xs[4] = { q[0].x, q[1].x, q[2].x, q[3].x }, ys[4] = { q[0].y, q[1].y, q[2].y, q[3].y };
+#pragma unroll
+  for(int i = 1; i < 4; i++)
+    for(int j = i; j > 0; j--)
+    {
+      if(xs[j] < xs[j - 1])
+      {
+        const double tmp = xs[j];
+        xs[j] = xs[j - 1];
+        xs[j - 1] = tmp;
+      }
+      if(ys[j] < ys[j - 1])
+      {
+        const double tmp = ys[j];
+        ys[j] = ys[j - 1];
+        ys[j - 1] = tmp;
+      }
+    }
+  // segment map: rows x cells (:314-345); neighbour flags only matter for empty cells
+  int cellNb[3][3]; // bit r set: neighborExists[r]
+  double lowerY = ys[0];
+  for(int yi = 1; yi < 4; yi++)
+  {
+    if(!(lowerY < ys[yi]))
+      continue;
+    const int r = t.nrow++;
+    t.row_upper_y[r] = ys[yi];
+    t.ncell[r] = 0;
+    double lowerX = xs[0];
+    for(int xi = 1; xi < 4; xi++)
+    {
+      if(!(lowerX < xs[xi]))
+        continue;
+      const int c = t.ncell[r]++;
+      t.cell_upper_x[r][c] = xs[xi];
+      const SectorD cx = sector_make(lowerX, xs[xi]), cy = sector_make(lowerY, ys[yi]);
+      int nseg = 0, nb = 0;
+      int ids[4];
+      for(int si = 0; si < 4; si++)
+      {
+        SectorD sx, sy;
+        sx.lo = t.seg[si].lo_x;
+        sx.hi = t.seg[si].hi_x;
+        sy.lo = t.seg[si].lo_y;
+        sy.hi = t.seg[si].hi_y;
+        if(sector_overlaps(cx, sx) && sector_overlaps(cy, sy))
+          ids[nseg++] = si;
+        if(nseg == 0)
+        {
+          int rel = 0; // BBox::getRelativePosition (:96-113)
+          if(sector_overlaps(cy, sy))
+          {
+            if(sector_is_above(cx, sx))
+              rel = 1;
+            else if(sector_is_below(cx, sx))
+              rel = 2;
+          }
+          if(rel == 0 && sector_overlaps(cx, sx))
+          {
+            if(sector_is_above(cy, sy))
+              rel = 3;
+            else if(sector_is_below(cy, sy))
+              rel = 4;
+          }
+          nb |= 1 << rel;
+        }
+      }
+      if(nseg > 2)
+        t.status = 1; // :357-358 (reported after the map is built; no side effects in between)
+      t.cell_nseg[r][c] = (signed char)nseg;
+      t.cell_seg[r][c][0] = (signed char)(nseg > 0 ? ids[0] : 0);
+      t.cell_seg[r][c][1] = (signed char)(nseg > 1 ? ids[1] : 0);
+      cellNb[r][c] = nb;
+      lowerX = xs[xi];
+    }
+    lowerY = ys[yi];
+  }
+  if(t.nrow == 0)
+  {
+    t.status = 1; // :347-348
+    return;
+  }
+  for(int r = 0; r < t.nrow; r++)
+    if(t.ncell[r] == 0)
+      t.status = 1; // :352-353
+  if(t.status)
+    return;
+  // merge equal neighbours (:362-380)
+  for(int r = 0; r < t.nrow; r++)
+  {
+    int ci = 0;
+    while(ci != t.ncell[r] - 1)
+    {
+      const int n0 = t.cell_nseg[r][ci], n1 = t.cell_nseg[r][ci + 1];
+      if((n0 == 0 && n1 == 0) || (n0 > 1 && n1 > 1))
+      {
+        t.status = 1;
+        return;
+      }
+      bool same = n0 == n1;
+      for(int s = 0; same && s < n0; s++)
+        same = t.cell_seg[r][ci][s] == t.cell_seg[r][ci + 1][s];
+      if(same)
+      {
+        for(int k = ci; k < t.ncell[r] - 1; k++)
+        {
+          t.cell_upper_x[r][k] = t.cell_upper_x[r][k + 1];
+          t.cell_nseg[r][k] = t.cell_nseg[r][k + 1];
+          t.cell_seg[r][k][0] = t.cell_seg[r][k + 1][0];
+          t.cell_seg[r][k][1] = t.cell_seg[r][k + 1][1];
+          cellNb[r][k] = cellNb[r][k + 1];
+        }
+        t.ncell[r]--;
+      }
+      else
+        ci++;
+    }
+  }
+  // set0Segments(...) constant (:387-392): all four neighbour directions seen
+  for(int r = 0; r < t.nrow; r++)
+    for(int c = 0; c < t.ncell[r]; c++)
+      if(t.cell_nseg[r][c] == 0)
+        t.cell_seg[r][c][0] = (signed char)((cellNb[r][c] & 0x1e) == 0x1e);
+}
+
+// isPointWithin (quadrilateralTest.cpp:445-451 and the selector/tester lambdas :453-598)
+__device__ __forceinline__ bool quadtest_within(const QuadTestDev &t, double x, double y)
+{
+  if(!(t.tb_lo_x < x && x < t.tb_hi_x && t.tb_lo_y < y && y < t.tb_hi_y))
+    return false;
+  int r = 0;
+  if(t.nrow == 2)
+    r = y < t.row_upper_y[0] ? 0 : 1;
+  else if(t.nrow == 3)
+    r = y < t.row_upper_y[0] ? 0 : (y < t.row_upper_y[1] ? 1 : 2);
+  int c = 0;
+  if(t.ncell[r] == 2)
+    c = x < t.cell_upper_x[r][0] ? 0 : 1;
+  else if(t.ncell[r] == 3)
+    c = x < t.cell_upper_x[r][0] ? 0 : (x < t.cell_upper_x[r][1] ? 1 : 2);
+  const int n = t.cell_nseg[r][c];
+  if(n == 0)
+    return t.cell_seg[r][c][0] != 0;
+  bool in = (int)segment_is_left(t.seg[t.cell_seg[r][c][0]], x, y) == t.inside_is_left;
+  if(n == 2)
+    in = in && (int)segment_is_left(t.seg[t.cell_seg[r][c][1]], x, y) == t.inside_is_left;
+  return in;
+}
+
+// fixed-point z for the order-independent (deterministic) per-step sum
+__device__ __forceinline__ long long z_to_fix(double z)
+{
+  return __double2ll_rn(z * (double)(1ull << SSD_FIX_SHIFT));
+}

@@ -1,0 +1,800 @@
+// ssd_gpu.cu -- context, launch chain and C ABI (include/ssd_gpu.h) of the B200 stair-step geometry path.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (see build.py). No CPU fallback.
+#include "ssd_device.cuh"
+#include "ssd_kernels_points.cuh"
+#include "ssd_kernels_outline.cuh"
+#include "scene_model.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#define SSD_PT_ITERS 4
+#define SSD_TILE_POINTS (SSD_PT_THREADS * 4 * SSD_PT_ITERS)
+
+static thread_local std::string g_create_error;
+
+struct ssd_gpu_ctx
+{
+  int device = 0;
+  int max_frames = 0;
+  int chunk_frames = 0;
+  ssd_gpu_config cfg{};
+  ssd_gpu_transform xf{};
+  DevParams dp{};
+  size_t bm_words = 0;        // words per BEV bitmap
+  size_t smem_cap_words = 0;  // dynamic shared memory available to the band (words)
+  size_t ol_dyn_smem = 0;
+  cudaStream_t stream[2]{};
+  cudaStream_t copy_stream{};
+  cudaEvent_t ev_start{}, ev_stop{}, ev_h2d0{}, ev_h2d1{};
+  cudaEvent_t ev_in_ready[2]{}, ev_in_free[2]{}, ev_chunk_done[2]{};
+  FrameDev *d_frames = nullptr;   // max_frames
+  FrameOut *d_out = nullptr;      // max_frames
+  FrameOut *h_out = nullptr;      // pinned
+  unsigned char *d_labels = nullptr; // max_frames * N
+  unsigned *d_bev = nullptr, *d_bev2 = nullptr; // 2 x chunk_frames * MAX_PLATEAUS * bm_words (per stream)
+  float *d_stage[2]{};            // host-input staging, chunk_frames frames each
+  int n_frames_last = 0;
+  int flags_last = 0;
+  ssd_gpu_timing timing{};
+  std::string err;
+  // single-stage scratch
+  unsigned char *d_img = nullptr;
+};
+
+#define CK(call)                                                                                         \
+  do                                                                                                     \
+  {                                                                                                      \
+    cudaError_t e_ = (call);                                                                             \
+    if(e_ != cudaSuccess)                                                                                \
+    {                                                                                                    \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                     \
+      return SSD_E_CUDA;                                                                                 \
+    }                                                                                                    \
+  } while(0)
+
+static int fail(ssd_gpu_ctx *ctx, int code, const std::string &msg)
+{
+  if(ctx)
+    ctx->err = msg;
+  else
+    g_create_error = msg;
+  return code;
+}
+
+// ProcessingConfiguration / Projection2D (pointcloud.cpp:60-106)
+static int derive_params(const ssd_gpu_config &c, const ssd_gpu_transform &t, DevParams &d)
+{
+  memset(&d, 0, sizeof(d));
+  if(c.width <= 0 || c.height <= 0 || !(c.x_max > c.x_min) || !(c.y_max > c.y_min) || !(c.z_max > c.z_min) || !(c.height_interval > 0))
+    return SSD_E_INVALID_ARG;
+  d.W = c.width;
+  d.H = c.height;
+  d.N = c.width * c.height;
+  d.wpr = (c.width + 31) / 32;
+  d.hir = 1.0 / c.height_interval;
+  d.min_height = (uint16_t)((c.min_height_above_ground - c.z_min) * d.hir);
+  d.min_img_y_extent = (int)(c.min_step_depth * c.height / (c.y_max - c.y_min));
+  d.x_to_image = c.width / (c.x_max - c.x_min);
+  d.y_to_image = c.height / (c.y_max - c.y_min);
+  d.x_to_world = 1 / d.x_to_image;
+  d.y_to_world = 1 / d.y_to_image;
+  d.xy_ratio = d.x_to_image / d.y_to_image;
+  d.n_bins = (int)((size_t)((c.z_max - c.z_min) * d.hir) + 1);
+  d.min_peak_points = c.min_peak_points;
+  d.bev_slots = SSD_GPU_MAX_PLATEAUS;
+  d.tiles_per_frame = (d.N + SSD_TILE_POINTS - 1) / SSD_TILE_POINTS;
+  memcpy(d.a, t.a, sizeof(d.a));
+  memcpy(d.b, t.b, sizeof(d.b));
+  memcpy(d.ext_a, t.ext_a, sizeof(d.ext_a));
+  memcpy(d.ext_b, t.ext_b, sizeof(d.ext_b));
+  d.ext_z = t.ext_z;
+  d.x_min = c.x_min;
+  d.x_max = c.x_max;
+  d.y_min = c.y_min;
+  d.y_max = c.y_max;
+  d.z_min = c.z_min;
+  d.z_max = c.z_max;
+  if(d.n_bins < 3 || d.n_bins > SSD_GPU_MAX_BINS)
+    return SSD_E_RANGE;
+  if(d.N % 4 != 0)
+    return SSD_E_INVALID_ARG; // vertices are loaded four at a time (three 16-byte loads)
+  if(c.width / 25 + 4 > SSD_MAX_SCANS || c.width / 50 + 6 > SSD_MAX_LINE_PTS || c.height / 10 + 2 > SSD_MAX_VPTS)
+    return SSD_E_RANGE;
+  return SSD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scene generation / deprojection kernels (synthetic input source)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_synth_frames(ssd_scene base, uint64_t base_seed, long long first_index, int n_frames, int min_steps, int max_steps,
+                               float *__restrict__ xyz, uint16_t *__restrict__ depth)
+{
+  __shared__ ssd_scene s;
+  __shared__ ssd_scene_rt rt;
+  const int f = blockIdx.y;
+  if(threadIdx.x == 0)
+  {
+    if(min_steps > 0)
+      ssd_scene_randomize_hd(&s, &base, base_seed, first_index + f, min_steps, max_steps);
+    else
+      s = base;
+    ssd_scene_prepare(&s, &rt);
+  }
+  __syncthreads();
+  const int N = s.width * s.height;
+  for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x)
+  {
+    const int v = i / s.width, u = i - v * s.width;
+    const uint16_t d = ssd_scene_depth(&s, &rt, u, v);
+    if(depth)
+      depth[(size_t)f * N + i] = d;
+    float o[3];
+    ssd_deproject_pixel(&s, u, v, d, o);
+    float *dst = xyz + ((size_t)f * N + i) * 3;
+    dst[0] = o[0];
+    dst[1] = o[1];
+    dst[2] = o[2];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// single-stage kernels (same device functions as the chain)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_pack_bitmap(const __grid_constant__ DevParams p, const unsigned char *__restrict__ img, unsigned *__restrict__ bm)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x; // word index
+  if(i >= p.H * p.wpr)
+    return;
+  const int y = i / p.wpr, w = i - y * p.wpr;
+  unsigned v = 0;
+  for(int b = 0; b < 32; b++)
+  {
+    const int x = w * 32 + b;
+    if(x < p.W && img[(size_t)y * p.W + x])
+      v |= 1u << b;
+  }
+  bm[i] = v;
+}
+
+__global__ void k_test_setup_plateau(FrameDev *frames, int H)
+{
+  FrameDev &F = frames[0];
+  F.n_plateaus = 1;
+  F.first_outlined = 0;
+  F.ground_index = -1;
+  F.first_valid = -1;
+  F.status = 0;
+  PlateauDev &P = F.plat[0];
+  P.outlined = 1;
+  P.valid = 0;
+  P.row_min = 0;
+  P.row_max = H - 1;
+}
+
+__global__ void __launch_bounds__(SSD_OL_THREADS) k_test_front_edge(const __grid_constant__ DevParams p, unsigned *__restrict__ bev,
+                                                                     unsigned *__restrict__ bev2, size_t smem_cap_words, double *out)
+{
+  extern __shared__ __align__(16) unsigned s_words[];
+  __shared__ OutlineShared S;
+  __shared__ Band bd;
+  __shared__ int s_smem_path;
+  const int tid = threadIdx.x;
+  if(tid == 0)
+    s_smem_path = band_setup(p, bd, 0, p.H - 1, s_words, smem_cap_words, bev, bev2);
+  __syncthreads();
+  band_close(p, bd, bev, s_smem_path ? bev : nullptr, tid, SSD_OL_THREADS);
+  P2d l, r;
+  int valid;
+  detect_front_edge_block(p, bd, S, l, r, valid, tid, SSD_OL_THREADS);
+  if(!s_smem_path)
+  {
+    __syncthreads();
+    band_clear_global(p, bd, tid, SSD_OL_THREADS);
+  }
+  if(tid == 0)
+  {
+    out[0] = l.x;
+    out[1] = l.y;
+    out[2] = r.x;
+    out[3] = r.y;
+    out[4] = valid;
+  }
+}
+
+__global__ void k_test_points_in_quad(const double *__restrict__ quad, const double *__restrict__ xy, int n, unsigned char *__restrict__ inside,
+                                      int *ctor_status)
+{
+  __shared__ QuadTestDev qt;
+  if(threadIdx.x == 0)
+  {
+    P2d q[4];
+    for(int i = 0; i < 4; i++)
+    {
+      q[i].x = quad[i * 2];
+      q[i].y = quad[i * 2 + 1];
+    }
+    quadtest_init(qt, q);
+    if(blockIdx.x == 0)
+      *ctor_status = qt.status;
+  }
+  __syncthreads();
+  for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    inside[i] = qt.status ? 0 : (unsigned char)quadtest_within(qt, xy[i * 2], xy[i * 2 + 1]);
+}
+
+__global__ void k_test_camera_to_world(const __grid_constant__ DevParams p, const float *__restrict__ xyz, int n, double *__restrict__ world)
+{
+  for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+  {
+    double x, y, z;
+    camera_to_world(p, xyz[i * 3], xyz[i * 3 + 1], xyz[i * 3 + 2], x, y, z);
+    world[i * 3] = x;
+    world[i * 3 + 1] = y;
+    world[i * 3 + 2] = z;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the launch chain for one chunk of frames on one stream
+// ---------------------------------------------------------------------------------------------
+static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, int frame0, int nf, int *launches)
+{
+  const DevParams &p = ctx->dp;
+  cudaStream_t st = ctx->stream[s];
+  FrameDev *frames = ctx->d_frames + frame0;
+  unsigned char *labels = ctx->d_labels + (size_t)frame0 * p.N;
+  unsigned *bev = ctx->d_bev + (size_t)s * ctx->chunk_frames * SSD_GPU_MAX_PLATEAUS * ctx->bm_words;
+  unsigned *bev2 = ctx->d_bev2 + (size_t)s * ctx->chunk_frames * SSD_GPU_MAX_PLATEAUS * ctx->bm_words;
+  const dim3 gpt(p.tiles_per_frame, nf);
+  const size_t qt_smem = sizeof(QuadTestDev) * SSD_GPU_MAX_PLATEAUS;
+
+  k_transform_bin<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, 0, st>>>(p, xyz_dev, labels, frames);
+  k_peaks<<<(nf + 31) / 32, 32, 0, st>>>(p, frames, nf);
+  k_label_bev<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, 0, st>>>(p, xyz_dev, labels, frames, bev, ctx->bm_words);
+  k_outline<<<dim3(SSD_GPU_MAX_PLATEAUS, nf), SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, bev, bev2, ctx->bm_words, ctx->smem_cap_words);
+  k_frame_logic<<<(nf + 31) / 32, 32, 0, st>>>(p, frames, nf);
+  k_quad_reduce<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, qt_smem, st>>>(p, xyz_dev, labels, frames, bev, ctx->bm_words);
+  k_finalize<<<nf, SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, ctx->d_out + frame0, bev, bev2, ctx->bm_words, ctx->smem_cap_words);
+  *launches += 7;
+  CK(cudaGetLastError());
+  return SSD_OK;
+}
+
+extern "C"
+{
+
+int ssd_gpu_device_count(void)
+{
+  int n = 0;
+  if(cudaGetDeviceCount(&n) != cudaSuccess)
+    return 0;
+  return n;
+}
+
+const char *ssd_gpu_last_error(const ssd_gpu_ctx *ctx)
+{
+  return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+void ssd_gpu_destroy(ssd_gpu_ctx *ctx)
+{
+  if(!ctx)
+    return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  cudaFree(ctx->d_frames);
+  cudaFree(ctx->d_out);
+  cudaFreeHost(ctx->h_out);
+  cudaFree(ctx->d_labels);
+  cudaFree(ctx->d_bev);
+  cudaFree(ctx->d_bev2);
+  cudaFree(ctx->d_stage[0]);
+  cudaFree(ctx->d_stage[1]);
+  cudaFree(ctx->d_img);
+  for(int i = 0; i < 2; i++)
+  {
+    if(ctx->stream[i])
+      cudaStreamDestroy(ctx->stream[i]);
+    if(ctx->ev_in_ready[i])
+      cudaEventDestroy(ctx->ev_in_ready[i]);
+    if(ctx->ev_in_free[i])
+      cudaEventDestroy(ctx->ev_in_free[i]);
+    if(ctx->ev_chunk_done[i])
+      cudaEventDestroy(ctx->ev_chunk_done[i]);
+  }
+  if(ctx->copy_stream)
+    cudaStreamDestroy(ctx->copy_stream);
+  for(cudaEvent_t e : { ctx->ev_start, ctx->ev_stop, ctx->ev_h2d0, ctx->ev_h2d1 })
+    if(e)
+      cudaEventDestroy(e);
+  delete ctx;
+}
+
+int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int device, int max_frames, ssd_gpu_ctx **out)
+{
+  if(!cfg || !xf || !out || max_frames <= 0)
+    return fail(nullptr, SSD_E_INVALID_ARG, "ssd_gpu_create: bad argument");
+  *out = nullptr;
+  int ndev = 0;
+  if(cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, SSD_E_CUDA, "ssd_gpu_create: no CUDA device (this library has no CPU fallback)");
+  if(device < 0 || device >= ndev)
+    return fail(nullptr, SSD_E_INVALID_ARG, "ssd_gpu_create: bad device index");
+  DevParams dp;
+  const int rc = derive_params(*cfg, *xf, dp);
+  if(rc)
+    return fail(nullptr, rc, "ssd_gpu_create: configuration out of range (bins <= 253, width*height % 4 == 0, width <= 4700)");
+
+  ssd_gpu_ctx *ctx = new ssd_gpu_ctx();
+  ctx->device = device;
+  ctx->max_frames = max_frames;
+  ctx->cfg = *cfg;
+  ctx->xf = *xf;
+  ctx->dp = dp;
+  ctx->bm_words = (size_t)dp.H * dp.wpr;
+
+  auto bail = [&](const std::string &m, int code)
+  {
+    g_create_error = m + (ctx->err.empty() ? "" : (": " + ctx->err));
+    ssd_gpu_destroy(ctx);
+    return code;
+  };
+  if(cudaSetDevice(device) != cudaSuccess)
+    return bail("cudaSetDevice failed", SSD_E_CUDA);
+
+  // frames per chunk: keep a chunk's vertices + labels L2-resident between the three point passes
+  // (B200: 126 MB L2). SSD_GPU_CHUNK_FRAMES overrides.
+  {
+    const double frame_bytes = (double)dp.N * 13.0;
+    int cf = (int)(48.0e6 / frame_bytes);
+    if(const char *e = getenv("SSD_GPU_CHUNK_FRAMES"))
+      cf = atoi(e);
+    cf = std::max(1, std::min(cf, max_frames));
+    ctx->chunk_frames = cf;
+  }
+
+  int max_optin = 0;
+  cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  cudaFuncAttributes fa{};
+  if(cudaFuncGetAttributes(&fa, k_outline) != cudaSuccess)
+    return bail("cudaFuncGetAttributes(k_outline) failed: was the library built for this GPU (sm_100a)?", SSD_E_CUDA);
+  cudaFuncAttributes fb{}, fc{};
+  cudaFuncGetAttributes(&fb, k_finalize);
+  cudaFuncGetAttributes(&fc, k_test_front_edge);
+  const size_t stat = std::max({ fa.sharedSizeBytes, fb.sharedSizeBytes, fc.sharedSizeBytes });
+  size_t dyn = (size_t)max_optin > stat + 1024 ? (size_t)max_optin - stat - 1024 : 0;
+  // no more than the full image needs
+  const size_t full = (size_t)2 * dp.H * (dp.wpr + 1) * 4;
+  dyn = std::min(dyn, full);
+  dyn &= ~(size_t)15;
+  ctx->ol_dyn_smem = dyn;
+  ctx->smem_cap_words = dyn / 4;
+  cudaFuncSetAttribute(k_outline, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  cudaFuncSetAttribute(k_test_front_edge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+
+#define CKC(call)                                                            \
+  do                                                                         \
+  {                                                                          \
+    cudaError_t e_ = (call);                                                 \
+    if(e_ != cudaSuccess)                                                    \
+    {                                                                        \
+      ctx->err = cudaGetErrorString(e_);                                     \
+      return bail(#call, e_ == cudaErrorMemoryAllocation ? SSD_E_NOMEM : SSD_E_CUDA); \
+    }                                                                        \
+  } while(0)
+  for(int i = 0; i < 2; i++)
+  {
+    CKC(cudaStreamCreateWithFlags(&ctx->stream[i], cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&ctx->ev_in_ready[i], cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&ctx->ev_in_free[i], cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&ctx->ev_chunk_done[i], cudaEventDisableTiming));
+  }
+  CKC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  CKC(cudaEventCreate(&ctx->ev_start));
+  CKC(cudaEventCreate(&ctx->ev_stop));
+  CKC(cudaEventCreate(&ctx->ev_h2d0));
+  CKC(cudaEventCreate(&ctx->ev_h2d1));
+  CKC(cudaMalloc(&ctx->d_frames, sizeof(FrameDev) * (size_t)max_frames));
+  CKC(cudaMalloc(&ctx->d_out, sizeof(FrameOut) * (size_t)max_frames));
+  CKC(cudaMallocHost(&ctx->h_out, sizeof(FrameOut) * (size_t)max_frames));
+  CKC(cudaMalloc(&ctx->d_labels, (size_t)max_frames * dp.N));
+  const size_t bev_bytes = (size_t)2 * ctx->chunk_frames * SSD_GPU_MAX_PLATEAUS * ctx->bm_words * 4;
+  CKC(cudaMalloc(&ctx->d_bev, bev_bytes));
+  CKC(cudaMalloc(&ctx->d_bev2, bev_bytes));
+  CKC(cudaMemset(ctx->d_bev, 0, bev_bytes)); // bitmaps are self-cleaning afterwards
+  CKC(cudaMemset(ctx->d_bev2, 0, bev_bytes));
+  CKC(cudaMemset(ctx->d_frames, 0, sizeof(FrameDev) * (size_t)max_frames));
+  CKC(cudaMemset(ctx->d_out, 0, sizeof(FrameOut) * (size_t)max_frames));
+  memset(ctx->h_out, 0, sizeof(FrameOut) * (size_t)max_frames);
+  CKC(cudaDeviceSynchronize());
+#undef CKC
+  *out = ctx;
+  return SSD_OK;
+}
+
+static int process_common(ssd_gpu_ctx *ctx, const float *xyz, bool host_input, int n_frames, int flags)
+{
+  if(!ctx || !xyz || n_frames <= 0)
+    return fail(ctx, SSD_E_INVALID_ARG, "process: bad argument");
+  if(n_frames > ctx->max_frames)
+    return fail(ctx, SSD_E_RANGE, "process: n_frames exceeds max_frames of the context");
+  CK(cudaSetDevice(ctx->device));
+  const DevParams &p = ctx->dp;
+  const size_t frame_floats = (size_t)p.N * 3;
+  const int cf = ctx->chunk_frames;
+  if(host_input)
+    for(int i = 0; i < 2; i++)
+      if(!ctx->d_stage[i])
+        CK(cudaMalloc(&ctx->d_stage[i], (size_t)cf * frame_floats * sizeof(float)));
+
+  int launches = 0;
+  ctx->n_frames_last = n_frames;
+  ctx->flags_last = flags;
+  // the whole call is ordered after ev_start on stream 0; stream 1 joins via events
+  CK(cudaEventRecord(ctx->ev_start, ctx->stream[0]));
+  CK(cudaStreamWaitEvent(ctx->stream[1], ctx->ev_start, 0));
+  CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_start, 0));
+  // per-frame state: histogram must start at zero
+  CK(cudaMemsetAsync(ctx->d_frames, 0, sizeof(FrameDev) * (size_t)n_frames, ctx->stream[0]));
+  CK(cudaEventRecord(ctx->ev_chunk_done[0], ctx->stream[0]));
+  CK(cudaStreamWaitEvent(ctx->stream[1], ctx->ev_chunk_done[0], 0));
+
+  int chunk = 0;
+  for(int f0 = 0; f0 < n_frames; f0 += cf, chunk++)
+  {
+    const int nf = std::min(cf, n_frames - f0);
+    const int s = chunk & 1;
+    const float *src = xyz + (size_t)f0 * frame_floats;
+    if(host_input)
+    {
+      // stage s may be overwritten once the chunk that last used it has finished
+      if(chunk >= 2)
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_in_free[s], 0));
+      CK(cudaMemcpyAsync(ctx->d_stage[s], src, (size_t)nf * frame_floats * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
+      CK(cudaEventRecord(ctx->ev_in_ready[s], ctx->copy_stream));
+      CK(cudaStreamWaitEvent(ctx->stream[s], ctx->ev_in_ready[s], 0));
+      src = ctx->d_stage[s];
+    }
+    const int rc = launch_chunk(ctx, s, src, f0, nf, &launches);
+    if(rc)
+      return rc;
+    if(host_input)
+      CK(cudaEventRecord(ctx->ev_in_free[s], ctx->stream[s]));
+  }
+  // join stream 1 into stream 0, then bring the compact results home
+  CK(cudaEventRecord(ctx->ev_chunk_done[1], ctx->stream[1]));
+  CK(cudaStreamWaitEvent(ctx->stream[0], ctx->ev_chunk_done[1], 0));
+  CK(cudaMemcpyAsync(ctx->h_out, ctx->d_out, sizeof(FrameOut) * (size_t)n_frames, cudaMemcpyDeviceToHost, ctx->stream[0]));
+  CK(cudaEventRecord(ctx->ev_stop, ctx->stream[0]));
+  CK(cudaEventSynchronize(ctx->ev_stop));
+  CK(cudaGetLastError());
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop));
+  ctx->timing.total_ms = ms;
+  ctx->timing.kernels_ms = ms;
+  ctx->timing.h2d_ms = 0;
+  ctx->timing.label_ms = 0;
+  ctx->timing.n_launches = launches;
+  return SSD_OK;
+}
+
+int ssd_gpu_process_host(ssd_gpu_ctx *ctx, const float *xyz_host, int n_frames)
+{
+  return process_common(ctx, xyz_host, true, n_frames, 0);
+}
+
+int ssd_gpu_process_device(ssd_gpu_ctx *ctx, const float *xyz_dev, int n_frames)
+{
+  return process_common(ctx, xyz_dev, false, n_frames, 0);
+}
+
+int ssd_gpu_process_device_ex(ssd_gpu_ctx *ctx, const float *xyz_dev, int n_frames, int flags)
+{
+  return process_common(ctx, xyz_dev, false, n_frames, flags);
+}
+
+static int check_frame(ssd_gpu_ctx *ctx, int frame)
+{
+  if(!ctx)
+    return SSD_E_INVALID_ARG;
+  if(ctx->n_frames_last <= 0)
+    return fail(ctx, SSD_E_STATE, "no processed batch in this context");
+  if(frame < 0 || frame >= ctx->n_frames_last)
+    return fail(ctx, SSD_E_RANGE, "frame index out of range");
+  return SSD_OK;
+}
+
+int ssd_gpu_get_steps(ssd_gpu_ctx *ctx, int frame, ssd_gpu_step *out, int cap, int *n, uint32_t *status)
+{
+  const int rc = check_frame(ctx, frame);
+  if(rc)
+    return rc;
+  const FrameOut &o = ctx->h_out[frame];
+  if(n)
+    *n = o.info.n_steps;
+  if(status)
+    *status = o.info.status;
+  if(out)
+    for(int i = 0; i < o.info.n_steps && i < cap; i++)
+      out[i] = o.steps[i];
+  return SSD_OK;
+}
+
+int ssd_gpu_get_frame_info(ssd_gpu_ctx *ctx, int frame, ssd_gpu_frame_info *out)
+{
+  const int rc = check_frame(ctx, frame);
+  if(rc)
+    return rc;
+  if(!out)
+    return SSD_E_INVALID_ARG;
+  *out = ctx->h_out[frame].info;
+  return SSD_OK;
+}
+
+int ssd_gpu_get_plateaus(ssd_gpu_ctx *ctx, int frame, ssd_gpu_plateau *out, int cap, int *n)
+{
+  const int rc = check_frame(ctx, frame);
+  if(rc)
+    return rc;
+  CK(cudaSetDevice(ctx->device));
+  std::vector<PlateauDev> tmp(SSD_GPU_MAX_PLATEAUS);
+  CK(cudaMemcpy(tmp.data(), ctx->d_frames[frame].plat, sizeof(PlateauDev) * SSD_GPU_MAX_PLATEAUS, cudaMemcpyDeviceToHost));
+  const int K = ctx->h_out[frame].info.n_plateaus;
+  if(n)
+    *n = K;
+  for(int k = 0; k < K && k < cap && out; k++)
+  {
+    const PlateauDev &P = tmp[k];
+    ssd_gpu_plateau &o = out[k];
+    o.height = P.height;
+    o.hmin = P.hmin;
+    o.hmax = P.hmax;
+    o.n_points = P.n_points;
+    o.valid = P.valid;
+    o.outlined = P.outlined;
+    o.n_in_quad = P.n_in_quad;
+    o.quad_status = P.quad_status;
+    memcpy(o.quad_world, P.quad_world, sizeof(o.quad_world));
+    o.mean_z = P.mean_z;
+  }
+  return SSD_OK;
+}
+
+int ssd_gpu_get_labels(ssd_gpu_ctx *ctx, int frame, uint8_t *out_host)
+{
+  const int rc = check_frame(ctx, frame);
+  if(rc)
+    return rc;
+  if(!out_host)
+    return SSD_E_INVALID_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpy(out_host, ctx->d_labels + (size_t)frame * ctx->dp.N, (size_t)ctx->dp.N, cudaMemcpyDeviceToHost));
+  return SSD_OK;
+}
+
+int ssd_gpu_get_histogram(ssd_gpu_ctx *ctx, int frame, uint32_t *out, int cap, int *n_bins)
+{
+  const int rc = check_frame(ctx, frame);
+  if(rc)
+    return rc;
+  CK(cudaSetDevice(ctx->device));
+  uint32_t tmp[SSD_BINS_PAD];
+  CK(cudaMemcpy(tmp, ctx->d_frames[frame].hist, sizeof(tmp), cudaMemcpyDeviceToHost));
+  if(n_bins)
+    *n_bins = ctx->dp.n_bins;
+  for(int i = 0; i < ctx->dp.n_bins && i < cap && out; i++)
+    out[i] = tmp[i];
+  return SSD_OK;
+}
+
+int ssd_gpu_get_timing(ssd_gpu_ctx *ctx, ssd_gpu_timing *out)
+{
+  if(!ctx || !out)
+    return SSD_E_INVALID_ARG;
+  *out = ctx->timing;
+  return SSD_OK;
+}
+
+int ssd_gpu_labels_device_ptr(ssd_gpu_ctx *ctx, const uint8_t **out)
+{
+  if(!ctx || !out)
+    return SSD_E_INVALID_ARG;
+  *out = ctx->d_labels;
+  return SSD_OK;
+}
+
+// ---- single-stage entry points ----
+static int upload_image(ssd_gpu_ctx *ctx, const uint8_t *image_host)
+{
+  const DevParams &p = ctx->dp;
+  CK(cudaSetDevice(ctx->device));
+  if(!ctx->d_img)
+    CK(cudaMalloc(&ctx->d_img, (size_t)p.N));
+  CK(cudaMemcpyAsync(ctx->d_img, image_host, (size_t)p.N, cudaMemcpyHostToDevice, ctx->stream[0]));
+  const int words = p.H * p.wpr;
+  k_pack_bitmap<<<(words + 255) / 256, 256, 0, ctx->stream[0]>>>(p, ctx->d_img, ctx->d_bev);
+  CK(cudaGetLastError());
+  return SSD_OK;
+}
+
+int ssd_gpu_detect_outline(ssd_gpu_ctx *ctx, const uint8_t *image_host, int min_img_y_extent, double xy_ratio, double quad_px[8], int *valid)
+{
+  if(!ctx || !image_host || !quad_px || !valid)
+    return SSD_E_INVALID_ARG;
+  int rc = upload_image(ctx, image_host);
+  if(rc)
+    return rc;
+  DevParams p = ctx->dp;
+  p.min_img_y_extent = min_img_y_extent;
+  p.xy_ratio = xy_ratio;
+  cudaStream_t st = ctx->stream[0];
+  k_test_setup_plateau<<<1, 1, 0, st>>>(ctx->d_frames, p.H);
+  k_outline<<<dim3(1, 1), SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, ctx->d_frames, ctx->d_bev, ctx->d_bev2, ctx->bm_words, ctx->smem_cap_words);
+  CK(cudaGetLastError());
+  PlateauDev P;
+  CK(cudaMemcpyAsync(&P, &ctx->d_frames[0].plat[0], sizeof(P), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  memcpy(quad_px, P.quad_px, sizeof(double) * 8);
+  *valid = P.valid;
+  ctx->n_frames_last = 0;
+  return SSD_OK;
+}
+
+int ssd_gpu_detect_front_edge(ssd_gpu_ctx *ctx, const uint8_t *image_host, double left_px[2], double right_px[2], int *valid)
+{
+  if(!ctx || !image_host || !left_px || !right_px || !valid)
+    return SSD_E_INVALID_ARG;
+  int rc = upload_image(ctx, image_host);
+  if(rc)
+    return rc;
+  cudaStream_t st = ctx->stream[0];
+  double *d_out = nullptr;
+  CK(cudaMalloc(&d_out, sizeof(double) * 8));
+  k_test_front_edge<<<1, SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(ctx->dp, ctx->d_bev, ctx->d_bev2, ctx->smem_cap_words, d_out);
+  double h[8];
+  cudaError_t e = cudaMemcpyAsync(h, d_out, sizeof(double) * 5, cudaMemcpyDeviceToHost, st);
+  if(e == cudaSuccess)
+    e = cudaStreamSynchronize(st);
+  cudaFree(d_out);
+  CK(e);
+  left_px[0] = h[0];
+  left_px[1] = h[1];
+  right_px[0] = h[2];
+  right_px[1] = h[3];
+  *valid = (int)h[4];
+  ctx->n_frames_last = 0;
+  return SSD_OK;
+}
+
+int ssd_gpu_points_in_quad(ssd_gpu_ctx *ctx, const double quad[8], const double *xy_host, int n, uint8_t *inside_host, int *ctor_status)
+{
+  if(!ctx || !quad || !xy_host || !inside_host || !ctor_status || n <= 0)
+    return SSD_E_INVALID_ARG;
+  CK(cudaSetDevice(ctx->device));
+  double *d_q = nullptr, *d_xy = nullptr;
+  unsigned char *d_in = nullptr;
+  int *d_st = nullptr;
+  cudaStream_t st = ctx->stream[0];
+  CK(cudaMalloc(&d_q, sizeof(double) * 8));
+  CK(cudaMalloc(&d_xy, sizeof(double) * 2 * (size_t)n));
+  CK(cudaMalloc(&d_in, (size_t)n));
+  CK(cudaMalloc(&d_st, sizeof(int)));
+  cudaMemcpyAsync(d_q, quad, sizeof(double) * 8, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(d_xy, xy_host, sizeof(double) * 2 * (size_t)n, cudaMemcpyHostToDevice, st);
+  k_test_points_in_quad<<<std::min(1024, (n + 255) / 256), 256, 0, st>>>(d_q, d_xy, n, d_in, d_st);
+  cudaMemcpyAsync(inside_host, d_in, (size_t)n, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(ctor_status, d_st, sizeof(int), cudaMemcpyDeviceToHost, st);
+  const cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(d_q);
+  cudaFree(d_xy);
+  cudaFree(d_in);
+  cudaFree(d_st);
+  CK(e);
+  return SSD_OK;
+}
+
+int ssd_gpu_camera_to_world(ssd_gpu_ctx *ctx, const float *xyz_host, int n, double *world_host)
+{
+  if(!ctx || !xyz_host || !world_host || n <= 0)
+    return SSD_E_INVALID_ARG;
+  CK(cudaSetDevice(ctx->device));
+  float *d_in = nullptr;
+  double *d_out = nullptr;
+  cudaStream_t st = ctx->stream[0];
+  CK(cudaMalloc(&d_in, sizeof(float) * 3 * (size_t)n));
+  CK(cudaMalloc(&d_out, sizeof(double) * 3 * (size_t)n));
+  cudaMemcpyAsync(d_in, xyz_host, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, st);
+  k_test_camera_to_world<<<std::min(1024, (n + 255) / 256), 256, 0, st>>>(ctx->dp, d_in, n, d_out);
+  cudaMemcpyAsync(world_host, d_out, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, st);
+  const cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(d_in);
+  cudaFree(d_out);
+  CK(e);
+  return SSD_OK;
+}
+
+// ---- synthetic frames on the device ----
+int ssd_gpu_synth_frames(ssd_gpu_ctx *ctx, const ssd_scene *base, uint64_t base_seed, int64_t first_index, int n_frames, int min_steps,
+                         int max_steps, float *xyz_dev, uint16_t *depth_dev)
+{
+  if(!ctx || !base || !xyz_dev || n_frames <= 0)
+    return SSD_E_INVALID_ARG;
+  if(base->width != ctx->dp.W || base->height != ctx->dp.H)
+    return fail(ctx, SSD_E_INVALID_ARG, "scene size differs from the context's configuration");
+  CK(cudaSetDevice(ctx->device));
+  const int N = ctx->dp.N;
+  const int bx = std::min((N + 255) / 256, 512);
+  for(int f0 = 0; f0 < n_frames; f0 += 32768)
+  {
+    const int nf = std::min(32768, n_frames - f0);
+    k_synth_frames<<<dim3(bx, nf), 256, 0, ctx->stream[0]>>>(*base, base_seed, first_index + f0, nf, min_steps, max_steps,
+                                                               xyz_dev + (size_t)f0 * N * 3, depth_dev ? depth_dev + (size_t)f0 * N : nullptr);
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream[0]));
+  return SSD_OK;
+}
+
+// ---- raw memory helpers ----
+int ssd_gpu_malloc(ssd_gpu_ctx *ctx, size_t bytes, void **dev_ptr)
+{
+  if(!ctx || !dev_ptr)
+    return SSD_E_INVALID_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const cudaError_t e = cudaMalloc(dev_ptr, bytes);
+  if(e == cudaErrorMemoryAllocation)
+  {
+    cudaGetLastError();
+    return fail(ctx, SSD_E_NOMEM, "cudaMalloc: out of memory");
+  }
+  CK(e);
+  return SSD_OK;
+}
+
+int ssd_gpu_free(ssd_gpu_ctx *ctx, void *dev_ptr)
+{
+  if(!ctx)
+    return SSD_E_INVALID_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaFree(dev_ptr));
+  return SSD_OK;
+}
+
+int ssd_gpu_memcpy_h2d(ssd_gpu_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes)
+{
+  if(!ctx)
+    return SSD_E_INVALID_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpy(dst_dev, src_host, bytes, cudaMemcpyHostToDevice));
+  return SSD_OK;
+}
+
+int ssd_gpu_memcpy_d2h(ssd_gpu_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes)
+{
+  if(!ctx)
+    return SSD_E_INVALID_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost));
+  return SSD_OK;
+}
+
+int ssd_gpu_malloc_host(size_t bytes, void **host_ptr)
+{
+  if(!host_ptr)
+    return SSD_E_INVALID_ARG;
+  return cudaMallocHost(host_ptr, bytes) == cudaSuccess ? SSD_OK : SSD_E_NOMEM;
+}
+
+int ssd_gpu_free_host(void *host_ptr)
+{
+  return cudaFreeHost(host_ptr) == cudaSuccess ? SSD_OK : SSD_E_CUDA;
+}
+
+} // extern "C"

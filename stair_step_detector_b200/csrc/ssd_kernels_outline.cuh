@@ -1,0 +1,956 @@
+// ssd_kernels_outline.cuh -- the per-plateau geometry kernels:
+//   k_outline     : Segmentation::detectOutline (segmentation.cpp:919-971) on each plateau's BEV bitmap
+//   k_frame_logic : first-valid / ground quadrilateral / QuadrilateralTest construction
+//   k_finalize    : Segmentation::detectFrontEdge for the ground (segmentation.cpp:879-917), step assembly,
+//                   ToExternalWorld, result records
+// A BEV image is a bit-packed W x H occupancy bitmap (1 bit/pixel). Only the band of rows a plateau touched
+// is staged into shared memory (coalesced), closed there with word-parallel 3x3 dilate/erode, and probed;
+// the global bitmap is zeroed behind the read so it is clean for the next batch.
+#pragma once
+#include "ssd_device.cuh"
+
+#define SSD_OL_THREADS 256
+
+// Closed band of a BEV bitmap: rows [b0, b0+nb) with row stride rs words; rows outside are all zero.
+struct Band
+{
+  unsigned *A; // closed image (result)
+  unsigned *B; // dilated image (scratch)
+  int b0, nb, rs;
+};
+
+__device__ __forceinline__ unsigned band_word(const Band &bd, int y, int w)
+{
+  const int r = y - bd.b0;
+  if(r < 0 || r >= bd.nb)
+    return 0u;
+  return bd.A[(size_t)r * bd.rs + w];
+}
+__device__ __forceinline__ int band_bit(const Band &bd, int x, int y)
+{
+  return (band_word(bd, y, x >> 5) >> (x & 31)) & 1u;
+}
+
+// cv::morphologyEx(MORPH_CLOSE, 3x3) (call sites segmentation.cpp:888,928) on bit rows.
+// dilate: out-of-image = 0; erode: out-of-image = 1 (OpenCV's default border values for the two ops).
+// src rows [r0raw, r1raw] hold data, everything else is zero. Cooperative over the block.
+__device__ inline void band_close(const DevParams &p, Band &bd, const unsigned *__restrict__ gsrc, unsigned *__restrict__ gzero, int tid,
+                                  int nthreads)
+{
+  const int wpr = p.wpr, H = p.H, W = p.W;
+  // stage raw rows into A (and clear the global bitmap behind the read)
+  for(int i = tid; i < bd.nb * wpr; i += nthreads)
+  {
+    const int r = i / wpr, w = i - r * wpr;
+    const size_t g = (size_t)(bd.b0 + r) * wpr + w;
+    const unsigned v = gsrc[g];
+    if(gzero && v)
+      gzero[g] = 0u;
+    bd.A[(size_t)r * bd.rs + w] = v;
+  }
+  __syncthreads();
+  // dilate A -> B
+  for(int i = tid; i < bd.nb * wpr; i += nthreads)
+  {
+    const int r = i / wpr, w = i - r * wpr;
+    unsigned acc = 0;
+#pragma unroll
+    for(int dr = -1; dr <= 1; dr++)
+    {
+      const int rr = r + dr;
+      if(rr < 0 || rr >= bd.nb)
+        continue; // outside the band the raw image is zero (or outside the image: ignored)
+      const unsigned *row = bd.A + (size_t)rr * bd.rs;
+      const unsigned c = row[w];
+      const unsigned l = w > 0 ? row[w - 1] : 0u;
+      const unsigned n = w + 1 < wpr ? row[w + 1] : 0u;
+      acc |= c | (c << 1) | (l >> 31) | (c >> 1) | (n << 31);
+    }
+    // keep bits beyond the image width clear
+    if(w == wpr - 1 && (W & 31))
+      acc &= (1u << (W & 31)) - 1u;
+    bd.B[(size_t)r * bd.rs + w] = acc;
+  }
+  __syncthreads();
+  // erode B -> A
+  for(int i = tid; i < bd.nb * wpr; i += nthreads)
+  {
+    const int r = i / wpr, w = i - r * wpr;
+    unsigned acc = 0xffffffffu;
+#pragma unroll
+    for(int dr = -1; dr <= 1; dr++)
+    {
+      const int rr = r + dr;
+      const int y = bd.b0 + rr;
+      if(y < 0 || y >= H)
+        continue; // outside the image: ignored
+      if(rr < 0 || rr >= bd.nb)
+      {
+        acc = 0u; // inside the image but outside the band: the dilated image is zero there
+        continue;
+      }
+      const unsigned *row = bd.B + (size_t)rr * bd.rs;
+      unsigned c = row[w];
+      unsigned l = w > 0 ? row[w - 1] : 0xffffffffu;
+      unsigned n = w + 1 < wpr ? row[w + 1] : 0xffffffffu;
+      if(w == wpr - 1 && (W & 31))
+        c |= ~((1u << (W & 31)) - 1u); // pixels right of the image: ignored
+      if(w + 1 == wpr - 1 && (W & 31))
+        n |= ~((1u << (W & 31)) - 1u);
+      acc &= c & ((c << 1) | (l >> 31)) & ((c >> 1) | (n << 31));
+    }
+    if(w == wpr - 1 && (W & 31))
+      acc &= (1u << (W & 31)) - 1u;
+    bd.A[(size_t)r * bd.rs + w] = acc;
+  }
+  __syncthreads();
+}
+
+// first / last set row of column x in the closed band (Scanner::probeVertical, segmentation.cpp:85-111);
+// one warp per column
+__device__ __forceinline__ bool probe_column(const Band &bd, int x, int ylo, int yhi, int lane, int &yFirst, int &ySecond)
+{
+  // rows [ylo, yhi] inclusive
+  int first = 0x7fffffff, last = -1;
+  const int lo = max(ylo, bd.b0), hi = min(yhi, bd.b0 + bd.nb - 1);
+  const int w = x >> 5, sh = x & 31;
+  for(int base = lo; base <= hi; base += 32)
+  {
+    const int y = base + lane;
+    const unsigned bit = y <= hi ? (bd.A[(size_t)(y - bd.b0) * bd.rs + w] >> sh) & 1u : 0u;
+    const unsigned m = __ballot_sync(0xffffffffu, bit);
+    if(m)
+    {
+      if(first == 0x7fffffff)
+        first = base + __ffs(m) - 1;
+      last = base + 31 - __clz(m);
+    }
+  }
+  yFirst = first;
+  ySecond = last;
+  return last >= 0;
+}
+
+// ---- BestLine (segmentation.cpp:409-487): every pair (p,q), residual = mean of the n smallest integer
+// distances of the other points / hypot(a,b); winner = first minimal residual in (p,q) order. One pair per
+// thread; block-wide arg-min on (residual, pair index).
+struct BestLineWork
+{
+  double res[SSD_OL_THREADS];
+  int idx[SSD_OL_THREADS];
+};
+
+__device__ inline double pair_residual(const P2id *pts, int n, int pi, int qi, LineId l)
+{
+  if(n <= 2)
+    return 0.0;
+  const int m = n - 2;
+  const int cnt = m > 4 ? (m - 1) / 2 : 1;
+  long long sum = 0;
+  if(cnt <= 24)
+  {
+    // repeated minimum extraction without materialising the list: extract in (value, index) order
+    int lastv = -1, lasti = -1;
+    for(int t = 0; t < cnt; t++)
+    {
+      int bestv = 0x7fffffff, besti = -1;
+      for(int i = 0; i < n; i++)
+      {
+        if(i == pi || i == qi)
+          continue;
+        const int d = abs(pts[i].x * l.a + pts[i].y * l.b + l.c);
+        if((d > lastv || (d == lastv && i > lasti)) && d < bestv)
+        {
+          bestv = d;
+          besti = i;
+        }
+      }
+      sum += bestv;
+      lastv = bestv;
+      lasti = besti;
+    }
+  }
+  else
+  {
+    // value bisection: smallest T with count(d <= T) >= cnt; sum = sum(d < T) + (cnt - count(d < T)) * T
+    int lo = 0, hi = 0;
+    for(int i = 0; i < n; i++)
+      if(i != pi && i != qi)
+        hi = max(hi, abs(pts[i].x * l.a + pts[i].y * l.b + l.c));
+    while(lo < hi)
+    {
+      const int mid = lo + ((hi - lo) >> 1);
+      int c = 0;
+      for(int i = 0; i < n; i++)
+        if(i != pi && i != qi)
+          c += abs(pts[i].x * l.a + pts[i].y * l.b + l.c) <= mid;
+      if(c >= cnt)
+        hi = mid;
+      else
+        lo = mid + 1;
+    }
+    int below = 0;
+    for(int i = 0; i < n; i++)
+      if(i != pi && i != qi)
+      {
+        const int d = abs(pts[i].x * l.a + pts[i].y * l.b + l.c);
+        if(d < lo)
+        {
+          sum += d;
+          below++;
+        }
+      }
+    sum += (long long)(cnt - below) * lo;
+  }
+  // the reference sums into int (segmentation.cpp:434); keep its wrap-around semantics
+  const int isum = (int)sum;
+  return isum / ((double)(size_t)cnt * hypot_cr((double)l.a, (double)l.b)); // :442
+}
+
+// all threads of the block must call; returns the winning line in *out (valid for all threads after return)
+__device__ inline void best_line_block(const P2id *pts, int n, BestLineWork &wk, LineId *out, int tid, int nthreads)
+{
+  const int npairs = n * (n - 1) / 2;
+  double bres = 1e308 * 10; // +inf
+  int bidx = 0x7fffffff;
+  // enumerate pairs in (p,q) lexicographic order; index -> (p,q) by running counters
+  for(int t = tid; t < npairs; t += nthreads)
+  {
+    // invert t = p*n - p*(p+1)/2 + (q-p-1)
+    int pI = (int)((2.0 * n - 1.0 - sqrt((2.0 * n - 1.0) * (2.0 * n - 1.0) - 8.0 * t)) * 0.5);
+    while(pI > 0 && pI * n - pI * (pI + 1) / 2 > t)
+      pI--;
+    while((pI + 1) * n - (pI + 1) * (pI + 2) / 2 <= t)
+      pI++;
+    const int qI = t - (pI * n - pI * (pI + 1) / 2) + pI + 1;
+    const LineId l = linei_from(pts[pI], pts[qI]);
+    const double r = pair_residual(pts, n, pI, qI, l);
+    if(bidx == 0x7fffffff || r < bres) // t ascends: the first of equal residuals is kept (min_element, :473-477)
+    {
+      bres = r;
+      bidx = t;
+    }
+  }
+  wk.res[tid] = bres;
+  wk.idx[tid] = bidx;
+  __syncthreads();
+  for(int s = nthreads >> 1; s > 0; s >>= 1)
+  {
+    if(tid < s)
+    {
+      const double r1 = wk.res[tid], r2 = wk.res[tid + s];
+      const int i1 = wk.idx[tid], i2 = wk.idx[tid + s];
+      // lowest pair index among the minimal residuals
+      if(i2 != 0x7fffffff && (i1 == 0x7fffffff || r2 < r1 || (r2 == r1 && i2 < i1)))
+      {
+        wk.res[tid] = r2;
+        wk.idx[tid] = i2;
+      }
+    }
+    __syncthreads();
+  }
+  if(tid == 0)
+  {
+    const int t = wk.idx[0];
+    int pI = 0;
+    while((pI + 1) * n - (pI + 1) * (pI + 2) / 2 <= t)
+      pI++;
+    const int qI = t - (pI * n - pI * (pI + 1) / 2) + pI + 1;
+    *out = linei_from(pts[pI], pts[qI]);
+  }
+  __syncthreads();
+}
+
+// FlatLine (segmentation.cpp:490-519)
+struct FlatLineD
+{
+  double m, n;
+};
+__device__ __forceinline__ FlatLineD flat_from(LineId l)
+{
+  FlatLineD f;
+  f.m = (double)(-l.a) / l.b;
+  f.n = (double)(-l.c) / l.b;
+  return f;
+}
+__device__ __forceinline__ P2d flat_point(FlatLineD f, double x)
+{
+  P2d r;
+  r.x = x;
+  r.y = x * f.m + f.n;
+  return r;
+}
+// BoundaryPoints::outer (segmentation.cpp:545-547): last list point within 10 px of the line, snapped onto it
+__device__ inline P2d boundary_outer(const P2id *pts, int n, FlatLineD line)
+{
+  P2d r;
+  r.x = -1;
+  r.y = -1;
+  for(int i = n - 1; i >= 0; i--)
+  {
+    const P2d pd = flat_point(line, pts[i].x);
+    if(fabs(pd.y - pts[i].y) < 10)
+    {
+      r = pd;
+      break;
+    }
+  }
+  return r;
+}
+
+struct OutlineShared
+{
+  // column scans
+  int scan_found[SSD_MAX_SCANS];
+  int scan_yf[SSD_MAX_SCANS];
+  int scan_ys[SSD_MAX_SCANS];
+  // the four edge point lists (segmentation.cpp:557-567)
+  P2id frontLeft[SSD_MAX_LINE_PTS], backLeft[SSD_MAX_LINE_PTS], frontRight[SSD_MAX_LINE_PTS], backRight[SSD_MAX_LINE_PTS];
+  int nLeft, nRight, ok;
+  LineId line[4]; // frontLeft, frontRight, backLeft, backRight
+  BestLineWork wk;
+  // vertical edge probing
+  P2id vpts[SSD_MAX_VPTS];
+  int vfound[SSD_MAX_VPTS];
+  double vdist[SSD_MAX_VPTS];
+  int vn;
+  int ve_left, ve_right, ve_ystart, ve_yend, ve_go;
+  LineDd base;
+  P2d outer[4];
+  int best_pt;
+};
+
+// Segmentation::detectOutline after the close (segmentation.cpp:930-946). Block-cooperative.
+// Thread 0 ends up with the quadrilateral (image pixels) and the valid flag.
+__device__ inline void detect_outline_block(const DevParams &p, const Band &bd, OutlineShared &S, int min_img_y_extent, double xy_ratio,
+                                            P2d quad[4], int &valid, int tid, int nthreads)
+{
+  const int W = p.W, H = p.H;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+  const int xStep = 25, xCenter = W / 2; // HorizontalEdgesDetector (segmentation.cpp:605-611)
+  // candidate columns: right = xCenter + j*25 (< W); left = xCenter - 25 - j*25 (>= 0)
+  const int nRc = (W - 1 - xCenter) / xStep + 1;
+  const int nLc = xCenter - xStep >= 0 ? (xCenter - xStep) / xStep + 1 : 0;
+  for(int c = warp; c < nRc + nLc; c += nwarps)
+  {
+    const int x = c < nRc ? xCenter + c * xStep : xCenter - xStep - (c - nRc) * xStep;
+    int yf, ys;
+    const bool f = probe_column(bd, x, 0, H - 1, lane, yf, ys);
+    if(lane == 0)
+    {
+      S.scan_found[c] = f;
+      S.scan_yf[c] = yf;
+      S.scan_ys[c] = ys;
+    }
+  }
+  __syncthreads();
+  if(tid == 0)
+  {
+    // Scanner::scan stop rule (segmentation.cpp:68-80): stop at the first empty or too short column
+    int nr = 0, nl = 0;
+    while(nr < nRc && S.scan_found[nr] && S.scan_ys[nr] - S.scan_yf[nr] >= min_img_y_extent)
+      nr++;
+    if(nr > 0)
+      while(nl < nLc && S.scan_found[nRc + nl] && S.scan_ys[nRc + nl] - S.scan_yf[nRc + nl] >= min_img_y_extent)
+        nl++;
+    S.ok = nr > 0 && nl + nr >= 3; // :612-616
+    S.nLeft = S.nRight = 0;
+    if(S.ok)
+    {
+      // Scanner::obtainLinePoints (:129-156); scansRight[i] = column i, scansLeft[i] = column nRc+i
+      const int total = nl + nr, half = total / 2 + 1;
+      int indLeft = 0, indRight = 0;
+      auto pushL = [&](int c)
+      {
+        const int x = c < nRc ? xCenter + c * xStep : xCenter - xStep - (c - nRc) * xStep;
+        S.frontLeft[S.nLeft].x = x;
+        S.frontLeft[S.nLeft].y = S.scan_ys[c];
+        S.backLeft[S.nLeft].x = x;
+        S.backLeft[S.nLeft].y = S.scan_yf[c];
+        S.nLeft++;
+      };
+      auto pushR = [&](int c)
+      {
+        const int x = c < nRc ? xCenter + c * xStep : xCenter - xStep - (c - nRc) * xStep;
+        S.frontRight[S.nRight].x = x;
+        S.frontRight[S.nRight].y = S.scan_ys[c];
+        S.backRight[S.nRight].x = x;
+        S.backRight[S.nRight].y = S.scan_yf[c];
+        S.nRight++;
+      };
+      if(nl >= half)
+      {
+        indLeft = nl - half;
+        for(int i = indLeft; i >= 0; i--)
+          pushR(nRc + i);
+      }
+      else
+      {
+        if(nr > half)
+          indRight = nr - half;
+        for(int i = indRight; i >= 0; i--)
+          pushL(i);
+      }
+      for(; indRight < nr; indRight++)
+        pushR(indRight);
+      for(; indLeft < nl; indLeft++)
+        pushL(nRc + indLeft);
+    }
+  }
+  __syncthreads();
+  valid = 0;
+  if(tid == 0)
+    for(int i = 0; i < 4; i++)
+      quad[i].x = quad[i].y = 0; // Outline{} value-initialised
+  if(!S.ok)
+    return;
+
+  // HorizontalEdges (:592-599): four best lines
+  best_line_block(S.frontLeft, S.nLeft, S.wk, &S.line[0], tid, nthreads);
+  best_line_block(S.frontRight, S.nRight, S.wk, &S.line[1], tid, nthreads);
+  best_line_block(S.backLeft, S.nLeft, S.wk, &S.line[2], tid, nthreads);
+  best_line_block(S.backRight, S.nRight, S.wk, &S.line[3], tid, nthreads);
+
+  if(tid == 0)
+  {
+    S.outer[0] = boundary_outer(S.frontLeft, S.nLeft, flat_from(S.line[0]));
+    S.outer[1] = boundary_outer(S.frontRight, S.nRight, flat_from(S.line[1]));
+    S.outer[2] = boundary_outer(S.backLeft, S.nLeft, flat_from(S.line[2]));
+    S.outer[3] = boundary_outer(S.backRight, S.nRight, flat_from(S.line[3]));
+    // VerticalEdgesDetector::calcBaseLine (:672-679)
+    LineId rfl, rbl;
+    rfl.a = -S.line[0].a;
+    rfl.b = -S.line[0].b;
+    rfl.c = -S.line[0].c;
+    rbl.a = -S.line[2].a;
+    rbl.b = -S.line[2].b;
+    rbl.c = -S.line[2].c;
+    const LineDd front = bisector(lined_normalized(lined_from_i(rfl)), lined_normalized(lined_from_i(S.line[1])));
+    const LineDd back = bisector(lined_normalized(lined_from_i(rbl)), lined_normalized(lined_from_i(S.line[3])));
+    const LineDd center = bisector(lined_normalized(front), lined_normalized(back));
+    const double cf = xy_ratio * xy_ratio;
+    LineDd corr;
+    corr.a = center.a * cf; // slopeCorrection (:377-380)
+    corr.b = center.b;
+    corr.c = center.c;
+    const P2id p0 = S.frontLeft[0];
+    S.base.a = -corr.b; // perpendicular (:372-376)
+    S.base.b = corr.a;
+    S.base.c = corr.b * p0.x - corr.a * p0.y;
+    for(int i = 0; i < 4; i++)
+      quad[i] = S.outer[i]; // value_or fall-backs (:939-945)
+  }
+  __syncthreads();
+
+  // VerticalEdgesDetector::detect (:653-669): left edge (probe to the right), right edge (probe to the left)
+  for(int e = 0; e < 2; e++)
+  {
+    if(tid == 0)
+    {
+      const P2d front = S.outer[e], back = S.outer[2 + e];
+      const int yStep = 10;
+      int left = (int)((front.x < back.x ? front.x : back.x) - xStep); // detectEdge (:681-697)
+      int right = (int)((front.x < back.x ? back.x : front.x) + xStep);
+      int yStart = (int)(front.y - yStep);
+      int yEnd = (int)(back.y + yStep);
+      if(left < 0)
+        left = 0;
+      if(right >= W)
+        right = W - 1;
+      if(yStart >= H)
+        yStart = H - 1;
+      if(yEnd < 0)
+        yEnd = 0;
+      S.ve_go = !(yStart < yEnd) && right > left && left < W && yStart >= 0;
+      S.ve_left = left;
+      S.ve_right = right;
+      S.ve_ystart = yStart;
+      S.ve_yend = yEnd;
+      S.vn = 0;
+    }
+    __syncthreads();
+    if(S.ve_go)
+    {
+      const int left = S.ve_left, right = S.ve_right, yStart = S.ve_ystart, yEnd = S.ve_yend;
+      const int nrows = (yStart - yEnd) / 10 + 1;
+      // window: left edge scans x in [left, right-1] ascending; right edge scans x in [left+1, right] descending
+      // (VerticalEdgePointsDetector, :243-312)
+      const int x0 = e == 0 ? left : left + 1, x1 = e == 0 ? right - 1 : right;
+      const int w0 = x0 >> 5, w1 = x1 >> 5;
+      for(int r = warp; r < nrows && r < SSD_MAX_VPTS; r += nwarps)
+      {
+        const int y = yStart - r * 10;
+        int fx = -1;
+        if(e == 0)
+        {
+          for(int wb = w0; wb <= w1 && fx < 0; wb += 32)
+          {
+            const int w = wb + lane;
+            unsigned v = w <= w1 ? band_word(bd, y, w) : 0u;
+            if(w == w0)
+              v &= 0xffffffffu << (x0 & 31);
+            if(w == w1 && (x1 & 31) != 31)
+              v &= (1u << ((x1 & 31) + 1)) - 1u;
+            const unsigned m = __ballot_sync(0xffffffffu, v != 0u);
+            if(m)
+            {
+              const int src = __ffs(m) - 1;
+              const unsigned vv = __shfl_sync(0xffffffffu, v, src);
+              fx = ((wb + src) << 5) + __ffs(vv) - 1;
+            }
+          }
+        }
+        else
+        {
+          for(int wb = w1; wb >= w0 && fx < 0; wb -= 32)
+          {
+            const int w = wb - lane;
+            unsigned v = w >= w0 ? band_word(bd, y, w) : 0u;
+            if(w == w0)
+              v &= 0xffffffffu << (x0 & 31);
+            if(w == w1 && (x1 & 31) != 31)
+              v &= (1u << ((x1 & 31) + 1)) - 1u;
+            const unsigned m = __ballot_sync(0xffffffffu, v != 0u);
+            if(m)
+            {
+              const int src = __ffs(m) - 1; // lowest lane = highest word
+              const unsigned vv = __shfl_sync(0xffffffffu, v, src);
+              fx = ((wb - src) << 5) + 31 - __clz(vv);
+            }
+          }
+        }
+        if(lane == 0)
+        {
+          S.vfound[r] = fx >= 0;
+          S.vpts[r].x = fx;
+          S.vpts[r].y = y;
+        }
+      }
+      __syncthreads();
+      if(tid == 0)
+      {
+        // compact in probing order (top of the list = yStart)
+        int n = 0;
+        const int lim = nrows < SSD_MAX_VPTS ? nrows : SSD_MAX_VPTS;
+        for(int r = 0; r < lim; r++)
+          if(S.vfound[r])
+          {
+            S.vpts[n] = S.vpts[r];
+            n++;
+          }
+        S.vn = n;
+        for(int i = 0; i < n; i++)
+          S.vdist[i] = fabs(S.vpts[i].x * S.base.a + S.vpts[i].y * S.base.b + S.base.c); // comparableDistance (:397-400)
+        S.best_pt = -1;
+      }
+      __syncthreads();
+      // findBestPoint (:708-728): element of rank 2n/3 by distance (ties: list order)
+      const int n = S.vn;
+      if(n > 0)
+      {
+        const int want = 2 * n / 3;
+        for(int i = tid; i < n; i += nthreads)
+        {
+          const double di = S.vdist[i];
+          int rank = 0;
+          for(int j = 0; j < n; j++)
+          {
+            const double dj = S.vdist[j];
+            rank += (dj < di) || (dj == di && j < i);
+          }
+          if(rank == want)
+            S.best_pt = i;
+        }
+      }
+      __syncthreads();
+      if(tid == 0 && S.vn > 0 && S.best_pt >= 0)
+      {
+        const P2id bp = S.vpts[S.best_pt];
+        LineDd edge; // Line::parallel (:367-371)
+        edge.a = S.base.a;
+        edge.b = S.base.b;
+        edge.c = -S.base.a * bp.x - S.base.b * bp.y;
+        P2d c;
+        // Corners (:738-750): front with lines 0/1, back with lines 2/3
+        if(lined_intersection(edge, lined_from_i(S.line[e]), c))
+          quad[e] = c;
+        if(lined_intersection(edge, lined_from_i(S.line[2 + e]), c))
+          quad[2 + e] = c;
+      }
+    }
+    __syncthreads();
+  }
+  if(tid == 0)
+    valid = quad_is_convex(quad);
+}
+
+// BottomScanner::scan + detectFrontEdge after the close (segmentation.cpp:169-241, 890-904). Block-cooperative;
+// thread 0 gets the result.
+__device__ inline void detect_front_edge_block(const DevParams &p, const Band &bd, OutlineShared &S, P2d &left, P2d &right, int &valid, int tid,
+                                               int nthreads)
+{
+  const int W = p.W, H = p.H;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+  const int xStep = 50, xCenter = W / 2;
+  // all candidate columns x = xCenter + j*50 for j in [-jl, jr]
+  const int jr = (W - 1 - xCenter) / xStep, jl = xCenter / xStep;
+  const int ncols = jl + jr + 1;
+  for(int c = warp; c < ncols; c += nwarps)
+  {
+    const int x = xCenter + (c - jl) * xStep;
+    int yf, ys;
+    // probeBottomUp (:225-240): lowest set pixel with y > H/2
+    const bool f = probe_column(bd, x, H / 2 + 1, H - 1, lane, yf, ys);
+    if(lane == 0)
+    {
+      S.scan_found[c] = f;
+      S.scan_ys[c] = ys;
+    }
+  }
+  __syncthreads();
+  if(tid == 0)
+  {
+    // scan order (:177-221): first hit to the right of the centre (incl.), else to the left; then the
+    // contiguous run right of it, then the contiguous run left of it
+    int n = 0, start = -1;
+    for(int c = jl; c < ncols; c++)
+      if(S.scan_found[c])
+      {
+        start = c;
+        break;
+      }
+    if(start < 0)
+      for(int c = jl - 1; c >= 0; c--)
+        if(S.scan_found[c])
+        {
+          start = c;
+          break;
+        }
+    if(start >= 0)
+    {
+      auto push = [&](int c)
+      {
+        S.frontLeft[n].x = xCenter + (c - jl) * xStep;
+        S.frontLeft[n].y = S.scan_ys[c];
+        n++;
+      };
+      push(start);
+      for(int c = start + 1; c < ncols && S.scan_found[c]; c++)
+        push(c);
+      for(int c = start - 1; c >= 0 && S.scan_found[c]; c--)
+        push(c);
+    }
+    S.nLeft = n;
+  }
+  __syncthreads();
+  valid = 0;
+  left.x = left.y = right.x = right.y = 0;
+  const int n = S.nLeft;
+  if(n < 2)
+    return;
+  best_line_block(S.frontLeft, n, S.wk, &S.line[0], tid, nthreads);
+  if(tid == 0)
+  {
+    const FlatLineD edge = flat_from(S.line[0]);
+    int lo = 0, hi = 0; // ranges::minmax by x (:897-900)
+    for(int i = 1; i < n; i++)
+    {
+      if(S.frontLeft[i].x < S.frontLeft[lo].x)
+        lo = i;
+      if(!(S.frontLeft[i].x < S.frontLeft[hi].x))
+        hi = i;
+    }
+    left = flat_point(edge, S.frontLeft[lo].x);
+    right = flat_point(edge, S.frontLeft[hi].x);
+    valid = 1;
+  }
+}
+
+// Prepare the band descriptor of one bitmap in shared memory (smem path) or global scratch (large images).
+__device__ inline bool band_setup(const DevParams &p, Band &bd, int row_min, int row_max, unsigned *smem_words, size_t smem_cap_words,
+                                  unsigned *gbitmap, unsigned *gscratch)
+{
+  bd.b0 = max(0, row_min - 2);
+  const int b1 = min(p.H - 1, row_max + 2);
+  bd.nb = b1 - bd.b0 + 1;
+  const int rs = p.wpr + 1; // +1 word: conflict-free column probing
+  if((size_t)2 * bd.nb * rs <= smem_cap_words)
+  {
+    bd.rs = rs;
+    bd.A = smem_words;
+    bd.B = smem_words + (size_t)bd.nb * rs;
+    return true;
+  }
+  // image band too large for shared memory: close in global memory (A = the bitmap band itself, B = scratch)
+  bd.rs = p.wpr;
+  bd.A = gbitmap + (size_t)bd.b0 * p.wpr;
+  bd.B = gscratch + (size_t)bd.b0 * p.wpr;
+  return false;
+}
+
+__device__ inline void band_clear_global(const DevParams &p, const Band &bd, int tid, int nthreads)
+{
+  for(int i = tid; i < bd.nb * p.wpr; i += nthreads)
+    bd.A[i] = 0u;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_outline: grid = (SSD_GPU_MAX_PLATEAUS, frames); one block per outlined plateau
+// (loop B of detectStairSteps, pointcloud.cpp:419-429, incl. imgPointsToWorld :476-487)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SSD_OL_THREADS) k_outline(const __grid_constant__ DevParams p, FrameDev *__restrict__ frames,
+                                                             unsigned *__restrict__ bev, unsigned *__restrict__ bev2, size_t bm_words,
+                                                             size_t smem_cap_words)
+{
+  extern __shared__ __align__(16) unsigned s_words[];
+  __shared__ OutlineShared S;
+  __shared__ Band bd;
+  __shared__ int s_smem_path;
+  const int k = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x;
+  FrameDev &F = frames[frame];
+  if(k >= F.n_plateaus || !F.plat[k].outlined)
+    return;
+  PlateauDev &P = F.plat[k];
+  P2d quad[4];
+  int valid = 0;
+  if(P.row_max >= 0)
+  {
+    unsigned *gb = bev + ((size_t)frame * SSD_GPU_MAX_PLATEAUS + k) * bm_words;
+    unsigned *gs = bev2 + ((size_t)frame * SSD_GPU_MAX_PLATEAUS + k) * bm_words;
+    if(tid == 0)
+      s_smem_path = band_setup(p, bd, P.row_min, P.row_max, s_words, smem_cap_words, gb, gs);
+    __syncthreads();
+    if(s_smem_path)
+      band_close(p, bd, gb, gb, tid, SSD_OL_THREADS);
+    else
+      band_close(p, bd, gb, nullptr, tid, SSD_OL_THREADS); // A aliases the global band: staging copy is a no-op
+    detect_outline_block(p, bd, S, p.min_img_y_extent, p.xy_ratio, quad, valid, tid, SSD_OL_THREADS);
+    if(!s_smem_path)
+    {
+      __syncthreads();
+      band_clear_global(p, bd, tid, SSD_OL_THREADS);
+    }
+  }
+  else if(tid == 0)
+  {
+    for(int i = 0; i < 4; i++)
+      quad[i].x = quad[i].y = 0;
+  }
+  if(tid == 0)
+  {
+    for(int c = 0; c < 4; c++)
+    {
+      P.quad_px[c][0] = quad[c].x;
+      P.quad_px[c][1] = quad[c].y;
+      const P2d w = image_to_world(p, quad[c]);
+      P.quad_world[c][0] = w.x;
+      P.quad_world[c][1] = w.y;
+    }
+    P.valid = valid;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_frame_logic: the rest of detectStairSteps (pointcloud.cpp:427-443): first valid plateau, the ground
+// quadrilateral (calcGroundQuadrilateral, :489-512) and one QuadrilateralTest per emitted step.
+// One thread per frame.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_frame_logic(const __grid_constant__ DevParams p, FrameDev *__restrict__ frames, int n_frames)
+{
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if(f >= n_frames)
+    return;
+  FrameDev &F = frames[f];
+  const int K = F.n_plateaus;
+  int firstValid = -1;
+  for(int i = F.first_outlined; i < K; i++)
+    if(F.plat[i].valid)
+    {
+      firstValid = i;
+      break;
+    }
+  F.first_valid = firstValid;
+  if(firstValid < 0)
+    return;
+  if(F.ground_index >= 0)
+  {
+    PlateauDev &G = F.plat[F.ground_index];
+    const double(*q)[2] = F.plat[firstValid].quad_world;
+    const double yMin = p.y_min;
+    P2d gq[4];
+    if(q[0][1] < q[1][1])
+    {
+      gq[0].x = q[0][0];
+      gq[0].y = yMin;
+      gq[1].x = q[1][0] + (q[1][1] - yMin) * (q[1][1] - q[0][1]) / (q[1][0] - q[0][0]); // calcDx(q0,q1)
+      gq[1].y = yMin;
+    }
+    else
+    {
+      gq[0].x = q[0][0] + (q[0][1] - yMin) * (q[0][1] - q[1][1]) / (q[0][0] - q[1][0]); // calcDx(q1,q0)
+      gq[0].y = yMin;
+      gq[1].x = q[1][0];
+      gq[1].y = yMin;
+    }
+    gq[2].x = q[0][0];
+    gq[2].y = q[0][1];
+    gq[3].x = q[1][0];
+    gq[3].y = q[1][1];
+    for(int c = 0; c < 4; c++)
+    {
+      G.quad_world[c][0] = gq[c].x;
+      G.quad_world[c][1] = gq[c].y;
+    }
+    G.valid = 1;
+  }
+  for(int i = 0; i < K; i++)
+  {
+    PlateauDev &P = F.plat[i];
+    if(!P.valid)
+      continue;
+    P2d q[4];
+    for(int c = 0; c < 4; c++)
+    {
+      q[c].x = P.quad_world[c][0];
+      q[c].y = P.quad_world[c][1];
+    }
+    quadtest_init(P.qt, q);
+    P.quad_status = P.qt.status;
+    if(P.qt.status)
+      F.status |= SSD_STATUS_DEGENERATE_QUAD;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_finalize: calcGround's front edge (pointcloud.cpp:531-547), calcStairStep (:549-558), the result
+// assembly of detectStairs with ToExternalWorld (:370-383, transformation.cpp:190-194).
+// grid = frames, one block per frame.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SSD_OL_THREADS) k_finalize(const __grid_constant__ DevParams p, FrameDev *__restrict__ frames,
+                                                              FrameOut *__restrict__ out, unsigned *__restrict__ bev,
+                                                              unsigned *__restrict__ bev2, size_t bm_words, size_t smem_cap_words)
+{
+  extern __shared__ __align__(16) unsigned s_words[];
+  __shared__ OutlineShared S;
+  __shared__ Band bd;
+  __shared__ int s_smem_path;
+  const int frame = blockIdx.x, tid = threadIdx.x;
+  FrameDev &F = frames[frame];
+  FrameOut &O = out[frame];
+  const int K = F.n_plateaus, ground = F.ground_index, firstValid = F.first_valid;
+
+  P2d fl, fr;
+  int frontValid = 0;
+  const bool groundStep = firstValid >= 0 && ground >= 0 && F.plat[ground].quad_status == 0;
+  if(groundStep)
+  {
+    PlateauDev &G = F.plat[ground];
+    if(G.row_max >= 0)
+    {
+      unsigned *gb = bev + ((size_t)frame * SSD_GPU_MAX_PLATEAUS + ground) * bm_words;
+      unsigned *gs = bev2 + ((size_t)frame * SSD_GPU_MAX_PLATEAUS + ground) * bm_words;
+      if(tid == 0)
+        s_smem_path = band_setup(p, bd, G.row_min, G.row_max, s_words, smem_cap_words, gb, gs);
+      __syncthreads();
+      band_close(p, bd, gb, s_smem_path ? gb : nullptr, tid, SSD_OL_THREADS);
+      detect_front_edge_block(p, bd, S, fl, fr, frontValid, tid, SSD_OL_THREADS);
+      if(!s_smem_path)
+      {
+        __syncthreads();
+        band_clear_global(p, bd, tid, SSD_OL_THREADS);
+      }
+    }
+  }
+  if(tid != 0)
+    return;
+
+  unsigned status = F.status;
+  int nSteps = 0;
+  double sq[SSD_GPU_MAX_STEPS][4][3];
+  if(firstValid >= 0)
+  {
+    for(int i = 0; i < K; i++)
+    {
+      PlateauDev &P = F.plat[i];
+      if(P.valid && P.quad_status == 0)
+        P.mean_z = ((double)(long long)P.sum_fix / (double)(1ull << SSD_FIX_SHIFT)) / (double)P.n_in_quad; // calcAverageZ (:574-581)
+    }
+    if(groundStep)
+    {
+      PlateauDev &G = F.plat[ground];
+      G.front_valid = frontValid;
+      double(*s)[3] = sq[nSteps++];
+      if(frontValid)
+      {
+        const P2d wl = image_to_world(p, fl), wr = image_to_world(p, fr);
+        const LineDd frontLine = lined_from_pts(wl, wr);
+        P2d g0, g1, g2, g3;
+        g0.x = G.quad_world[0][0];
+        g0.y = G.quad_world[0][1];
+        g1.x = G.quad_world[1][0];
+        g1.y = G.quad_world[1][1];
+        g2.x = G.quad_world[2][0];
+        g2.y = G.quad_world[2][1];
+        g3.x = G.quad_world[3][0];
+        g3.y = G.quad_world[3][1];
+        const P2d frontLeft = line_intersection_plain(frontLine, lined_from_pts(g0, g2));
+        const P2d frontRight = line_intersection_plain(frontLine, lined_from_pts(g1, g3));
+        s[0][0] = frontLeft.x;
+        s[0][1] = frontLeft.y;
+        s[1][0] = frontRight.x;
+        s[1][1] = frontRight.y;
+        s[2][0] = g2.x;
+        s[2][1] = g2.y;
+        s[3][0] = g3.x;
+        s[3][1] = g3.y;
+        for(int c = 0; c < 4; c++)
+          s[c][2] = G.mean_z;
+        if(G.n_in_quad == 0)
+          status |= SSD_STATUS_EMPTY_MEAN;
+      }
+      else
+      {
+        for(int c = 0; c < 4; c++)
+          s[c][0] = s[c][1] = s[c][2] = 0; // return{} (:546)
+        status |= SSD_STATUS_INVALID_FRONT_EDGE;
+      }
+    }
+    for(int i = firstValid; i < K; i++)
+    {
+      const PlateauDev &P = F.plat[i];
+      if(!P.valid || P.quad_status != 0)
+        continue;
+      double(*s)[3] = sq[nSteps++];
+      for(int c = 0; c < 4; c++)
+      {
+        s[c][0] = P.quad_world[c][0];
+        s[c][1] = P.quad_world[c][1];
+        s[c][2] = P.mean_z;
+      }
+      if(P.n_in_quad == 0)
+        status |= SSD_STATUS_EMPTY_MEAN;
+    }
+  }
+  if(nSteps == 0)
+    status |= SSD_STATUS_NO_STEPS;
+  for(int s = 0; s < nSteps; s++)
+  {
+    for(int c = 0; c < 4; c++)
+    {
+      const double x = sq[s][c][0], y = sq[s][c][1];
+      O.steps[s].quad[c][0] = (p.ext_a[0] * x + p.ext_a[1] * y) + p.ext_b[0];
+      O.steps[s].quad[c][1] = (p.ext_a[2] * x + p.ext_a[3] * y) + p.ext_b[1];
+    }
+    O.steps[s].height = p.ext_z + sq[s][0][2];
+  }
+  F.n_steps = nSteps;
+  F.status = status;
+  O.info.status = status;
+  O.info.n_bins = p.n_bins;
+  O.info.n_plateaus = K;
+  O.info.ground_index = ground;
+  O.info.first_valid_index = firstValid;
+  O.info.n_steps = nSteps;
+  O.info.n_nonzero = F.n_nonzero;
+  O.info.n_in_range = F.n_in_range;
+}

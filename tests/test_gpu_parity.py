@@ -1,0 +1,220 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle (oracle/ssd_oracle.c)
+on the same seeded inputs. Bars (BASELINE.json north_star): labels / histogram / peaks bit-exact, step
+heights and corners within 0.1 mm (TOL below; in practice they agree to ~1e-12 m)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import helpers as H
+from stair_step_detector_b200 import _abi as A
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4  # metres: 0.1 mm
+
+NOISY = dict(noise_sigma=0.0025, dropout=0.03, n_holes=3)
+
+
+def gpu_result(S, det, frame):
+    info = det.frame_info(frame)
+    plats, _ = det.plateaus(frame)
+    steps = (A.Step * A.MAX_STEPS)()
+    n = C.c_int()
+    det._ck(det._l.ssd_gpu_get_steps(det._h, frame, steps, A.MAX_STEPS, C.byref(n), None), "get_steps")
+    hist = np.zeros(A.MAX_BINS, np.uint32)
+    hist[:info.n_bins] = det.histogram(frame)
+    return H._collect(det.labels(frame), hist, info, plats, steps)
+
+
+def run_frames(S, oracle, cfg, scenes, max_bad=0):
+    xf = S.scene_transform(scenes[0])
+    xyz = np.stack([S.deproject_host(sc, S.synth_depth_host(sc)) for sc in scenes])
+    with S.Detector(cfg, xf, max_frames=len(scenes)) as det:
+        det.process_host(xyz)
+        out = []
+        for f in range(len(scenes)):
+            g = gpu_result(S, det, f)
+            o = H.oracle_process(oracle, cfg, xf, xyz[f])
+            bad = H.compare_results(o, g, tol=TOL)
+            assert g.info["status"] == o.info["status"], (f, hex(g.info["status"]), hex(o.info["status"]))
+            assert not bad, (f, bad)
+            out.append((g, o))
+        return out
+
+
+@pytest.mark.parametrize("w,h", [(1024, 768), (640, 480), (320, 240)])
+def test_clean_frame(S, oracle, w, h):
+    cfg = S.default_config(w, h)
+    (g, o), = run_frames(S, oracle, cfg, [S.default_scene(w, h)])
+    assert g.info["n_steps"] == 4  # ground + 3 steps
+    heights = [s["height"] for s in g.steps]
+    assert np.allclose(heights, [0.004, 0.177, 0.350, 0.523], atol=2e-3)
+
+
+def test_noisy_frame(S, oracle):
+    cfg = S.default_config(1024, 768)
+    (g, o), = run_frames(S, oracle, cfg, [S.default_scene(1024, 768, **NOISY)])
+    assert g.info["n_steps"] >= 3
+
+
+def test_descending_occluded(S, oracle):
+    cfg = S.default_config(1024, 768)
+    base = S.default_scene(1024, 768, rotate180=1, n_occluders=2, **NOISY)
+    run_frames(S, oracle, cfg, [base])
+
+
+def test_batch_random_scenes(S, oracle):
+    """config 3 distribution, one shared calibration (camera pose fixed, stairs vary)."""
+    cfg = S.default_config(1024, 768)
+    base = S.default_scene(1024, 768, **NOISY)
+    scenes = []
+    for i in range(24):
+        sc = S.randomize_scene(base, 4242, i, 3, 8)
+        # one transform per context: keep the base camera pose, vary the staircase only
+        for k in ("cam_height", "cam_pitch_deg", "cam_roll_deg", "cam_yaw_deg"):
+            setattr(sc, k, getattr(base, k))
+        scenes.append(sc)
+    res = run_frames(S, oracle, cfg, scenes)
+    assert sum(g.info["n_steps"] for g, _ in res) > 24 * 3
+
+
+def test_empty_and_garbage_frames(S, oracle):
+    cfg = S.default_config(640, 480)
+    sc = S.default_scene(640, 480)
+    xf = S.scene_transform(sc)
+    rng = np.random.default_rng(1)
+    frames = np.zeros((3, 480, 640, 3), np.float32)  # frame 0: all invalid
+    frames[1] = rng.uniform(-2, 2, (480, 640, 3)).astype(np.float32)  # uniform noise
+    frames[2, ..., 2] = 1.0  # a fronto-parallel wall
+    with S.Detector(cfg, xf, max_frames=3) as det:
+        det.process_host(frames)
+        for f in range(3):
+            g = gpu_result(S, det, f)
+            o = H.oracle_process(oracle, cfg, xf, frames[f])
+            assert not H.compare_results(o, g, tol=TOL), f
+            assert g.info["status"] == o.info["status"]
+
+
+def test_hires_extended_range(S, oracle):
+    cfg = S.default_config(4096, 3072, y_max=3.7, z_max=2.3)
+    sc = S.default_scene(4096, 3072, n_steps=12, riser=0.17, tread=0.26, cam_height=3.2, cam_pitch_deg=48.0,
+                         first_riser_y=0.5, **NOISY)
+    run_frames(S, oracle, cfg, [sc])
+
+
+def test_camera_to_world_exact(S, oracle):
+    cfg = S.default_config(320, 240)
+    sc = S.default_scene(320, 240, cam_roll_deg=3.0, cam_yaw_deg=-7.0)
+    xf = S.scene_transform(sc)
+    rng = np.random.default_rng(7)
+    pts = rng.normal(0, 1.5, (200000, 3)).astype(np.float32)
+    with S.Detector(cfg, xf) as det:
+        g = det.camera_to_world(pts)
+    o = np.empty_like(g)
+    oracle.ssd_oracle_camera_to_world(C.byref(xf), H.ptr(pts), len(pts), H.ptr(o))
+    assert np.array_equal(g.view(np.uint64), o.view(np.uint64))
+
+
+def random_quads(rng, n):
+    for _ in range(n):
+        c = rng.uniform(-0.3, 0.3, 2)
+        w, d = rng.uniform(0.2, 0.6), rng.uniform(0.1, 0.5)
+        q = np.array([[-w, -d], [w, -d], [-w, d], [w, d]]) * 0.5
+        th = rng.uniform(-0.4, 0.4)
+        R = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+        yield q @ R.T + c + rng.normal(0, 0.02, (4, 2))
+
+
+def test_points_in_quad_exact(S, oracle):
+    cfg = S.default_config(320, 240)
+    xf = S.scene_transform(S.default_scene(320, 240))
+    rng = np.random.default_rng(3)
+    with S.Detector(cfg, xf) as det:
+        quads = list(random_quads(rng, 40))
+        quads.append(np.array([[0, 0], [1, 0], [0, 1], [1, 1.0]]))       # axis aligned
+        quads.append(np.array([[0, 0], [1, 0], [1, 1], [0, 1.0]]))       # bow-tie: ctor throws
+        quads.append(np.array([[0, 0], [1, 0], [0, 0], [1, 0.0]]))       # no y extent
+        for q in quads:
+            xy = rng.uniform(-0.8, 0.8, (50000, 2))
+            xy[:8] = np.repeat(q, 2, axis=0)  # the vertices themselves
+            g, gs = det.points_in_quad(q, xy)
+            o = np.empty(len(xy), np.uint8)
+            st = C.c_int()
+            qq = (C.c_double * 8)(*q.ravel())
+            oracle.ssd_oracle_points_in_quad(qq, H.ptr(xy), len(xy), H.ptr(o), C.byref(st))
+            assert gs == st.value
+            assert np.array_equal(g, o)
+
+
+def blob_image(rng, w, h, kind):
+    """binary BEV-like test images: filled quadrilaterals with ragged edges, holes and speckle"""
+    yy, xx = np.mgrid[0:h, 0:w]
+    cx, cy = w * rng.uniform(0.4, 0.6), h * rng.uniform(0.3, 0.8)
+    hw, hh = w * rng.uniform(0.15, 0.45), h * rng.uniform(0.08, 0.3)
+    th = rng.uniform(-0.15, 0.15)
+    u = (xx - cx) * np.cos(th) + (yy - cy) * np.sin(th)
+    v = -(xx - cx) * np.sin(th) + (yy - cy) * np.cos(th)
+    img = ((np.abs(u) < hw) & (np.abs(v) < hh)).astype(np.uint8) * 255
+    if kind >= 1:
+        img[rng.random((h, w)) < 0.25] = 0           # dropouts (the close fills most)
+    if kind >= 2:
+        img[rng.random((h, w)) < 0.002] = 255        # speckle
+    if kind == 3:
+        img[:, : w // 2 - 30] = 0                    # cut: few scan columns on the left
+    return img
+
+
+@pytest.mark.parametrize("w,h", [(320, 240), (1024, 768)])
+def test_outline_and_front_edge_images(S, oracle, w, h):
+    cfg = S.default_config(w, h)
+    xf = S.scene_transform(S.default_scene(w, h))
+    rng = np.random.default_rng(11)
+    der = H.Derived()
+    oracle.ssd_oracle_derive(C.byref(cfg), C.byref(der))
+    n_valid = 0
+    with S.Detector(cfg, xf) as det:
+        for i in range(24):
+            img = blob_image(rng, w, h, i % 4)
+            gq, gv = det.detect_outline(img, der.min_img_y_extent, der.xy_ratio)
+            oq = (C.c_double * 8)()
+            ov = C.c_int()
+            oracle.ssd_oracle_detect_outline(H.ptr(img), w, h, der.min_img_y_extent, der.xy_ratio, oq, C.byref(ov))
+            assert gv == ov.value, i
+            assert np.allclose(gq, np.array(oq[:]).reshape(4, 2), rtol=0, atol=1e-7), i
+            n_valid += gv
+            gl, gr, gfv = det.detect_front_edge(img)
+            ol = (C.c_double * 2)()
+            orr = (C.c_double * 2)()
+            ofv = C.c_int()
+            oracle.ssd_oracle_detect_front_edge(H.ptr(img), w, h, ol, orr, C.byref(ofv))
+            assert gfv == ofv.value, i
+            assert np.allclose(gl, ol[:], rtol=0, atol=1e-7) and np.allclose(gr, orr[:], rtol=0, atol=1e-7), i
+    assert n_valid >= 6
+
+
+def test_device_input_and_determinism(S, oracle):
+    """device-resident input (synthetic frames generated in HBM) gives the same results as host input,
+    and two runs are bit-identical (fixed-point z accumulation)."""
+    cfg = S.default_config(1024, 768)
+    base = S.default_scene(1024, 768, **NOISY)
+    xf = S.scene_transform(base)
+    nF, N = 6, 1024 * 768
+    with S.Detector(cfg, xf, max_frames=nF) as det:
+        d_xyz = det.malloc(nF * N * 12)
+        det.synth_frames(base, 99, 0, nF, 3, 8, d_xyz)
+        xyz = np.empty((nF, N, 3), np.float32)
+        det.d2h(xyz, d_xyz)
+        det.process_device(d_xyz, nF)
+        first = [(det.steps(f), det.labels(f).copy()) for f in range(nF)]
+        det.process_device(d_xyz, nF)
+        for f in range(nF):
+            (s, st), lab = first[f]
+            (s2, st2) = det.steps(f)
+            assert st == st2 and len(s) == len(s2)
+            for (h1, q1), (h2, q2) in zip(s, s2):
+                assert h1 == h2 and np.array_equal(q1, q2)
+            assert np.array_equal(lab, det.labels(f))
+            g = gpu_result(S, det, f)
+            o = H.oracle_process(oracle, cfg, xf, xyz[f])
+            assert not H.compare_results(o, g, tol=TOL), f
+        det.free(d_xyz)
