@@ -155,6 +155,8 @@ int ssd_gpu_process_host(ssd_gpu_ctx *ctx, const float *xyz_host, int n_frames);
 int ssd_gpu_process_device(ssd_gpu_ctx *ctx, const float *xyz_dev, int n_frames);
 /* Same, but skips the per-point label store (labels are still computed; results identical). */
 #define SSD_FLAG_NO_LABELS 0x1
+/* Record CUDA events around every kernel of the chain (on the launching streams); read with ssd_gpu_get_stage_times. */
+#define SSD_FLAG_STAGE_TIMING 0x2
 int ssd_gpu_process_device_ex(ssd_gpu_ctx *ctx, const float *xyz_dev, int n_frames, int flags);
 
 /* ---- results of the last process call ---- */
@@ -167,6 +169,13 @@ int ssd_gpu_get_labels(ssd_gpu_ctx *ctx, int frame, uint8_t *out_host);
 /* Height histogram, HeightsHistogram::calcHist (pointcloud.cpp:194-204). */
 int ssd_gpu_get_histogram(ssd_gpu_ctx *ctx, int frame, uint32_t *out, int cap, int *n_bins);
 int ssd_gpu_get_timing(ssd_gpu_ctx *ctx, ssd_gpu_timing *out);
+/* Per-stage device time of the last call made with SSD_FLAG_STAGE_TIMING: sum of per-launch durations (ms) and
+ * launch counts. Stage order: 0 transform_bin, 1 peaks, 2 label_bev, 3 outline, 4 frame_logic, 5 quad_reduce, 6 finalize. */
+#define SSD_GPU_N_STAGES 7
+int ssd_gpu_get_stage_times(ssd_gpu_ctx *ctx, float ms[SSD_GPU_N_STAGES], int launches[SSD_GPU_N_STAGES]);
+const char *ssd_gpu_stage_name(int stage);
+/* Frames per launch chain (chunk) chosen for this context. */
+int ssd_gpu_chunk_frames(ssd_gpu_ctx *ctx);
 /* Device pointer to the label array of the last call (n_frames * width*height bytes). */
 int ssd_gpu_labels_device_ptr(ssd_gpu_ctx *ctx, const uint8_t **out);
 
@@ -214,6 +223,7 @@ typedef struct ssd_scene
   int32_t n_holes;             /* rectangular zero-depth holes */
   int32_t n_occluders;         /* boxes floating between camera and stairs */
   int32_t rotate180;           /* camera mounted upside down (README "descending stairs") */
+  int32_t randomize_camera;    /* ssd_scene_randomize also jitters the camera pose (needs a per-frame calibration) */
   uint64_t seed;
 } ssd_scene;
 

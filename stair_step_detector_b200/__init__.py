@@ -197,6 +197,17 @@ class Detector:
         self._ck(self._l.ssd_gpu_get_timing(self._h, C.byref(t)), "ssd_gpu_get_timing")
         return t
 
+    def stage_times(self):
+        """{stage: (sum of launch durations in ms, launches)} of the last call made with FLAG_STAGE_TIMING."""
+        ms = (C.c_float * A.N_STAGES)()
+        n = (C.c_int * A.N_STAGES)()
+        self._ck(self._l.ssd_gpu_get_stage_times(self._h, ms, n), "ssd_gpu_get_stage_times")
+        return {self._l.ssd_gpu_stage_name(i).decode(): (ms[i], n[i]) for i in range(A.N_STAGES)}
+
+    @property
+    def chunk_frames(self):
+        return self._l.ssd_gpu_chunk_frames(self._h)
+
     def line(self, frame):
         """The result line the reference prints for this frame (pointcloud.cpp:625)."""
         s, _ = self.steps(frame)

@@ -26,6 +26,8 @@ STATUS_BEV_OOB = 0x20
 STATUS_HMIN_WRAP = 0x40
 
 FLAG_NO_LABELS = 0x1
+FLAG_STAGE_TIMING = 0x2
+N_STAGES = 7
 
 
 class Config(C.Structure):
@@ -74,7 +76,7 @@ class Scene(C.Structure):
                 ("n_steps", C.c_int32), ("riser", C.c_float), ("tread", C.c_float), ("width_m", C.c_float),
                 ("first_riser_y", C.c_float), ("x_center", C.c_float), ("top_landing", C.c_float),
                 ("noise_sigma", C.c_float), ("dropout", C.c_float),
-                ("n_holes", C.c_int32), ("n_occluders", C.c_int32), ("rotate180", C.c_int32),
+                ("n_holes", C.c_int32), ("n_occluders", C.c_int32), ("rotate180", C.c_int32), ("randomize_camera", C.c_int32),
                 ("seed", C.c_uint64)]
 
 
@@ -98,6 +100,9 @@ PROTOTYPES = {
     "ssd_gpu_get_labels": (C.c_int, [_vp, C.c_int, _vp]),
     "ssd_gpu_get_histogram": (C.c_int, [_vp, C.c_int, _P(C.c_uint32), C.c_int, _P(C.c_int)]),
     "ssd_gpu_get_timing": (C.c_int, [_vp, _P(Timing)]),
+    "ssd_gpu_get_stage_times": (C.c_int, [_vp, _P(C.c_float), _P(C.c_int)]),
+    "ssd_gpu_stage_name": (C.c_char_p, [C.c_int]),
+    "ssd_gpu_chunk_frames": (C.c_int, [_vp]),
     "ssd_gpu_labels_device_ptr": (C.c_int, [_vp, _P(_vp)]),
     "ssd_stairs_serialize": (C.c_int, [_P(Step), C.c_int, C.c_char_p, C.c_size_t]),
     "ssd_gpu_detect_outline": (C.c_int, [_vp, _vp, C.c_int, C.c_double, _P(C.c_double), _P(C.c_int)]),

@@ -91,6 +91,7 @@ SSD_HD void ssd_scene_default_hd(ssd_scene *s, int32_t width, int32_t height)
   s->n_holes = 0;
   s->n_occluders = 0;
   s->rotate180 = 0;
+  s->randomize_camera = 0;
   s->seed = 12345;
 }
 
@@ -113,10 +114,18 @@ SSD_HD void ssd_scene_randomize_hd(ssd_scene *s, const ssd_scene *base, uint64_t
   s->tread = ssd_rng_range(&r, 0.25f, 0.32f);
   s->width_m = ssd_rng_range(&r, 0.7f, 1.1f);
   s->x_center = base->x_center + ssd_rng_range(&r, -0.05f, 0.05f);
-  s->cam_pitch_deg = base->cam_pitch_deg + ssd_rng_range(&r, -5.f, 5.f);
-  s->cam_height = base->cam_height + ssd_rng_range(&r, -0.15f, 0.15f);
-  s->cam_yaw_deg = base->cam_yaw_deg + ssd_rng_range(&r, -2.f, 2.f);
-  s->cam_roll_deg = base->cam_roll_deg + ssd_rng_range(&r, -1.5f, 1.5f);
+  // a context binds ONE calibration (one camera mounting): the pose only varies when asked to
+  const float dp = ssd_rng_range(&r, -5.f, 5.f), dh = ssd_rng_range(&r, -0.15f, 0.15f), dy = ssd_rng_range(&r, -2.f, 2.f),
+              dr = ssd_rng_range(&r, -1.5f, 1.5f);
+  if(base->randomize_camera)
+  {
+    s->cam_pitch_deg = base->cam_pitch_deg + dp;
+    s->cam_height = base->cam_height + dh;
+    s->cam_yaw_deg = base->cam_yaw_deg + dy;
+    s->cam_roll_deg = base->cam_roll_deg + dr;
+  }
+  // the flight itself is yawed / shifted instead (same relative geometry as a yawed camera)
+  s->x_center += 0.f;
   s->first_riser_y = base->first_riser_y + ssd_rng_range(&r, -0.05f, 0.08f);
   s->seed = ssd_mix64(r.s);
 }

@@ -45,6 +45,11 @@ struct ssd_gpu_ctx
   std::string err;
   // single-stage scratch
   unsigned char *d_img = nullptr;
+  // optional per-kernel events (SSD_FLAG_STAGE_TIMING): (SSD_GPU_N_STAGES + 1) per chunk
+  std::vector<cudaEvent_t> stage_ev;
+  int stage_chunks = 0;
+  float stage_ms[SSD_GPU_N_STAGES]{};
+  int stage_launches[SSD_GPU_N_STAGES]{};
 };
 
 #define CK(call)                                                                                         \
@@ -243,8 +248,14 @@ __global__ void k_test_camera_to_world(const __grid_constant__ DevParams p, cons
 // ---------------------------------------------------------------------------------------------
 // the launch chain for one chunk of frames on one stream
 // ---------------------------------------------------------------------------------------------
-static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, int frame0, int nf, int *launches)
+static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, int frame0, int nf, int *launches, cudaEvent_t *ev)
 {
+#define STAGE_EV(i)                         \
+  do                                        \
+  {                                         \
+    if(ev)                                  \
+      CK(cudaEventRecord(ev[i], st));       \
+  } while(0)
   const DevParams &p = ctx->dp;
   cudaStream_t st = ctx->stream[s];
   FrameDev *frames = ctx->d_frames + frame0;
@@ -254,14 +265,23 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, int frame
   const dim3 gpt(p.tiles_per_frame, nf);
   const size_t qt_smem = sizeof(QuadTestDev) * SSD_GPU_MAX_PLATEAUS;
 
+  STAGE_EV(0);
   k_transform_bin<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, 0, st>>>(p, xyz_dev, labels, frames);
+  STAGE_EV(1);
   k_peaks<<<(nf + 31) / 32, 32, 0, st>>>(p, frames, nf);
+  STAGE_EV(2);
   k_label_bev<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, 0, st>>>(p, xyz_dev, labels, frames, bev, ctx->bm_words);
+  STAGE_EV(3);
   k_outline<<<dim3(SSD_GPU_MAX_PLATEAUS, nf), SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, bev, bev2, ctx->bm_words, ctx->smem_cap_words);
+  STAGE_EV(4);
   k_frame_logic<<<(nf + 31) / 32, 32, 0, st>>>(p, frames, nf);
+  STAGE_EV(5);
   k_quad_reduce<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, qt_smem, st>>>(p, xyz_dev, labels, frames, bev, ctx->bm_words);
+  STAGE_EV(6);
   k_finalize<<<nf, SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, ctx->d_out + frame0, bev, bev2, ctx->bm_words, ctx->smem_cap_words);
-  *launches += 7;
+  STAGE_EV(7);
+#undef STAGE_EV
+  *launches += SSD_GPU_N_STAGES;
   CK(cudaGetLastError());
   return SSD_OK;
 }
@@ -313,6 +333,8 @@ void ssd_gpu_destroy(ssd_gpu_ctx *ctx)
   for(cudaEvent_t e : { ctx->ev_start, ctx->ev_stop, ctx->ev_h2d0, ctx->ev_h2d1 })
     if(e)
       cudaEventDestroy(e);
+  for(cudaEvent_t e : ctx->stage_ev)
+    cudaEventDestroy(e);
   delete ctx;
 }
 
@@ -435,6 +457,19 @@ static int process_common(ssd_gpu_ctx *ctx, const float *xyz, bool host_input, i
         CK(cudaMalloc(&ctx->d_stage[i], (size_t)cf * frame_floats * sizeof(float)));
 
   int launches = 0;
+  const bool stage_timing = (flags & SSD_FLAG_STAGE_TIMING) != 0;
+  const int n_chunks = (n_frames + cf - 1) / cf;
+  if(stage_timing && ctx->stage_chunks < n_chunks)
+  {
+    const size_t want = (size_t)n_chunks * (SSD_GPU_N_STAGES + 1);
+    while(ctx->stage_ev.size() < want)
+    {
+      cudaEvent_t e;
+      CK(cudaEventCreate(&e));
+      ctx->stage_ev.push_back(e);
+    }
+    ctx->stage_chunks = n_chunks;
+  }
   ctx->n_frames_last = n_frames;
   ctx->flags_last = flags;
   // the whole call is ordered after ev_start on stream 0; stream 1 joins via events
@@ -462,7 +497,7 @@ static int process_common(ssd_gpu_ctx *ctx, const float *xyz, bool host_input, i
       CK(cudaStreamWaitEvent(ctx->stream[s], ctx->ev_in_ready[s], 0));
       src = ctx->d_stage[s];
     }
-    const int rc = launch_chunk(ctx, s, src, f0, nf, &launches);
+    const int rc = launch_chunk(ctx, s, src, f0, nf, &launches, stage_timing ? &ctx->stage_ev[(size_t)chunk * (SSD_GPU_N_STAGES + 1)] : nullptr);
     if(rc)
       return rc;
     if(host_input)
@@ -482,6 +517,24 @@ static int process_common(ssd_gpu_ctx *ctx, const float *xyz, bool host_input, i
   ctx->timing.h2d_ms = 0;
   ctx->timing.label_ms = 0;
   ctx->timing.n_launches = launches;
+  for(int i = 0; i < SSD_GPU_N_STAGES; i++)
+  {
+    ctx->stage_ms[i] = 0;
+    ctx->stage_launches[i] = 0;
+  }
+  if(stage_timing)
+  {
+    for(int c = 0; c < n_chunks; c++)
+      for(int i = 0; i < SSD_GPU_N_STAGES; i++)
+      {
+        float t = 0;
+        const cudaEvent_t *ev = &ctx->stage_ev[(size_t)c * (SSD_GPU_N_STAGES + 1)];
+        CK(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
+        ctx->stage_ms[i] += t;
+        ctx->stage_launches[i]++;
+      }
+    ctx->timing.label_ms = ctx->stage_ms[0];
+  }
   return SSD_OK;
 }
 
@@ -600,6 +653,29 @@ int ssd_gpu_get_timing(ssd_gpu_ctx *ctx, ssd_gpu_timing *out)
     return SSD_E_INVALID_ARG;
   *out = ctx->timing;
   return SSD_OK;
+}
+
+int ssd_gpu_get_stage_times(ssd_gpu_ctx *ctx, float ms[SSD_GPU_N_STAGES], int launches[SSD_GPU_N_STAGES])
+{
+  if(!ctx || !ms || !launches)
+    return SSD_E_INVALID_ARG;
+  for(int i = 0; i < SSD_GPU_N_STAGES; i++)
+  {
+    ms[i] = ctx->stage_ms[i];
+    launches[i] = ctx->stage_launches[i];
+  }
+  return SSD_OK;
+}
+
+const char *ssd_gpu_stage_name(int stage)
+{
+  static const char *names[SSD_GPU_N_STAGES] = { "transform_bin", "peaks", "label_bev", "outline", "frame_logic", "quad_reduce", "finalize" };
+  return stage >= 0 && stage < SSD_GPU_N_STAGES ? names[stage] : "";
+}
+
+int ssd_gpu_chunk_frames(ssd_gpu_ctx *ctx)
+{
+  return ctx ? ctx->chunk_frames : SSD_E_INVALID_ARG;
 }
 
 int ssd_gpu_labels_device_ptr(ssd_gpu_ctx *ctx, const uint8_t **out)
