@@ -37,7 +37,7 @@ struct ssd_gpu_ctx
   FrameOut *d_out = nullptr;      // max_frames
   FrameOut *h_out = nullptr;      // pinned
   unsigned char *d_labels = nullptr; // max_frames * N
-  unsigned *d_bev = nullptr, *d_bev2 = nullptr; // 2 x chunk_frames * MAX_PLATEAUS * bm_words (per stream)
+  unsigned *d_bev = nullptr; // 2 x chunk_frames * MAX_PLATEAUS * bm_words (per stream)
   float *d_stage[2]{};            // host-input staging, chunk_frames frames each
   int n_frames_last = 0;
   int flags_last = 0;
@@ -183,7 +183,7 @@ __global__ void k_test_setup_plateau(FrameDev *frames, int H)
 }
 
 __global__ void __launch_bounds__(SSD_OL_THREADS) k_test_front_edge(const __grid_constant__ DevParams p, unsigned *__restrict__ bev,
-                                                                     unsigned *__restrict__ bev2, size_t smem_cap_words, double *out)
+                                                                     size_t smem_cap_words, double *out)
 {
   extern __shared__ __align__(16) unsigned s_words[];
   __shared__ OutlineShared S;
@@ -191,16 +191,17 @@ __global__ void __launch_bounds__(SSD_OL_THREADS) k_test_front_edge(const __grid
   __shared__ int s_smem_path;
   const int tid = threadIdx.x;
   if(tid == 0)
-    s_smem_path = band_setup(p, bd, 0, p.H - 1, s_words, smem_cap_words, bev, bev2);
+    s_smem_path = band_setup(p, bd, 0, p.H - 1, s_words, smem_cap_words, bev);
   __syncthreads();
-  band_close(p, bd, bev, s_smem_path ? bev : nullptr, tid, SSD_OL_THREADS);
+  if(s_smem_path)
+    band_stage(p, s_words, bd, bev, tid, SSD_OL_THREADS);
   P2d l, r;
   int valid;
   detect_front_edge_block(p, bd, S, l, r, valid, tid, SSD_OL_THREADS);
   if(!s_smem_path)
   {
     __syncthreads();
-    band_clear_global(p, bd, tid, SSD_OL_THREADS);
+    band_clear_global(p, bd, bev, tid, SSD_OL_THREADS);
   }
   if(tid == 0)
   {
@@ -261,24 +262,23 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, int frame
   FrameDev *frames = ctx->d_frames + frame0;
   unsigned char *labels = ctx->d_labels + (size_t)frame0 * p.N;
   unsigned *bev = ctx->d_bev + (size_t)s * ctx->chunk_frames * SSD_GPU_MAX_PLATEAUS * ctx->bm_words;
-  unsigned *bev2 = ctx->d_bev2 + (size_t)s * ctx->chunk_frames * SSD_GPU_MAX_PLATEAUS * ctx->bm_words;
   const dim3 gpt(p.tiles_per_frame, nf);
   const size_t qt_smem = sizeof(QuadTestDev) * SSD_GPU_MAX_PLATEAUS;
 
   STAGE_EV(0);
   k_transform_bin<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, 0, st>>>(p, xyz_dev, labels, frames);
   STAGE_EV(1);
-  k_peaks<<<(nf + 31) / 32, 32, 0, st>>>(p, frames, nf);
+  k_peaks<<<nf, 32, 0, st>>>(p, frames, nf);
   STAGE_EV(2);
   k_label_bev<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, 0, st>>>(p, xyz_dev, labels, frames, bev, ctx->bm_words);
   STAGE_EV(3);
-  k_outline<<<dim3(SSD_GPU_MAX_PLATEAUS, nf), SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, bev, bev2, ctx->bm_words, ctx->smem_cap_words);
+  k_outline<<<dim3(SSD_GPU_MAX_PLATEAUS, nf), SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, bev, ctx->bm_words, ctx->smem_cap_words);
   STAGE_EV(4);
-  k_frame_logic<<<(nf + 31) / 32, 32, 0, st>>>(p, frames, nf);
+  k_frame_logic<<<nf, 32, 0, st>>>(p, frames, nf);
   STAGE_EV(5);
   k_quad_reduce<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, qt_smem, st>>>(p, xyz_dev, labels, frames, bev, ctx->bm_words);
   STAGE_EV(6);
-  k_finalize<<<nf, SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, ctx->d_out + frame0, bev, bev2, ctx->bm_words, ctx->smem_cap_words);
+  k_finalize<<<nf, SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, ctx->d_out + frame0, bev, ctx->bm_words, ctx->smem_cap_words);
   STAGE_EV(7);
 #undef STAGE_EV
   *launches += SSD_GPU_N_STAGES;
@@ -313,7 +313,6 @@ void ssd_gpu_destroy(ssd_gpu_ctx *ctx)
   cudaFreeHost(ctx->h_out);
   cudaFree(ctx->d_labels);
   cudaFree(ctx->d_bev);
-  cudaFree(ctx->d_bev2);
   cudaFree(ctx->d_stage[0]);
   cudaFree(ctx->d_stage[1]);
   cudaFree(ctx->d_img);
@@ -391,9 +390,13 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
   cudaFuncGetAttributes(&fc, k_test_front_edge);
   const size_t stat = std::max({ fa.sharedSizeBytes, fb.sharedSizeBytes, fc.sharedSizeBytes });
   size_t dyn = (size_t)max_optin > stat + 1024 ? (size_t)max_optin - stat - 1024 : 0;
-  // no more than the full image needs
-  const size_t full = (size_t)2 * dp.H * (dp.wpr + 1) * 4;
-  dyn = std::min(dyn, full);
+  // raw band only (the close is evaluated on the fly); no more than the full image needs, and by default
+  // small enough for three resident blocks per SM (larger bands fall back to probing global memory)
+  const size_t full = (size_t)dp.H * (dp.wpr + 1) * 4;
+  size_t want = 48 * 1024;
+  if(const char *e = getenv("SSD_GPU_OUTLINE_SMEM_KB"))
+    want = (size_t)atoi(e) * 1024;
+  dyn = std::min(dyn, std::min(full, want));
   dyn &= ~(size_t)15;
   ctx->ol_dyn_smem = dyn;
   ctx->smem_cap_words = dyn / 4;
@@ -429,9 +432,7 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
   CKC(cudaMalloc(&ctx->d_labels, (size_t)max_frames * dp.N));
   const size_t bev_bytes = (size_t)2 * ctx->chunk_frames * SSD_GPU_MAX_PLATEAUS * ctx->bm_words * 4;
   CKC(cudaMalloc(&ctx->d_bev, bev_bytes));
-  CKC(cudaMalloc(&ctx->d_bev2, bev_bytes));
   CKC(cudaMemset(ctx->d_bev, 0, bev_bytes)); // bitmaps are self-cleaning afterwards
-  CKC(cudaMemset(ctx->d_bev2, 0, bev_bytes));
   CKC(cudaMemset(ctx->d_frames, 0, sizeof(FrameDev) * (size_t)max_frames));
   CKC(cudaMemset(ctx->d_out, 0, sizeof(FrameOut) * (size_t)max_frames));
   memset(ctx->h_out, 0, sizeof(FrameOut) * (size_t)max_frames);
@@ -712,7 +713,7 @@ int ssd_gpu_detect_outline(ssd_gpu_ctx *ctx, const uint8_t *image_host, int min_
   p.xy_ratio = xy_ratio;
   cudaStream_t st = ctx->stream[0];
   k_test_setup_plateau<<<1, 1, 0, st>>>(ctx->d_frames, p.H);
-  k_outline<<<dim3(1, 1), SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, ctx->d_frames, ctx->d_bev, ctx->d_bev2, ctx->bm_words, ctx->smem_cap_words);
+  k_outline<<<dim3(1, 1), SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, ctx->d_frames, ctx->d_bev, ctx->bm_words, ctx->smem_cap_words);
   CK(cudaGetLastError());
   PlateauDev P;
   CK(cudaMemcpyAsync(&P, &ctx->d_frames[0].plat[0], sizeof(P), cudaMemcpyDeviceToHost, st));
@@ -733,7 +734,7 @@ int ssd_gpu_detect_front_edge(ssd_gpu_ctx *ctx, const uint8_t *image_host, doubl
   cudaStream_t st = ctx->stream[0];
   double *d_out = nullptr;
   CK(cudaMalloc(&d_out, sizeof(double) * 8));
-  k_test_front_edge<<<1, SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(ctx->dp, ctx->d_bev, ctx->d_bev2, ctx->smem_cap_words, d_out);
+  k_test_front_edge<<<1, SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(ctx->dp, ctx->d_bev, ctx->smem_cap_words, d_out);
   double h[8];
   cudaError_t e = cudaMemcpyAsync(h, d_out, sizeof(double) * 5, cudaMemcpyDeviceToHost, st);
   if(e == cudaSuccess)

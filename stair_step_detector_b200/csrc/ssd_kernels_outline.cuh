@@ -11,113 +11,106 @@
 
 #define SSD_OL_THREADS 256
 
-// Closed band of a BEV bitmap: rows [b0, b0+nb) with row stride rs words; rows outside are all zero.
+// Band of a raw BEV bitmap: rows [b0, b0+nb) with row stride rs words, staged in shared memory (or left
+// in global memory for images too large); rows outside the band are all zero. The 3x3 close is evaluated
+// on the fly, word-parallel, wherever a probe needs it.
 struct Band
 {
-  unsigned *A; // closed image (result)
-  unsigned *B; // dilated image (scratch)
+  const unsigned *A;
   int b0, nb, rs;
 };
 
-__device__ __forceinline__ unsigned band_word(const Band &bd, int y, int w)
+__device__ __forceinline__ unsigned raw_word(const Band &bd, int r, int w, int wpr)
 {
-  const int r = y - bd.b0;
-  if(r < 0 || r >= bd.nb)
-    return 0u;
-  return bd.A[(size_t)r * bd.rs + w];
-}
-__device__ __forceinline__ int band_bit(const Band &bd, int x, int y)
-{
-  return (band_word(bd, y, x >> 5) >> (x & 31)) & 1u;
+  // r is band-relative; caller guarantees 0 <= r < nb
+  return (w >= 0 && w < wpr) ? bd.A[(size_t)r * bd.rs + w] : 0u;
 }
 
-// cv::morphologyEx(MORPH_CLOSE, 3x3) (call sites segmentation.cpp:888,928) on bit rows.
-// dilate: out-of-image = 0; erode: out-of-image = 1 (OpenCV's default border values for the two ops).
-// src rows [r0raw, r1raw] hold data, everything else is zero. Cooperative over the block.
-__device__ inline void band_close(const DevParams &p, Band &bd, const unsigned *__restrict__ gsrc, unsigned *__restrict__ gzero, int tid,
-                                  int nthreads)
+// 64-bit window of raw row r: bit p <-> image column 32*w - 16 + p
+__device__ __forceinline__ unsigned long long raw_win(const Band &bd, int r, int w, int wpr)
+{
+  const unsigned long long l = raw_word(bd, r, w - 1, wpr), c = raw_word(bd, r, w, wpr), n = raw_word(bd, r, w + 1, wpr);
+  return (l >> 16) | (c << 16) | (n << 48);
+}
+
+// One 32-pixel word of cv::morphologyEx(MORPH_CLOSE, 3x3) (call sites segmentation.cpp:888,928) at image
+// row y, word w: dilate (out-of-image = 0) then erode (out-of-image ignored = 1), OpenCV's default borders.
+__device__ inline unsigned closed_word(const DevParams &p, const Band &bd, int y, int w)
 {
   const int wpr = p.wpr, H = p.H, W = p.W;
-  // stage raw rows into A (and clear the global bitmap behind the read)
-  for(int i = tid; i < bd.nb * wpr; i += nthreads)
-  {
-    const int r = i / wpr, w = i - r * wpr;
-    const size_t g = (size_t)(bd.b0 + r) * wpr + w;
-    const unsigned v = gsrc[g];
-    if(gzero && v)
-      gzero[g] = 0u;
-    bd.A[(size_t)r * bd.rs + w] = v;
-  }
-  __syncthreads();
-  // dilate A -> B
-  for(int i = tid; i < bd.nb * wpr; i += nthreads)
-  {
-    const int r = i / wpr, w = i - r * wpr;
-    unsigned acc = 0;
+  // horizontally dilated raw rows y-2 .. y+2 (zero outside the band / image)
+  unsigned long long hd[5];
 #pragma unroll
-    for(int dr = -1; dr <= 1; dr++)
+  for(int k = 0; k < 5; k++)
+  {
+    const int r = y - 2 + k - bd.b0;
+    unsigned long long v = 0;
+    if(r >= 0 && r < bd.nb)
     {
-      const int rr = r + dr;
-      if(rr < 0 || rr >= bd.nb)
-        continue; // outside the band the raw image is zero (or outside the image: ignored)
-      const unsigned *row = bd.A + (size_t)rr * bd.rs;
-      const unsigned c = row[w];
-      const unsigned l = w > 0 ? row[w - 1] : 0u;
-      const unsigned n = w + 1 < wpr ? row[w + 1] : 0u;
-      acc |= c | (c << 1) | (l >> 31) | (c >> 1) | (n << 31);
+      const unsigned long long R = raw_win(bd, r, w, wpr);
+      v = R | (R << 1) | (R >> 1);
     }
-    // keep bits beyond the image width clear
-    if(w == wpr - 1 && (W & 31))
-      acc &= (1u << (W & 31)) - 1u;
-    bd.B[(size_t)r * bd.rs + w] = acc;
+    hd[k] = v;
   }
-  __syncthreads();
-  // erode B -> A
+  // columns outside the image count as set for the erosion
+  unsigned long long outside = 0;
+  {
+    const long long x0 = (long long)32 * w - 16; // image column of bit 0
+    if(x0 < 0)
+      outside |= (1ull << (-x0)) - 1ull;
+    const long long over = x0 + 64 - W; // number of window bits at columns >= W
+    if(over > 0)
+      outside |= over >= 64 ? ~0ull : ~((1ull << (64 - over)) - 1ull);
+  }
+  unsigned long long acc = ~0ull;
+#pragma unroll
+  for(int k = 1; k <= 3; k++) // dilated rows y-1, y, y+1
+  {
+    const int yy = y - 2 + k;
+    if(yy < 0 || yy >= H)
+      continue; // row outside the image: ignored by the erosion
+    unsigned long long D = hd[k];
+    if(yy - 1 >= 0)
+      D |= hd[k - 1];
+    if(yy + 1 < H)
+      D |= hd[k + 1];
+    D |= outside;
+    acc &= D & (D << 1 | 1ull) & (D >> 1 | (1ull << 63));
+  }
+  unsigned out = (unsigned)(acc >> 16);
+  if(w == wpr - 1 && (W & 31))
+    out &= (1u << (W & 31)) - 1u;
+  return out;
+}
+
+// stage the raw rows of a band into shared memory (coalesced) and clear the global bitmap behind the read
+__device__ inline void band_stage(const DevParams &p, unsigned *sm, const Band &bd, unsigned *__restrict__ g, int tid, int nthreads)
+{
+  const int wpr = p.wpr;
   for(int i = tid; i < bd.nb * wpr; i += nthreads)
   {
     const int r = i / wpr, w = i - r * wpr;
-    unsigned acc = 0xffffffffu;
-#pragma unroll
-    for(int dr = -1; dr <= 1; dr++)
-    {
-      const int rr = r + dr;
-      const int y = bd.b0 + rr;
-      if(y < 0 || y >= H)
-        continue; // outside the image: ignored
-      if(rr < 0 || rr >= bd.nb)
-      {
-        acc = 0u; // inside the image but outside the band: the dilated image is zero there
-        continue;
-      }
-      const unsigned *row = bd.B + (size_t)rr * bd.rs;
-      unsigned c = row[w];
-      unsigned l = w > 0 ? row[w - 1] : 0xffffffffu;
-      unsigned n = w + 1 < wpr ? row[w + 1] : 0xffffffffu;
-      if(w == wpr - 1 && (W & 31))
-        c |= ~((1u << (W & 31)) - 1u); // pixels right of the image: ignored
-      if(w + 1 == wpr - 1 && (W & 31))
-        n |= ~((1u << (W & 31)) - 1u);
-      acc &= c & ((c << 1) | (l >> 31)) & ((c >> 1) | (n << 31));
-    }
-    if(w == wpr - 1 && (W & 31))
-      acc &= (1u << (W & 31)) - 1u;
-    bd.A[(size_t)r * bd.rs + w] = acc;
+    const size_t gi = (size_t)(bd.b0 + r) * wpr + w;
+    const unsigned v = g[gi];
+    if(v)
+      g[gi] = 0u;
+    sm[(size_t)r * bd.rs + w] = v;
   }
   __syncthreads();
 }
 
-// first / last set row of column x in the closed band (Scanner::probeVertical, segmentation.cpp:85-111);
-// one warp per column
-__device__ __forceinline__ bool probe_column(const Band &bd, int x, int ylo, int yhi, int lane, int &yFirst, int &ySecond)
+// first / last set row of column x of the closed image within rows [ylo, yhi]
+// (Scanner::probeVertical, segmentation.cpp:85-111; BottomScanner::probeBottomUp :225-240); one warp per column
+__device__ __forceinline__ bool probe_column(const DevParams &p, const Band &bd, int x, int ylo, int yhi, int lane, int &yFirst, int &ySecond)
 {
-  // rows [ylo, yhi] inclusive
   int first = 0x7fffffff, last = -1;
+  // the closed image can only be set within one row of the raw band
   const int lo = max(ylo, bd.b0), hi = min(yhi, bd.b0 + bd.nb - 1);
   const int w = x >> 5, sh = x & 31;
   for(int base = lo; base <= hi; base += 32)
   {
     const int y = base + lane;
-    const unsigned bit = y <= hi ? (bd.A[(size_t)(y - bd.b0) * bd.rs + w] >> sh) & 1u : 0u;
+    const unsigned bit = y <= hi ? (closed_word(p, bd, y, w) >> sh) & 1u : 0u;
     const unsigned m = __ballot_sync(0xffffffffu, bit);
     if(m)
     {
@@ -132,12 +125,13 @@ __device__ __forceinline__ bool probe_column(const Band &bd, int x, int ylo, int
 }
 
 // ---- BestLine (segmentation.cpp:409-487): every pair (p,q), residual = mean of the n smallest integer
-// distances of the other points / hypot(a,b); winner = first minimal residual in (p,q) order. One pair per
-// thread; block-wide arg-min on (residual, pair index).
+// distances of the other points / hypot(a,b); winner = first minimal residual in (p,q) order.
+// Up to four point lists are fitted in one pass: one (list, pair) task per thread, warp-shuffle arg-min on
+// (residual, pair index) per list, one shared-memory round across the warps.
 struct BestLineWork
 {
-  double res[SSD_OL_THREADS];
-  int idx[SSD_OL_THREADS];
+  double res[SSD_OL_THREADS / 32][4];
+  int idx[SSD_OL_THREADS / 32][4];
 };
 
 __device__ inline double pair_residual(const P2id *pts, int n, int pi, int qi, LineId l)
@@ -202,61 +196,105 @@ __device__ inline double pair_residual(const P2id *pts, int n, int pi, int qi, L
       }
     sum += (long long)(cnt - below) * lo;
   }
-  // the reference sums into int (segmentation.cpp:434); keep its wrap-around semantics
+  // the reference sums into int (segmentation.cpp:434); keep its wrap-around semantics.
+  // hypot of two ints: a*a+b*b is exact in double, so the IEEE square root is the correctly rounded hypot.
   const int isum = (int)sum;
-  return isum / ((double)(size_t)cnt * hypot_cr((double)l.a, (double)l.b)); // :442
+  const double h = sqrt((double)((long long)l.a * l.a + (long long)l.b * l.b));
+  return isum / ((double)(size_t)cnt * h); // :442
 }
 
-// all threads of the block must call; returns the winning line in *out (valid for all threads after return)
-__device__ inline void best_line_block(const P2id *pts, int n, BestLineWork &wk, LineId *out, int tid, int nthreads)
+// all threads of the block must call. lists[e] with n[e] points (n[e] < 2: skipped); out[e] = winning line.
+__device__ inline void best_lines_block(const P2id *const lists[4], const int n[4], BestLineWork &wk, LineId *out, int tid, int nthreads)
 {
-  const int npairs = n * (n - 1) / 2;
-  double bres = 1e308 * 10; // +inf
-  int bidx = 0x7fffffff;
-  // enumerate pairs in (p,q) lexicographic order; index -> (p,q) by running counters
-  for(int t = tid; t < npairs; t += nthreads)
+  int off[5];
+  off[0] = 0;
+  for(int e = 0; e < 4; e++)
+    off[e + 1] = off[e] + (n[e] >= 2 ? n[e] * (n[e] - 1) / 2 : 0);
+  double bres[4];
+  int bidx[4];
+#pragma unroll
+  for(int e = 0; e < 4; e++)
   {
-    // invert t = p*n - p*(p+1)/2 + (q-p-1)
-    int pI = (int)((2.0 * n - 1.0 - sqrt((2.0 * n - 1.0) * (2.0 * n - 1.0) - 8.0 * t)) * 0.5);
-    while(pI > 0 && pI * n - pI * (pI + 1) / 2 > t)
-      pI--;
-    while((pI + 1) * n - (pI + 1) * (pI + 2) / 2 <= t)
-      pI++;
-    const int qI = t - (pI * n - pI * (pI + 1) / 2) + pI + 1;
-    const LineId l = linei_from(pts[pI], pts[qI]);
-    const double r = pair_residual(pts, n, pI, qI, l);
-    if(bidx == 0x7fffffff || r < bres) // t ascends: the first of equal residuals is kept (min_element, :473-477)
-    {
-      bres = r;
-      bidx = t;
-    }
+    bres[e] = 0;
+    bidx[e] = 0x7fffffff;
   }
-  wk.res[tid] = bres;
-  wk.idx[tid] = bidx;
-  __syncthreads();
-  for(int s = nthreads >> 1; s > 0; s >>= 1)
+  for(int t = tid; t < off[4]; t += nthreads)
   {
-    if(tid < s)
+    int e = 0;
+    while(t >= off[e + 1])
+      e++;
+    const int local = t - off[e], ne = n[e];
+    // local = pI*ne - pI*(pI+1)/2 + (qI - pI - 1), pairs in (p,q) lexicographic order
+    int pI = 0, rowStart = 0;
+    while(rowStart + (ne - 1 - pI) <= local)
     {
-      const double r1 = wk.res[tid], r2 = wk.res[tid + s];
-      const int i1 = wk.idx[tid], i2 = wk.idx[tid + s];
-      // lowest pair index among the minimal residuals
+      rowStart += ne - 1 - pI;
+      pI++;
+    }
+    const int qI = local - rowStart + pI + 1;
+    const P2id *pts = lists[e];
+    const LineId l = linei_from(pts[pI], pts[qI]);
+    const double r = pair_residual(pts, ne, pI, qI, l);
+#pragma unroll
+    for(int k = 0; k < 4; k++)
+      if(k == e && (bidx[k] == 0x7fffffff || r < bres[k])) // local ascends per thread: first of equals kept
+      {
+        bres[k] = r;
+        bidx[k] = local;
+      }
+  }
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+#pragma unroll
+  for(int e = 0; e < 4; e++)
+  {
+    double r1 = bres[e];
+    int i1 = bidx[e];
+#pragma unroll
+    for(int s = 16; s > 0; s >>= 1)
+    {
+      const double r2 = __shfl_xor_sync(0xffffffffu, r1, s);
+      const int i2 = __shfl_xor_sync(0xffffffffu, i1, s);
+      // lowest pair index among the minimal residuals (min_element, segmentation.cpp:473-477)
       if(i2 != 0x7fffffff && (i1 == 0x7fffffff || r2 < r1 || (r2 == r1 && i2 < i1)))
       {
-        wk.res[tid] = r2;
-        wk.idx[tid] = i2;
+        r1 = r2;
+        i1 = i2;
       }
     }
-    __syncthreads();
+    if(lane == 0)
+    {
+      wk.res[warp][e] = r1;
+      wk.idx[warp][e] = i1;
+    }
   }
-  if(tid == 0)
+  __syncthreads();
+  if(tid < 4)
   {
-    const int t = wk.idx[0];
-    int pI = 0;
-    while((pI + 1) * n - (pI + 1) * (pI + 2) / 2 <= t)
-      pI++;
-    const int qI = t - (pI * n - pI * (pI + 1) / 2) + pI + 1;
-    *out = linei_from(pts[pI], pts[qI]);
+    const int e = tid;
+    double r1 = wk.res[0][e];
+    int i1 = wk.idx[0][e];
+    for(int w = 1; w < nwarps; w++)
+    {
+      const double r2 = wk.res[w][e];
+      const int i2 = wk.idx[w][e];
+      if(i2 != 0x7fffffff && (i1 == 0x7fffffff || r2 < r1 || (r2 == r1 && i2 < i1)))
+      {
+        r1 = r2;
+        i1 = i2;
+      }
+    }
+    if(i1 != 0x7fffffff)
+    {
+      const int ne = n[e];
+      int pI = 0, rowStart = 0;
+      while(rowStart + (ne - 1 - pI) <= i1)
+      {
+        rowStart += ne - 1 - pI;
+        pI++;
+      }
+      const int qI = i1 - rowStart + pI + 1;
+      out[e] = linei_from(lists[e][pI], lists[e][qI]);
+    }
   }
   __syncthreads();
 }
@@ -335,7 +373,7 @@ __device__ inline void detect_outline_block(const DevParams &p, const Band &bd, 
   {
     const int x = c < nRc ? xCenter + c * xStep : xCenter - xStep - (c - nRc) * xStep;
     int yf, ys;
-    const bool f = probe_column(bd, x, 0, H - 1, lane, yf, ys);
+    const bool f = probe_column(p, bd, x, 0, H - 1, lane, yf, ys);
     if(lane == 0)
     {
       S.scan_found[c] = f;
@@ -406,10 +444,11 @@ __device__ inline void detect_outline_block(const DevParams &p, const Band &bd, 
     return;
 
   // HorizontalEdges (:592-599): four best lines
-  best_line_block(S.frontLeft, S.nLeft, S.wk, &S.line[0], tid, nthreads);
-  best_line_block(S.frontRight, S.nRight, S.wk, &S.line[1], tid, nthreads);
-  best_line_block(S.backLeft, S.nLeft, S.wk, &S.line[2], tid, nthreads);
-  best_line_block(S.backRight, S.nRight, S.wk, &S.line[3], tid, nthreads);
+  {
+    const P2id *const lists[4] = { S.frontLeft, S.frontRight, S.backLeft, S.backRight };
+    const int ns[4] = { S.nLeft, S.nRight, S.nLeft, S.nRight };
+    best_lines_block(lists, ns, S.wk, S.line, tid, nthreads);
+  }
 
   if(tid == 0)
   {
@@ -486,7 +525,7 @@ __device__ inline void detect_outline_block(const DevParams &p, const Band &bd, 
           for(int wb = w0; wb <= w1 && fx < 0; wb += 32)
           {
             const int w = wb + lane;
-            unsigned v = w <= w1 ? band_word(bd, y, w) : 0u;
+            unsigned v = w <= w1 ? closed_word(p, bd, y, w) : 0u;
             if(w == w0)
               v &= 0xffffffffu << (x0 & 31);
             if(w == w1 && (x1 & 31) != 31)
@@ -505,7 +544,7 @@ __device__ inline void detect_outline_block(const DevParams &p, const Band &bd, 
           for(int wb = w1; wb >= w0 && fx < 0; wb -= 32)
           {
             const int w = wb - lane;
-            unsigned v = w >= w0 ? band_word(bd, y, w) : 0u;
+            unsigned v = w >= w0 ? closed_word(p, bd, y, w) : 0u;
             if(w == w0)
               v &= 0xffffffffu << (x0 & 31);
             if(w == w1 && (x1 & 31) != 31)
@@ -600,7 +639,7 @@ __device__ inline void detect_front_edge_block(const DevParams &p, const Band &b
     const int x = xCenter + (c - jl) * xStep;
     int yf, ys;
     // probeBottomUp (:225-240): lowest set pixel with y > H/2
-    const bool f = probe_column(bd, x, H / 2 + 1, H - 1, lane, yf, ys);
+    const bool f = probe_column(p, bd, x, H / 2 + 1, H - 1, lane, yf, ys);
     if(lane == 0)
     {
       S.scan_found[c] = f;
@@ -648,7 +687,11 @@ __device__ inline void detect_front_edge_block(const DevParams &p, const Band &b
   const int n = S.nLeft;
   if(n < 2)
     return;
-  best_line_block(S.frontLeft, n, S.wk, &S.line[0], tid, nthreads);
+  {
+    const P2id *const lists[4] = { S.frontLeft, S.frontLeft, S.frontLeft, S.frontLeft };
+    const int ns[4] = { n, 0, 0, 0 };
+    best_lines_block(lists, ns, S.wk, S.line, tid, nthreads);
+  }
   if(tid == 0)
   {
     const FlatLineD edge = flat_from(S.line[0]);
@@ -666,32 +709,30 @@ __device__ inline void detect_front_edge_block(const DevParams &p, const Band &b
   }
 }
 
-// Prepare the band descriptor of one bitmap in shared memory (smem path) or global scratch (large images).
+// Band descriptor of one bitmap: shared memory if the touched rows fit, else the global bitmap itself.
 __device__ inline bool band_setup(const DevParams &p, Band &bd, int row_min, int row_max, unsigned *smem_words, size_t smem_cap_words,
-                                  unsigned *gbitmap, unsigned *gscratch)
+                                  const unsigned *gbitmap)
 {
   bd.b0 = max(0, row_min - 2);
   const int b1 = min(p.H - 1, row_max + 2);
   bd.nb = b1 - bd.b0 + 1;
   const int rs = p.wpr + 1; // +1 word: conflict-free column probing
-  if((size_t)2 * bd.nb * rs <= smem_cap_words)
+  if((size_t)bd.nb * rs <= smem_cap_words)
   {
     bd.rs = rs;
     bd.A = smem_words;
-    bd.B = smem_words + (size_t)bd.nb * rs;
     return true;
   }
-  // image band too large for shared memory: close in global memory (A = the bitmap band itself, B = scratch)
   bd.rs = p.wpr;
   bd.A = gbitmap + (size_t)bd.b0 * p.wpr;
-  bd.B = gscratch + (size_t)bd.b0 * p.wpr;
   return false;
 }
 
-__device__ inline void band_clear_global(const DevParams &p, const Band &bd, int tid, int nthreads)
+__device__ inline void band_clear_global(const DevParams &p, const Band &bd, unsigned *g, int tid, int nthreads)
 {
+  unsigned *base = g + (size_t)bd.b0 * p.wpr;
   for(int i = tid; i < bd.nb * p.wpr; i += nthreads)
-    bd.A[i] = 0u;
+    base[i] = 0u;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -699,8 +740,7 @@ __device__ inline void band_clear_global(const DevParams &p, const Band &bd, int
 // (loop B of detectStairSteps, pointcloud.cpp:419-429, incl. imgPointsToWorld :476-487)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SSD_OL_THREADS) k_outline(const __grid_constant__ DevParams p, FrameDev *__restrict__ frames,
-                                                             unsigned *__restrict__ bev, unsigned *__restrict__ bev2, size_t bm_words,
-                                                             size_t smem_cap_words)
+                                                             unsigned *__restrict__ bev, size_t bm_words, size_t smem_cap_words)
 {
   extern __shared__ __align__(16) unsigned s_words[];
   __shared__ OutlineShared S;
@@ -716,19 +756,16 @@ __global__ void __launch_bounds__(SSD_OL_THREADS) k_outline(const __grid_constan
   if(P.row_max >= 0)
   {
     unsigned *gb = bev + ((size_t)frame * SSD_GPU_MAX_PLATEAUS + k) * bm_words;
-    unsigned *gs = bev2 + ((size_t)frame * SSD_GPU_MAX_PLATEAUS + k) * bm_words;
     if(tid == 0)
-      s_smem_path = band_setup(p, bd, P.row_min, P.row_max, s_words, smem_cap_words, gb, gs);
+      s_smem_path = band_setup(p, bd, P.row_min, P.row_max, s_words, smem_cap_words, gb);
     __syncthreads();
     if(s_smem_path)
-      band_close(p, bd, gb, gb, tid, SSD_OL_THREADS);
-    else
-      band_close(p, bd, gb, nullptr, tid, SSD_OL_THREADS); // A aliases the global band: staging copy is a no-op
+      band_stage(p, s_words, bd, gb, tid, SSD_OL_THREADS);
     detect_outline_block(p, bd, S, p.min_img_y_extent, p.xy_ratio, quad, valid, tid, SSD_OL_THREADS);
     if(!s_smem_path)
     {
       __syncthreads();
-      band_clear_global(p, bd, tid, SSD_OL_THREADS);
+      band_clear_global(p, bd, gb, tid, SSD_OL_THREADS);
     }
   }
   else if(tid == 0)
@@ -753,72 +790,84 @@ __global__ void __launch_bounds__(SSD_OL_THREADS) k_outline(const __grid_constan
 // ---------------------------------------------------------------------------------------------
 // k_frame_logic: the rest of detectStairSteps (pointcloud.cpp:427-443): first valid plateau, the ground
 // quadrilateral (calcGroundQuadrilateral, :489-512) and one QuadrilateralTest per emitted step.
-// One thread per frame.
+// One warp per frame, one lane per plateau.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_frame_logic(const __grid_constant__ DevParams p, FrameDev *__restrict__ frames, int n_frames)
+__global__ void __launch_bounds__(32) k_frame_logic(const __grid_constant__ DevParams p, FrameDev *__restrict__ frames, int n_frames)
 {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ QuadTestDev s_qt[SSD_GPU_MAX_PLATEAUS];
+  __shared__ double s_gq[4][2];
+  const int f = blockIdx.x, lane = threadIdx.x;
   if(f >= n_frames)
     return;
   FrameDev &F = frames[f];
-  const int K = F.n_plateaus;
-  int firstValid = -1;
-  for(int i = F.first_outlined; i < K; i++)
-    if(F.plat[i].valid)
-    {
-      firstValid = i;
-      break;
-    }
-  F.first_valid = firstValid;
+  const int K = F.n_plateaus, ground = F.ground_index;
+  const bool myValid = lane < K && lane >= F.first_outlined && F.plat[lane].valid;
+  const unsigned vm = __ballot_sync(0xffffffffu, myValid);
+  const int firstValid = vm ? __ffs(vm) - 1 : -1;
+  if(lane == 0)
+    F.first_valid = firstValid;
   if(firstValid < 0)
     return;
-  if(F.ground_index >= 0)
+  if(lane == 0 && ground >= 0)
   {
-    PlateauDev &G = F.plat[F.ground_index];
     const double(*q)[2] = F.plat[firstValid].quad_world;
     const double yMin = p.y_min;
-    P2d gq[4];
     if(q[0][1] < q[1][1])
     {
-      gq[0].x = q[0][0];
-      gq[0].y = yMin;
-      gq[1].x = q[1][0] + (q[1][1] - yMin) * (q[1][1] - q[0][1]) / (q[1][0] - q[0][0]); // calcDx(q0,q1)
-      gq[1].y = yMin;
+      s_gq[0][0] = q[0][0];
+      s_gq[1][0] = q[1][0] + (q[1][1] - yMin) * (q[1][1] - q[0][1]) / (q[1][0] - q[0][0]); // calcDx(q0,q1)
     }
     else
     {
-      gq[0].x = q[0][0] + (q[0][1] - yMin) * (q[0][1] - q[1][1]) / (q[0][0] - q[1][0]); // calcDx(q1,q0)
-      gq[0].y = yMin;
-      gq[1].x = q[1][0];
-      gq[1].y = yMin;
+      s_gq[0][0] = q[0][0] + (q[0][1] - yMin) * (q[0][1] - q[1][1]) / (q[0][0] - q[1][0]); // calcDx(q1,q0)
+      s_gq[1][0] = q[1][0];
     }
-    gq[2].x = q[0][0];
-    gq[2].y = q[0][1];
-    gq[3].x = q[1][0];
-    gq[3].y = q[1][1];
-    for(int c = 0; c < 4; c++)
-    {
-      G.quad_world[c][0] = gq[c].x;
-      G.quad_world[c][1] = gq[c].y;
-    }
-    G.valid = 1;
+    s_gq[0][1] = yMin;
+    s_gq[1][1] = yMin;
+    s_gq[2][0] = q[0][0];
+    s_gq[2][1] = q[0][1];
+    s_gq[3][0] = q[1][0];
+    s_gq[3][1] = q[1][1];
   }
-  for(int i = 0; i < K; i++)
+  __syncwarp();
+  const bool emit = myValid || (lane == ground && ground >= 0);
+  if(emit)
   {
-    PlateauDev &P = F.plat[i];
-    if(!P.valid)
-      continue;
+    PlateauDev &P = F.plat[lane];
     P2d q[4];
     for(int c = 0; c < 4; c++)
     {
-      q[c].x = P.quad_world[c][0];
-      q[c].y = P.quad_world[c][1];
+      if(lane == ground)
+      {
+        q[c].x = s_gq[c][0];
+        q[c].y = s_gq[c][1];
+        P.quad_world[c][0] = q[c].x;
+        P.quad_world[c][1] = q[c].y;
+      }
+      else
+      {
+        q[c].x = P.quad_world[c][0];
+        q[c].y = P.quad_world[c][1];
+      }
     }
-    quadtest_init(P.qt, q);
-    P.quad_status = P.qt.status;
-    if(P.qt.status)
-      F.status |= SSD_STATUS_DEGENERATE_QUAD;
+    quadtest_init(s_qt[lane], q);
+    P.valid = 1;
+    P.quad_status = s_qt[lane].status;
   }
+  const unsigned em = __ballot_sync(0xffffffffu, emit);
+  const unsigned bad = __ballot_sync(0xffffffffu, emit && s_qt[lane].status != 0);
+  __syncwarp();
+  // coalesced copy of the emitted tests to global memory
+  for(int k = 0; k < K; k++)
+    if(em >> k & 1u)
+    {
+      const unsigned *src = reinterpret_cast<const unsigned *>(&s_qt[k]);
+      unsigned *dst = reinterpret_cast<unsigned *>(&F.plat[k].qt);
+      for(int i = lane; i < (int)(sizeof(QuadTestDev) / 4); i += 32)
+        dst[i] = src[i];
+    }
+  if(lane == 0 && bad)
+    F.status |= SSD_STATUS_DEGENERATE_QUAD;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -827,8 +876,8 @@ __global__ void k_frame_logic(const __grid_constant__ DevParams p, FrameDev *__r
 // grid = frames, one block per frame.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SSD_OL_THREADS) k_finalize(const __grid_constant__ DevParams p, FrameDev *__restrict__ frames,
-                                                              FrameOut *__restrict__ out, unsigned *__restrict__ bev,
-                                                              unsigned *__restrict__ bev2, size_t bm_words, size_t smem_cap_words)
+                                                              FrameOut *__restrict__ out, unsigned *__restrict__ bev, size_t bm_words,
+                                                              size_t smem_cap_words)
 {
   extern __shared__ __align__(16) unsigned s_words[];
   __shared__ OutlineShared S;
@@ -848,16 +897,16 @@ __global__ void __launch_bounds__(SSD_OL_THREADS) k_finalize(const __grid_consta
     if(G.row_max >= 0)
     {
       unsigned *gb = bev + ((size_t)frame * SSD_GPU_MAX_PLATEAUS + ground) * bm_words;
-      unsigned *gs = bev2 + ((size_t)frame * SSD_GPU_MAX_PLATEAUS + ground) * bm_words;
       if(tid == 0)
-        s_smem_path = band_setup(p, bd, G.row_min, G.row_max, s_words, smem_cap_words, gb, gs);
+        s_smem_path = band_setup(p, bd, G.row_min, G.row_max, s_words, smem_cap_words, gb);
       __syncthreads();
-      band_close(p, bd, gb, s_smem_path ? gb : nullptr, tid, SSD_OL_THREADS);
+      if(s_smem_path)
+        band_stage(p, s_words, bd, gb, tid, SSD_OL_THREADS);
       detect_front_edge_block(p, bd, S, fl, fr, frontValid, tid, SSD_OL_THREADS);
       if(!s_smem_path)
       {
         __syncthreads();
-        band_clear_global(p, bd, tid, SSD_OL_THREADS);
+        band_clear_global(p, bd, gb, tid, SSD_OL_THREADS);
       }
     }
   }

@@ -96,111 +96,132 @@ __global__ void __launch_bounds__(SSD_PT_THREADS) k_transform_bin(const __grid_c
 // ---------------------------------------------------------------------------------------------
 // k_peaks: HeightsHistogram::findPeaks/filterPeaks (pointcloud.cpp:214-256), the plateau bands of
 // PlateausExtraction::extractPlateauPoints (:300-335) folded into a bin->label LUT, and the ground /
-// first-outlined bookkeeping of StairsDetector::detectStairSteps (:402-418). One thread per frame.
+// first-outlined bookkeeping of StairsDetector::detectStairSteps (:402-418).
+// One warp per frame: the histogram and the LUT live in shared memory, lane 0 walks the <= 253 bins,
+// the lanes write the LUT and the plateau records back in parallel.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_peaks(const __grid_constant__ DevParams p, FrameDev *__restrict__ frames, int n_frames)
+__global__ void __launch_bounds__(32) k_peaks(const __grid_constant__ DevParams p, FrameDev *__restrict__ frames, int n_frames)
 {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ unsigned s_hist[SSD_BINS_PAD];
+  __shared__ __align__(8) unsigned char s_lut[SSD_BINS_PAD];
+  __shared__ int s_height[SSD_GPU_MAX_PLATEAUS], s_hmin[SSD_GPU_MAX_PLATEAUS], s_hmax[SSD_GPU_MAX_PLATEAUS];
+  __shared__ unsigned s_np[SSD_GPU_MAX_PLATEAUS];
+  __shared__ int s_K, s_first_outlined;
+  const int f = blockIdx.x, lane = threadIdx.x;
   if(f >= n_frames)
     return;
   FrameDev &F = frames[f];
-  const unsigned *hist = F.hist;
-  unsigned status = 0;
-  F.n_nonzero = (unsigned)p.N - hist[SSD_CODE_INVALID];
-  F.n_in_range = (unsigned)p.N - hist[SSD_CODE_INVALID] - hist[SSD_CODE_OUT_OF_RANGE];
-
-  for(int b = 0; b < SSD_BINS_PAD; b++)
-    F.lut[b] = (unsigned char)SSD_LABEL_REMAINDER;
-  F.lut[SSD_CODE_OUT_OF_RANGE] = (unsigned char)SSD_LABEL_OUT_OF_RANGE;
-  F.lut[SSD_CODE_INVALID] = (unsigned char)SSD_LABEL_INVALID;
-
-  int K = 0;
-  bool ascending = false, wrapped = false;
-  const int last = p.n_bins - 1;
-  for(int i = 0; i < last; i++)
+  for(int b = lane; b < SSD_BINS_PAD; b += 32)
   {
-    const unsigned c = hist[i], s = hist[i + 1];
-    if(c < s)
+    s_hist[b] = F.hist[b];
+    s_lut[b] = (unsigned char)SSD_LABEL_REMAINDER;
+  }
+  __syncwarp();
+  if(lane == 0)
+  {
+    const unsigned *hist = s_hist;
+    unsigned status = 0;
+    s_lut[SSD_CODE_OUT_OF_RANGE] = (unsigned char)SSD_LABEL_OUT_OF_RANGE;
+    s_lut[SSD_CODE_INVALID] = (unsigned char)SSD_LABEL_INVALID;
+    int K = 0;
+    bool ascending = false, wrapped = false;
+    const int last = p.n_bins - 1;
+    for(int i = 0; i < last; i++)
     {
-      ascending = true;
-      continue;
-    }
-    if(c > s)
-    {
-      if(ascending && !(c < p.min_peak_points) && (unsigned)((c * 2u - hist[i - 1] - hist[i + 1]) * 2u) > c)
+      const unsigned c = hist[i], s = hist[i + 1];
+      if(c < s)
       {
-        if(K >= SSD_GPU_MAX_PLATEAUS)
-          status |= SSD_STATUS_TOO_MANY_PLATEAUS;
-        else
+        ascending = true;
+        continue;
+      }
+      if(c > s)
+      {
+        if(ascending && !(c < p.min_peak_points) && (unsigned)((c * 2u - hist[i - 1] - hist[i + 1]) * 2u) > c)
         {
-          PlateauDev &P = F.plat[K];
-          int hmin, hmax;
-          if(hist[i - 1] > hist[i + 1]) // :307-316
-          {
-            hmin = i - 1;
-            hmax = i;
-          }
+          if(K >= SSD_GPU_MAX_PLATEAUS)
+            status |= SSD_STATUS_TOO_MANY_PLATEAUS;
           else
           {
-            hmin = i;
-            hmax = i + 1;
+            int hmin, hmax;
+            if(hist[i - 1] > hist[i + 1]) // :307-316
+            {
+              hmin = i - 1;
+              hmax = i;
+            }
+            else
+            {
+              hmin = i;
+              hmax = i + 1;
+            }
+            unsigned np = 0;
+            if(hmin == 0)
+            {
+              // uint16 wrap of heightMin - 1 (:324): everything left goes to the remainder, this plateau
+              // and all later ones stay empty
+              wrapped = true;
+              status |= SSD_STATUS_HMIN_WRAP;
+            }
+            if(!wrapped)
+              for(int b = hmin; b <= hmax; b++)
+                if(s_lut[b] == SSD_LABEL_REMAINDER)
+                {
+                  s_lut[b] = (unsigned char)K;
+                  np += hist[b];
+                }
+            s_height[K] = i;
+            s_hmin[K] = hmin;
+            s_hmax[K] = hmax;
+            s_np[K] = np;
+            K++;
           }
-          unsigned np = 0;
-          if(hmin == 0)
-          {
-            // uint16 wrap of heightMin - 1 (:324): everything left goes to the remainder, this plateau
-            // and all later ones stay empty
-            wrapped = true;
-            status |= SSD_STATUS_HMIN_WRAP;
-          }
-          if(!wrapped)
-            for(int b = hmin; b <= hmax; b++)
-              if(F.lut[b] == SSD_LABEL_REMAINDER)
-              {
-                F.lut[b] = (unsigned char)K;
-                np += hist[b];
-              }
-          P.height = i;
-          P.hmin = hmin;
-          P.hmax = hmax;
-          P.n_points = np;
-          P.valid = 0;
-          P.outlined = 0;
-          P.n_in_quad = 0;
-          P.quad_status = -1;
-          P.mean_z = 0;
-          P.sum_fix = 0;
-          P.row_min = 0x7fffffff;
-          P.row_max = -1;
-          P.front_valid = 0;
-          for(int c4 = 0; c4 < 4; c4++)
-            P.quad_px[c4][0] = P.quad_px[c4][1] = P.quad_world[c4][0] = P.quad_world[c4][1] = 0;
-          K++;
         }
+        ascending = false;
       }
-      ascending = false;
     }
-  }
-  F.n_plateaus = K;
-  int ground = -1, i = 0;
-  unsigned maxGround = 0;
-  for(; i < K; i++)
-  {
-    if(F.plat[i].height >= p.min_height)
-      break;
-    if(maxGround < F.plat[i].n_points)
+    int ground = -1, i = 0;
+    unsigned maxGround = 0;
+    for(; i < K; i++)
     {
-      maxGround = F.plat[i].n_points;
-      ground = i;
+      if(s_height[i] >= p.min_height)
+        break;
+      if(maxGround < s_np[i])
+      {
+        maxGround = s_np[i];
+        ground = i;
+      }
     }
+    s_K = K;
+    s_first_outlined = i;
+    F.n_nonzero = (unsigned)p.N - hist[SSD_CODE_INVALID];
+    F.n_in_range = (unsigned)p.N - hist[SSD_CODE_INVALID] - hist[SSD_CODE_OUT_OF_RANGE];
+    F.n_plateaus = K;
+    F.ground_index = ground;
+    F.first_outlined = i;
+    F.first_valid = -1;
+    F.n_steps = 0;
+    F.status = status;
   }
-  F.ground_index = ground;
-  F.first_outlined = i;
-  for(; i < K; i++)
-    F.plat[i].outlined = 1;
-  F.first_valid = -1;
-  F.n_steps = 0;
-  F.status = status;
+  __syncwarp();
+  reinterpret_cast<unsigned long long *>(F.lut)[lane] = reinterpret_cast<const unsigned long long *>(s_lut)[lane];
+  if(lane < s_K)
+  {
+    PlateauDev &P = F.plat[lane];
+    P.height = s_height[lane];
+    P.hmin = s_hmin[lane];
+    P.hmax = s_hmax[lane];
+    P.n_points = s_np[lane];
+    P.valid = 0;
+    P.outlined = lane >= s_first_outlined;
+    P.n_in_quad = 0;
+    P.quad_status = -1;
+    P.mean_z = 0;
+    P.sum_fix = 0;
+    P.row_min = 0x7fffffff;
+    P.row_max = -1;
+    P.front_valid = 0;
+    for(int c4 = 0; c4 < 4; c4++)
+      P.quad_px[c4][0] = P.quad_px[c4][1] = P.quad_world[c4][0] = P.quad_world[c4][1] = 0;
+  }
 }
 
 // warp-aggregated row-range tracking + OR into a BEV bitmap word

@@ -11,6 +11,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--frames", type=int, default=1024)
 ap.add_argument("--chunks", default="4,8,16,32,64,128")
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--warm", type=int, default=3)
 ap.add_argument("--w", type=int, default=1024)
 ap.add_argument("--h", type=int, default=768)
 args = ap.parse_args()
@@ -24,7 +25,7 @@ for cf in [int(c) for c in args.chunks.split(",")]:
     det = S.Detector(cfg, xf, max_frames=args.frames)
     d = det.malloc(args.frames * N * 12)
     det.synth_frames(base, 1, 0, args.frames, 3, 8, d)
-    for _ in range(3):
+    for _ in range(args.warm):
         det.process_device(d, args.frames)
     ts = []
     for _ in range(args.reps):
