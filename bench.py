@@ -240,13 +240,9 @@ def run_ours(args):
 
     # ---- max over ranks ----
     if dist is not None:
-        import torch
-        tt = torch.tensor([my_ms, my_e2e, wall_ms], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        my_ms, my_e2e, wall_ms = (float(x) for x in tt.cpu())
-        ll = torch.tensor([launches, n_steps_found], dtype=torch.int64, device=f"cuda:{local}")
-        dist.all_reduce(ll, op=dist.ReduceOp.SUM)
-        launches, n_steps_found = (int(x) for x in ll.cpu())
+        from stair_step_detector_b200 import sharding
+        (my_ms, my_e2e, wall_ms), (launches, n_steps_found) = sharding.reduce_timing(
+            dist, [my_ms, my_e2e, wall_ms], [launches, n_steps_found], device=f"cuda:{local}")
 
     if rank == 0:
         ms_per_step = my_ms / args.steps

@@ -369,13 +369,18 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
   if(cudaSetDevice(device) != cudaSuccess)
     return bail("cudaSetDevice failed", SSD_E_CUDA);
 
-  // frames per chunk: keep a chunk's vertices + labels L2-resident between the three point passes
-  // (B200: 126 MB L2). SSD_GPU_CHUNK_FRAMES overrides.
+  // frames per launch chain (chunk). Two chains are in flight on two streams, so one chain's latency-bound
+  // per-plateau kernels overlap the other's HBM-bound point kernels. Measured on B200 (tools/sweep.py):
+  // throughput grows with the chunk size up to ~256 frames. SSD_GPU_CHUNK_FRAMES overrides.
   {
-    const double frame_bytes = (double)dp.N * 13.0;
-    int cf = (int)(48.0e6 / frame_bytes);
+    int cf = 256;
     if(const char *e = getenv("SSD_GPU_CHUNK_FRAMES"))
       cf = atoi(e);
+    // the BEV bitmaps (2 streams x chunk x 32 slots) must stay a small part of HBM
+    const size_t per_frame = (size_t)2 * SSD_GPU_MAX_PLATEAUS * ctx->bm_words * 4;
+    const size_t budget = (size_t)8 << 30;
+    if((size_t)cf * per_frame > budget)
+      cf = (int)(budget / per_frame);
     cf = std::max(1, std::min(cf, max_frames));
     ctx->chunk_frames = cf;
   }
