@@ -1,0 +1,35 @@
+// Host mirror of the reference's 2-D outline detector interface (segmentation.h:32-58): same static
+// functions and result structs. The work runs in the k_outline / front-edge CUDA code on the plateau's
+// top-down image; the extra leading argument is the GPU context (the reference's functions are free of
+// state, ours need the device).
+#pragma once
+#include "types.h"
+#include <string>
+
+struct ssd_gpu_ctx;
+
+namespace stairs
+{
+
+class Image;
+
+class Segmentation
+{
+public:
+  struct FrontEdge
+  {
+    Point2 pointLeft, pointRight;
+    bool valid = false;
+  };
+  static FrontEdge detectFrontEdge(ssd_gpu_ctx *ctx, const Image &image, const std::string &windowName = "");
+
+  struct Outline
+  {
+    // vertex order: 0 front-left, 1 front-right, 2 back-left, 3 back-right (image y grows towards the front)
+    Quadrilateral_t quadrilateral;
+    bool valid = false;
+  };
+  static Outline detectOutline(ssd_gpu_ctx *ctx, const Image &image, int minImgYExtent, double xyRatio, const std::string &windowName = "");
+};
+
+} // namespace stairs

@@ -214,3 +214,30 @@ def test_device_input_and_determinism(S, oracle):
             o = H.oracle_process(oracle, cfg, xf, xyz[f])
             assert not H.compare_results(o, g, tol=TOL), f
         det.free(d_xyz)
+
+
+def test_cpp_host_classes_main_loop(S, oracle, tmp_path):
+    """the reference's main loop on the kept class surface (examples/detect_stairs_synthetic.cpp): same lines
+    as the oracle for the same synthetic frames"""
+    import json
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "detect_stairs_synthetic")
+    libdir = os.path.join(root, "stair_step_detector_b200", "lib")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-o", exe, os.path.join(root, "examples", "detect_stairs_synthetic.cpp"),
+                    "-L" + libdir, "-lssd_gpu", "-Wl,-rpath," + libdir], check=True)
+    w, h, n = 640, 480, 3
+    out = subprocess.run([exe, str(w), str(h), str(n)], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    assert len(out) == n
+    cfg = S.default_config(w, h)
+    base = S.default_scene(w, h, **NOISY)
+    xf = S.scene_transform(base)
+    for f in range(n):
+        sc = S.randomize_scene(base, 2026, f, 3, 8)
+        o = H.oracle_process(oracle, cfg, xf, S.deproject_host(sc, S.synth_depth_host(sc)))
+        got = json.loads(out[f])
+        assert got[0] == "stairs" and got[1] == ["stairSteps", len(o.steps)]
+        for s, g in zip(o.steps, got[2] if len(o.steps) else []):
+            assert abs(g[0][1] - s["height"]) < 1.1e-3
+            assert np.abs(np.array(g[1][1:]) - s["quad"]).max() < 1.1e-3
