@@ -169,6 +169,16 @@ int ssd_gpu_get_labels(ssd_gpu_ctx *ctx, int frame, uint8_t *out_host);
 /* Height histogram, HeightsHistogram::calcHist (pointcloud.cpp:194-204). */
 int ssd_gpu_get_histogram(ssd_gpu_ctx *ctx, int frame, uint32_t *out, int cap, int *n_bins);
 int ssd_gpu_get_timing(ssd_gpu_ctx *ctx, ssd_gpu_timing *out);
+/* Counters of the last call. n_exact_fallback: points whose single-precision transform lay within the proven
+ * f32 error bound (eps = filter_eps1 * max|x,y,z| + filter_eps0 metres) of a range / height-bin threshold, so the
+ * decision was taken by the exact double-precision chain instead (results are bit-identical either way). */
+typedef struct ssd_gpu_stats
+{
+  uint64_t n_points;
+  uint64_t n_exact_fallback;
+  double filter_eps0, filter_eps1;
+} ssd_gpu_stats;
+int ssd_gpu_get_stats(ssd_gpu_ctx *ctx, ssd_gpu_stats *out);
 /* Per-stage device time of the last call made with SSD_FLAG_STAGE_TIMING: sum of per-launch durations (ms) and
  * launch counts. Stage order: 0 transform_bin, 1 peaks, 2 label_bev, 3 outline, 4 frame_logic, 5 quad_reduce, 6 finalize. */
 #define SSD_GPU_N_STAGES 7

@@ -197,6 +197,11 @@ class Detector:
         self._ck(self._l.ssd_gpu_get_timing(self._h, C.byref(t)), "ssd_gpu_get_timing")
         return t
 
+    def stats(self):
+        st = A.Stats()
+        self._ck(self._l.ssd_gpu_get_stats(self._h, C.byref(st)), "ssd_gpu_get_stats")
+        return st
+
     def stage_times(self):
         """{stage: (sum of launch durations in ms, launches)} of the last call made with FLAG_STAGE_TIMING."""
         ms = (C.c_float * A.N_STAGES)()

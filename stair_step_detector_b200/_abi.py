@@ -67,6 +67,10 @@ class Timing(C.Structure):
                 ("label_ms", C.c_float), ("n_launches", C.c_int32), ("reserved", C.c_int32)]
 
 
+class Stats(C.Structure):
+    _fields_ = [("n_points", C.c_uint64), ("n_exact_fallback", C.c_uint64), ("filter_eps0", C.c_double), ("filter_eps1", C.c_double)]
+
+
 class Scene(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32),
                 ("fx", C.c_float), ("fy", C.c_float), ("ppx", C.c_float), ("ppy", C.c_float),
@@ -100,6 +104,7 @@ PROTOTYPES = {
     "ssd_gpu_get_labels": (C.c_int, [_vp, C.c_int, _vp]),
     "ssd_gpu_get_histogram": (C.c_int, [_vp, C.c_int, _P(C.c_uint32), C.c_int, _P(C.c_int)]),
     "ssd_gpu_get_timing": (C.c_int, [_vp, _P(Timing)]),
+    "ssd_gpu_get_stats": (C.c_int, [_vp, _P(Stats)]),
     "ssd_gpu_get_stage_times": (C.c_int, [_vp, _P(C.c_float), _P(C.c_int)]),
     "ssd_gpu_stage_name": (C.c_char_p, [C.c_int]),
     "ssd_gpu_chunk_frames": (C.c_int, [_vp]),

@@ -33,6 +33,12 @@ struct DevParams
   double x_min, x_max, y_min, y_max, z_min, z_max;
   double hir;              // heightIntervalReciprocal (pointcloud.cpp:101)
   double x_to_image, y_to_image, x_to_world, y_to_world, xy_ratio; // Projection2D (pointcloud.cpp:73-76,95)
+  // single-precision filter of k_transform_bin (see point_code_filtered): f32-rounded transform, range
+  // centres / half widths, and the coefficients of the rigorous error bound eps = E1 * max|p| + E0
+  float af[9], bf[3];
+  float cf[3], hf[3];
+  float hirf, k0f;         // t = wz * hirf + k0f ~ (wz - z_min) * hir
+  float E0, E1, dbin0;
 };
 
 struct SegmentDev
@@ -131,6 +137,44 @@ __device__ __forceinline__ unsigned point_code(const DevParams &p, float fx, flo
   if(!in)
     return SSD_CODE_OUT_OF_RANGE;
   return (unsigned)(unsigned short)((wz - p.z_min) * p.hir);
+}
+
+// out-of-line copy for the rare fallback of the filtered kernel (keeps its hot loop small)
+__device__ __noinline__ unsigned point_code_slow(const DevParams &p, float fx, float fy, float fz)
+{
+  return point_code(p, fx, fy, fz);
+}
+
+// The same decision from single-precision arithmetic plus a rigorous error bound; `uncertain` is set when the
+// f32 value is within the bound of any threshold, and only then the exact double path above has to run.
+//   w^ = fma chain with f32-rounded coefficients:  |w^_i - w_ref,i| <= 5u (|b_i| + sum_j |a_ij| |p_j|),  u = 2^-24
+//   (coefficient rounding u*M, three fma roundings ~3u*M, the reference's own f64 roundings ~2^-51*M), and the
+//   f32 range centre / half width / bin arithmetic add <= 8u * max|threshold| and 4u * n_bins.
+// derive_params() sets E0, E1, dbin0 with a factor 2 of slack on top of these bounds.
+__device__ __forceinline__ unsigned point_code_filtered(const DevParams &p, float x, float y, float z, bool &uncertain)
+{
+  const float m = fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z));
+  const float eps = fmaf(p.E1, m, p.E0);
+  const float wx = fmaf(p.af[2], z, fmaf(p.af[1], y, fmaf(p.af[0], x, p.bf[0])));
+  const float wy = fmaf(p.af[5], z, fmaf(p.af[4], y, fmaf(p.af[3], x, p.bf[1])));
+  const float wz = fmaf(p.af[8], z, fmaf(p.af[7], y, fmaf(p.af[6], x, p.bf[2])));
+  // r_i < 0 inside the open range, > 0 outside
+  const float rx = fabsf(wx - p.cf[0]) - p.hf[0];
+  const float ry = fabsf(wy - p.cf[1]) - p.hf[1];
+  const float rz = fabsf(wz - p.cf[2]) - p.hf[2];
+  const float rmax = fmaxf(rx, fmaxf(ry, rz));
+  const bool out = rmax > eps, in = rmax < -eps;
+  // floor(t) without a conversion instruction: adding 1.5*2^23 rounds t to the nearest integer in the mantissa
+  const float t = fmaf(wz, p.hirf, p.k0f);
+  const float MAGIC = 12582912.0f;
+  const float s = t + MAGIC;
+  const float d = t - (s - MAGIC); // in [-0.5, 0.5]: distance to the nearest integer
+  const int k = __float_as_int(s) - 0x4B400000;
+  const unsigned bin = (unsigned)(k - (d < 0.f ? 1 : 0));
+  const bool bin_ok = fabsf(d) > fmaf(eps, p.hirf, p.dbin0);
+  const bool valid = z > 0.f;
+  uncertain = valid && !(out || (in && bin_ok));
+  return valid ? (out ? SSD_CODE_OUT_OF_RANGE : bin) : SSD_CODE_INVALID;
 }
 
 // Projection2D::worldToImage (pointcloud.cpp:79-83)

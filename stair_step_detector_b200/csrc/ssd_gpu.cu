@@ -45,6 +45,7 @@ struct ssd_gpu_ctx
   std::string err;
   // single-stage scratch
   unsigned char *d_img = nullptr;
+  unsigned long long *d_counters = nullptr; // [0] points that needed the exact double path in k_transform_bin
   // optional per-kernel events (SSD_FLAG_STAGE_TIMING): (SSD_GPU_N_STAGES + 1) per chunk
   std::vector<cudaEvent_t> stage_ev;
   int stage_chunks = 0;
@@ -105,6 +106,31 @@ static int derive_params(const ssd_gpu_config &c, const ssd_gpu_transform &t, De
   d.y_max = c.y_max;
   d.z_min = c.z_min;
   d.z_max = c.z_max;
+  // single-precision filter constants (point_code_filtered): everything rounded so the bound stays an upper bound
+  {
+    const double u = 1.0 / 16777216.0; // 2^-24
+    double e0 = 0, e1 = 0, T = 0;
+    const double lo[3] = { c.x_min, c.y_min, c.z_min }, hi[3] = { c.x_max, c.y_max, c.z_max };
+    for(int i = 0; i < 3; i++)
+    {
+      const double S = std::fabs(t.a[i * 3]) + std::fabs(t.a[i * 3 + 1]) + std::fabs(t.a[i * 3 + 2]);
+      e0 = std::max(e0, std::fabs(t.b[i]));
+      e1 = std::max(e1, S);
+      T = std::max({ T, std::fabs(lo[i]), std::fabs(hi[i]) });
+      for(int j = 0; j < 3; j++)
+        d.af[i * 3 + j] = (float)t.a[i * 3 + j];
+      d.bf[i] = (float)t.b[i];
+      d.cf[i] = (float)((lo[i] + hi[i]) * 0.5);
+      d.hf[i] = (float)((hi[i] - lo[i]) * 0.5);
+    }
+    // proven bound: 5u*(|b| + S*m) + 8u*T ; used: twice that, rounded up
+    d.E0 = (float)((10.0 * u * e0 + 16.0 * u * T) * 1.001) + 1e-12f;
+    d.E1 = (float)(10.0 * u * e1 * 1.001);
+    d.hirf = (float)d.hir;
+    d.k0f = (float)(-c.z_min * d.hir);
+    // bin arithmetic: |t^ - t_ref| <= hir*eps + 4u*(n_bins + |z_min|*hir) (+ f32 rounding of hir itself)
+    d.dbin0 = (float)(16.0 * u * (d.n_bins + std::fabs(c.z_min) * d.hir + 1.0) + 1e-6);
+  }
   if(d.n_bins < 3 || d.n_bins > SSD_GPU_MAX_BINS)
     return SSD_E_RANGE;
   if(d.N % 4 != 0)
@@ -266,7 +292,7 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, int frame
   const size_t qt_smem = sizeof(QuadTestDev) * SSD_GPU_MAX_PLATEAUS;
 
   STAGE_EV(0);
-  k_transform_bin<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, 0, st>>>(p, xyz_dev, labels, frames);
+  k_transform_bin<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, 0, st>>>(p, xyz_dev, labels, frames, ctx->d_counters);
   STAGE_EV(1);
   k_peaks<<<nf, 32, 0, st>>>(p, frames, nf);
   STAGE_EV(2);
@@ -316,6 +342,7 @@ void ssd_gpu_destroy(ssd_gpu_ctx *ctx)
   cudaFree(ctx->d_stage[0]);
   cudaFree(ctx->d_stage[1]);
   cudaFree(ctx->d_img);
+  cudaFree(ctx->d_counters);
   for(int i = 0; i < 2; i++)
   {
     if(ctx->stream[i])
@@ -438,6 +465,8 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
   const size_t bev_bytes = (size_t)2 * ctx->chunk_frames * SSD_GPU_MAX_PLATEAUS * ctx->bm_words * 4;
   CKC(cudaMalloc(&ctx->d_bev, bev_bytes));
   CKC(cudaMemset(ctx->d_bev, 0, bev_bytes)); // bitmaps are self-cleaning afterwards
+  CKC(cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)));
+  CKC(cudaMemset(ctx->d_counters, 0, 8 * sizeof(unsigned long long)));
   CKC(cudaMemset(ctx->d_frames, 0, sizeof(FrameDev) * (size_t)max_frames));
   CKC(cudaMemset(ctx->d_out, 0, sizeof(FrameOut) * (size_t)max_frames));
   memset(ctx->h_out, 0, sizeof(FrameOut) * (size_t)max_frames);
@@ -484,6 +513,7 @@ static int process_common(ssd_gpu_ctx *ctx, const float *xyz, bool host_input, i
   CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_start, 0));
   // per-frame state: histogram must start at zero
   CK(cudaMemsetAsync(ctx->d_frames, 0, sizeof(FrameDev) * (size_t)n_frames, ctx->stream[0]));
+  CK(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream[0]));
   CK(cudaEventRecord(ctx->ev_chunk_done[0], ctx->stream[0]));
   CK(cudaStreamWaitEvent(ctx->stream[1], ctx->ev_chunk_done[0], 0));
 
@@ -658,6 +688,20 @@ int ssd_gpu_get_timing(ssd_gpu_ctx *ctx, ssd_gpu_timing *out)
   if(!ctx || !out)
     return SSD_E_INVALID_ARG;
   *out = ctx->timing;
+  return SSD_OK;
+}
+
+int ssd_gpu_get_stats(ssd_gpu_ctx *ctx, ssd_gpu_stats *out)
+{
+  if(!ctx || !out)
+    return SSD_E_INVALID_ARG;
+  CK(cudaSetDevice(ctx->device));
+  unsigned long long c[8];
+  CK(cudaMemcpy(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+  out->n_points = (uint64_t)ctx->n_frames_last * (uint64_t)ctx->dp.N;
+  out->n_exact_fallback = c[0];
+  out->filter_eps0 = ctx->dp.E0;
+  out->filter_eps1 = ctx->dp.E1;
   return SSD_OK;
 }
 

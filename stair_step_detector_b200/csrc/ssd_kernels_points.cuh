@@ -39,58 +39,75 @@ __device__ __forceinline__ Quad4 load_quad(const float4 *__restrict__ xyz4, size
 // k_transform_bin: PointsExtraction::extract + HeightsHistogram::calcHist
 // (pointcloud.cpp:122-178, 194-204). grid = (tiles_per_frame, frames), block = 256.
 // Each thread handles 4 consecutive points per iteration: three 16 B loads, one 4 B store.
-// Histogram: per-warp private shared-memory histograms, warp-aggregated with match.any, one global
-// atomic per non-empty bin per block.
+// The camera->world transform, range filter and height bin are decided in single precision with a rigorous
+// error bound (point_code_filtered); the exact double-precision chain runs only for the few points whose
+// f32 value lies within that bound of a threshold, so the result is bit-identical to the all-double chain.
+// Histogram: each thread run-length merges its own codes (neighbouring pixels mostly share a bin) and adds
+// the runs to one shared-memory histogram per block; one global atomic per non-empty bin per block.
 // ---------------------------------------------------------------------------------------------
 template<int ITERS>
 __global__ void __launch_bounds__(SSD_PT_THREADS) k_transform_bin(const __grid_constant__ DevParams p, const float *__restrict__ xyz,
-                                                                   unsigned char *__restrict__ codes, FrameDev *__restrict__ frames)
+                                                                   unsigned char *__restrict__ codes, FrameDev *__restrict__ frames,
+                                                                   unsigned long long *__restrict__ n_exact)
 {
-  __shared__ unsigned s_hist[SSD_PT_WARPS][SSD_BINS_PAD];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ unsigned s_hist[SSD_BINS_PAD];
+  const int tid = threadIdx.x;
   const int frame = blockIdx.y;
-  for(int i = tid; i < SSD_PT_WARPS * SSD_BINS_PAD; i += SSD_PT_THREADS)
-    (&s_hist[0][0])[i] = 0;
+  s_hist[tid] = 0; // SSD_PT_THREADS == SSD_BINS_PAD
   __syncthreads();
 
   const size_t fbase = (size_t)frame * p.N;
   const float4 *xyz4 = reinterpret_cast<const float4 *>(xyz + fbase * 3);
   unsigned *codes32 = reinterpret_cast<unsigned *>(codes + fbase);
   const int nquads = p.N >> 2;
-  unsigned *wh = s_hist[warp];
+  unsigned run_code = 0xffffffffu, run_n = 0, exact = 0;
 
 #pragma unroll
   for(int it = 0; it < ITERS; it++)
   {
     const int q = (blockIdx.x * ITERS + it) * SSD_PT_THREADS + tid;
-    unsigned c[4] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu };
     if(q < nquads)
     {
       const Quad4 v = load_quad(xyz4, q);
+      unsigned c[4];
+      bool unc[4];
 #pragma unroll
       for(int j = 0; j < 4; j++)
-        c[j] = point_code(p, v.x[j], v.y[j], v.z[j]);
+        c[j] = point_code_filtered(p, v.x[j], v.y[j], v.z[j], unc[j]);
+      if(unc[0] | unc[1] | unc[2] | unc[3])
+      {
+#pragma unroll
+        for(int j = 0; j < 4; j++)
+          if(unc[j])
+          {
+            c[j] = point_code_slow(p, v.x[j], v.y[j], v.z[j]);
+            exact++;
+          }
+      }
       codes32[q] = c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24);
-    }
 #pragma unroll
-    for(int j = 0; j < 4; j++)
-    {
-      const unsigned m = __match_any_sync(0xffffffffu, c[j]);
-      if(c[j] != 0xffffffffu && lane == __ffs(m) - 1)
-        wh[c[j]] += __popc(m); // one lane per distinct code: no intra-warp race; the histogram is warp-private
-      __syncwarp();
+      for(int j = 0; j < 4; j++)
+      {
+        if(c[j] == run_code)
+          run_n++;
+        else
+        {
+          if(run_n)
+            atomicAdd(&s_hist[run_code], run_n);
+          run_code = c[j];
+          run_n = 1;
+        }
+      }
     }
   }
+  if(run_n)
+    atomicAdd(&s_hist[run_code], run_n);
+  if(exact && n_exact)
+    atomicAdd(n_exact, (unsigned long long)exact);
   __syncthreads();
-  for(int b = tid; b < SSD_BINS_PAD; b += SSD_PT_THREADS)
-  {
-    unsigned s = 0;
-#pragma unroll
-    for(int w = 0; w < SSD_PT_WARPS; w++)
-      s += s_hist[w][b];
-    if(s)
-      atomicAdd(&frames[frame].hist[b], s);
-  }
+  const unsigned sum = s_hist[tid];
+  if(sum)
+    atomicAdd(&frames[frame].hist[tid], sum);
 }
 
 // ---------------------------------------------------------------------------------------------
