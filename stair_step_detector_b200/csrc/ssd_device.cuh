@@ -126,6 +126,19 @@ __device__ __forceinline__ void camera_to_world(const DevParams &p, float fx, fl
   wz = ((p.a[6] * x + p.a[7] * y) + p.a[8] * z) + p.b[2];
 }
 
+// x,y rows only (BEV projection, point-in-quadrilateral) and the z row alone (height sum): same roundings
+__device__ __forceinline__ void camera_to_world_xy(const DevParams &p, float fx, float fy, float fz, double &wx, double &wy)
+{
+  const double x = fx, y = fy, z = fz;
+  wx = ((p.a[0] * x + p.a[1] * y) + p.a[2] * z) + p.b[0];
+  wy = ((p.a[3] * x + p.a[4] * y) + p.a[5] * z) + p.b[1];
+}
+__device__ __forceinline__ double camera_to_world_z(const DevParams &p, float fx, float fy, float fz)
+{
+  const double x = fx, y = fy, z = fz;
+  return ((p.a[6] * x + p.a[7] * y) + p.a[8] * z) + p.b[2];
+}
+
 // z>0 (pointcloud.cpp:143-146), range (pointcloud.cpp:155-163), height index (pointcloud.cpp:175)
 __device__ __forceinline__ unsigned point_code(const DevParams &p, float fx, float fy, float fz)
 {
@@ -182,6 +195,20 @@ __device__ __forceinline__ void world_to_image(const DevParams &p, double wx, do
 {
   ix = (int)((wx - p.x_min) * p.x_to_image);
   iy = (int)((p.y_max - wy) * p.y_to_image);
+}
+
+// BEV pixel of an in-range point the way the reference addresses it: *Mat::ptr(iy, ix) with no bounds check
+// (pointcloud.cpp:468), i.e. linear offset iy*W + ix. In range means 0 <= ix <= W and 0 <= iy <= H (the upper
+// ends only by rounding), so ix == W wraps to the next row and iy == H falls past the image.
+__device__ __forceinline__ bool bev_pixel(const DevParams &p, double wx, double wy, int &x, int &y)
+{
+  world_to_image(p, wx, wy, x, y);
+  if(x >= p.W)
+  {
+    x -= p.W;
+    y += 1;
+  }
+  return x >= 0 && x < p.W && y >= 0 && y < p.H;
 }
 
 // Projection2D::imageToWorld (pointcloud.cpp:84-88)

@@ -13,8 +13,10 @@
 #include <string>
 #include <vector>
 
-#define SSD_PT_ITERS 4
+#define SSD_PT_ITERS 4   // k_transform_bin: 4096 points per block
+#define SSD_PT_ITERS2 8  // k_label_bev / k_quad_reduce: 8192 points per block (amortises their per-block prologue)
 #define SSD_TILE_POINTS (SSD_PT_THREADS * 4 * SSD_PT_ITERS)
+#define SSD_TILE_POINTS2 (SSD_PT_THREADS * 4 * SSD_PT_ITERS2)
 
 static thread_local std::string g_create_error;
 
@@ -289,6 +291,7 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, int frame
   unsigned char *labels = ctx->d_labels + (size_t)frame0 * p.N;
   unsigned *bev = ctx->d_bev + (size_t)s * ctx->chunk_frames * SSD_GPU_MAX_PLATEAUS * ctx->bm_words;
   const dim3 gpt(p.tiles_per_frame, nf);
+  const dim3 gpt2((p.N + SSD_TILE_POINTS2 - 1) / SSD_TILE_POINTS2, nf);
   const size_t qt_smem = sizeof(QuadTestDev) * SSD_GPU_MAX_PLATEAUS;
 
   STAGE_EV(0);
@@ -296,13 +299,13 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, int frame
   STAGE_EV(1);
   k_peaks<<<nf, 32, 0, st>>>(p, frames, nf);
   STAGE_EV(2);
-  k_label_bev<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, 0, st>>>(p, xyz_dev, labels, frames, bev, ctx->bm_words);
+  k_label_bev<SSD_PT_ITERS2><<<gpt2, SSD_PT_THREADS, 0, st>>>(p, xyz_dev, labels, frames, bev, ctx->bm_words);
   STAGE_EV(3);
   k_outline<<<dim3(SSD_GPU_MAX_PLATEAUS, nf), SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, bev, ctx->bm_words, ctx->smem_cap_words);
   STAGE_EV(4);
   k_frame_logic<<<nf, 32, 0, st>>>(p, frames, nf);
   STAGE_EV(5);
-  k_quad_reduce<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, qt_smem, st>>>(p, xyz_dev, labels, frames, bev, ctx->bm_words);
+  k_quad_reduce<SSD_PT_ITERS2><<<gpt2, SSD_PT_THREADS, qt_smem, st>>>(p, xyz_dev, labels, frames, bev, ctx->bm_words);
   STAGE_EV(6);
   k_finalize<<<nf, SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, ctx->d_out + frame0, bev, ctx->bm_words, ctx->smem_cap_words);
   STAGE_EV(7);

@@ -241,30 +241,13 @@ __global__ void __launch_bounds__(32) k_peaks(const __grid_constant__ DevParams 
   }
 }
 
-// warp-aggregated row-range tracking + OR into a BEV bitmap word
-__device__ __forceinline__ void bev_set(const DevParams &p, unsigned *__restrict__ bm, double wx, double wy, int *s_rmin, int *s_rmax, int k,
-                                        unsigned &oob)
-{
-  int ix, iy;
-  world_to_image(p, wx, wy, ix, iy);
-  const long long off = (long long)iy * p.W + ix; // cv::Mat::ptr(y, x) arithmetic, no bounds check (pointcloud.cpp:468)
-  if(off < 0 || off >= (long long)p.N)
-  {
-    oob = 1;
-    return;
-  }
-  const int y = (int)(off / p.W), x = (int)(off - (long long)y * p.W);
-  atomicOr(bm + (size_t)y * p.wpr + (x >> 5), 1u << (x & 31));
-  if(y < s_rmin[k])
-    atomicMin(&s_rmin[k], y);
-  if(y > s_rmax[k])
-    atomicMax(&s_rmax[k], y);
-}
-
 // ---------------------------------------------------------------------------------------------
 // k_label_bev: the per-point segment label (PlateausExtraction::extractPlateaus, pointcloud.cpp:280-343,
 // as a LUT lookup) and StairsDetector::projectToBinaryImage (:458-471) for every outlined plateau.
-// Rewrites the bin codes in place as labels. grid = (tiles_per_frame, frames).
+// Rewrites the bin codes in place as labels. grid = (ceil(N / (1024*ITERS)), frames).
+// Only the points of outlined plateaus (~1/4 of a frame) re-read their vertex and need the x,y rows of the
+// transform; their BEV bits go to the plateau's global bitmap with atomicOr, the touched row range is
+// tracked per thread run and merged through shared memory.
 // ---------------------------------------------------------------------------------------------
 template<int ITERS>
 __global__ void __launch_bounds__(SSD_PT_THREADS) k_label_bev(const __grid_constant__ DevParams p, const float *__restrict__ xyz,
@@ -294,8 +277,12 @@ __global__ void __launch_bounds__(SSD_PT_THREADS) k_label_bev(const __grid_const
   unsigned *fbev = bev + (size_t)frame * SSD_GPU_MAX_PLATEAUS * bm_words;
   const int nquads = p.N >> 2;
   unsigned oob = 0;
+  int run_k = -1, run_min = 0x7fffffff, run_max = -1;
+  // pending OR into one bitmap word
+  unsigned *pend_addr = nullptr;
+  unsigned pend_bits = 0;
 
-#pragma unroll
+#pragma unroll 2
   for(int it = 0; it < ITERS; it++)
   {
     const int q = (blockIdx.x * ITERS + it) * SSD_PT_THREADS + tid;
@@ -318,11 +305,46 @@ __global__ void __launch_bounds__(SSD_PT_THREADS) k_label_bev(const __grid_const
       for(int j = 0; j < 4; j++)
         if((int)l[j] >= first_outlined && (int)l[j] < K)
         {
-          double wx, wy, wz;
-          camera_to_world(p, v.x[j], v.y[j], v.z[j], wx, wy, wz);
-          bev_set(p, fbev + (size_t)l[j] * bm_words, wx, wy, s_rmin, s_rmax, (int)l[j], oob);
+          double wx, wy;
+          camera_to_world_xy(p, v.x[j], v.y[j], v.z[j], wx, wy);
+          int x, y;
+          if(!bev_pixel(p, wx, wy, x, y))
+          {
+            oob = 1;
+            continue;
+          }
+          if((int)l[j] != run_k)
+          {
+            if(run_max >= 0)
+            {
+              atomicMin(&s_rmin[run_k], run_min);
+              atomicMax(&s_rmax[run_k], run_max);
+            }
+            run_k = (int)l[j];
+            run_min = 0x7fffffff;
+            run_max = -1;
+          }
+          run_min = min(run_min, y);
+          run_max = max(run_max, y);
+          unsigned *addr = fbev + (size_t)l[j] * bm_words + (size_t)y * p.wpr + (x >> 5);
+          const unsigned bit = 1u << (x & 31);
+          if(addr != pend_addr)
+          {
+            if(pend_bits)
+              atomicOr(pend_addr, pend_bits);
+            pend_addr = addr;
+            pend_bits = 0;
+          }
+          pend_bits |= bit;
         }
     }
+  }
+  if(pend_bits)
+    atomicOr(pend_addr, pend_bits);
+  if(run_max >= 0)
+  {
+    atomicMin(&s_rmin[run_k], run_min);
+    atomicMax(&s_rmax[run_k], run_max);
   }
   if(oob)
     s_oob = 1;
@@ -336,11 +358,21 @@ __global__ void __launch_bounds__(SSD_PT_THREADS) k_label_bev(const __grid_const
     atomicOr(&F.status, SSD_STATUS_BEV_OOB);
 }
 
+__device__ __forceinline__ long long warp_sum_s64(long long v)
+{
+#pragma unroll
+  for(int s = 16; s > 0; s >>= 1)
+    v += __shfl_xor_sync(0xffffffffu, v, s);
+  return v;
+}
+
 // ---------------------------------------------------------------------------------------------
 // k_quad_reduce: StairsDetector::getPointsInQuadrilateral + calcAverageZ (pointcloud.cpp:560-581) for the
 // ground and every valid plateau, and the ground's BEV image (calcGround, :530-531).
 // z is accumulated in 2^-36 m fixed point: integer sums are order independent, so the result is
 // deterministic; the error (<= 2^-37 m per point) is eight orders below the 0.1 mm tolerance.
+// Each thread sums its own run of points, the warp merges equal labels with shuffles (single-pass segmented
+// reduce over the warp) and one lane issues the global 64-bit add.
 // ---------------------------------------------------------------------------------------------
 template<int ITERS>
 __global__ void __launch_bounds__(SSD_PT_THREADS) k_quad_reduce(const __grid_constant__ DevParams p, const float *__restrict__ xyz,
@@ -348,9 +380,7 @@ __global__ void __launch_bounds__(SSD_PT_THREADS) k_quad_reduce(const __grid_con
                                                                  unsigned *__restrict__ bev, size_t bm_words)
 {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  __shared__ unsigned long long s_sum[SSD_GPU_MAX_PLATEAUS];
-  __shared__ unsigned s_cnt[SSD_GPU_MAX_PLATEAUS];
-  __shared__ int s_active[SSD_GPU_MAX_PLATEAUS];
+  __shared__ unsigned char s_active[SSD_BINS_PAD]; // label -> tested?
   __shared__ int s_rmin, s_rmax;
   __shared__ unsigned s_oob;
   QuadTestDev *s_qt = reinterpret_cast<QuadTestDev *>(s_raw);
@@ -360,12 +390,7 @@ __global__ void __launch_bounds__(SSD_PT_THREADS) k_quad_reduce(const __grid_con
   if(F.first_valid < 0)
     return; // no valid plateau: nothing is emitted (pointcloud.cpp:434)
   const int K = F.n_plateaus, ground = F.ground_index;
-  if(tid < SSD_GPU_MAX_PLATEAUS)
-  {
-    s_sum[tid] = 0;
-    s_cnt[tid] = 0;
-    s_active[tid] = tid < K && F.plat[tid].valid && F.plat[tid].quad_status == 0;
-  }
+  s_active[tid] = tid < K && F.plat[tid].valid && F.plat[tid].quad_status == 0; // SSD_PT_THREADS == SSD_BINS_PAD
   if(tid == 0)
   {
     s_rmin = 0x7fffffff;
@@ -373,14 +398,11 @@ __global__ void __launch_bounds__(SSD_PT_THREADS) k_quad_reduce(const __grid_con
     s_oob = 0;
   }
   {
-    const unsigned *src = reinterpret_cast<const unsigned *>(&F.plat[0]);
-    (void)src;
-    for(int k = 0; k < K; k++)
+    const int words = (int)(sizeof(QuadTestDev) / 4);
+    for(int i = tid; i < K * words; i += SSD_PT_THREADS)
     {
-      const unsigned *g = reinterpret_cast<const unsigned *>(&F.plat[k].qt);
-      unsigned *d = reinterpret_cast<unsigned *>(&s_qt[k]);
-      for(int i = tid; i < (int)(sizeof(QuadTestDev) / 4); i += SSD_PT_THREADS)
-        d[i] = g[i];
+      const int k = i / words, w = i - k * words;
+      reinterpret_cast<unsigned *>(&s_qt[k])[w] = reinterpret_cast<const unsigned *>(&F.plat[k].qt)[w];
     }
   }
   __syncthreads();
@@ -396,56 +418,48 @@ __global__ void __launch_bounds__(SSD_PT_THREADS) k_quad_reduce(const __grid_con
   long long acc = 0;
   unsigned acc_n = 0;
   int acc_k = -1;
-#pragma unroll
+#pragma unroll 2
   for(int it = 0; it < ITERS; it++)
   {
     const int q = (blockIdx.x * ITERS + it) * SSD_PT_THREADS + tid;
     if(q >= nquads)
       continue;
     const unsigned lw = __ldg(lab32 + q);
-    bool any = false;
-#pragma unroll
-    for(int j = 0; j < 4; j++)
-    {
-      const unsigned l = (lw >> (8 * j)) & 0xff;
-      any |= l < SSD_GPU_MAX_PLATEAUS && s_active[l];
-    }
-    if(!any)
+    const unsigned l0 = lw & 0xff, l1 = (lw >> 8) & 0xff, l2 = (lw >> 16) & 0xff, l3 = lw >> 24;
+    if(!(s_active[l0] | s_active[l1] | s_active[l2] | s_active[l3]))
       continue;
     const Quad4 v = load_quad(xyz4, q);
 #pragma unroll
     for(int j = 0; j < 4; j++)
     {
       const unsigned l = (lw >> (8 * j)) & 0xff;
-      if(!(l < SSD_GPU_MAX_PLATEAUS && s_active[l]))
+      if(!s_active[l])
         continue;
-      double wx, wy, wz;
-      camera_to_world(p, v.x[j], v.y[j], v.z[j], wx, wy, wz);
+      double wx, wy;
+      camera_to_world_xy(p, v.x[j], v.y[j], v.z[j], wx, wy);
       if(!quadtest_within(s_qt[l], wx, wy))
         continue;
       if((int)l != acc_k)
       {
         if(acc_n)
         {
-          atomicAdd(&s_sum[acc_k], (unsigned long long)acc);
-          atomicAdd(&s_cnt[acc_k], acc_n);
+          // label changed inside this thread's run (plateau border): flush straight to global memory
+          atomicAdd(&F.plat[acc_k].sum_fix, (unsigned long long)acc);
+          atomicAdd(&F.plat[acc_k].n_in_quad, acc_n);
         }
         acc = 0;
         acc_n = 0;
         acc_k = (int)l;
       }
-      acc += z_to_fix(wz);
+      acc += z_to_fix(camera_to_world_z(p, v.x[j], v.y[j], v.z[j]));
       acc_n++;
       if((int)l == ground)
       {
-        int ix, iy;
-        world_to_image(p, wx, wy, ix, iy);
-        const long long off = (long long)iy * p.W + ix;
-        if(off < 0 || off >= (long long)p.N)
+        int x, y;
+        if(!bev_pixel(p, wx, wy, x, y))
           oob = 1;
         else
         {
-          const int y = (int)(off / p.W), x = (int)(off - (long long)y * p.W);
           atomicOr(gbev + (size_t)y * p.wpr + (x >> 5), 1u << (x & 31));
           rmin = min(rmin, y);
           rmax = max(rmax, y);
@@ -453,24 +467,39 @@ __global__ void __launch_bounds__(SSD_PT_THREADS) k_quad_reduce(const __grid_con
       }
     }
   }
-  if(acc_n)
+  // segmented reduce over the warp: one round per distinct label present
   {
-    atomicAdd(&s_sum[acc_k], (unsigned long long)acc);
-    atomicAdd(&s_cnt[acc_k], acc_n);
+    const int lane = tid & 31;
+    unsigned todo = __ballot_sync(0xffffffffu, acc_n > 0);
+    while(todo)
+    {
+      const int leader = __ffs(todo) - 1;
+      const int kk = __shfl_sync(0xffffffffu, acc_k, leader);
+      const bool mine = acc_n > 0 && acc_k == kk;
+      const long long vs = warp_sum_s64(mine ? acc : 0ll);
+      const unsigned ns = __reduce_add_sync(0xffffffffu, mine ? acc_n : 0u);
+      if(lane == leader)
+      {
+        atomicAdd(&F.plat[kk].sum_fix, (unsigned long long)vs);
+        atomicAdd(&F.plat[kk].n_in_quad, ns);
+      }
+      todo &= ~__ballot_sync(0xffffffffu, mine);
+    }
+    rmin = __reduce_min_sync(0xffffffffu, rmin);
+    rmax = __reduce_max_sync(0xffffffffu, rmax);
+    oob = __reduce_or_sync(0xffffffffu, oob);
+    if(lane == 0)
+    {
+      if(rmax >= 0)
+      {
+        atomicMin(&s_rmin, rmin);
+        atomicMax(&s_rmax, rmax);
+      }
+      if(oob)
+        s_oob = 1;
+    }
   }
-  if(rmax >= 0)
-  {
-    atomicMin(&s_rmin, rmin);
-    atomicMax(&s_rmax, rmax);
-  }
-  if(oob)
-    s_oob = 1;
   __syncthreads();
-  if(tid < K && s_cnt[tid])
-  {
-    atomicAdd(&F.plat[tid].sum_fix, s_sum[tid]);
-    atomicAdd(&F.plat[tid].n_in_quad, s_cnt[tid]);
-  }
   if(tid == 0)
   {
     if(s_rmax >= 0)
