@@ -62,6 +62,9 @@ struct QuadTestDev
   signed char cell_seg[3][3][2];
   int inside_is_left;
   int status; // 0 ok, 1 the reference ctor would throw
+  // Axis-aligned box (centre / half width, metres) every point of which passes the test above -- verified
+  // cell by cell in quadtest_inner_box(). ib_hx < 0: no box. Used as a single-precision fast accept.
+  float ib_cx, ib_hx, ib_cy, ib_hy;
 };
 
 struct PlateauDev
@@ -547,6 +550,85 @@ __device__ __forceinline__ bool quadtest_within(const QuadTestDev &t, double x, 
   if(n == 2)
     in = in && (int)segment_is_left(t.seg[t.cell_seg[r][c][1]], x, y) == t.inside_is_left;
   return in;
+}
+
+// the predicate of one map cell at an arbitrary point (no bounding-box test, no cell selection)
+__device__ __forceinline__ bool quadtest_cell_pred(const QuadTestDev &t, int r, int c, double x, double y)
+{
+  const int n = t.cell_nseg[r][c];
+  if(n == 0)
+    return t.cell_seg[r][c][0] != 0;
+  bool in = (int)segment_is_left(t.seg[t.cell_seg[r][c][0]], x, y) == t.inside_is_left;
+  if(n == 2)
+    in = in && (int)segment_is_left(t.seg[t.cell_seg[r][c][1]], x, y) == t.inside_is_left;
+  return in;
+}
+
+// Inner box for the fast accept. Candidate: the middle interval of the sorted corner coordinates, shrunk by
+// 2 %. It is accepted only if, for every map cell it overlaps, the cell's predicate holds at the four corners
+// of (box intersect cell): each half-plane value fl(fl(x*k)+y)+c is monotone in x and in y (IEEE operations
+// are monotone), so its minimum over a rectangle is attained at a corner -- the predicate then holds on the
+// whole intersection, hence isPointWithin() is true for every point of the box.
+__device__ inline void quadtest_inner_box(QuadTestDev &t, const P2d q[4])
+{
+  t.ib_cx = t.ib_cy = 0.f;
+  t.ib_hx = t.ib_hy = -1.f;
+  if(t.status)
+    return;
+  double xs[4] = { q[0].x, q[1].x, q[2].x, q[3].x }, ys[4] = { q[0].y, q[1].y, q[2].y, q[3].y };
+  for(int i = 1; i < 4; i++)
+    for(int j = i; j > 0; j--)
+    {
+      if(xs[j] < xs[j - 1])
+      {
+        const double tmp = xs[j];
+        xs[j] = xs[j - 1];
+        xs[j - 1] = tmp;
+      }
+      if(ys[j] < ys[j - 1])
+      {
+        const double tmp = ys[j];
+        ys[j] = ys[j - 1];
+        ys[j - 1] = tmp;
+      }
+    }
+  const double sx = 0.02 * (xs[2] - xs[1]) + 1e-6, sy = 0.02 * (ys[2] - ys[1]) + 1e-6;
+  const double bx0 = xs[1] + sx, bx1 = xs[2] - sx, by0 = ys[1] + sy, by1 = ys[2] - sy;
+  if(!(bx0 < bx1 && by0 < by1))
+    return;
+  if(!(t.tb_lo_x < bx0 && bx1 < t.tb_hi_x && t.tb_lo_y < by0 && by1 < t.tb_hi_y))
+    return;
+  for(int r = 0; r < t.nrow; r++)
+  {
+    const double ry0 = r == 0 ? t.tb_lo_y : t.row_upper_y[r - 1];
+    const double ry1 = r == t.nrow - 1 ? t.tb_hi_y : t.row_upper_y[r];
+    const double ay = by0 > ry0 ? by0 : ry0, cy = by1 < ry1 ? by1 : ry1;
+    if(!(ay <= cy))
+      continue;
+    for(int c = 0; c < t.ncell[r]; c++)
+    {
+      const double rx0 = c == 0 ? t.tb_lo_x : t.cell_upper_x[r][c - 1];
+      const double rx1 = c == t.ncell[r] - 1 ? t.tb_hi_x : t.cell_upper_x[r][c];
+      const double ax = bx0 > rx0 ? bx0 : rx0, cx = bx1 < rx1 ? bx1 : rx1;
+      if(!(ax <= cx))
+        continue;
+      if(!(quadtest_cell_pred(t, r, c, ax, ay) && quadtest_cell_pred(t, r, c, cx, ay) && quadtest_cell_pred(t, r, c, ax, cy) &&
+           quadtest_cell_pred(t, r, c, cx, cy)))
+        return;
+    }
+  }
+  // single-precision centre / half width, rounded so the f32 box lies inside the verified box
+  const double u = 1.0 / 16777216.0;
+  const double mx = fmax(fabs(bx0), fabs(bx1)), my = fmax(fabs(by0), fabs(by1));
+  const float cxf = (float)((bx0 + bx1) * 0.5), cyf = (float)((by0 + by1) * 0.5);
+  const double hx = fmin((double)cxf - bx0, bx1 - (double)cxf) - 4.0 * u * mx;
+  const double hy = fmin((double)cyf - by0, by1 - (double)cyf) - 4.0 * u * my;
+  if(!(hx > 0 && hy > 0))
+    return;
+  t.ib_cx = cxf;
+  t.ib_cy = cyf;
+  t.ib_hx = __double2float_rd(hx);
+  t.ib_hy = __double2float_rd(hy);
 }
 
 // fixed-point z for the order-independent (deterministic) per-step sum

@@ -851,6 +851,7 @@ __global__ void __launch_bounds__(32) k_frame_logic(const __grid_constant__ DevP
       }
     }
     quadtest_init(s_qt[lane], q);
+    quadtest_inner_box(s_qt[lane], q);
     P.valid = 1;
     P.quad_status = s_qt[lane].status;
   }

@@ -74,28 +74,44 @@ __global__ void __launch_bounds__(SSD_PT_THREADS) k_transform_bin(const __grid_c
 #pragma unroll
       for(int j = 0; j < 4; j++)
         c[j] = point_code_filtered(p, v.x[j], v.y[j], v.z[j], unc[j]);
-      if(unc[0] | unc[1] | unc[2] | unc[3])
+      unsigned um = (unc[0] ? 1u : 0u) | (unc[1] ? 2u : 0u) | (unc[2] ? 4u : 0u) | (unc[3] ? 8u : 0u);
+      if(um)
+      {
+        // rare: one out-of-line exact evaluation per uncertain point
+        exact += __popc(um);
+#pragma unroll 1
+        while(um)
+        {
+          const int j = __ffs(um) - 1;
+          um &= um - 1;
+          const float fx = j == 0 ? v.x[0] : (j == 1 ? v.x[1] : (j == 2 ? v.x[2] : v.x[3]));
+          const float fy = j == 0 ? v.y[0] : (j == 1 ? v.y[1] : (j == 2 ? v.y[2] : v.y[3]));
+          const float fz = j == 0 ? v.z[0] : (j == 1 ? v.z[1] : (j == 2 ? v.z[2] : v.z[3]));
+          const unsigned ce = point_code_slow(p, fx, fy, fz);
+          c[0] = j == 0 ? ce : c[0];
+          c[1] = j == 1 ? ce : c[1];
+          c[2] = j == 2 ? ce : c[2];
+          c[3] = j == 3 ? ce : c[3];
+        }
+      }
+      const unsigned cw = c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24);
+      codes32[q] = cw;
+      if(cw == run_code * 0x01010101u)
+        run_n += 4; // all four in the current run (neighbouring pixels mostly share a bin)
+      else
       {
 #pragma unroll
         for(int j = 0; j < 4; j++)
-          if(unc[j])
-          {
-            c[j] = point_code_slow(p, v.x[j], v.y[j], v.z[j]);
-            exact++;
-          }
-      }
-      codes32[q] = c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24);
-#pragma unroll
-      for(int j = 0; j < 4; j++)
-      {
-        if(c[j] == run_code)
-          run_n++;
-        else
         {
-          if(run_n)
-            atomicAdd(&s_hist[run_code], run_n);
-          run_code = c[j];
-          run_n = 1;
+          if(c[j] == run_code)
+            run_n++;
+          else
+          {
+            if(run_n)
+              atomicAdd(&s_hist[run_code], run_n);
+            run_code = c[j];
+            run_n = 1;
+          }
         }
       }
     }
@@ -381,6 +397,7 @@ __global__ void __launch_bounds__(SSD_PT_THREADS) k_quad_reduce(const __grid_con
 {
   extern __shared__ __align__(16) unsigned char s_raw[];
   __shared__ unsigned char s_active[SSD_BINS_PAD]; // label -> tested?
+  __shared__ float4 s_box[SSD_GPU_MAX_PLATEAUS];   // verified inner box of each step (cx, hx, cy, hy)
   __shared__ int s_rmin, s_rmax;
   __shared__ unsigned s_oob;
   QuadTestDev *s_qt = reinterpret_cast<QuadTestDev *>(s_raw);
@@ -404,6 +421,12 @@ __global__ void __launch_bounds__(SSD_PT_THREADS) k_quad_reduce(const __grid_con
       const int k = i / words, w = i - k * words;
       reinterpret_cast<unsigned *>(&s_qt[k])[w] = reinterpret_cast<const unsigned *>(&F.plat[k].qt)[w];
     }
+  }
+  if(tid < K)
+  {
+    const QuadTestDev &g = F.plat[tid].qt;
+    // the ground also needs the exact x,y of every accepted point for its BEV image: no fast accept there
+    s_box[tid] = make_float4(g.ib_cx, tid == ground ? -1.f : g.ib_hx, g.ib_cy, g.ib_hy);
   }
   __syncthreads();
 
@@ -435,10 +458,21 @@ __global__ void __launch_bounds__(SSD_PT_THREADS) k_quad_reduce(const __grid_con
       const unsigned l = (lw >> (8 * j)) & 0xff;
       if(!s_active[l])
         continue;
-      double wx, wy;
-      camera_to_world_xy(p, v.x[j], v.y[j], v.z[j], wx, wy);
-      if(!quadtest_within(s_qt[l], wx, wy))
-        continue;
+      // fast accept: single-precision position inside the verified inner box by more than its error bound
+      // (same bound as point_code_filtered: |w^ - w_ref| <= eps = E1 * max|p| + E0)
+      const float4 bx = s_box[l];
+      const float fx = v.x[j], fy = v.y[j], fz = v.z[j];
+      const float eps = fmaf(p.E1, fmaxf(fmaxf(fabsf(fx), fabsf(fy)), fabsf(fz)), p.E0);
+      const float wxf = fmaf(p.af[2], fz, fmaf(p.af[1], fy, fmaf(p.af[0], fx, p.bf[0])));
+      const float wyf = fmaf(p.af[5], fz, fmaf(p.af[4], fy, fmaf(p.af[3], fx, p.bf[1])));
+      const bool fast = fmaxf(fabsf(wxf - bx.x) - bx.y, fabsf(wyf - bx.z) - bx.w) < -eps;
+      double wx = 0, wy = 0;
+      if(!fast)
+      {
+        camera_to_world_xy(p, fx, fy, fz, wx, wy);
+        if(!quadtest_within(s_qt[l], wx, wy))
+          continue;
+      }
       if((int)l != acc_k)
       {
         if(acc_n)
