@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(SSD_PT_THREADS) k_transform_bin(const __grid_c
   const float4 *xyz4 = reinterpret_cast<const float4 *>(xyz + fbase * 3);
   unsigned *codes32 = reinterpret_cast<unsigned *>(codes + fbase);
   const int nquads = p.N >> 2;
-  unsigned run_code = 0xffffffffu, run_n = 0, exact = 0;
+  unsigned run_code = SSD_CODE_INVALID, run_n = 0, exact = 0; // an empty run of a valid code: no sentinel pattern to collide with
 
 #pragma unroll
   for(int it = 0; it < ITERS; it++)
