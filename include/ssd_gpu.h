@@ -176,6 +176,8 @@ typedef struct ssd_gpu_stats
 {
   uint64_t n_points;
   uint64_t n_exact_fallback;
+  uint64_t n_quad_fast;   /* point-in-quadrilateral decisions taken by the verified inner-box fast accept */
+  uint64_t n_quad_exact;  /* ... taken by the exact QuadrilateralTest evaluation */
   double filter_eps0, filter_eps1;
 } ssd_gpu_stats;
 int ssd_gpu_get_stats(ssd_gpu_ctx *ctx, ssd_gpu_stats *out);

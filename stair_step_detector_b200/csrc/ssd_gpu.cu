@@ -135,8 +135,8 @@ static int derive_params(const ssd_gpu_config &c, const ssd_gpu_transform &t, De
   }
   if(d.n_bins < 3 || d.n_bins > SSD_GPU_MAX_BINS)
     return SSD_E_RANGE;
-  if(d.N % 4 != 0)
-    return SSD_E_INVALID_ARG; // vertices are loaded four at a time (three 16-byte loads)
+  if(d.N % 16 != 0)
+    return SSD_E_INVALID_ARG; // vertices are loaded four at a time (three 16-byte loads), labels sixteen at a time
   if(c.width / 25 + 4 > SSD_MAX_SCANS || c.width / 50 + 6 > SSD_MAX_LINE_PTS || c.height / 10 + 2 > SSD_MAX_VPTS)
     return SSD_E_RANGE;
   return SSD_OK;
@@ -299,13 +299,13 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, int frame
   STAGE_EV(1);
   k_peaks<<<nf, 32, 0, st>>>(p, frames, nf);
   STAGE_EV(2);
-  k_label_bev<SSD_PT_ITERS2><<<gpt2, SSD_PT_THREADS, 0, st>>>(p, xyz_dev, labels, frames, bev, ctx->bm_words);
+  k_label_bev<<<gpt2, SSD_PT_THREADS, 0, st>>>(p, xyz_dev, labels, frames, bev, ctx->bm_words);
   STAGE_EV(3);
   k_outline<<<dim3(SSD_GPU_MAX_PLATEAUS, nf), SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, bev, ctx->bm_words, ctx->smem_cap_words);
   STAGE_EV(4);
   k_frame_logic<<<nf, 32, 0, st>>>(p, frames, nf);
   STAGE_EV(5);
-  k_quad_reduce<SSD_PT_ITERS2><<<gpt2, SSD_PT_THREADS, qt_smem, st>>>(p, xyz_dev, labels, frames, bev, ctx->bm_words);
+  k_quad_reduce<<<gpt2, SSD_PT_THREADS, qt_smem, st>>>(p, xyz_dev, labels, frames, bev, ctx->bm_words, ctx->d_counters);
   STAGE_EV(6);
   k_finalize<<<nf, SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, ctx->d_out + frame0, bev, ctx->bm_words, ctx->smem_cap_words);
   STAGE_EV(7);
@@ -703,6 +703,8 @@ int ssd_gpu_get_stats(ssd_gpu_ctx *ctx, ssd_gpu_stats *out)
   CK(cudaMemcpy(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
   out->n_points = (uint64_t)ctx->n_frames_last * (uint64_t)ctx->dp.N;
   out->n_exact_fallback = c[0];
+  out->n_quad_fast = c[1];
+  out->n_quad_exact = c[2];
   out->filter_eps0 = ctx->dp.E0;
   out->filter_eps1 = ctx->dp.E1;
   return SSD_OK;

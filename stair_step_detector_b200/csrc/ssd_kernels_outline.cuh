@@ -923,7 +923,7 @@ __global__ void __launch_bounds__(SSD_OL_THREADS) k_finalize(const __grid_consta
     {
       PlateauDev &P = F.plat[i];
       if(P.valid && P.quad_status == 0)
-        P.mean_z = ((double)(long long)P.sum_fix / (double)(1ull << SSD_FIX_SHIFT)) / (double)P.n_in_quad; // calcAverageZ (:574-581)
+        P.mean_z = ((double)((long long)P.sum_fix - (long long)P.n_in_quad * (1ll << 37)) / (double)(1ull << SSD_FIX_SHIFT)) / (double)P.n_in_quad; // calcAverageZ (:574-581); the sum carries a 2^37 bias per point
     }
     if(groundStep)
     {

@@ -38,6 +38,6 @@ for cf in [int(c) for c in args.chunks.split(",")]:
     fps = args.frames / (ms * 1e-3)
     print(json.dumps({"chunk": det.chunk_frames, "ms_best": round(ms, 3), "ms_med": round(float(np.median(ts)), 3), "kfps": round(fps / 1e3, 1),
                       "Gpts": round(fps * N / 1e9, 1), "chain_GBs": round(13 * fps * N / 1e9, 0), "staged_total": round(tot, 3),
-                      "stages": {k: round(v[0], 3) for k, v in st.items()}, "steps": int(det.n_steps_all(args.frames).sum()), "exact_frac": det.stats().n_exact_fallback / max(1, det.stats().n_points)}), flush=True)
+                      "stages": {k: round(v[0], 3) for k, v in st.items()}, "steps": int(det.n_steps_all(args.frames).sum()), "exact_frac": det.stats().n_exact_fallback / max(1, det.stats().n_points), "quad_fast": det.stats().n_quad_fast, "quad_exact": det.stats().n_quad_exact}), flush=True)
     det.free(d)
     det.close()
