@@ -438,6 +438,9 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
   cudaFuncSetAttribute(k_outline, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
   cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
   cudaFuncSetAttribute(k_test_front_edge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  // k_quad_reduce: static compaction list + dynamic QuadrilateralTest table exceed the 48 KB default together
+  if(cudaFuncSetAttribute(k_quad_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(QuadTestDev) * SSD_GPU_MAX_PLATEAUS)) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(k_quad_reduce) failed", SSD_E_CUDA);
 
 #define CKC(call)                                                            \
   do                                                                         \
