@@ -283,7 +283,7 @@ def run_ours(args):
                 "clocks": clocks,
                 "e2e": {"value": e2e_fps * N / 1e6, "unit": "Mpoints/s", "frames_per_s": e2e_fps, "frames_per_step": e2e_frames * world,
                         "ms_per_step": my_e2e, "h2d_bytes_per_step": e2e_frames * N * 12,
-                        "d2h_bytes_per_step": e2e_frames * (32 + 72 * A.MAX_STEPS),
+                        "d2h_bytes_per_step": e2e_frames * (32 + 72 * A.MAX_STEPS + 16),
                         "note": "ssd_gpu_process_host on pinned host vertices; PCIe-bound"},
                 "gpu_launches": launches,
                 "roofline": roofline}

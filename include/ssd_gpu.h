@@ -176,9 +176,10 @@ typedef struct ssd_gpu_stats
 {
   uint64_t n_points;
   uint64_t n_exact_fallback;
-  uint64_t n_quad_fast;   /* point-in-quadrilateral decisions taken by the verified inner-box fast accept */
-  uint64_t n_quad_exact;  /* ... taken by the exact QuadrilateralTest evaluation */
+  uint64_t n_quad_fast;   /* point-in-quadrilateral decisions taken in single precision (inner box / filtered test) */
+  uint64_t n_quad_exact;  /* ... taken by the exact QuadrilateralTest evaluation (compacted exact pass) */
   double filter_eps0, filter_eps1;
+  uint64_t n_bev_exact;   /* BEV pixels of outlined plateaus computed by the exact double chain */
 } ssd_gpu_stats;
 int ssd_gpu_get_stats(ssd_gpu_ctx *ctx, ssd_gpu_stats *out);
 /* Per-stage device time of the last call made with SSD_FLAG_STAGE_TIMING: sum of per-launch durations (ms) and

@@ -68,7 +68,7 @@ class Timing(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [("n_points", C.c_uint64), ("n_exact_fallback", C.c_uint64), ("n_quad_fast", C.c_uint64), ("n_quad_exact", C.c_uint64), ("filter_eps0", C.c_double), ("filter_eps1", C.c_double)]
+    _fields_ = [("n_points", C.c_uint64), ("n_exact_fallback", C.c_uint64), ("n_quad_fast", C.c_uint64), ("n_quad_exact", C.c_uint64), ("filter_eps0", C.c_double), ("filter_eps1", C.c_double), ("n_bev_exact", C.c_uint64)]
 
 
 class Scene(C.Structure):

@@ -39,6 +39,15 @@ struct DevParams
   float cf[3], hf[3];
   float hirf, k0f;         // t = wz * hirf + k0f ~ (wz - z_min) * hir
   float E0, E1, dbin0;
+  // single-precision BEV pixel (fast_pixel): u = au . p + bu ~ (wx - x_min) * x_to_image, v = av . p + bv ~
+  // (y_max - wy) * y_to_image, with the error bounds |u^ - u_ref| <= Eu1 * max|p| + Eu0 (same for v)
+  float au[3], bu, av[3], bv;
+  float Eu0, Eu1, Ev0, Ev1;
+  float Tf;                // max |x|, |y| of an in-range world point (quadfilter margins)
+  // the same bounds for ANY in-range point: max|p| <= Mmax (derive_params), so eps <= epsc etc. are constants
+  float epsc, euc, evc;
+  // packed pairs for the f32x2 pipes: {af[j], af[3+j]}, {bf[0], bf[1]} (world x,y) and {au[j], av[j]}, {bu, bv} (BEV pixel)
+  unsigned long long axy2[3], bxy2, auv2[3], buv2;
 };
 
 struct SegmentDev
@@ -67,6 +76,22 @@ struct QuadTestDev
   float ib_cx, ib_hx, ib_cy, ib_hy;
 };
 
+// Single-precision image of one QuadTestDev for the filtered point-in-quadrilateral decision (quadfilter_eval):
+// the same bounding box / row / cell / half-plane structure evaluated in f32 with rigorous margins; a point
+// whose f32 evaluation comes within a margin of any comparison is re-decided by the exact double test.
+struct QuadFilterDev
+{
+  float4 ib;             // verified inner box (quadtest_inner_box): cx, hx, cy, hy; hx < 0: none
+  float4 bb;             // bounding box: lo_x, hi_x, lo_y, hi_y
+  float4 seg[6];         // kx, ky, c, margin; signed so that "passes" <=> kx*x + ky*y + c > 0. [4] always true, [5] always false
+  float row_thr[2];      // y thresholds between rows (+inf when unused)
+  float cell_thr[3][2];  // x thresholds between the cells of a row
+  unsigned char cell_s[3][3][2]; // the two half-plane slots of each cell (indices into seg[])
+  unsigned char ok, pad8;        // ok = 0: no filter for this quadrilateral (every point takes the exact test)
+  float pad[3];
+  float4 ibe;            // inner box for the constant-eps fast accept: cx, cy, hx - epsc, hy - epsc (negative: none)
+};
+
 struct PlateauDev
 {
   int height, hmin, hmax;
@@ -87,12 +112,20 @@ struct PlateauDev
 struct FrameDev
 {
   unsigned hist[SSD_BINS_PAD];
-  unsigned char lut[SSD_BINS_PAD]; // bin code -> segment label
+  unsigned short lut16[SSD_BINS_PAD]; // bin code -> segment label | 0x100 if that label gets a BEV image (k_peaks)
+  unsigned quad_amask;                // labels k_quad_reduce reduces: ground + valid plateaus with a usable test (k_frame_logic)
+  unsigned pad_a[3];
+  QuadFilterDev qf[SSD_GPU_MAX_PLATEAUS]; // f32 image of each step's QuadrilateralTest (k_frame_logic)
   unsigned status;
   int n_plateaus;
   int ground_index, first_outlined, first_valid;
   int n_steps;
   unsigned n_nonzero, n_in_range;
+  // counters of the filtered decisions (ssd_gpu_get_stats)
+  unsigned n_exact_bin;  // k_transform_bin: points decided by the exact double chain
+  unsigned n_quad_pts;   // k_quad_reduce: points tested against a quadrilateral
+  unsigned n_def_quad;   // ... of which went to the compacted exact pass
+  unsigned n_def_bev;    // k_label_bev: BEV pixels computed by the exact double chain
   PlateauDev plat[SSD_GPU_MAX_PLATEAUS];
 };
 
@@ -101,6 +134,7 @@ struct FrameOut
 {
   ssd_gpu_frame_info info;
   ssd_gpu_step steps[SSD_GPU_MAX_STEPS];
+  unsigned n_exact_bin, n_quad_pts, n_def_quad, n_def_bev;
 };
 
 struct P2d
@@ -140,6 +174,43 @@ __device__ __forceinline__ double camera_to_world_z(const DevParams &p, float fx
 {
   const double x = fx, y = fy, z = fz;
   return ((p.a[6] * x + p.a[7] * y) + p.a[8] * z) + p.b[2];
+}
+
+// ---- packed f32x2 arithmetic (Blackwell FFMA2 / FADD2: two single-precision operations per instruction) ----
+typedef unsigned long long f32x2_t;
+__host__ __device__ __forceinline__ f32x2_t f2_pack_bits(float lo, float hi)
+{
+  union { float f[2]; unsigned long long u; } c;
+  c.f[0] = lo;
+  c.f[1] = hi;
+  return c.u;
+}
+__device__ __forceinline__ f32x2_t f2_pack(float lo, float hi)
+{
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2_t v, float &lo, float &hi)
+{
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c)
+{
+  f32x2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2_t f2_add(f32x2_t a, f32x2_t b)
+{
+  f32x2_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// {c0.lo*x + ..., c0.hi*x + ...}: two rows of an affine map applied to one point, same fma order as the scalar chains
+__device__ __forceinline__ f32x2_t f2_affine(const f32x2_t c[3], f32x2_t b, float x, float y, float z)
+{
+  return f2_fma(c[2], f2_pack(z, z), f2_fma(c[1], f2_pack(y, y), f2_fma(c[0], f2_pack(x, x), b)));
 }
 
 // z>0 (pointcloud.cpp:143-146), range (pointcloud.cpp:155-163), height index (pointcloud.cpp:175)
@@ -191,6 +262,24 @@ __device__ __forceinline__ unsigned point_code_filtered(const DevParams &p, floa
   const bool valid = z > 0.f;
   uncertain = valid && !(out || (in && bin_ok));
   return valid ? (out ? SSD_CODE_OUT_OF_RANGE : bin) : SSD_CODE_INVALID;
+}
+
+// fast_pixel with the constant error bounds euc / evc and packed arithmetic (for points known to be in range)
+__device__ __forceinline__ bool fast_pixel2(const DevParams &p, float x, float y, float z, int &ix, int &iy)
+{
+  const float MAGIC = 12582912.0f;
+  const f32x2_t uv = f2_affine(p.auv2, p.buv2, x, y, z);
+  const f32x2_t s = f2_add(uv, f2_pack(MAGIC, MAGIC));
+  const f32x2_t d = f2_add(uv, f2_add(f2_pack(MAGIC, MAGIC), s ^ 0x8000000080000000ull)); // uv - (s - MAGIC), exact inner difference
+  float uu, vv, su, sv, du, dv;
+  f2_unpack(uv, uu, vv);
+  f2_unpack(s, su, sv);
+  f2_unpack(d, du, dv);
+  ix = __float_as_int(su) - 0x4B400000 - (du < 0.f ? 1 : 0);
+  iy = __float_as_int(sv) - 0x4B400000 - (dv < 0.f ? 1 : 0);
+  const bool ok_u = fabsf(du) > p.euc && uu > p.euc && uu < (float)p.W - p.euc;
+  const bool ok_v = fabsf(dv) > p.evc && vv > p.evc && vv < (float)p.H - p.evc;
+  return ok_u && ok_v;
 }
 
 // Projection2D::worldToImage (pointcloud.cpp:79-83)
@@ -629,6 +718,113 @@ __device__ inline void quadtest_inner_box(QuadTestDev &t, const P2d q[4])
   t.ib_cy = cyf;
   t.ib_hx = __double2float_rd(hx);
   t.ib_hy = __double2float_rd(hy);
+}
+
+// ---- filtered point-in-quadrilateral -------------------------------------------------------------------
+// f32 image of the test: called once per emitted step by k_frame_logic, after quadtest_init/inner_box.
+// T bounds |x|, |y| of every point the filter will see (in-range world points).
+__device__ inline void quadfilter_build(QuadFilterDev &f, const QuadTestDev &t, float T, float epsc)
+{
+  // |w^ - cx| < hx - epsc  =>  |w_ref - cx| < hx (the subtraction rounds down: the accept region only shrinks)
+  f.ibe = make_float4(t.ib_cx, t.ib_cy, t.ib_hx > 0.f ? __fadd_rd(t.ib_hx, -epsc) : -1.f, t.ib_hy > 0.f ? __fadd_rd(t.ib_hy, -epsc) : -1.f);
+  const float u = 5.9604645e-08f; // 2^-24
+  const float inf = __int_as_float(0x7f800000);
+  f.ok = t.status == 0;
+  f.pad8 = 0;
+  f.ib = make_float4(t.ib_cx, t.ib_hx, t.ib_cy, t.ib_hy);
+  for(int i = 0; i < 4; i++)
+  {
+    const SegmentDev &s = t.seg[i];
+    // passes <=> isLeft == insideIsLeft <=> (val > 0) == (left_is_pos == inside_is_left)
+    const double sg = (s.left_is_pos != 0) == (t.inside_is_left != 0) ? 1.0 : -1.0;
+    const double kx = s.steep ? 1.0 : s.k, ky = s.steep ? s.k : 1.0;
+    // |v^ - v_ref| <= 2 eps + 4u (T|kx| + T|ky| + |c|); stored with a factor 2 of slack (eps part added at run time)
+    f.seg[i] = make_float4((float)(sg * kx), (float)(sg * ky), (float)(sg * s.c),
+                           8.f * u * (float)(T * (fabs(kx) + fabs(ky)) + fabs(s.c)) * 1.001f + 1e-30f);
+  }
+  f.seg[4] = make_float4(0.f, 0.f, 1.f, 0.f);
+  f.seg[5] = make_float4(0.f, 0.f, -1.f, 0.f);
+  f.bb = make_float4((float)t.tb_lo_x, (float)t.tb_hi_x, (float)t.tb_lo_y, (float)t.tb_hi_y);
+  f.row_thr[0] = f.row_thr[1] = inf;
+  for(int r = 0; r < 3; r++)
+  {
+    f.cell_thr[r][0] = f.cell_thr[r][1] = inf;
+    for(int c = 0; c < 3; c++)
+      f.cell_s[r][c][0] = f.cell_s[r][c][1] = 5;
+  }
+  if(!f.ok)
+    return;
+  for(int r = 0; r < t.nrow; r++)
+  {
+    if(r < t.nrow - 1)
+      f.row_thr[r] = (float)t.row_upper_y[r];
+    for(int c = 0; c < t.ncell[r]; c++)
+    {
+      if(c < t.ncell[r] - 1)
+        f.cell_thr[r][c] = (float)t.cell_upper_x[r][c];
+      const int n = t.cell_nseg[r][c];
+      if(n == 0)
+        f.cell_s[r][c][0] = f.cell_s[r][c][1] = t.cell_seg[r][c][0] ? 4 : 5;
+      else
+      {
+        f.cell_s[r][c][0] = (unsigned char)t.cell_seg[r][c][0];
+        f.cell_s[r][c][1] = n == 2 ? (unsigned char)t.cell_seg[r][c][1] : 4;
+      }
+    }
+  }
+}
+
+// f32 evaluation of isPointWithin at (x, y) = single-precision world position with |error| <= eps per coordinate.
+// Returns the decision; `uncertain` is set when any comparison came within its margin (then the exact test decides).
+// Margins: thresholds and the bounding box are f32-rounded doubles (<= u*T off) compared with x, y (<= eps off):
+// 2*eps covers both because eps >= 16u*T (derive_params). Half planes: 3*eps + seg.w (quadfilter_build).
+__device__ __forceinline__ bool quadfilter_eval(const QuadFilterDev &f, float x, float y, float eps, bool &uncertain)
+{
+  const float M = eps + eps;
+  const float4 bb = f.bb;
+  const float dbb = fminf(fminf(x - bb.x, bb.y - x), fminf(y - bb.z, bb.w - y));
+  const float r0 = f.row_thr[0], r1 = f.row_thr[1];
+  const int r = (y >= r0 ? 1 : 0) + (y >= r1 ? 1 : 0);
+  const float c0 = f.cell_thr[r][0], c1 = f.cell_thr[r][1];
+  const int c = (x >= c0 ? 1 : 0) + (x >= c1 ? 1 : 0);
+  const float dthr = fminf(fminf(fabsf(y - r0), fabsf(y - r1)), fminf(fabsf(x - c0), fabsf(x - c1)));
+  const float4 s0 = f.seg[f.cell_s[r][c][0]], s1 = f.seg[f.cell_s[r][c][1]];
+  const float v0 = fmaf(x, s0.x, fmaf(y, s0.y, s0.z)), v1 = fmaf(x, s1.x, fmaf(y, s1.y, s1.z));
+  const float m0 = fmaf(3.f, eps, s0.w), m1 = fmaf(3.f, eps, s1.w);
+  const bool in = v0 > m0 && v1 > m1, out = v0 < -m0 || v1 < -m1;
+  const bool sel = dthr > M; // row / cell selection is certain
+  const bool cin = dbb > M && sel && in;
+  const bool cout = dbb < -M || (sel && out);
+  uncertain = !(cin || cout) || !f.ok;
+  return cin;
+}
+
+// Single-precision BEV pixel of an in-range point. Returns true when (ix, iy) is certainly the pixel the exact
+// double chain (camera_to_world_xy + bev_pixel) produces: u^, v^ are further than their error bound from every
+// integer boundary and from the image edges (so neither the x == W wrap nor an out-of-image pixel can occur).
+// m = max(|x|,|y|,|z|). floor() via the 1.5*2^23 trick (no conversion instruction).
+__device__ __forceinline__ bool fast_pixel(const DevParams &p, float x, float y, float z, float m, int &ix, int &iy)
+{
+  const float MAGIC = 12582912.0f;
+  const float uu = fmaf(p.au[2], z, fmaf(p.au[1], y, fmaf(p.au[0], x, p.bu)));
+  const float vv = fmaf(p.av[2], z, fmaf(p.av[1], y, fmaf(p.av[0], x, p.bv)));
+  const float eu = fmaf(p.Eu1, m, p.Eu0), ev = fmaf(p.Ev1, m, p.Ev0);
+  const float su = uu + MAGIC, sv = vv + MAGIC;
+  const float du = uu - (su - MAGIC), dv = vv - (sv - MAGIC); // signed distance to the nearest integer
+  ix = __float_as_int(su) - 0x4B400000 - (du < 0.f ? 1 : 0);
+  iy = __float_as_int(sv) - 0x4B400000 - (dv < 0.f ? 1 : 0);
+  const bool ok_u = fabsf(du) > eu && uu > eu && uu < (float)p.W - eu;
+  const bool ok_v = fabsf(dv) > ev && vv > ev && vv < (float)p.H - ev;
+  return ok_u && ok_v;
+}
+
+// world z of a vertex in 2^-36 m fixed point, straight from the f32 camera coordinates: three fused multiply-adds
+// with the coefficients pre-scaled by 2^36 (exact), one conversion. Differs from rounding the reference's
+// double wz by < 2^-37 m + 4 ulp(double): far inside the error the fixed-point sum itself allows.
+__device__ __forceinline__ long long z_to_fix_fused(const DevParams &p, float fx, float fy, float fz)
+{
+  const double S = (double)(1ull << SSD_FIX_SHIFT);
+  return __double2ll_rn(__fma_rn(p.a[8] * S, (double)fz, __fma_rn(p.a[7] * S, (double)fy, __fma_rn(p.a[6] * S, (double)fx, p.b[2] * S))));
 }
 
 // fixed-point z for the order-independent (deterministic) per-step sum

@@ -14,9 +14,7 @@
 #include <vector>
 
 #define SSD_PT_ITERS 4   // k_transform_bin: 4096 points per block
-#define SSD_PT_ITERS2 8  // k_label_bev / k_quad_reduce: 8192 points per block (amortises their per-block prologue)
 #define SSD_TILE_POINTS (SSD_PT_THREADS * 4 * SSD_PT_ITERS)
-#define SSD_TILE_POINTS2 (SSD_PT_THREADS * 4 * SSD_PT_ITERS2)
 
 static thread_local std::string g_create_error;
 
@@ -41,13 +39,13 @@ struct ssd_gpu_ctx
   unsigned char *d_labels = nullptr; // max_frames * N
   unsigned *d_bev = nullptr; // 2 x chunk_frames * MAX_PLATEAUS * bm_words (per stream)
   float *d_stage[2]{};            // host-input staging, chunk_frames frames each
+  int pt_blocks_target = 0;       // blocks per launch of the tile-looping point kernels
   int n_frames_last = 0;
   int flags_last = 0;
   ssd_gpu_timing timing{};
   std::string err;
   // single-stage scratch
   unsigned char *d_img = nullptr;
-  unsigned long long *d_counters = nullptr; // [0] points that needed the exact double path in k_transform_bin
   // optional per-kernel events (SSD_FLAG_STAGE_TIMING): (SSD_GPU_N_STAGES + 1) per chunk
   std::vector<cudaEvent_t> stage_ev;
   int stage_chunks = 0;
@@ -132,6 +130,59 @@ static int derive_params(const ssd_gpu_config &c, const ssd_gpu_transform &t, De
     d.k0f = (float)(-c.z_min * d.hir);
     // bin arithmetic: |t^ - t_ref| <= hir*eps + 4u*(n_bins + |z_min|*hir) (+ f32 rounding of hir itself)
     d.dbin0 = (float)(16.0 * u * (d.n_bins + std::fabs(c.z_min) * d.hir + 1.0) + 1e-6);
+    // BEV pixel in single precision (fast_pixel): u = sx*(wx - x_min), v = sy*(y_max - wy) folded into one fma chain.
+    // |u^ - u_ref| <= 4u (S'm + |b'|) (coefficient rounding + three fma roundings; the reference's own f64
+    // roundings are ~2^-50 of that); used: 10u, i.e. a factor 2.5 of slack, plus an absolute 1e-6 px.
+    const double sx = d.x_to_image, sy = d.y_to_image;
+    double Su = 0, Sv = 0;
+    for(int j = 0; j < 3; j++)
+    {
+      d.au[j] = (float)(t.a[j] * sx);
+      d.av[j] = (float)(-t.a[3 + j] * sy);
+      Su += std::fabs(t.a[j] * sx);
+      Sv += std::fabs(t.a[3 + j] * sy);
+    }
+    const double bu = (t.b[0] - c.x_min) * sx, bv = (c.y_max - t.b[1]) * sy;
+    d.bu = (float)bu;
+    d.bv = (float)bv;
+    d.Eu1 = (float)(10.0 * u * Su * 1.001);
+    d.Eu0 = (float)(10.0 * u * std::fabs(bu) * 1.001 + 1e-6);
+    d.Ev1 = (float)(10.0 * u * Sv * 1.001);
+    d.Ev0 = (float)(10.0 * u * std::fabs(bv) * 1.001 + 1e-6);
+    d.Tf = (float)(std::max({ std::fabs(c.x_min), std::fabs(c.x_max), std::fabs(c.y_min), std::fabs(c.y_max) }) * 1.001 + 1e-3);
+    // Constant bounds for points that are known to be in range (everything k_label_bev / k_quad_reduce touch):
+    // p = A^-1 (w - b), so max|p| <= max_i sum_j |A^-1_ij| (T_j + |b_j|) =: Mmax (1 % slack). A singular A gives
+    // infinite bounds: every decision then goes to the exact pass.
+    {
+      const double *a = t.a;
+      const double det = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
+      double Mmax = INFINITY;
+      if(std::fabs(det) > 1e-12)
+      {
+        const double inv[9] = { (a[4] * a[8] - a[5] * a[7]) / det, (a[2] * a[7] - a[1] * a[8]) / det, (a[1] * a[5] - a[2] * a[4]) / det,
+                                (a[5] * a[6] - a[3] * a[8]) / det, (a[0] * a[8] - a[2] * a[6]) / det, (a[2] * a[3] - a[0] * a[5]) / det,
+                                (a[3] * a[7] - a[4] * a[6]) / det, (a[1] * a[6] - a[0] * a[7]) / det, (a[0] * a[4] - a[1] * a[3]) / det };
+        Mmax = 0;
+        for(int i = 0; i < 3; i++)
+        {
+          double r = 0;
+          for(int j = 0; j < 3; j++)
+            r += std::fabs(inv[i * 3 + j]) * (std::max(std::fabs(lo[j]), std::fabs(hi[j])) + std::fabs(t.b[j]));
+          Mmax = std::max(Mmax, r);
+        }
+        Mmax *= 1.01;
+      }
+      d.epsc = (float)((double)d.E1 * Mmax * 1.0001) + d.E0;
+      d.euc = (float)((double)d.Eu1 * Mmax * 1.0001) + d.Eu0;
+      d.evc = (float)((double)d.Ev1 * Mmax * 1.0001) + d.Ev0;
+    }
+    for(int j = 0; j < 3; j++)
+    {
+      d.axy2[j] = f2_pack_bits(d.af[j], d.af[3 + j]);
+      d.auv2[j] = f2_pack_bits(d.au[j], d.av[j]);
+    }
+    d.bxy2 = f2_pack_bits(d.bf[0], d.bf[1]);
+    d.buv2 = f2_pack_bits(d.bu, d.bv);
   }
   if(d.n_bins < 3 || d.n_bins > SSD_GPU_MAX_BINS)
     return SSD_E_RANGE;
@@ -291,11 +342,13 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, int frame
   unsigned char *labels = ctx->d_labels + (size_t)frame0 * p.N;
   unsigned *bev = ctx->d_bev + (size_t)s * ctx->chunk_frames * SSD_GPU_MAX_PLATEAUS * ctx->bm_words;
   const dim3 gpt(p.tiles_per_frame, nf);
-  const dim3 gpt2((p.N + SSD_TILE_POINTS2 - 1) / SSD_TILE_POINTS2, nf);
-  const size_t qt_smem = sizeof(QuadTestDev) * SSD_GPU_MAX_PLATEAUS;
+  // k_label_bev / k_quad_reduce: each block loops over tiles of its frame; enough blocks for ~6 waves of the GPU
+  const int tiles2 = (p.N + SSD_WT_PX * SSD_PT_WARPS - 1) / (SSD_WT_PX * SSD_PT_WARPS); // at least one warp-tile per warp
+  const int bpf = std::max(1, std::min(tiles2, (ctx->pt_blocks_target + nf - 1) / nf));
+  const dim3 gpt2(bpf, nf);
 
   STAGE_EV(0);
-  k_transform_bin<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, 0, st>>>(p, xyz_dev, labels, frames, ctx->d_counters);
+  k_transform_bin<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, 0, st>>>(p, xyz_dev, labels, frames);
   STAGE_EV(1);
   k_peaks<<<nf, 32, 0, st>>>(p, frames, nf);
   STAGE_EV(2);
@@ -305,7 +358,7 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, int frame
   STAGE_EV(4);
   k_frame_logic<<<nf, 32, 0, st>>>(p, frames, nf);
   STAGE_EV(5);
-  k_quad_reduce<<<gpt2, SSD_PT_THREADS, qt_smem, st>>>(p, xyz_dev, labels, frames, bev, ctx->bm_words, ctx->d_counters);
+  k_quad_reduce<<<gpt2, SSD_PT_THREADS, 0, st>>>(p, xyz_dev, labels, frames, bev, ctx->bm_words);
   STAGE_EV(6);
   k_finalize<<<nf, SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, ctx->d_out + frame0, bev, ctx->bm_words, ctx->smem_cap_words);
   STAGE_EV(7);
@@ -345,7 +398,6 @@ void ssd_gpu_destroy(ssd_gpu_ctx *ctx)
   cudaFree(ctx->d_stage[0]);
   cudaFree(ctx->d_stage[1]);
   cudaFree(ctx->d_img);
-  cudaFree(ctx->d_counters);
   for(int i = 0; i < 2; i++)
   {
     if(ctx->stream[i])
@@ -415,6 +467,14 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
     ctx->chunk_frames = cf;
   }
 
+  {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    int bt = sms * 4 * 6;
+    if(const char *e = getenv("SSD_GPU_PT_BLOCKS"))
+      bt = atoi(e);
+    ctx->pt_blocks_target = std::max(1, bt);
+  }
   int max_optin = 0;
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   cudaFuncAttributes fa{};
@@ -438,9 +498,7 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
   cudaFuncSetAttribute(k_outline, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
   cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
   cudaFuncSetAttribute(k_test_front_edge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-  // k_quad_reduce: static compaction list + dynamic QuadrilateralTest table exceed the 48 KB default together
-  if(cudaFuncSetAttribute(k_quad_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(QuadTestDev) * SSD_GPU_MAX_PLATEAUS)) != cudaSuccess)
-    return bail("cudaFuncSetAttribute(k_quad_reduce) failed", SSD_E_CUDA);
+
 
 #define CKC(call)                                                            \
   do                                                                         \
@@ -471,8 +529,6 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
   const size_t bev_bytes = (size_t)2 * ctx->chunk_frames * SSD_GPU_MAX_PLATEAUS * ctx->bm_words * 4;
   CKC(cudaMalloc(&ctx->d_bev, bev_bytes));
   CKC(cudaMemset(ctx->d_bev, 0, bev_bytes)); // bitmaps are self-cleaning afterwards
-  CKC(cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)));
-  CKC(cudaMemset(ctx->d_counters, 0, 8 * sizeof(unsigned long long)));
   CKC(cudaMemset(ctx->d_frames, 0, sizeof(FrameDev) * (size_t)max_frames));
   CKC(cudaMemset(ctx->d_out, 0, sizeof(FrameOut) * (size_t)max_frames));
   memset(ctx->h_out, 0, sizeof(FrameOut) * (size_t)max_frames);
@@ -519,7 +575,6 @@ static int process_common(ssd_gpu_ctx *ctx, const float *xyz, bool host_input, i
   CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_start, 0));
   // per-frame state: histogram must start at zero
   CK(cudaMemsetAsync(ctx->d_frames, 0, sizeof(FrameDev) * (size_t)n_frames, ctx->stream[0]));
-  CK(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream[0]));
   CK(cudaEventRecord(ctx->ev_chunk_done[0], ctx->stream[0]));
   CK(cudaStreamWaitEvent(ctx->stream[1], ctx->ev_chunk_done[0], 0));
 
@@ -701,13 +756,20 @@ int ssd_gpu_get_stats(ssd_gpu_ctx *ctx, ssd_gpu_stats *out)
 {
   if(!ctx || !out)
     return SSD_E_INVALID_ARG;
-  CK(cudaSetDevice(ctx->device));
-  unsigned long long c[8];
-  CK(cudaMemcpy(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+  uint64_t c[4] = { 0, 0, 0, 0 };
+  for(int f = 0; f < ctx->n_frames_last; f++)
+  {
+    const FrameOut &o = ctx->h_out[f];
+    c[0] += o.n_exact_bin;
+    c[1] += o.n_quad_pts;
+    c[2] += o.n_def_quad;
+    c[3] += o.n_def_bev;
+  }
   out->n_points = (uint64_t)ctx->n_frames_last * (uint64_t)ctx->dp.N;
   out->n_exact_fallback = c[0];
-  out->n_quad_fast = c[1];
+  out->n_quad_fast = c[1] - c[2];
   out->n_quad_exact = c[2];
+  out->n_bev_exact = c[3];
   out->filter_eps0 = ctx->dp.E0;
   out->filter_eps1 = ctx->dp.E1;
   return SSD_OK;

@@ -852,11 +852,14 @@ __global__ void __launch_bounds__(32) k_frame_logic(const __grid_constant__ DevP
     }
     quadtest_init(s_qt[lane], q);
     quadtest_inner_box(s_qt[lane], q);
+    quadfilter_build(F.qf[lane], s_qt[lane], p.Tf, p.epsc);
     P.valid = 1;
     P.quad_status = s_qt[lane].status;
   }
   const unsigned em = __ballot_sync(0xffffffffu, emit);
   const unsigned bad = __ballot_sync(0xffffffffu, emit && s_qt[lane].status != 0);
+  if(lane == 0)
+    F.quad_amask = em & ~bad;
   __syncwarp();
   // coalesced copy of the emitted tests to global memory
   for(int k = 0; k < K; k++)
@@ -923,7 +926,7 @@ __global__ void __launch_bounds__(SSD_OL_THREADS) k_finalize(const __grid_consta
     {
       PlateauDev &P = F.plat[i];
       if(P.valid && P.quad_status == 0)
-        P.mean_z = ((double)((long long)P.sum_fix - (long long)P.n_in_quad * (1ll << 37)) / (double)(1ull << SSD_FIX_SHIFT)) / (double)P.n_in_quad; // calcAverageZ (:574-581); the sum carries a 2^37 bias per point
+        P.mean_z = ((double)(long long)P.sum_fix / (double)(1ull << SSD_FIX_SHIFT)) / (double)P.n_in_quad; // calcAverageZ (:574-581)
     }
     if(groundStep)
     {
@@ -1003,4 +1006,8 @@ __global__ void __launch_bounds__(SSD_OL_THREADS) k_finalize(const __grid_consta
   O.info.n_steps = nSteps;
   O.info.n_nonzero = F.n_nonzero;
   O.info.n_in_range = F.n_in_range;
+  O.n_exact_bin = F.n_exact_bin;
+  O.n_quad_pts = F.n_quad_pts;
+  O.n_def_quad = F.n_def_quad;
+  O.n_def_bev = F.n_def_bev;
 }

@@ -47,13 +47,15 @@ __device__ __forceinline__ Quad4 load_quad(const float4 *__restrict__ xyz4, size
 // ---------------------------------------------------------------------------------------------
 template<int ITERS>
 __global__ void __launch_bounds__(SSD_PT_THREADS) k_transform_bin(const __grid_constant__ DevParams p, const float *__restrict__ xyz,
-                                                                   unsigned char *__restrict__ codes, FrameDev *__restrict__ frames,
-                                                                   unsigned long long *__restrict__ n_exact)
+                                                                   unsigned char *__restrict__ codes, FrameDev *__restrict__ frames)
 {
   __shared__ unsigned s_hist[SSD_BINS_PAD];
+  __shared__ unsigned s_exact;
   const int tid = threadIdx.x;
   const int frame = blockIdx.y;
   s_hist[tid] = 0; // SSD_PT_THREADS == SSD_BINS_PAD
+  if(tid == 0)
+    s_exact = 0;
   __syncthreads();
 
   const size_t fbase = (size_t)frame * p.N;
@@ -118,12 +120,14 @@ __global__ void __launch_bounds__(SSD_PT_THREADS) k_transform_bin(const __grid_c
   }
   if(run_n)
     atomicAdd(&s_hist[run_code], run_n);
-  if(exact && n_exact)
-    atomicAdd(n_exact, (unsigned long long)exact);
+  if(exact)
+    atomicAdd(&s_exact, exact);
   __syncthreads();
   const unsigned sum = s_hist[tid];
   if(sum)
     atomicAdd(&frames[frame].hist[tid], sum);
+  if(tid == 0 && s_exact)
+    atomicAdd(&frames[frame].n_exact_bin, s_exact);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -235,7 +239,15 @@ __global__ void __launch_bounds__(32) k_peaks(const __grid_constant__ DevParams 
     F.status = status;
   }
   __syncwarp();
-  reinterpret_cast<unsigned long long *>(F.lut)[lane] = reinterpret_cast<const unsigned long long *>(s_lut)[lane];
+  {
+    // bin code -> label | 0x100 for the labels that get a BEV image (first_outlined .. K-1)
+    const int K = s_K, fo = s_first_outlined;
+    for(int b = lane; b < SSD_BINS_PAD; b += 32)
+    {
+      const unsigned l = s_lut[b];
+      F.lut16[b] = (unsigned short)(l | (((int)l >= fo && (int)l < K) ? 0x100u : 0u));
+    }
+  }
   if(lane < s_K)
   {
     PlateauDev &P = F.plat[lane];
@@ -258,426 +270,577 @@ __global__ void __launch_bounds__(32) k_peaks(const __grid_constant__ DevParams 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Block-level stream compaction shared by k_label_bev and k_quad_reduce.
-// A block owns a tile of SSD_TILE2 consecutive pixels. Phase A: every thread reads 16 labels (one 16 B load),
-// decides which of them need per-point geometry, and the block compacts those (label, local index) pairs
-// into shared memory in pixel order (warp-shuffle scan + one shared-memory round). Phase B walks the compact
-// list densely: full warps, coalesced 12 B vertex gathers, no divergence on "does this point matter".
+// Shared machinery of k_label_bev and k_quad_reduce: warp-level stream compaction per segment.
+// Both walk a frame in pixel order. grid = (blocks per frame, frames): a block loads the frame's small tables
+// once; each of its warps then works through its own contiguous run of warp-tiles (1024 consecutive pixels,
+// i.e. eight coalesced 128 B label loads per warp), with no block-level barrier until the very end.
+//   Phase A (all pixels, a handful of instructions per 4-pixel word): label word -> which of its pixels matter
+//     -> the warp compacts the words with at least one such pixel into its private list in shared memory
+//     (ballot + popc prefix, no atomics). The next warp-tile's label words are requested as soon as the
+//     current ones are consumed.
+//   Phase B (dense): the warp walks the compacted list 32 words = 128 pixels at a time: three aligned 16 B
+//     vertex loads per lane, issued one step ahead; only words that matter are ever fetched.
+// Every per-point decision in phase B is first taken in single precision with a rigorous error bound
+// (fast_pixel, quadfilter_eval). The few points that come within the bound of a threshold are appended to a
+// second compacted list and re-decided by the exact double-precision chain in a dense pass at the end of the
+// warp-tile, instead of diverging the warp in line. Both lists have one slot per word / pixel: no overflow.
 // ---------------------------------------------------------------------------------------------
-#define SSD_TILE2 8192
-#define SSD_ROUND2 (SSD_PT_THREADS * 16) // points per phase-A round
+#define SSD_WT_PX 1024   // pixels per warp-tile = 32 lanes x 8 label words x 4 pixels
+#define SSD_WT_WORDS 8
+#define SSD_DEF_BEVONLY 0x8000u
 
-struct CompactList
+struct WarpLists
 {
-  unsigned entry[SSD_TILE2]; // label << 16 | local index
-  unsigned warp_tot[SSD_PT_WARPS];
-  unsigned count;
+  unsigned lab[SSD_PT_WARPS][SSD_WT_PX / 4];        // the warp-tile's label words
+  unsigned short act[SSD_PT_WARPS][SSD_WT_PX / 4];  // word index << 4 | mask of the pixels that matter
+  unsigned short def[SSD_PT_WARPS][SSD_WT_PX];      // flag | word index << 2 | pixel of the word
+  unsigned ndef[SSD_PT_WARPS];
 };
 
-// append the set bits of mask16 (points tid*16+b of this round) in order; all threads of the block call
-__device__ __forceinline__ void compact_append(CompactList &L, unsigned mask16, const unsigned lab[4], int round, int tid)
+// Append word (it*32+lane) with pixel mask am4 to the warp's list (length n, warp-uniform); returns the new
+// length. All 32 lanes call.
+__device__ __forceinline__ unsigned compact_append(unsigned short *list, unsigned n, unsigned am4, int it, int lane)
 {
-  const int lane = tid & 31, warp = tid >> 5;
-  const unsigned n = __popc(mask16);
-  unsigned incl = n;
-#pragma unroll
-  for(int d = 1; d < 32; d <<= 1)
-  {
-    const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
-    if(lane >= d)
-      incl += t;
-  }
-  if(lane == 31)
-    L.warp_tot[warp] = incl;
-  __syncthreads();
-  unsigned base = L.count;
-#pragma unroll
-  for(int w = 0; w < SSD_PT_WARPS; w++)
-    base += w < warp ? L.warp_tot[w] : 0u;
-  unsigned off = base + incl - n;
-  unsigned m = mask16;
-  while(m)
-  {
-    const int b = __ffs(m) - 1;
-    m &= m - 1;
-    const unsigned l = (lab[b >> 2] >> (8 * (b & 3))) & 0xffu;
-    L.entry[off++] = (l << 16) | (unsigned)(round * SSD_ROUND2 + tid * 16 + b);
-  }
-  __syncthreads();
-  if(tid == SSD_PT_THREADS - 1)
-    L.count = base + incl; // last thread's inclusive end = new total
-  __syncthreads();
+  const unsigned b = __ballot_sync(0xffffffffu, am4 != 0u);
+  if(am4)
+    list[n + __popc(b & ((1u << lane) - 1u))] = (unsigned short)(((unsigned)(it * 32 + lane) << 4) | am4);
+  return n + __popc(b);
 }
 
-// per-byte "label is one of the first 32 and its bit is set in amask"
-__device__ __forceinline__ unsigned active_mask4(unsigned w, unsigned amask)
+__device__ __forceinline__ void defer_push(WarpLists &L, int warp, unsigned e)
 {
-  unsigned m = 0;
-#pragma unroll
-  for(int j = 0; j < 4; j++)
-  {
-    const unsigned l = (w >> (8 * j)) & 0xffu;
-    m |= (l < 32u && ((amask >> l) & 1u)) ? (1u << j) : 0u;
-  }
-  return m;
+  const unsigned slot = atomicAdd(&L.ndef[warp], 1u);
+  L.def[warp][slot] = (unsigned short)e;
+}
+
+// contiguous run of warp-tiles [first, end) of this warp: the frame's warp-tiles are split evenly over the
+// blocks of the frame, a block's share evenly over its warps
+__device__ __forceinline__ void warp_tile_range(int n_wt, int warp, int &first, int &end)
+{
+  const int per_block = (n_wt + gridDim.x - 1) / gridDim.x;
+  const int b0 = blockIdx.x * per_block, b1 = min(n_wt, b0 + per_block);
+  const int per_warp = (per_block + SSD_PT_WARPS - 1) / SSD_PT_WARPS;
+  first = min(b1, b0 + warp * per_warp);
+  end = min(b1, first + per_warp);
+}
+
+__device__ __forceinline__ void load3(const float4 *__restrict__ src, float4 &a, float4 &b, float4 &c)
+{
+  a = __ldg(src);
+  b = __ldg(src + 1);
+  c = __ldg(src + 2);
 }
 
 // ---------------------------------------------------------------------------------------------
 // k_label_bev: the per-point segment label (PlateausExtraction::extractPlateaus, pointcloud.cpp:280-343,
 // as a LUT lookup) and StairsDetector::projectToBinaryImage (:458-471) for every outlined plateau.
-// Rewrites the bin codes in place as labels. grid = (ceil(N / 8192), frames).
-// Phase B: x,y rows of the exact transform, BEV pixel, warp-aggregated OR into the plateau's bitmap
-// (match.any on the bitmap word + redux.or: one atomic per distinct word per warp).
+// Rewrites the bin codes in place as labels (a word is stored only if it changes: invalid / out-of-range
+// codes equal their labels).
 // ---------------------------------------------------------------------------------------------
+struct LabelBevShared
+{
+  unsigned short lut[SSD_BINS_PAD]; // label | 0x100 if the label gets a BEV image
+  int rmin[SSD_GPU_MAX_PLATEAUS], rmax[SSD_GPU_MAX_PLATEAUS];
+  unsigned oob, n_def;
+  WarpLists L;
+};
+
+__device__ __forceinline__ void label_bev_exact_point(const DevParams &p, const float *__restrict__ v, unsigned l, unsigned *__restrict__ fbev,
+                                                      size_t bm_words, LabelBevShared &S)
+{
+  double wx, wy;
+  camera_to_world_xy(p, __ldg(v), __ldg(v + 1), __ldg(v + 2), wx, wy);
+  int x, y;
+  if(bev_pixel(p, wx, wy, x, y))
+  {
+    atomicOr(fbev + (size_t)l * bm_words + (size_t)y * p.wpr + (x >> 5), 1u << (x & 31));
+    atomicMin(&S.rmin[l], y);
+    atomicMax(&S.rmax[l], y);
+  }
+  else
+    S.oob = 1;
+}
+
 __global__ void __launch_bounds__(SSD_PT_THREADS) k_label_bev(const __grid_constant__ DevParams p, const float *__restrict__ xyz,
                                                                unsigned char *__restrict__ labels, FrameDev *__restrict__ frames,
                                                                unsigned *__restrict__ bev, size_t bm_words)
 {
-  __shared__ CompactList L;
-  __shared__ unsigned char s_lut[SSD_BINS_PAD];
-  __shared__ int s_rmin[SSD_GPU_MAX_PLATEAUS], s_rmax[SSD_GPU_MAX_PLATEAUS];
-  __shared__ unsigned s_oob;
-  const int tid = threadIdx.x;
+  __shared__ LabelBevShared S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int frame = blockIdx.y;
   FrameDev &F = frames[frame];
-  s_lut[tid] = F.lut[tid]; // SSD_PT_THREADS == SSD_BINS_PAD
+  const size_t fbase = (size_t)frame * p.N;
+  unsigned *lab32 = reinterpret_cast<unsigned *>(labels + fbase);
+  unsigned *fbev = bev + (size_t)frame * SSD_GPU_MAX_PLATEAUS * bm_words;
+  const int nquads = p.N >> 2;
+  int wt, wt_end;
+  warp_tile_range((p.N + SSD_WT_PX - 1) / SSD_WT_PX, warp, wt, wt_end);
+
+  // the first warp-tile's code words are requested before the tables arrive
+  unsigned labw[SSD_WT_WORDS];
+#pragma unroll
+  for(int it = 0; it < SSD_WT_WORDS; it++)
+  {
+    const int q = wt * (SSD_WT_PX / 4) + it * 32 + lane;
+    labw[it] = (wt < wt_end && q < nquads) ? lab32[q] : 0xffffffffu;
+  }
+  S.lut[tid] = F.lut16[tid]; // SSD_PT_THREADS == SSD_BINS_PAD
   if(tid < SSD_GPU_MAX_PLATEAUS)
   {
-    s_rmin[tid] = 0x7fffffff;
-    s_rmax[tid] = -1;
+    S.rmin[tid] = 0x7fffffff;
+    S.rmax[tid] = -1;
+  }
+  if(tid < SSD_PT_WARPS)
+    S.L.ndef[tid] = 0;
+  if(tid == 0)
+  {
+    S.oob = 0;
+    S.n_def = 0;
+  }
+  __syncthreads();
+
+  unsigned short *act = S.L.act[warp];
+  unsigned *labs = S.L.lab[warp];
+  const unsigned bmw = (unsigned)bm_words, wpr = (unsigned)p.wpr;
+  unsigned rl = 0xffu; // label of the lane's current row-range run
+  int rlo = 0x7fffffff, rhi = -1;
+  unsigned n_def = 0;
+
+  for(; wt < wt_end; wt++)
+  {
+    // ---- phase A: codes -> labels, compaction of the words with pixels of outlined plateaus ----
+    unsigned n = 0;
+#pragma unroll
+    for(int it = 0; it < SSD_WT_WORDS; it++)
+    {
+      const unsigned cw = labw[it];
+      unsigned am4 = 0;
+      // codes 254 / 255 (out of range / invalid) are their own labels and never matter: skip such words outright
+      if((cw & 0xfefefefeu) != 0xfefefefeu)
+      {
+        const unsigned e0 = S.lut[cw & 0xffu], e1 = S.lut[(cw >> 8) & 0xffu], e2 = S.lut[(cw >> 16) & 0xffu], e3 = S.lut[cw >> 24];
+        const unsigned lab = (e0 & 0xffu) | ((e1 & 0xffu) << 8) | ((e2 & 0xffu) << 16) | (e3 << 24);
+        am4 = ((e0 >> 8) & 1u) | ((e1 >> 7) & 2u) | ((e2 >> 6) & 4u) | ((e3 >> 5) & 8u);
+        lab32[wt * (SSD_WT_PX / 4) + it * 32 + lane] = lab; // (cw is never the all-ones padding here)
+        labs[it * 32 + lane] = lab;
+      }
+      if(__any_sync(0xffffffffu, am4 != 0u))
+        n = compact_append(act, n, am4, it, lane);
+    }
+    // next warp-tile's code words
+#pragma unroll
+    for(int it = 0; it < SSD_WT_WORDS; it++)
+    {
+      const int q = (wt + 1) * (SSD_WT_PX / 4) + it * 32 + lane;
+      labw[it] = (wt + 1 < wt_end && q < nquads) ? lab32[q] : 0xffffffffu;
+    }
+    if(n == 0)
+      continue;
+    __syncwarp();
+
+    // ---- phase B: dense walk over the compacted words ----
+    const float4 *tile4 = reinterpret_cast<const float4 *>(xyz + (fbase + (size_t)wt * SSD_WT_PX) * 3);
+    unsigned e = lane < n ? act[lane] : 0u;
+    float4 c0, c1, c2, n0, n1, n2;
+    c0 = c1 = c2 = n0 = n1 = n2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if(e)
+      load3(tile4 + (e >> 4) * 3, c0, c1, c2);
+    for(unsigned s0 = 0; s0 < n; s0 += 32)
+    {
+      const unsigned i1 = s0 + 32 + lane;
+      const unsigned e1 = i1 < n ? act[i1] : 0u;
+      if(e1)
+        load3(tile4 + (e1 >> 4) * 3, n0, n1, n2);
+      const unsigned lab = labs[e >> 4];
+      const float vx[4] = { c0.x, c0.w, c1.z, c2.y }, vy[4] = { c0.y, c1.x, c1.w, c2.z }, vz[4] = { c0.z, c1.y, c2.x, c2.w };
+#pragma unroll
+      for(int j = 0; j < 4; j++)
+      {
+        if((e >> j) & 1u)
+        {
+          const unsigned l = (lab >> (8 * j)) & 0xffu;
+          int ix, iy;
+          if(fast_pixel2(p, vx[j], vy[j], vz[j], ix, iy))
+          {
+            atomicOr(fbev + (l * bmw + (unsigned)iy * wpr + (unsigned)(ix >> 5)), 1u << (ix & 31));
+            if(l != rl)
+            {
+              if(rhi >= 0)
+              {
+                atomicMin(&S.rmin[rl], rlo);
+                atomicMax(&S.rmax[rl], rhi);
+              }
+              rl = l;
+              rlo = 0x7fffffff;
+              rhi = -1;
+            }
+            rlo = min(rlo, iy);
+            rhi = max(rhi, iy);
+          }
+          else
+            defer_push(S.L, warp, ((e >> 4) << 2) | (unsigned)j);
+        }
+      }
+      e = e1;
+      c0 = n0;
+      c1 = n1;
+      c2 = n2;
+    }
+    // ---- dense exact pass over the warp's compacted uncertain points ----
+    __syncwarp();
+    const unsigned nd = S.L.ndef[warp];
+    if(nd)
+    {
+      const float *tile = reinterpret_cast<const float *>(tile4);
+      for(unsigned i = lane; i < nd; i += 32)
+      {
+        const unsigned d = S.L.def[warp][i];
+        const unsigned w = (d >> 2) & 0xffu, j = d & 3u;
+        label_bev_exact_point(p, tile + (w * 4 + j) * 3, (labs[w] >> (8 * j)) & 0xffu, fbev, bm_words, S);
+      }
+      __syncwarp();
+      n_def += nd;
+      if(lane == 0)
+        S.L.ndef[warp] = 0;
+    }
+    __syncwarp();
+  }
+  if(rhi >= 0)
+  {
+    atomicMin(&S.rmin[rl], rlo);
+    atomicMax(&S.rmax[rl], rhi);
+  }
+  if(lane == 0 && n_def)
+    atomicAdd(&S.n_def, n_def);
+  __syncthreads();
+  if(tid < SSD_GPU_MAX_PLATEAUS && S.rmax[tid] >= 0)
+  {
+    atomicMin(&F.plat[tid].row_min, S.rmin[tid]);
+    atomicMax(&F.plat[tid].row_max, S.rmax[tid]);
   }
   if(tid == 0)
   {
-    s_oob = 0;
-    L.count = 0;
+    if(S.oob)
+      atomicOr(&F.status, SSD_STATUS_BEV_OOB);
+    if(S.n_def)
+      atomicAdd(&F.n_def_bev, S.n_def);
   }
-  const int first_outlined = F.first_outlined, K = F.n_plateaus;
-  // labels first_outlined .. K-1 get a BEV image
-  const unsigned amask = (K >= 32 ? 0xffffffffu : ((1u << K) - 1u)) & ~((first_outlined >= 32) ? 0xffffffffu : ((1u << first_outlined) - 1u));
-  __syncthreads();
-
-  const size_t fbase = (size_t)frame * p.N;
-  const int tile0 = blockIdx.x * SSD_TILE2; // first pixel of the tile
-  uint4 *lab128 = reinterpret_cast<uint4 *>(labels + fbase + tile0);
-  const int tile_n = min(SSD_TILE2, p.N - tile0);
-
-  // ---- phase A: codes -> labels, compaction of the BEV points ----
-#pragma unroll
-  for(int r = 0; r < SSD_TILE2 / SSD_ROUND2; r++)
-  {
-    const int pt0 = r * SSD_ROUND2 + tid * 16;
-    unsigned lab[4] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu };
-    unsigned mask16 = 0;
-    if(pt0 + 16 <= tile_n)
-    {
-      const uint4 cw = lab128[pt0 >> 4];
-      const unsigned c[4] = { cw.x, cw.y, cw.z, cw.w };
-#pragma unroll
-      for(int i = 0; i < 4; i++)
-      {
-        lab[i] = (unsigned)s_lut[c[i] & 0xff] | ((unsigned)s_lut[(c[i] >> 8) & 0xff] << 8) | ((unsigned)s_lut[(c[i] >> 16) & 0xff] << 16) |
-                 ((unsigned)s_lut[c[i] >> 24] << 24);
-        mask16 |= active_mask4(lab[i], amask) << (4 * i);
-      }
-      lab128[pt0 >> 4] = make_uint4(lab[0], lab[1], lab[2], lab[3]);
-    }
-    else if(pt0 < tile_n)
-    {
-      // ragged tail of the frame (N is a multiple of 4, not necessarily of 16)
-      unsigned *lab32 = reinterpret_cast<unsigned *>(labels + fbase + tile0);
-      for(int i = 0; i < 4 && pt0 + 4 * i < tile_n; i++)
-      {
-        const unsigned c = lab32[(pt0 >> 2) + i];
-        lab[i] = (unsigned)s_lut[c & 0xff] | ((unsigned)s_lut[(c >> 8) & 0xff] << 8) | ((unsigned)s_lut[(c >> 16) & 0xff] << 16) |
-                 ((unsigned)s_lut[c >> 24] << 24);
-        mask16 |= active_mask4(lab[i], amask) << (4 * i);
-        lab32[(pt0 >> 2) + i] = lab[i];
-      }
-    }
-    compact_append(L, mask16, lab, r, tid);
-  }
-
-  // ---- phase B: dense walk over the compacted points ----
-  const int n_act = (int)L.count;
-  const float *fxyz = xyz + (fbase + tile0) * 3;
-  unsigned *fbev = bev + (size_t)frame * SSD_GPU_MAX_PLATEAUS * bm_words;
-  const int lane = tid & 31;
-  unsigned oob = 0;
-  for(int base = 0; base < n_act; base += SSD_PT_THREADS)
-  {
-    const int i = base + tid;
-    const bool live = i < n_act;
-    unsigned key = 0xffffffffu, bit = 0, l = 0xffu;
-    int y = 0;
-    if(live)
-    {
-      const unsigned e = L.entry[i];
-      l = e >> 16;
-      const float *v = fxyz + (size_t)(e & 0xffffu) * 3;
-      double wx, wy;
-      camera_to_world_xy(p, __ldg(v), __ldg(v + 1), __ldg(v + 2), wx, wy);
-      int x;
-      if(bev_pixel(p, wx, wy, x, y))
-      {
-        key = l * (unsigned)bm_words + (unsigned)y * (unsigned)p.wpr + (unsigned)(x >> 5);
-        bit = 1u << (x & 31);
-      }
-      else
-        oob = 1;
-    }
-    // one OR per distinct bitmap word in the warp
-    const unsigned grp = __match_any_sync(0xffffffffu, key);
-    const unsigned bits = __reduce_or_sync(grp, bit);
-    if(key != 0xffffffffu && lane == __ffs(grp) - 1)
-      atomicOr(fbev + key, bits);
-    // touched row range per label
-    const unsigned lkey = key != 0xffffffffu ? l : 0xffu;
-    const unsigned lgrp = __match_any_sync(0xffffffffu, lkey);
-    const int ymin = __reduce_min_sync(lgrp, y), ymax = __reduce_max_sync(lgrp, y);
-    if(lkey != 0xffu && lane == __ffs(lgrp) - 1)
-    {
-      if(ymin < s_rmin[lkey])
-        atomicMin(&s_rmin[lkey], ymin);
-      if(ymax > s_rmax[lkey])
-        atomicMax(&s_rmax[lkey], ymax);
-    }
-  }
-  if(oob)
-    s_oob = 1;
-  __syncthreads();
-  if(tid < K && s_rmax[tid] >= 0)
-  {
-    atomicMin(&F.plat[tid].row_min, s_rmin[tid]);
-    atomicMax(&F.plat[tid].row_max, s_rmax[tid]);
-  }
-  if(tid == 0 && s_oob)
-    atomicOr(&F.status, SSD_STATUS_BEV_OOB);
 }
 
 // ---------------------------------------------------------------------------------------------
 // k_quad_reduce: StairsDetector::getPointsInQuadrilateral + calcAverageZ (pointcloud.cpp:560-581) for the
 // ground and every valid plateau, and the ground's BEV image (calcGround, :530-531).
-// z is accumulated in 2^-36 m fixed point (biased by 2^37 to stay non-negative): integer sums are order
-// independent, so the result is deterministic; the error (<= 2^-37 m per point) is eight orders below the
-// 0.1 mm tolerance. Per iteration the warp groups its lanes by label (match.any) and reduces each group with
-// redux (single-pass segmented reduce); one lane per group adds into the warp's shared-memory accumulators.
-// Point-in-quadrilateral: single-precision fast accept against the verified inner box of the step
-// (quadtest_inner_box), exact QuadrilateralTest evaluation otherwise.
+// Point-in-quadrilateral: single-precision fast accept against the verified inner box; the warp steps that
+// still have undecided points evaluate the f32 image of the reference's own test structure
+// (quadfilter_eval); what stays uncertain goes to the compacted exact pass.
+// z is accumulated in 2^-36 m fixed point: integer sums are order independent, so the result is deterministic;
+// the error (<= 2^-37 m per point) is seven orders below the 0.1 mm tolerance. Each lane keeps a running
+// (label, sum, count) segment in registers -- consecutive words of a lane mostly share a label -- and
+// adds it to the block's shared-memory accumulators when the label changes; at the end the warp combines its
+// 32 open segments with one match.any + redux pass (single-pass segmented reduce): one shared-memory add per
+// distinct label and warp, one global atomic per step and block.
 // Ground BEV: only the pixel columns Segmentation::detectFrontEdge can see (BottomScanner probes columns
 // W/2 + 50 j; the 3x3 close reaches two columns to either side) are written.
 // ---------------------------------------------------------------------------------------------
-#define SSD_ZFIX_BIAS (1ll << 37)
-
-__global__ void __launch_bounds__(SSD_PT_THREADS) k_quad_reduce(const __grid_constant__ DevParams p, const float *__restrict__ xyz,
-                                                                 const unsigned char *__restrict__ labels, FrameDev *__restrict__ frames,
-                                                                 unsigned *__restrict__ bev, size_t bm_words,
-                                                                 unsigned long long *__restrict__ counters)
+__device__ __forceinline__ bool ground_col_needed(const DevParams &p, int x)
 {
-  extern __shared__ __align__(16) unsigned char s_raw[];
-  __shared__ CompactList L;
-  __shared__ float4 s_box[SSD_GPU_MAX_PLATEAUS]; // verified inner box of each step (cx, hx, cy, hy)
-  __shared__ unsigned long long s_wsum[SSD_PT_WARPS][SSD_GPU_MAX_PLATEAUS];
-  __shared__ unsigned s_wcnt[SSD_PT_WARPS][SSD_GPU_MAX_PLATEAUS];
-  __shared__ int s_rmin, s_rmax;
-  __shared__ unsigned s_oob, s_amask;
-  QuadTestDev *s_qt = reinterpret_cast<QuadTestDev *>(s_raw);
+  const unsigned v = (unsigned)(x - (p.W / 2 - 2) + 50 * 128); // non-negative for W <= 12800
+  return v % 50u < 5u;
+}
+
+struct QuadReduceShared
+{
+  QuadFilterDev qf[SSD_GPU_MAX_PLATEAUS];
+  unsigned long long sum[SSD_GPU_MAX_PLATEAUS];
+  unsigned cnt[SSD_GPU_MAX_PLATEAUS];
+  int rmin, rmax;
+  unsigned oob, n_act, n_def, pad;
+  WarpLists L;
+};
+
+__device__ __forceinline__ void quad_reduce_exact_point(const DevParams &p, const float *__restrict__ v, unsigned l, bool bevonly, const FrameDev &F,
+                                                        int ground, unsigned *__restrict__ gbev, QuadReduceShared &S)
+{
+  const float fx = __ldg(v), fy = __ldg(v + 1), fz = __ldg(v + 2);
+  double wx, wy;
+  camera_to_world_xy(p, fx, fy, fz, wx, wy);
+  if(!bevonly)
+  {
+    if(!quadtest_within(F.plat[l].qt, wx, wy))
+      return;
+    atomicAdd(&S.sum[l], (unsigned long long)z_to_fix(camera_to_world_z(p, fx, fy, fz)));
+    atomicAdd(&S.cnt[l], 1u);
+  }
+  if((int)l == ground)
+  {
+    int x, y;
+    if(!bev_pixel(p, wx, wy, x, y))
+      S.oob = 1;
+    else if(ground_col_needed(p, x))
+    {
+      atomicOr(gbev + (size_t)y * p.wpr + (x >> 5), 1u << (x & 31));
+      atomicMin(&S.rmin, y);
+      atomicMax(&S.rmax, y);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(SSD_PT_THREADS, 3) k_quad_reduce(const __grid_constant__ DevParams p, const float *__restrict__ xyz,
+                                                                 const unsigned char *__restrict__ labels, FrameDev *__restrict__ frames,
+                                                                 unsigned *__restrict__ bev, size_t bm_words)
+{
+  __shared__ QuadReduceShared S;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int frame = blockIdx.y;
   FrameDev &F = frames[frame];
-  if(F.first_valid < 0)
+  const unsigned amask = F.quad_amask;
+  if(amask == 0u)
     return; // no valid plateau: nothing is emitted (pointcloud.cpp:434)
-  const int K = F.n_plateaus, ground = F.ground_index;
+  const int ground = F.ground_index;
+  const size_t fbase = (size_t)frame * p.N;
+  const unsigned *lab32 = reinterpret_cast<const unsigned *>(labels + fbase);
+  unsigned *gbev = ground >= 0 ? bev + ((size_t)frame * SSD_GPU_MAX_PLATEAUS + ground) * bm_words : nullptr;
+  const int nquads = p.N >> 2;
+  int wt, wt_end;
+  warp_tile_range((p.N + SSD_WT_PX - 1) / SSD_WT_PX, warp, wt, wt_end);
+
+  unsigned labw[SSD_WT_WORDS];
+#pragma unroll
+  for(int it = 0; it < SSD_WT_WORDS; it++)
   {
-    const bool act = tid < K && F.plat[tid].valid && F.plat[tid].quad_status == 0;
-    const unsigned am = __ballot_sync(0xffffffffu, act);
+    const int q = wt * (SSD_WT_PX / 4) + it * 32 + lane;
+    labw[it] = (wt < wt_end && q < nquads) ? __ldg(lab32 + q) : 0xffffffffu;
+  }
+  {
+    // the frame's filter tables: one coalesced copy, independent of anything else
+    const unsigned *src = reinterpret_cast<const unsigned *>(F.qf);
+    unsigned *dst = reinterpret_cast<unsigned *>(S.qf);
+    for(int i = tid; i < (int)(sizeof(S.qf) / 4); i += SSD_PT_THREADS)
+      dst[i] = src[i];
+    if(tid < SSD_GPU_MAX_PLATEAUS)
+    {
+      S.sum[tid] = 0;
+      S.cnt[tid] = 0;
+    }
+    if(tid < SSD_PT_WARPS)
+      S.L.ndef[tid] = 0;
     if(tid == 0)
     {
-      s_amask = am;
-      s_rmin = 0x7fffffff;
-      s_rmax = -1;
-      s_oob = 0;
-      L.count = 0;
-    }
-    if(tid < K)
-    {
-      const QuadTestDev &g = F.plat[tid].qt;
-      s_box[tid] = make_float4(g.ib_cx, act ? g.ib_hx : -1.f, g.ib_cy, g.ib_hy);
-    }
-    for(int i = tid; i < SSD_PT_WARPS * SSD_GPU_MAX_PLATEAUS; i += SSD_PT_THREADS)
-    {
-      (&s_wsum[0][0])[i] = 0;
-      (&s_wcnt[0][0])[i] = 0;
-    }
-    const int words = (int)(sizeof(QuadTestDev) / 4);
-    for(int i = tid; i < K * words; i += SSD_PT_THREADS)
-    {
-      const int k = i / words, w = i - k * words;
-      reinterpret_cast<unsigned *>(&s_qt[k])[w] = reinterpret_cast<const unsigned *>(&F.plat[k].qt)[w];
+      S.rmin = 0x7fffffff;
+      S.rmax = -1;
+      S.oob = 0;
+      S.n_act = 0;
+      S.n_def = 0;
     }
   }
   __syncthreads();
-  const unsigned amask = s_amask;
 
-  const size_t fbase = (size_t)frame * p.N;
-  const int tile0 = blockIdx.x * SSD_TILE2;
-  const uint4 *lab128 = reinterpret_cast<const uint4 *>(labels + fbase + tile0);
-  const int tile_n = min(SSD_TILE2, p.N - tile0);
-
-  // ---- phase A: compaction of the points whose label is an emitted step ----
-#pragma unroll
-  for(int r = 0; r < SSD_TILE2 / SSD_ROUND2; r++)
-  {
-    const int pt0 = r * SSD_ROUND2 + tid * 16;
-    unsigned lab[4] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu };
-    unsigned mask16 = 0;
-    if(pt0 + 16 <= tile_n)
-    {
-      const uint4 lw = __ldg(lab128 + (pt0 >> 4));
-      lab[0] = lw.x;
-      lab[1] = lw.y;
-      lab[2] = lw.z;
-      lab[3] = lw.w;
-    }
-    else if(pt0 < tile_n)
-    {
-      const unsigned *lab32 = reinterpret_cast<const unsigned *>(labels + fbase + tile0);
-      for(int i = 0; i < 4 && pt0 + 4 * i < tile_n; i++)
-        lab[i] = __ldg(lab32 + (pt0 >> 2) + i);
-    }
-#pragma unroll
-    for(int i = 0; i < 4; i++)
-      if(__vcmpltu4(lab[i], 0x20202020u)) // any plateau label in this word at all?
-        mask16 |= active_mask4(lab[i], amask) << (4 * i);
-    compact_append(L, mask16, lab, r, tid);
-  }
-
-  // ---- phase B ----
-  const int n_act = (int)L.count;
-  const float *fxyz = xyz + (fbase + tile0) * 3;
-  unsigned *gbev = ground >= 0 ? bev + ((size_t)frame * SSD_GPU_MAX_PLATEAUS + ground) * bm_words : nullptr;
-  unsigned oob = 0, n_fast = 0, n_slow = 0;
+  unsigned short *act = S.L.act[warp];
+  unsigned *labs = S.L.lab[warp];
+  unsigned seg_l = 0xffu, seg_n = 0, n_act = 0, n_def = 0;
+  long long seg_sum = 0;
   int rmin = 0x7fffffff, rmax = -1;
-  // ground BEV column filter: pixel column u needed iff (u - (W/2 - 2)) mod 50 in [0, 5)
-  const float sxf = (float)p.x_to_image, kxf = (float)(-p.x_min * p.x_to_image) - (float)(p.W / 2 - 2);
-  const float dux = (float)(p.x_to_image * 1.0001) , du0 = (float)(8.0 * p.W / 16777216.0) + 1e-3f;
+  // ground BEV column pre-filter in f32: u' = (wx - x_min) * sx - (W/2 - 2); needed iff u' mod 50 in [0, 5)
+  const float gsx = (float)p.x_to_image, gk = (float)(-p.x_min * p.x_to_image) - (float)(p.W / 2 - 2);
+  const float gdcol = fmaf(p.epsc, (float)(p.x_to_image * 1.0001), (float)(8.0 * p.W / 16777216.0) + 1e-3f);
 
-  for(int base = 0; base < n_act; base += SSD_PT_THREADS)
+  for(; wt < wt_end; wt++)
   {
-    const int i = base + tid;
-    unsigned l = 0xffu;
-    unsigned long long zf = 0;
-    bool inside = false;
-    if(i < n_act)
+    // ---- phase A: compaction of the words holding plateau labels (bit 7 of a label byte clear <=> label < 128) ----
+    unsigned n = 0;
+#pragma unroll
+    for(int it = 0; it < SSD_WT_WORDS; it++)
     {
-      const unsigned e = L.entry[i];
-      const unsigned le = e >> 16;
-      const float *v = fxyz + (size_t)(e & 0xffffu) * 3;
-      const float fx = __ldg(v), fy = __ldg(v + 1), fz = __ldg(v + 2);
-      // fast accept: single-precision position inside the verified inner box by more than its error bound
-      // (same bound as point_code_filtered: |w^ - w_ref| <= eps = E1 * max|p| + E0)
-      const float4 bx = s_box[le];
-      const float eps = fmaf(p.E1, fmaxf(fmaxf(fabsf(fx), fabsf(fy)), fabsf(fz)), p.E0);
-      const float wxf = fmaf(p.af[2], fz, fmaf(p.af[1], fy, fmaf(p.af[0], fx, p.bf[0])));
-      const float wyf = fmaf(p.af[5], fz, fmaf(p.af[4], fy, fmaf(p.af[3], fx, p.bf[1])));
-      const bool fast = fmaxf(fabsf(wxf - bx.x) - bx.y, fabsf(wyf - bx.z) - bx.w) < -eps;
-      double wx = 0, wy = 0;
-      bool have_xy = false;
-      inside = fast;
-      n_fast += fast;
-      n_slow += !fast;
-      if(!fast)
+      const unsigned lw = labw[it];
+      const unsigned am4 = (((~lw >> 7) & 0x01010101u) * 0x10204080u) >> 28; // bit j <-> byte j < 128
+      if(__any_sync(0xffffffffu, am4 != 0u))
       {
-        camera_to_world_xy(p, fx, fy, fz, wx, wy);
-        have_xy = true;
-        inside = quadtest_within(s_qt[le], wx, wy);
+        if(am4)
+          labs[it * 32 + lane] = lw;
+        n = compact_append(act, n, am4, it, lane);
       }
-      if(inside)
+    }
+#pragma unroll
+    for(int it = 0; it < SSD_WT_WORDS; it++)
+    {
+      const int q = (wt + 1) * (SSD_WT_PX / 4) + it * 32 + lane;
+      labw[it] = (wt + 1 < wt_end && q < nquads) ? __ldg(lab32 + q) : 0xffffffffu;
+    }
+    if(n == 0)
+      continue;
+    __syncwarp();
+
+    // ---- phase B: dense walk over the compacted words ----
+    const float4 *tile4 = reinterpret_cast<const float4 *>(xyz + (fbase + (size_t)wt * SSD_WT_PX) * 3);
+    unsigned e = lane < n ? act[lane] : 0u;
+    float4 c0, c1, c2, n0, n1, n2;
+    c0 = c1 = c2 = n0 = n1 = n2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if(e)
+      load3(tile4 + (e >> 4) * 3, c0, c1, c2);
+    for(unsigned s0 = 0; s0 < n; s0 += 32)
+    {
+      const unsigned i1 = s0 + 32 + lane;
+      const unsigned e1 = i1 < n ? act[i1] : 0u;
+      if(e1)
+        load3(tile4 + (e1 >> 4) * 3, n0, n1, n2);
+      const unsigned lw = labs[e >> 4];
+      const float vx[4] = { c0.x, c0.w, c1.z, c2.y }, vy[4] = { c0.y, c1.x, c1.w, c2.z }, vz[4] = { c0.z, c1.y, c2.x, c2.w };
+      // fast accept: single-precision world x, y inside the step's verified inner box by more than the error bound
+      float wxs[4];
+      unsigned ins = 0, und = 0;
+#pragma unroll
+      for(int j = 0; j < 4; j++)
       {
-        l = le;
-        zf = (unsigned long long)(z_to_fix(camera_to_world_z(p, fx, fy, fz)) + SSD_ZFIX_BIAS);
-        if((int)le == ground)
+        const unsigned l = (lw >> (8 * j)) & 0x1fu;
+        const bool live = ((e >> j) & 1u) && ((amask >> l) & 1u);
+        float wxf, wyf;
+        f2_unpack(f2_affine(p.axy2, p.bxy2, vx[j], vy[j], vz[j]), wxf, wyf);
+        wxs[j] = wxf;
+        const float4 ib = S.qf[l].ibe;
+        const bool in = fabsf(wxf - ib.x) < ib.z && fabsf(wyf - ib.y) < ib.w;
+        ins |= (live && in) ? (1u << j) : 0u;
+        und |= (live && !in) ? (1u << j) : 0u;
+      }
+      n_act += __popc(ins | und);
+      // the rest: reject against the bounding box, else the f32 image of the full test, else the exact pass
+      if(__any_sync(0xffffffffu, und != 0u))
+      {
+#pragma unroll
+        for(int j = 0; j < 4; j++)
         {
-          // is the pixel column one the front-edge scanner can see? (f32 estimate, conservative margin)
-          const float uf = fmaf(wxf, sxf, kxf);              // pixel x coordinate relative to W/2 - 2
-          const float q50 = floorf(uf * 0.02f);
-          const float tcol = fmaf(q50, -50.f, uf);            // uf mod 50 (approximately, in [-tiny, 50+tiny])
-          const float dcol = fmaf(eps, dux, du0);
-          // (a pixel that rounds to column W wraps to column 0 of the next row: keep the right edge too)
-          if(tcol < 5.f + dcol || tcol > 50.f - dcol || uf > (float)(p.W - 2 - (p.W / 2 - 2)))
+          if((und >> j) & 1u)
           {
-            if(!have_xy)
-              camera_to_world_xy(p, fx, fy, fz, wx, wy);
-            int x, y;
-            if(!bev_pixel(p, wx, wy, x, y))
-              oob = 1;
-            else
+            const unsigned l = (lw >> (8 * j)) & 0x1fu;
+            const QuadFilterDev &f = S.qf[l];
+            float wxf, wyf;
+            f2_unpack(f2_affine(p.axy2, p.bxy2, vx[j], vy[j], vz[j]), wxf, wyf);
+            const float4 bb = f.bb;
+            const float dbb = fminf(fminf(wxf - bb.x, bb.y - wxf), fminf(wyf - bb.z, bb.w - wyf));
+            if(!(dbb < -(p.epsc + p.epsc)))
             {
-              atomicOr(gbev + (size_t)y * p.wpr + (x >> 5), 1u << (x & 31));
-              rmin = min(rmin, y);
-              rmax = max(rmax, y);
+              bool unc;
+              const bool in = quadfilter_eval(f, wxf, wyf, p.epsc, unc);
+              if(unc)
+                defer_push(S.L, warp, ((e >> 4) << 2) | (unsigned)j);
+              else if(in)
+                ins |= 1u << j;
             }
           }
         }
       }
+#pragma unroll
+      for(int j = 0; j < 4; j++)
+      {
+        if((ins >> j) & 1u)
+        {
+          const unsigned l = (lw >> (8 * j)) & 0x1fu;
+          const long long zf = z_to_fix_fused(p, vx[j], vy[j], vz[j]);
+          if(l != seg_l)
+          {
+            if(seg_n)
+            {
+              atomicAdd(&S.sum[seg_l], (unsigned long long)seg_sum);
+              atomicAdd(&S.cnt[seg_l], seg_n);
+            }
+            seg_l = l;
+            seg_sum = 0;
+            seg_n = 0;
+          }
+          seg_sum += zf;
+          seg_n++;
+          if((int)l == ground)
+          {
+            // cheap column pre-filter (f32, conservative margin) before the pixel is computed
+            const float uf = fmaf(wxs[j], gsx, gk);
+            const float tcol = fmaf(floorf(uf * 0.02f), -50.f, uf); // uf mod 50, approximately
+            if(tcol < 5.f + gdcol || tcol > 50.f - gdcol || uf > (float)(p.W - 2 - (p.W / 2 - 2)))
+            {
+              int ix, iy;
+              if(fast_pixel2(p, vx[j], vy[j], vz[j], ix, iy))
+              {
+                if(ground_col_needed(p, ix))
+                {
+                  atomicOr(gbev + (unsigned)iy * (unsigned)p.wpr + (unsigned)(ix >> 5), 1u << (ix & 31));
+                  rmin = min(rmin, iy);
+                  rmax = max(rmax, iy);
+                }
+              }
+              else
+                defer_push(S.L, warp, SSD_DEF_BEVONLY | ((e >> 4) << 2) | (unsigned)j);
+            }
+          }
+        }
+      }
+      e = e1;
+      c0 = n0;
+      c1 = n1;
+      c2 = n2;
     }
-    // single-pass segmented reduce over the warp: lanes grouped by label
-    const unsigned grp = __match_any_sync(0xffffffffu, l);
-    const unsigned lo = __reduce_add_sync(grp, (unsigned)(zf & 0xfffffu));          // 20 + 19 bits: sums of 32 fit in 32 bits
-    const unsigned hi = __reduce_add_sync(grp, (unsigned)(zf >> 20));
-    if(l != 0xffu && lane == __ffs(grp) - 1)
+    // ---- dense exact pass over the warp's compacted uncertain points ----
+    __syncwarp();
+    const unsigned nd = S.L.ndef[warp];
+    if(nd)
     {
-      s_wsum[warp][l] += ((unsigned long long)hi << 20) + lo; // one lane per label per warp: no race
-      s_wcnt[warp][l] += __popc(grp);
+      const float *tile = reinterpret_cast<const float *>(tile4);
+      for(unsigned i = lane; i < nd; i += 32)
+      {
+        const unsigned d = S.L.def[warp][i];
+        const unsigned w = (d >> 2) & 0xffu, j = d & 3u;
+        quad_reduce_exact_point(p, tile + (w * 4 + j) * 3, (labs[w] >> (8 * j)) & 0x1fu, (d & SSD_DEF_BEVONLY) != 0u, F, ground, gbev, S);
+      }
+      __syncwarp();
+      n_def += nd;
+      if(lane == 0)
+        S.L.ndef[warp] = 0;
     }
     __syncwarp();
   }
   {
-    n_fast = __reduce_add_sync(0xffffffffu, n_fast);
-    n_slow = __reduce_add_sync(0xffffffffu, n_slow);
-    if(lane == 0 && counters && (n_fast | n_slow))
+    // combine the warp's 32 open segments: lanes grouped by label, 64-bit sum as 21 low bits + the rest
+    const unsigned key = seg_n ? seg_l : 0xffu;
+    const unsigned grp = __match_any_sync(0xffffffffu, key);
+    const unsigned lo = __reduce_add_sync(grp, (unsigned)(seg_sum & 0x1fffffll));
+    const int hi = __reduce_add_sync(grp, (int)(seg_sum >> 21)); // |sum| < 2^50: the high part fits 29 bits + sign
+    const unsigned cn = __reduce_add_sync(grp, seg_n);
+    if(key != 0xffu && lane == __ffs(grp) - 1)
     {
-      atomicAdd(counters + 1, (unsigned long long)n_fast);
-      atomicAdd(counters + 2, (unsigned long long)n_slow);
-    }
-    rmin = __reduce_min_sync(0xffffffffu, rmin);
-    rmax = __reduce_max_sync(0xffffffffu, rmax);
-    oob = __reduce_or_sync(0xffffffffu, oob);
-    if(lane == 0)
-    {
-      if(rmax >= 0)
-      {
-        atomicMin(&s_rmin, rmin);
-        atomicMax(&s_rmax, rmax);
-      }
-      if(oob)
-        s_oob = 1;
+      atomicAdd(&S.sum[key], (unsigned long long)(((long long)hi << 21) + (long long)lo));
+      atomicAdd(&S.cnt[key], cn);
     }
   }
-  __syncthreads();
-  if(tid < K)
+  rmin = __reduce_min_sync(0xffffffffu, rmin);
+  rmax = __reduce_max_sync(0xffffffffu, rmax);
+  n_act = __reduce_add_sync(0xffffffffu, n_act);
+  if(lane == 0)
   {
-    unsigned long long s = 0;
-    unsigned n = 0;
-#pragma unroll
-    for(int w = 0; w < SSD_PT_WARPS; w++)
+    if(rmax >= 0)
     {
-      s += s_wsum[w][tid];
-      n += s_wcnt[w][tid];
+      atomicMin(&S.rmin, rmin);
+      atomicMax(&S.rmax, rmax);
     }
-    if(n)
-    {
-      atomicAdd(&F.plat[tid].sum_fix, s);
-      atomicAdd(&F.plat[tid].n_in_quad, n);
-    }
+    if(n_act)
+      atomicAdd(&S.n_act, n_act);
+    if(n_def)
+      atomicAdd(&S.n_def, n_def);
+  }
+  __syncthreads();
+  if(tid < SSD_GPU_MAX_PLATEAUS && S.cnt[tid])
+  {
+    atomicAdd(&F.plat[tid].sum_fix, S.sum[tid]);
+    atomicAdd(&F.plat[tid].n_in_quad, S.cnt[tid]);
   }
   if(tid == 0)
   {
-    if(s_rmax >= 0)
+    if(S.rmax >= 0)
     {
-      atomicMin(&F.plat[ground].row_min, s_rmin);
-      atomicMax(&F.plat[ground].row_max, s_rmax);
+      atomicMin(&F.plat[ground].row_min, S.rmin);
+      atomicMax(&F.plat[ground].row_max, S.rmax);
     }
-    if(s_oob)
+    if(S.oob)
       atomicOr(&F.status, SSD_STATUS_BEV_OOB);
+    if(S.n_act)
+      atomicAdd(&F.n_quad_pts, S.n_act);
+    if(S.n_def)
+      atomicAdd(&F.n_def_quad, S.n_def);
   }
 }
