@@ -46,6 +46,14 @@ struct DevParams
   float Tf;                // max |x|, |y| of an in-range world point (quadfilter margins)
   // the same bounds for ANY in-range point: max|p| <= Mmax (derive_params), so eps <= epsc etc. are constants
   float epsc, euc, evc;
+  // k_transform_bin (point_code_scaled): rows of the transform scaled to the measuring range, v_i = (w_i - c_i) / h_i,
+  // so "in range" is max|v_i| < 1; height bin t = G * (v_z + 1) with G = h_z * hir; eps = E1s * max|p| + E0s bounds
+  // |v^_i - v_i| (8u (S_i m + B_i), derive_params); bin certain iff |frac distance| < thr0 - Gup * eps
+  float sa[9], sb[3];
+  float E0s, E1s, Gf, Gm, Gup, thr0;
+  // per-step z sum (z_fix_u): world z in single precision scaled by 2^zshift, rounded to an integer by the 1.5*2^23 add
+  float azf[3], bzf;
+  int zshift, pad2;
   // packed pairs for the f32x2 pipes: {af[j], af[3+j]}, {bf[0], bf[1]} (world x,y) and {au[j], av[j]}, {bu, bv} (BEV pixel)
   unsigned long long axy2[3], bxy2, auv2[3], buv2;
 };
@@ -90,6 +98,7 @@ struct QuadFilterDev
   unsigned char ok, pad8;        // ok = 0: no filter for this quadrilateral (every point takes the exact test)
   float pad[3];
   float4 ibe;            // inner box for the constant-eps fast accept: cx, cy, hx - epsc, hy - epsc (negative: none)
+  float4 rj;             // reject box around the same centre: |x - cx| > rj.x or |y - cy| > rj.y => certainly outside the bounding box
 };
 
 struct PlateauDev
@@ -262,6 +271,43 @@ __device__ __forceinline__ unsigned point_code_filtered(const DevParams &p, floa
   const bool valid = z > 0.f;
   uncertain = valid && !(out || (in && bin_ok));
   return valid ? (out ? SSD_CODE_OUT_OF_RANGE : bin) : SSD_CODE_INVALID;
+}
+
+// 3-input maximum of absolute values, NaN-propagating (one FMNMX3.NAN): a NaN coordinate must not be dropped
+__device__ __forceinline__ float max3abs_nan(float a, float b, float c)
+{
+  float r;
+  asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(fabsf(a)), "f"(fabsf(b)), "f"(fabsf(c)));
+  return r;
+}
+
+// The decision of point_code() from single-precision arithmetic on range-scaled rows plus a rigorous error bound.
+//   v^_i = fma chain with f32-rounded a_ij/h_i, (b_i-c_i)/h_i:  |v^_i - v_ref,i| <= 4.0001u (S_i m + B_i) + the
+//   reference's own f64 roundings (2^-50 of the same magnitudes), u = 2^-24, m = max|p|; eps carries 8u: factor 2 slack.
+//   in range  <=> max_i |v_i| < 1:   certain if |r - 1| > eps  (r - 1 is exact for r in [0.5, 2], elsewhere |r - 1| >> eps)
+//   bin = floor(t), t = G (v_z + 1): u_f = fma(v^_z, G, G - 0.5) ~ t - 0.5 within Gup*eps + dbin; k = round(u_f) via the
+//   1.5*2^23 trick (d = u_f - k is exact); floor(t) == k is certain iff |d| < 0.5 - (Gup*eps + dbin) = thr0 - Gup*eps.
+// NaN anywhere makes r or eps NaN, every comparison false => uncertain => exact path. Inf likewise through eps.
+// Returns the code when certain; `uncertain` asks for point_code().
+__device__ __forceinline__ unsigned point_code_scaled(const DevParams &p, float x, float y, float z, bool &uncertain)
+{
+  const float m = max3abs_nan(x, y, z);
+  const float eps = fmaf(p.E1s, m, p.E0s);
+  const float vx = fmaf(p.sa[2], z, fmaf(p.sa[1], y, fmaf(p.sa[0], x, p.sb[0])));
+  const float vy = fmaf(p.sa[5], z, fmaf(p.sa[4], y, fmaf(p.sa[3], x, p.sb[1])));
+  const float vz = fmaf(p.sa[8], z, fmaf(p.sa[7], y, fmaf(p.sa[6], x, p.sb[2])));
+  const float e1 = max3abs_nan(vx, vy, vz) - 1.0f;
+  const float MAGIC = 12582912.0f;
+  const float uf = fmaf(vz, p.Gf, p.Gm);
+  const float s = uf + MAGIC;
+  const float d = uf - (s - MAGIC);
+  const float thr = fmaf(-p.Gup, eps, p.thr0);
+  const bool out = e1 > eps;
+  const bool in_bin = e1 < -eps && fabsf(d) < thr;
+  const bool valid = z > 0.f;
+  uncertain = valid && !(out || in_bin);
+  const unsigned c = out ? SSD_CODE_OUT_OF_RANGE : ((unsigned)__float_as_int(s) & 0xffu);
+  return valid ? c : SSD_CODE_INVALID;
 }
 
 // fast_pixel with the constant error bounds euc / evc and packed arithmetic (for points known to be in range)
@@ -726,7 +772,17 @@ __device__ inline void quadtest_inner_box(QuadTestDev &t, const P2d q[4])
 __device__ inline void quadfilter_build(QuadFilterDev &f, const QuadTestDev &t, float T, float epsc)
 {
   // |w^ - cx| < hx - epsc  =>  |w_ref - cx| < hx (the subtraction rounds down: the accept region only shrinks)
-  f.ibe = make_float4(t.ib_cx, t.ib_cy, t.ib_hx > 0.f ? __fadd_rd(t.ib_hx, -epsc) : -1.f, t.ib_hy > 0.f ? __fadd_rd(t.ib_hy, -epsc) : -1.f);
+  {
+    const bool box = t.ib_hx > 0.f && t.ib_hy > 0.f;
+    const float cx = box ? t.ib_cx : (float)((t.tb_lo_x + t.tb_hi_x) * 0.5), cy = box ? t.ib_cy : (float)((t.tb_lo_y + t.tb_hi_y) * 0.5);
+    f.ibe = make_float4(cx, cy, box ? __fadd_rd(t.ib_hx, -epsc) : -1.f, box ? __fadd_rd(t.ib_hy, -epsc) : -1.f);
+    // |x^ - cx| > Rx with |x^ - x| <= epsc and the subtraction's own rounding (<= 2^-24 (|cx| + T)) implies x outside
+    // [lo, hi]: Rx = max(cx - lo, hi - cx) + 2 epsc + 2^-22 (|cx| + T), rounded up. No usable test: infinite box.
+    const float inf_ = __int_as_float(0x7f800000);
+    const double rx = fmax((double)cx - t.tb_lo_x, t.tb_hi_x - (double)cx) + 2.0 * epsc + 2.4e-7 * (fabs((double)cx) + T);
+    const double ry = fmax((double)cy - t.tb_lo_y, t.tb_hi_y - (double)cy) + 2.0 * epsc + 2.4e-7 * (fabs((double)cy) + T);
+    f.rj = t.status == 0 ? make_float4(__double2float_ru(rx), __double2float_ru(ry), 0.f, 0.f) : make_float4(inf_, inf_, 0.f, 0.f);
+  }
   const float u = 5.9604645e-08f; // 2^-24
   const float inf = __int_as_float(0x7f800000);
   f.ok = t.status == 0;
@@ -825,6 +881,18 @@ __device__ __forceinline__ long long z_to_fix_fused(const DevParams &p, float fx
 {
   const double S = (double)(1ull << SSD_FIX_SHIFT);
   return __double2ll_rn(__fma_rn(p.a[8] * S, (double)fz, __fma_rn(p.a[7] * S, (double)fy, __fma_rn(p.a[6] * S, (double)fx, p.b[2] * S))));
+}
+
+// World z for the per-step mean (calcAverageZ, pointcloud.cpp:574-581) as an unsigned integer: single-precision
+// fma chain on coefficients pre-scaled by 2^zshift (|error| <= 4u (S_z m + |b_z|) ~ 1e-6 m worst case, random sign),
+// rounded to the nearest integer by adding 1.5*2^23; the 23 mantissa bits are k + 2^22 with k = round(wz * 2^zshift),
+// |k| < 2^22 for every in-range point (derive_params picks zshift). Integer sums are order independent, so the
+// mean is deterministic; total error of a mean << 1e-6 m against the 1e-4 m tolerance.
+#define SSD_ZFIX_BIAS 4194304u
+__device__ __forceinline__ unsigned z_fix_u(const DevParams &p, float x, float y, float z)
+{
+  const float zq = fmaf(p.azf[2], z, fmaf(p.azf[1], y, fmaf(p.azf[0], x, p.bzf)));
+  return (unsigned)__float_as_int(zq + 12582912.0f) & 0x7fffffu;
 }
 
 // fixed-point z for the order-independent (deterministic) per-step sum

@@ -130,6 +130,44 @@ static int derive_params(const ssd_gpu_config &c, const ssd_gpu_transform &t, De
     d.k0f = (float)(-c.z_min * d.hir);
     // bin arithmetic: |t^ - t_ref| <= hir*eps + 4u*(n_bins + |z_min|*hir) (+ f32 rounding of hir itself)
     d.dbin0 = (float)(16.0 * u * (d.n_bins + std::fabs(c.z_min) * d.hir + 1.0) + 1e-6);
+    // range-scaled rows for point_code_scaled: v_i = (w_i - c_i)/h_i
+    {
+      double S1 = 0, B1 = 0, X1 = 0;
+      for(int i = 0; i < 3; i++)
+      {
+        const double ci = (lo[i] + hi[i]) * 0.5, hi_ = (hi[i] - lo[i]) * 0.5;
+        double Si = 0;
+        for(int j = 0; j < 3; j++)
+        {
+          d.sa[i * 3 + j] = (float)(t.a[i * 3 + j] / hi_);
+          Si += std::fabs(t.a[i * 3 + j]) / hi_;
+        }
+        d.sb[i] = (float)((t.b[i] - ci) / hi_);
+        S1 = std::max(S1, Si);
+        B1 = std::max(B1, std::fabs(t.b[i] - ci) / hi_ + 1.0);
+        X1 = std::max(X1, (std::fabs(t.b[i]) + std::fabs(ci)) / hi_);
+      }
+      d.E1s = (float)(8.0 * u * S1 * 1.001);
+      d.E0s = (float)((8.0 * u * B1 + 1e-15 * X1) * 1.001);
+      const double G = (c.z_max - c.z_min) * 0.5 * d.hir;
+      d.Gf = (float)G;
+      d.Gm = (float)(G - 0.5);
+      d.Gup = (float)(G * 1.001);
+      // |u_f - (t_ref - 0.5)| <= G eps + [f32 rounding of G, G - 0.5: 2u G (|v|+1)] + [fma rounding u (n_bins + 1)] + f64 roundings
+      const double dbin = 8.0 * u * (2.0 * G + d.n_bins + 2.0) + 1e-9;
+      d.thr0 = (float)((0.5 - dbin) * 0.9999);
+    }
+    // per-step z sum in 2^-zshift m units: |wz| * 2^zshift < 2^22 for every in-range point
+    {
+      const double zabs = std::max(std::fabs(c.z_min), std::fabs(c.z_max)) * 1.01 + 0.01;
+      int sh = 0;
+      while(sh < 30 && zabs * std::ldexp(1.0, sh + 1) < 4194304.0)
+        sh++;
+      d.zshift = sh;
+      for(int j = 0; j < 3; j++)
+        d.azf[j] = (float)std::ldexp((double)(float)t.a[6 + j], sh);
+      d.bzf = (float)std::ldexp((double)(float)t.b[2], sh);
+    }
     // BEV pixel in single precision (fast_pixel): u = sx*(wx - x_min), v = sy*(y_max - wy) folded into one fma chain.
     // |u^ - u_ref| <= 4u (S'm + |b'|) (coefficient rounding + three fma roundings; the reference's own f64
     // roundings are ~2^-50 of that); used: 10u, i.e. a factor 2.5 of slack, plus an absolute 1e-6 px.

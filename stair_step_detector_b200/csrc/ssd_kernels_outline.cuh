@@ -926,7 +926,7 @@ __global__ void __launch_bounds__(SSD_OL_THREADS) k_finalize(const __grid_consta
     {
       PlateauDev &P = F.plat[i];
       if(P.valid && P.quad_status == 0)
-        P.mean_z = ((double)(long long)P.sum_fix / (double)(1ull << SSD_FIX_SHIFT)) / (double)P.n_in_quad; // calcAverageZ (:574-581)
+        P.mean_z = (((double)P.sum_fix - (double)P.n_in_quad * (double)SSD_ZFIX_BIAS) / (double)(1u << p.zshift)) / (double)P.n_in_quad; // calcAverageZ (:574-581), see z_fix_u
     }
     if(groundStep)
     {

@@ -59,45 +59,38 @@ __global__ void __launch_bounds__(SSD_PT_THREADS) k_transform_bin(const __grid_c
   __syncthreads();
 
   const size_t fbase = (size_t)frame * p.N;
-  const float4 *xyz4 = reinterpret_cast<const float4 *>(xyz + fbase * 3);
-  unsigned *codes32 = reinterpret_cast<unsigned *>(codes + fbase);
   const int nquads = p.N >> 2;
+  const int q0 = blockIdx.x * (ITERS * SSD_PT_THREADS) + tid;
+  const float4 *src = reinterpret_cast<const float4 *>(xyz + fbase * 3) + (size_t)q0 * 3;
+  unsigned *dst = reinterpret_cast<unsigned *>(codes + fbase) + q0;
   unsigned run_code = SSD_CODE_INVALID, run_n = 0, exact = 0; // an empty run of a valid code: no sentinel pattern to collide with
 
 #pragma unroll
   for(int it = 0; it < ITERS; it++)
   {
-    const int q = (blockIdx.x * ITERS + it) * SSD_PT_THREADS + tid;
-    if(q < nquads)
+    if(q0 + it * SSD_PT_THREADS < nquads)
     {
-      const Quad4 v = load_quad(xyz4, q);
+      const float4 *s4 = src + it * (SSD_PT_THREADS * 3);
+      const float4 v0 = __ldg(s4), v1 = __ldg(s4 + 1), v2 = __ldg(s4 + 2);
+      const float vx[4] = { v0.x, v0.w, v1.z, v2.y }, vy[4] = { v0.y, v1.x, v1.w, v2.z }, vz[4] = { v0.z, v1.y, v2.x, v2.w };
       unsigned c[4];
       bool unc[4];
 #pragma unroll
       for(int j = 0; j < 4; j++)
-        c[j] = point_code_filtered(p, v.x[j], v.y[j], v.z[j], unc[j]);
-      unsigned um = (unc[0] ? 1u : 0u) | (unc[1] ? 2u : 0u) | (unc[2] ? 4u : 0u) | (unc[3] ? 8u : 0u);
-      if(um)
+        c[j] = point_code_scaled(p, vx[j], vy[j], vz[j], unc[j]);
+      if(unc[0] || unc[1] || unc[2] || unc[3])
       {
         // rare: one out-of-line exact evaluation per uncertain point
-        exact += __popc(um);
-#pragma unroll 1
-        while(um)
-        {
-          const int j = __ffs(um) - 1;
-          um &= um - 1;
-          const float fx = j == 0 ? v.x[0] : (j == 1 ? v.x[1] : (j == 2 ? v.x[2] : v.x[3]));
-          const float fy = j == 0 ? v.y[0] : (j == 1 ? v.y[1] : (j == 2 ? v.y[2] : v.y[3]));
-          const float fz = j == 0 ? v.z[0] : (j == 1 ? v.z[1] : (j == 2 ? v.z[2] : v.z[3]));
-          const unsigned ce = point_code_slow(p, fx, fy, fz);
-          c[0] = j == 0 ? ce : c[0];
-          c[1] = j == 1 ? ce : c[1];
-          c[2] = j == 2 ? ce : c[2];
-          c[3] = j == 3 ? ce : c[3];
-        }
+#pragma unroll
+        for(int j = 0; j < 4; j++)
+          if(unc[j])
+          {
+            c[j] = point_code_slow(p, vx[j], vy[j], vz[j]);
+            exact++;
+          }
       }
       const unsigned cw = c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24);
-      codes32[q] = cw;
+      dst[it * SSD_PT_THREADS] = cw;
       if(cw == run_code * 0x01010101u)
         run_n += 4; // all four in the current run (neighbouring pixels mostly share a bin)
       else
@@ -548,9 +541,17 @@ __device__ __forceinline__ bool ground_col_needed(const DevParams &p, int x)
   return v % 50u < 5u;
 }
 
+struct QuadFast
+{
+  float4 ibe; // cx, cy, inner half widths minus epsc (negative: no inner box)
+  float2 rj;  // reject half widths
+  float2 pad;
+};
+
 struct QuadReduceShared
 {
   QuadFilterDev qf[SSD_GPU_MAX_PLATEAUS];
+  QuadFast fast[SSD_GPU_MAX_PLATEAUS];
   unsigned long long sum[SSD_GPU_MAX_PLATEAUS];
   unsigned cnt[SSD_GPU_MAX_PLATEAUS];
   int rmin, rmax;
@@ -558,9 +559,12 @@ struct QuadReduceShared
   WarpLists L;
 };
 
+// one point of the compacted exact pass: the reference's own double-precision test
 __device__ __forceinline__ void quad_reduce_exact_point(const DevParams &p, const float *__restrict__ v, unsigned l, bool bevonly, const FrameDev &F,
-                                                        int ground, unsigned *__restrict__ gbev, QuadReduceShared &S)
+                                                        unsigned amask, int ground, unsigned *__restrict__ gbev, QuadReduceShared &S)
 {
+  if(l >= SSD_GPU_MAX_PLATEAUS || !((amask >> l) & 1u))
+    return;
   const float fx = __ldg(v), fy = __ldg(v + 1), fz = __ldg(v + 2);
   double wx, wy;
   camera_to_world_xy(p, fx, fy, fz, wx, wy);
@@ -568,7 +572,7 @@ __device__ __forceinline__ void quad_reduce_exact_point(const DevParams &p, cons
   {
     if(!quadtest_within(F.plat[l].qt, wx, wy))
       return;
-    atomicAdd(&S.sum[l], (unsigned long long)z_to_fix(camera_to_world_z(p, fx, fy, fz)));
+    atomicAdd(&S.sum[l], (unsigned long long)z_fix_u(p, fx, fy, fz));
     atomicAdd(&S.cnt[l], 1u);
   }
   if((int)l == ground)
@@ -584,6 +588,8 @@ __device__ __forceinline__ void quad_reduce_exact_point(const DevParams &p, cons
     }
   }
 }
+
+#define SSD_DEF_GENERIC 0x4000u // deferred point of a word with mixed labels: not yet checked against amask
 
 __global__ void __launch_bounds__(SSD_PT_THREADS, 3) k_quad_reduce(const __grid_constant__ DevParams p, const float *__restrict__ xyz,
                                                                  const unsigned char *__restrict__ labels, FrameDev *__restrict__ frames,
@@ -621,6 +627,11 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, 3) k_quad_reduce(const __grid_
     {
       S.sum[tid] = 0;
       S.cnt[tid] = 0;
+      const bool live = (amask >> tid) & 1u;
+      // labels outside amask: never inside, always rejected
+      S.fast[tid].ibe = live ? F.qf[tid].ibe : make_float4(0.f, 0.f, -1.f, -1.f);
+      const float4 rj = F.qf[tid].rj;
+      S.fast[tid].rj = live ? make_float2(rj.x, rj.y) : make_float2(-1.f, -1.f);
     }
     if(tid < SSD_PT_WARPS)
       S.L.ndef[tid] = 0;
@@ -638,7 +649,7 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, 3) k_quad_reduce(const __grid_
   unsigned short *act = S.L.act[warp];
   unsigned *labs = S.L.lab[warp];
   unsigned seg_l = 0xffu, seg_n = 0, n_act = 0, n_def = 0;
-  long long seg_sum = 0;
+  unsigned long long seg_sum = 0;
   int rmin = 0x7fffffff, rmax = -1;
   // ground BEV column pre-filter in f32: u' = (wx - x_min) * sx - (W/2 - 2); needed iff u' mod 50 in [0, 5)
   const float gsx = (float)p.x_to_image, gk = (float)(-p.x_min * p.x_to_image) - (float)(p.W / 2 - 2);
@@ -683,43 +694,54 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, 3) k_quad_reduce(const __grid_
       const unsigned e1 = i1 < n ? act[i1] : 0u;
       if(e1)
         load3(tile4 + (e1 >> 4) * 3, n0, n1, n2);
+      const unsigned m4 = e & 15u;
       const unsigned lw = labs[e >> 4];
+      // label of the word's first plateau point; the word is "uniform" when all its plateau points carry it
+      const unsigned l0 = (lw >> (8 * (__ffs(m4 | 16u) - 1) & 31)) & 0x1fu;
+      const unsigned bytes = ((m4 * 0x00204081u) & 0x01010101u) * 0xffu;
+      const bool uniform = ((lw ^ (l0 * 0x01010101u)) & bytes) == 0u;
       const float vx[4] = { c0.x, c0.w, c1.z, c2.y }, vy[4] = { c0.y, c1.x, c1.w, c2.z }, vz[4] = { c0.z, c1.y, c2.x, c2.w };
-      // fast accept: single-precision world x, y inside the step's verified inner box by more than the error bound
-      float wxs[4];
       unsigned ins = 0, und = 0;
-#pragma unroll
-      for(int j = 0; j < 4; j++)
+      float wxs[4], wys[4];
+      if(uniform)
       {
-        const unsigned l = (lw >> (8 * j)) & 0x1fu;
-        const bool live = ((e >> j) & 1u) && ((amask >> l) & 1u);
-        float wxf, wyf;
-        f2_unpack(f2_affine(p.axy2, p.bxy2, vx[j], vy[j], vz[j]), wxf, wyf);
-        wxs[j] = wxf;
-        const float4 ib = S.qf[l].ibe;
-        const bool in = fabsf(wxf - ib.x) < ib.z && fabsf(wyf - ib.y) < ib.w;
-        ins |= (live && in) ? (1u << j) : 0u;
-        und |= (live && !in) ? (1u << j) : 0u;
-      }
-      n_act += __popc(ins | und);
-      // the rest: reject against the bounding box, else the f32 image of the full test, else the exact pass
-      if(__any_sync(0xffffffffu, und != 0u))
-      {
+        const float4 ib = S.fast[l0].ibe;
+        const float2 rj = S.fast[l0].rj;
 #pragma unroll
         for(int j = 0; j < 4; j++)
         {
-          if((und >> j) & 1u)
+          f2_unpack(f2_affine(p.axy2, p.bxy2, vx[j], vy[j], vz[j]), wxs[j], wys[j]);
+          const float dx = fabsf(wxs[j] - ib.x), dy = fabsf(wys[j] - ib.y);
+          const bool in = dx < ib.z && dy < ib.w;
+          const bool mid = !in && !(dx > rj.x || dy > rj.y); // NaN: neither in nor rejected
+          ins |= in ? (1u << j) : 0u;
+          und |= mid ? (1u << j) : 0u;
+        }
+        ins &= m4;
+        und &= m4;
+        n_act += ((amask >> l0) & 1u) ? __popc(m4) : 0u;
+      }
+      else if(m4)
+      {
+        // mixed labels in one word (plateau boundaries in the image): every point goes to the exact pass
+#pragma unroll
+        for(int j = 0; j < 4; j++)
+          if((m4 >> j) & 1u)
+            defer_push(S.L, warp, SSD_DEF_GENERIC | ((e >> 4) << 2) | (unsigned)j);
+      }
+      // between the inner box and the reject box: the f32 image of the full test, else the exact pass
+      if(__any_sync(0xffffffffu, und != 0u))
+      {
+        if(und)
+        {
+          const QuadFilterDev &f = S.qf[l0];
+#pragma unroll
+          for(int j = 0; j < 4; j++)
           {
-            const unsigned l = (lw >> (8 * j)) & 0x1fu;
-            const QuadFilterDev &f = S.qf[l];
-            float wxf, wyf;
-            f2_unpack(f2_affine(p.axy2, p.bxy2, vx[j], vy[j], vz[j]), wxf, wyf);
-            const float4 bb = f.bb;
-            const float dbb = fminf(fminf(wxf - bb.x, bb.y - wxf), fminf(wyf - bb.z, bb.w - wyf));
-            if(!(dbb < -(p.epsc + p.epsc)))
+            if((und >> j) & 1u)
             {
               bool unc;
-              const bool in = quadfilter_eval(f, wxf, wyf, p.epsc, unc);
+              const bool in = quadfilter_eval(f, wxs[j], wys[j], p.epsc, unc);
               if(unc)
                 defer_push(S.L, warp, ((e >> 4) << 2) | (unsigned)j);
               else if(in)
@@ -728,45 +750,50 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, 3) k_quad_reduce(const __grid_
           }
         }
       }
-#pragma unroll
-      for(int j = 0; j < 4; j++)
+      if(ins)
       {
-        if((ins >> j) & 1u)
+        if(l0 != seg_l)
         {
-          const unsigned l = (lw >> (8 * j)) & 0x1fu;
-          const long long zf = z_to_fix_fused(p, vx[j], vy[j], vz[j]);
-          if(l != seg_l)
+          if(seg_n)
           {
-            if(seg_n)
-            {
-              atomicAdd(&S.sum[seg_l], (unsigned long long)seg_sum);
-              atomicAdd(&S.cnt[seg_l], seg_n);
-            }
-            seg_l = l;
-            seg_sum = 0;
-            seg_n = 0;
+            atomicAdd(&S.sum[seg_l], seg_sum);
+            atomicAdd(&S.cnt[seg_l], seg_n);
           }
-          seg_sum += zf;
-          seg_n++;
-          if((int)l == ground)
+          seg_l = l0;
+          seg_sum = 0;
+          seg_n = 0;
+        }
+        unsigned zs = 0;
+#pragma unroll
+        for(int j = 0; j < 4; j++)
+          zs += ((ins >> j) & 1u) ? z_fix_u(p, vx[j], vy[j], vz[j]) : 0u;
+        seg_sum += zs;
+        seg_n += __popc(ins);
+        if((int)l0 == ground)
+        {
+#pragma unroll
+          for(int j = 0; j < 4; j++)
           {
-            // cheap column pre-filter (f32, conservative margin) before the pixel is computed
-            const float uf = fmaf(wxs[j], gsx, gk);
-            const float tcol = fmaf(floorf(uf * 0.02f), -50.f, uf); // uf mod 50, approximately
-            if(tcol < 5.f + gdcol || tcol > 50.f - gdcol || uf > (float)(p.W - 2 - (p.W / 2 - 2)))
+            if((ins >> j) & 1u)
             {
-              int ix, iy;
-              if(fast_pixel2(p, vx[j], vy[j], vz[j], ix, iy))
+              // cheap column pre-filter (f32, conservative margin) before the pixel is computed
+              const float uf = fmaf(wxs[j], gsx, gk);
+              const float tcol = fmaf(floorf(uf * 0.02f), -50.f, uf); // uf mod 50, approximately
+              if(tcol < 5.f + gdcol || tcol > 50.f - gdcol || uf > (float)(p.W - 2 - (p.W / 2 - 2)))
               {
-                if(ground_col_needed(p, ix))
+                int ix, iy;
+                if(fast_pixel2(p, vx[j], vy[j], vz[j], ix, iy))
                 {
-                  atomicOr(gbev + (unsigned)iy * (unsigned)p.wpr + (unsigned)(ix >> 5), 1u << (ix & 31));
-                  rmin = min(rmin, iy);
-                  rmax = max(rmax, iy);
+                  if(ground_col_needed(p, ix))
+                  {
+                    atomicOr(gbev + (unsigned)iy * (unsigned)p.wpr + (unsigned)(ix >> 5), 1u << (ix & 31));
+                    rmin = min(rmin, iy);
+                    rmax = max(rmax, iy);
+                  }
                 }
+                else
+                  defer_push(S.L, warp, SSD_DEF_BEVONLY | ((e >> 4) << 2) | (unsigned)j);
               }
-              else
-                defer_push(S.L, warp, SSD_DEF_BEVONLY | ((e >> 4) << 2) | (unsigned)j);
             }
           }
         }
@@ -786,7 +813,10 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, 3) k_quad_reduce(const __grid_
       {
         const unsigned d = S.L.def[warp][i];
         const unsigned w = (d >> 2) & 0xffu, j = d & 3u;
-        quad_reduce_exact_point(p, tile + (w * 4 + j) * 3, (labs[w] >> (8 * j)) & 0x1fu, (d & SSD_DEF_BEVONLY) != 0u, F, ground, gbev, S);
+        const unsigned l = (labs[w] >> (8 * j)) & 0xffu;
+        if((d & SSD_DEF_GENERIC) && l < SSD_GPU_MAX_PLATEAUS && ((amask >> l) & 1u))
+          n_act++;
+        quad_reduce_exact_point(p, tile + (w * 4 + j) * 3, l, (d & SSD_DEF_BEVONLY) != 0u, F, amask, ground, gbev, S);
       }
       __syncwarp();
       n_def += nd;
@@ -799,12 +829,12 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, 3) k_quad_reduce(const __grid_
     // combine the warp's 32 open segments: lanes grouped by label, 64-bit sum as 21 low bits + the rest
     const unsigned key = seg_n ? seg_l : 0xffu;
     const unsigned grp = __match_any_sync(0xffffffffu, key);
-    const unsigned lo = __reduce_add_sync(grp, (unsigned)(seg_sum & 0x1fffffll));
-    const int hi = __reduce_add_sync(grp, (int)(seg_sum >> 21)); // |sum| < 2^50: the high part fits 29 bits + sign
+    const unsigned lo = __reduce_add_sync(grp, (unsigned)(seg_sum & 0x1fffffull));
+    const unsigned hi = __reduce_add_sync(grp, (unsigned)(seg_sum >> 21)); // sum < 2^23 * 2^20 points: the high part fits 22 bits + 5
     const unsigned cn = __reduce_add_sync(grp, seg_n);
     if(key != 0xffu && lane == __ffs(grp) - 1)
     {
-      atomicAdd(&S.sum[key], (unsigned long long)(((long long)hi << 21) + (long long)lo));
+      atomicAdd(&S.sum[key], ((unsigned long long)hi << 21) + (unsigned long long)lo);
       atomicAdd(&S.cnt[key], cn);
     }
   }

@@ -79,12 +79,17 @@ def test_empty_and_garbage_frames(S, oracle):
     sc = S.default_scene(640, 480)
     xf = S.scene_transform(sc)
     rng = np.random.default_rng(1)
-    frames = np.zeros((3, 480, 640, 3), np.float32)  # frame 0: all invalid
+    frames = np.zeros((4, 480, 640, 3), np.float32)  # frame 0: all invalid
     frames[1] = rng.uniform(-2, 2, (480, 640, 3)).astype(np.float32)  # uniform noise
     frames[2, ..., 2] = 1.0  # a fronto-parallel wall
-    with S.Detector(cfg, xf, max_frames=3) as det:
+    # frame 3: a valid scene salted with NaN / Inf / huge / denormal coordinates (the f32 filter must hand them to the exact path)
+    frames[3] = S.deproject_host(sc, S.synth_depth_host(sc)).reshape(480, 640, 3)
+    bad = np.array([np.nan, np.inf, -np.inf, 3e38, -3e38, 1e-42, 1e20], np.float32)
+    idx = rng.integers(0, 480 * 640 * 3, 20000)
+    frames[3].reshape(-1)[idx] = bad[rng.integers(0, len(bad), idx.size)]
+    with S.Detector(cfg, xf, max_frames=4) as det:
         det.process_host(frames)
-        for f in range(3):
+        for f in range(4):
             g = gpu_result(S, det, f)
             o = H.oracle_process(oracle, cfg, xf, frames[f])
             assert not H.compare_results(o, g, tol=TOL), f
