@@ -54,6 +54,8 @@ struct DevParams
   // per-step z sum (z_fix_u): world z in single precision scaled by 2^zshift, rounded to an integer by the 1.5*2^23 add
   float azf[3], bzf;
   int zshift, pad2;
+  // k_quad_reduce ground BEV column pre-filter: t = wx * gcol_a + gcol_b = ((wx - x_min) sx - (W/2 - 2)) / 50
+  float gcol_a, gcol_b, gcol_lo, gcol_hi, gcol_tmax, pad3;
   // packed pairs for the f32x2 pipes: {af[j], af[3+j]}, {bf[0], bf[1]} (world x,y) and {au[j], av[j]}, {bu, bv} (BEV pixel)
   unsigned long long axy2[3], bxy2, auv2[3], buv2;
 };

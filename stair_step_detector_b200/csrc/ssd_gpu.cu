@@ -214,6 +214,16 @@ static int derive_params(const ssd_gpu_config &c, const ssd_gpu_transform &t, De
       d.euc = (float)((double)d.Eu1 * Mmax * 1.0001) + d.Eu0;
       d.evc = (float)((double)d.Ev1 * Mmax * 1.0001) + d.Ev0;
     }
+    {
+      // ground BEV columns W/2 - 2 + 50 j + {0..4}: f32 pre-filter with a conservative margin (pixel error of the f32
+      // world x: epsc * sx, plus the rounding of the filter's own arithmetic)
+      const double gd = ((double)d.epsc * sx * 1.0001 + 8.0 * c.width / 16777216.0 + 1e-3) / 50.0;
+      d.gcol_a = (float)(sx / 50.0);
+      d.gcol_b = (float)((-c.x_min * sx - (c.width / 2 - 2)) / 50.0);
+      d.gcol_lo = (float)(0.1 + gd);
+      d.gcol_hi = (float)(1.0 - gd);
+      d.gcol_tmax = (float)((c.width - 2 - (c.width / 2 - 2)) / 50.0 - gd);
+    }
     for(int j = 0; j < 3; j++)
     {
       d.axy2[j] = f2_pack_bits(d.af[j], d.af[3 + j]);

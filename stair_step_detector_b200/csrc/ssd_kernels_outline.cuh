@@ -1007,7 +1007,15 @@ __global__ void __launch_bounds__(SSD_OL_THREADS) k_finalize(const __grid_consta
   O.info.n_nonzero = F.n_nonzero;
   O.info.n_in_range = F.n_in_range;
   O.n_exact_bin = F.n_exact_bin;
-  O.n_quad_pts = F.n_quad_pts;
+  {
+    // points tested against a quadrilateral: every point of the ground and of the valid plateaus (k_quad_reduce)
+    unsigned nq = 0;
+    if(firstValid >= 0)
+      for(int i = 0; i < K; i++)
+        if((F.quad_amask >> i) & 1u)
+          nq += F.plat[i].n_points;
+    O.n_quad_pts = nq;
+  }
   O.n_def_quad = F.n_def_quad;
   O.n_def_bev = F.n_def_bev;
 }

@@ -306,15 +306,14 @@ __device__ __forceinline__ void defer_push(WarpLists &L, int warp, unsigned e)
   L.def[warp][slot] = (unsigned short)e;
 }
 
-// contiguous run of warp-tiles [first, end) of this warp: the frame's warp-tiles are split evenly over the
-// blocks of the frame, a block's share evenly over its warps
-__device__ __forceinline__ void warp_tile_range(int n_wt, int warp, int &first, int &end)
+// warp-tiles of this warp: first, first + stride, ... < n_wt. Interleaved over all warps of the frame's blocks:
+// neighbouring image rows carry similar amounts of work, so every warp (and block) gets an even share and the
+// final block barrier does not wait for a straggler.
+__device__ __forceinline__ void warp_tile_range(int n_wt, int warp, int &first, int &end, int &stride)
 {
-  const int per_block = (n_wt + gridDim.x - 1) / gridDim.x;
-  const int b0 = blockIdx.x * per_block, b1 = min(n_wt, b0 + per_block);
-  const int per_warp = (per_block + SSD_PT_WARPS - 1) / SSD_PT_WARPS;
-  first = min(b1, b0 + warp * per_warp);
-  end = min(b1, first + per_warp);
+  first = blockIdx.x * SSD_PT_WARPS + warp;
+  stride = gridDim.x * SSD_PT_WARPS;
+  end = n_wt;
 }
 
 __device__ __forceinline__ void load3(const float4 *__restrict__ src, float4 &a, float4 &b, float4 &c)
@@ -366,8 +365,8 @@ __global__ void __launch_bounds__(SSD_PT_THREADS) k_label_bev(const __grid_const
   unsigned *lab32 = reinterpret_cast<unsigned *>(labels + fbase);
   unsigned *fbev = bev + (size_t)frame * SSD_GPU_MAX_PLATEAUS * bm_words;
   const int nquads = p.N >> 2;
-  int wt, wt_end;
-  warp_tile_range((p.N + SSD_WT_PX - 1) / SSD_WT_PX, warp, wt, wt_end);
+  int wt, wt_end, wt_stride;
+  warp_tile_range((p.N + SSD_WT_PX - 1) / SSD_WT_PX, warp, wt, wt_end, wt_stride);
 
   // the first warp-tile's code words are requested before the tables arrive
   unsigned labw[SSD_WT_WORDS];
@@ -399,7 +398,7 @@ __global__ void __launch_bounds__(SSD_PT_THREADS) k_label_bev(const __grid_const
   int rlo = 0x7fffffff, rhi = -1;
   unsigned n_def = 0;
 
-  for(; wt < wt_end; wt++)
+  for(; wt < wt_end; wt += wt_stride)
   {
     // ---- phase A: codes -> labels, compaction of the words with pixels of outlined plateaus ----
     unsigned n = 0;
@@ -424,8 +423,8 @@ __global__ void __launch_bounds__(SSD_PT_THREADS) k_label_bev(const __grid_const
 #pragma unroll
     for(int it = 0; it < SSD_WT_WORDS; it++)
     {
-      const int q = (wt + 1) * (SSD_WT_PX / 4) + it * 32 + lane;
-      labw[it] = (wt + 1 < wt_end && q < nquads) ? lab32[q] : 0xffffffffu;
+      const int q = (wt + wt_stride) * (SSD_WT_PX / 4) + it * 32 + lane;
+      labw[it] = (wt + wt_stride < wt_end && q < nquads) ? lab32[q] : 0xffffffffu;
     }
     if(n == 0)
       continue;
@@ -552,12 +551,20 @@ struct QuadReduceShared
 {
   QuadFilterDev qf[SSD_GPU_MAX_PLATEAUS];
   QuadFast fast[SSD_GPU_MAX_PLATEAUS];
-  unsigned long long sum[SSD_GPU_MAX_PLATEAUS];
+  unsigned slo[SSD_GPU_MAX_PLATEAUS], shi[SSD_GPU_MAX_PLATEAUS]; // per-step z sum: low 16 bits / the rest (native 32-bit shared atomics)
   unsigned cnt[SSD_GPU_MAX_PLATEAUS];
   int rmin, rmax;
-  unsigned oob, n_act, n_def, pad;
+  unsigned oob, n_def, pad, pad1;
   WarpLists L;
 };
+
+// add a (sum, count) segment of label l to the block's accumulators. sum < 2^23 * points of a block: fits 16 + 32 bits
+__device__ __forceinline__ void seg_flush(QuadReduceShared &S, unsigned l, unsigned long long sum, unsigned n)
+{
+  atomicAdd(&S.slo[l], (unsigned)sum & 0xffffu);
+  atomicAdd(&S.shi[l], (unsigned)(sum >> 16));
+  atomicAdd(&S.cnt[l], n);
+}
 
 // one point of the compacted exact pass: the reference's own double-precision test
 __device__ __forceinline__ void quad_reduce_exact_point(const DevParams &p, const float *__restrict__ v, unsigned l, bool bevonly, const FrameDev &F,
@@ -572,8 +579,7 @@ __device__ __forceinline__ void quad_reduce_exact_point(const DevParams &p, cons
   {
     if(!quadtest_within(F.plat[l].qt, wx, wy))
       return;
-    atomicAdd(&S.sum[l], (unsigned long long)z_fix_u(p, fx, fy, fz));
-    atomicAdd(&S.cnt[l], 1u);
+    seg_flush(S, l, z_fix_u(p, fx, fy, fz), 1u);
   }
   if((int)l == ground)
   {
@@ -589,6 +595,7 @@ __device__ __forceinline__ void quad_reduce_exact_point(const DevParams &p, cons
   }
 }
 
+#define SSD_DEF_MID 0x2000u     // deferred point between inner and reject box: f32 image of the test first
 #define SSD_DEF_GENERIC 0x4000u // deferred point of a word with mixed labels: not yet checked against amask
 
 __global__ void __launch_bounds__(SSD_PT_THREADS, 3) k_quad_reduce(const __grid_constant__ DevParams p, const float *__restrict__ xyz,
@@ -607,8 +614,8 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, 3) k_quad_reduce(const __grid_
   const unsigned *lab32 = reinterpret_cast<const unsigned *>(labels + fbase);
   unsigned *gbev = ground >= 0 ? bev + ((size_t)frame * SSD_GPU_MAX_PLATEAUS + ground) * bm_words : nullptr;
   const int nquads = p.N >> 2;
-  int wt, wt_end;
-  warp_tile_range((p.N + SSD_WT_PX - 1) / SSD_WT_PX, warp, wt, wt_end);
+  int wt, wt_end, wt_stride;
+  warp_tile_range((p.N + SSD_WT_PX - 1) / SSD_WT_PX, warp, wt, wt_end, wt_stride);
 
   unsigned labw[SSD_WT_WORDS];
 #pragma unroll
@@ -625,7 +632,8 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, 3) k_quad_reduce(const __grid_
       dst[i] = src[i];
     if(tid < SSD_GPU_MAX_PLATEAUS)
     {
-      S.sum[tid] = 0;
+      S.slo[tid] = 0;
+      S.shi[tid] = 0;
       S.cnt[tid] = 0;
       const bool live = (amask >> tid) & 1u;
       // labels outside amask: never inside, always rejected
@@ -640,7 +648,6 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, 3) k_quad_reduce(const __grid_
       S.rmin = 0x7fffffff;
       S.rmax = -1;
       S.oob = 0;
-      S.n_act = 0;
       S.n_def = 0;
     }
   }
@@ -648,14 +655,12 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, 3) k_quad_reduce(const __grid_
 
   unsigned short *act = S.L.act[warp];
   unsigned *labs = S.L.lab[warp];
-  unsigned seg_l = 0xffu, seg_n = 0, n_act = 0, n_def = 0;
+  unsigned seg_l = 0xffu, seg_n = 0, n_def = 0, n_mid = 0;
   unsigned long long seg_sum = 0;
   int rmin = 0x7fffffff, rmax = -1;
-  // ground BEV column pre-filter in f32: u' = (wx - x_min) * sx - (W/2 - 2); needed iff u' mod 50 in [0, 5)
-  const float gsx = (float)p.x_to_image, gk = (float)(-p.x_min * p.x_to_image) - (float)(p.W / 2 - 2);
-  const float gdcol = fmaf(p.epsc, (float)(p.x_to_image * 1.0001), (float)(8.0 * p.W / 16777216.0) + 1e-3f);
+  const float4 *frame4 = reinterpret_cast<const float4 *>(xyz + fbase * 3);
 
-  for(; wt < wt_end; wt++)
+  for(; wt < wt_end; wt += wt_stride)
   {
     // ---- phase A: compaction of the words holding plateau labels (bit 7 of a label byte clear <=> label < 128) ----
     unsigned n = 0;
@@ -674,15 +679,15 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, 3) k_quad_reduce(const __grid_
 #pragma unroll
     for(int it = 0; it < SSD_WT_WORDS; it++)
     {
-      const int q = (wt + 1) * (SSD_WT_PX / 4) + it * 32 + lane;
-      labw[it] = (wt + 1 < wt_end && q < nquads) ? __ldg(lab32 + q) : 0xffffffffu;
+      const int q = (wt + wt_stride) * (SSD_WT_PX / 4) + it * 32 + lane;
+      labw[it] = (wt + wt_stride < wt_end && q < nquads) ? __ldg(lab32 + q) : 0xffffffffu;
     }
     if(n == 0)
       continue;
     __syncwarp();
 
     // ---- phase B: dense walk over the compacted words ----
-    const float4 *tile4 = reinterpret_cast<const float4 *>(xyz + (fbase + (size_t)wt * SSD_WT_PX) * 3);
+    const float4 *tile4 = frame4 + (size_t)wt * (SSD_WT_PX / 4 * 3);
     unsigned e = lane < n ? act[lane] : 0u;
     float4 c0, c1, c2, n0, n1, n2;
     c0 = c1 = c2 = n0 = n1 = n2 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -701,85 +706,64 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, 3) k_quad_reduce(const __grid_
       const unsigned bytes = ((m4 * 0x00204081u) & 0x01010101u) * 0xffu;
       const bool uniform = ((lw ^ (l0 * 0x01010101u)) & bytes) == 0u;
       const float vx[4] = { c0.x, c0.w, c1.z, c2.y }, vy[4] = { c0.y, c1.x, c1.w, c2.z }, vz[4] = { c0.z, c1.y, c2.x, c2.w };
-      unsigned ins = 0, und = 0;
-      float wxs[4], wys[4];
       if(uniform)
       {
+        // Branch-free on sign bits (every operand is finite here: plateau points are valid and in range, the tables
+        // hold finite numbers or +inf). Labels outside amask have an empty inner box and an empty reject box.
+        //   in  <=> active && |wx - cx| < hx && |wy - cy| < hy      (sign of |d| - h, both set)
+        //   rej <=> |wx - cx| > Rx || |wy - cy| > Ry                 (sign of R - |d|, either set)
+        //   mid <=> active && !in && !rej  -> deferred
         const float4 ib = S.fast[l0].ibe;
         const float2 rj = S.fast[l0].rj;
-#pragma unroll
-        for(int j = 0; j < 4; j++)
-        {
-          f2_unpack(f2_affine(p.axy2, p.bxy2, vx[j], vy[j], vz[j]), wxs[j], wys[j]);
-          const float dx = fabsf(wxs[j] - ib.x), dy = fabsf(wys[j] - ib.y);
-          const bool in = dx < ib.z && dy < ib.w;
-          const bool mid = !in && !(dx > rj.x || dy > rj.y); // NaN: neither in nor rejected
-          ins |= in ? (1u << j) : 0u;
-          und |= mid ? (1u << j) : 0u;
-        }
-        ins &= m4;
-        und &= m4;
-        n_act += ((amask >> l0) & 1u) ? __popc(m4) : 0u;
-      }
-      else if(m4)
-      {
-        // mixed labels in one word (plateau boundaries in the image): every point goes to the exact pass
-#pragma unroll
-        for(int j = 0; j < 4; j++)
-          if((m4 >> j) & 1u)
-            defer_push(S.L, warp, SSD_DEF_GENERIC | ((e >> 4) << 2) | (unsigned)j);
-      }
-      // between the inner box and the reject box: the f32 image of the full test, else the exact pass
-      if(__any_sync(0xffffffffu, und != 0u))
-      {
-        if(und)
-        {
-          const QuadFilterDev &f = S.qf[l0];
-#pragma unroll
-          for(int j = 0; j < 4; j++)
-          {
-            if((und >> j) & 1u)
-            {
-              bool unc;
-              const bool in = quadfilter_eval(f, wxs[j], wys[j], p.epsc, unc);
-              if(unc)
-                defer_push(S.L, warp, ((e >> 4) << 2) | (unsigned)j);
-              else if(in)
-                ins |= 1u << j;
-            }
-          }
-        }
-      }
-      if(ins)
-      {
-        if(l0 != seg_l)
-        {
-          if(seg_n)
-          {
-            atomicAdd(&S.sum[seg_l], seg_sum);
-            atomicAdd(&S.cnt[seg_l], seg_n);
-          }
-          seg_l = l0;
-          seg_sum = 0;
-          seg_n = 0;
-        }
+        float wxs[4];
+        int inm[4], midm[4];
+        int cnt = 0;
         unsigned zs = 0;
 #pragma unroll
         for(int j = 0; j < 4; j++)
-          zs += ((ins >> j) & 1u) ? z_fix_u(p, vx[j], vy[j], vz[j]) : 0u;
-        seg_sum += zs;
-        seg_n += __popc(ins);
-        if((int)l0 == ground)
+        {
+          float wy;
+          f2_unpack(f2_affine(p.axy2, p.bxy2, vx[j], vy[j], vz[j]), wxs[j], wy);
+          const float dx = fabsf(wxs[j] - ib.x), dy = fabsf(wy - ib.y);
+          const int act = (int)(m4 << (31 - j));
+          const int ins = __float_as_int(dx - ib.z) & __float_as_int(dy - ib.w) & act;
+          const int rej = __float_as_int(rj.x - dx) | __float_as_int(rj.y - dy);
+          midm[j] = act & ~ins & ~rej;
+          inm[j] = ins >> 31; // all ones when inside
+          zs += z_fix_u(p, vx[j], vy[j], vz[j]) & (unsigned)inm[j];
+          cnt -= inm[j];
+        }
+        // between the inner box and the reject box (a few percent of the points, but in most warp steps): deferred to
+        // the dense pass at the end of the warp-tile, which evaluates the f32 image of the full test one point per lane
+        if((midm[0] | midm[1] | midm[2] | midm[3]) < 0)
         {
 #pragma unroll
           for(int j = 0; j < 4; j++)
+            if(midm[j] < 0)
+              defer_push(S.L, warp, SSD_DEF_MID | ((e >> 4) << 2) | (unsigned)j);
+        }
+        if(cnt)
+        {
+          if(l0 != seg_l)
           {
-            if((ins >> j) & 1u)
+            if(seg_n)
+              seg_flush(S, seg_l, seg_sum, seg_n);
+            seg_l = l0;
+            seg_sum = 0;
+            seg_n = 0;
+          }
+          seg_sum += zs;
+          seg_n += (unsigned)cnt;
+          if((int)l0 == ground)
+          {
+#pragma unroll
+            for(int j = 0; j < 4; j++)
             {
-              // cheap column pre-filter (f32, conservative margin) before the pixel is computed
-              const float uf = fmaf(wxs[j], gsx, gk);
-              const float tcol = fmaf(floorf(uf * 0.02f), -50.f, uf); // uf mod 50, approximately
-              if(tcol < 5.f + gdcol || tcol > 50.f - gdcol || uf > (float)(p.W - 2 - (p.W / 2 - 2)))
+              // cheap column pre-filter (f32, conservative margin) before the pixel is computed:
+              // t = ((wx - x_min) sx - (W/2 - 2)) / 50; the column is needed iff frac(t) in [0, 0.1)
+              const float t = fmaf(wxs[j], p.gcol_a, p.gcol_b);
+              const float fr = t - floorf(t);
+              if(inm[j] && (fr < p.gcol_lo || fr > p.gcol_hi || t > p.gcol_tmax))
               {
                 int ix, iy;
                 if(fast_pixel2(p, vx[j], vy[j], vz[j], ix, iy))
@@ -798,6 +782,14 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, 3) k_quad_reduce(const __grid_
           }
         }
       }
+      else
+      {
+        // mixed labels in one word (plateau boundaries in the image): every point goes to the exact pass
+#pragma unroll
+        for(int j = 0; j < 4; j++)
+          if((m4 >> j) & 1u)
+            defer_push(S.L, warp, SSD_DEF_GENERIC | ((e >> 4) << 2) | (unsigned)j);
+      }
       e = e1;
       c0 = n0;
       c1 = n1;
@@ -814,33 +806,63 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, 3) k_quad_reduce(const __grid_
         const unsigned d = S.L.def[warp][i];
         const unsigned w = (d >> 2) & 0xffu, j = d & 3u;
         const unsigned l = (labs[w] >> (8 * j)) & 0xffu;
-        if((d & SSD_DEF_GENERIC) && l < SSD_GPU_MAX_PLATEAUS && ((amask >> l) & 1u))
-          n_act++;
-        quad_reduce_exact_point(p, tile + (w * 4 + j) * 3, l, (d & SSD_DEF_BEVONLY) != 0u, F, amask, ground, gbev, S);
+        const float *v = tile + (w * 4 + j) * 3;
+        bool exact = true, bevonly = (d & SSD_DEF_BEVONLY) != 0u;
+        if(d & SSD_DEF_MID)
+        {
+          const float fx = __ldg(v), fy = __ldg(v + 1), fz = __ldg(v + 2);
+          float wxf, wyf;
+          f2_unpack(f2_affine(p.axy2, p.bxy2, fx, fy, fz), wxf, wyf);
+          bool unc;
+          const bool in = quadfilter_eval(S.qf[l & 31u], wxf, wyf, p.epsc, unc);
+          if(!unc)
+          {
+            n_mid++;
+            exact = in && (int)l == ground; // certain: count it here; an inside ground point still needs its BEV pixel
+            bevonly = true;
+            if(in)
+            {
+              // into the lane's running segment (no shared-memory atomics: 64-bit ones are CAS loops)
+              if(l != seg_l)
+              {
+                if(seg_n)
+                  seg_flush(S, seg_l, seg_sum, seg_n);
+                seg_l = l;
+                seg_sum = 0;
+                seg_n = 0;
+              }
+              seg_sum += z_fix_u(p, fx, fy, fz);
+              seg_n++;
+            }
+          }
+        }
+        if(exact)
+          quad_reduce_exact_point(p, v, l, bevonly, F, amask, ground, gbev, S);
       }
       __syncwarp();
       n_def += nd;
       if(lane == 0)
         S.L.ndef[warp] = 0;
     }
+    {
+      // end of the warp-tile: combine the warp's 32 open segments (single-pass segmented reduce: lanes grouped by
+      // label, 64-bit sums as 21 low bits + the rest), one set of shared-memory adds per distinct label
+      const unsigned key = seg_n ? seg_l : 0xffu;
+      const unsigned grp = __match_any_sync(0xffffffffu, key);
+      const unsigned lo = __reduce_add_sync(grp, (unsigned)seg_sum & 0x1fffffu);
+      const unsigned hi = __reduce_add_sync(grp, (unsigned)(seg_sum >> 21)); // a lane's sum < 2^23 * 2^10 points per tile
+      const unsigned cn = __reduce_add_sync(grp, seg_n);
+      if(key != 0xffu && lane == __ffs(grp) - 1)
+        seg_flush(S, key, ((unsigned long long)hi << 21) + (unsigned long long)lo, cn);
+      seg_l = 0xffu;
+      seg_sum = 0;
+      seg_n = 0;
+    }
     __syncwarp();
   }
-  {
-    // combine the warp's 32 open segments: lanes grouped by label, 64-bit sum as 21 low bits + the rest
-    const unsigned key = seg_n ? seg_l : 0xffu;
-    const unsigned grp = __match_any_sync(0xffffffffu, key);
-    const unsigned lo = __reduce_add_sync(grp, (unsigned)(seg_sum & 0x1fffffull));
-    const unsigned hi = __reduce_add_sync(grp, (unsigned)(seg_sum >> 21)); // sum < 2^23 * 2^20 points: the high part fits 22 bits + 5
-    const unsigned cn = __reduce_add_sync(grp, seg_n);
-    if(key != 0xffu && lane == __ffs(grp) - 1)
-    {
-      atomicAdd(&S.sum[key], ((unsigned long long)hi << 21) + (unsigned long long)lo);
-      atomicAdd(&S.cnt[key], cn);
-    }
-  }
+  n_def -= __reduce_add_sync(0xffffffffu, n_mid); // deferred points settled by the f32 image of the test are not exact decisions
   rmin = __reduce_min_sync(0xffffffffu, rmin);
   rmax = __reduce_max_sync(0xffffffffu, rmax);
-  n_act = __reduce_add_sync(0xffffffffu, n_act);
   if(lane == 0)
   {
     if(rmax >= 0)
@@ -848,15 +870,13 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, 3) k_quad_reduce(const __grid_
       atomicMin(&S.rmin, rmin);
       atomicMax(&S.rmax, rmax);
     }
-    if(n_act)
-      atomicAdd(&S.n_act, n_act);
     if(n_def)
       atomicAdd(&S.n_def, n_def);
   }
   __syncthreads();
   if(tid < SSD_GPU_MAX_PLATEAUS && S.cnt[tid])
   {
-    atomicAdd(&F.plat[tid].sum_fix, S.sum[tid]);
+    atomicAdd(&F.plat[tid].sum_fix, ((unsigned long long)S.shi[tid] << 16) + (unsigned long long)S.slo[tid]);
     atomicAdd(&F.plat[tid].n_in_quad, S.cnt[tid]);
   }
   if(tid == 0)
@@ -868,8 +888,6 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, 3) k_quad_reduce(const __grid_
     }
     if(S.oob)
       atomicOr(&F.status, SSD_STATUS_BEV_OOB);
-    if(S.n_act)
-      atomicAdd(&F.n_quad_pts, S.n_act);
     if(S.n_def)
       atomicAdd(&F.n_def_quad, S.n_def);
   }
