@@ -396,7 +396,7 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, int frame
   const dim3 gpt2(bpf, nf);
 
   STAGE_EV(0);
-  k_transform_bin<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, 0, st>>>(p, xyz_dev, labels, frames);
+  k_transform_bin<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, SSD_PT_ITERS * SSD_TB_STAGE_BYTES, st>>>(p, xyz_dev, labels, frames);
   STAGE_EV(1);
   k_peaks<<<nf, 32, 0, st>>>(p, frames, nf);
   STAGE_EV(2);
@@ -543,6 +543,8 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
   dyn &= ~(size_t)15;
   ctx->ol_dyn_smem = dyn;
   ctx->smem_cap_words = dyn / 4;
+  if(cudaFuncSetAttribute(k_transform_bin<SSD_PT_ITERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SSD_PT_ITERS * SSD_TB_STAGE_BYTES) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(k_transform_bin) failed", SSD_E_CUDA);
   cudaFuncSetAttribute(k_outline, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
   cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
   cudaFuncSetAttribute(k_test_front_edge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);

@@ -35,6 +35,47 @@ __device__ __forceinline__ Quad4 load_quad(const float4 *__restrict__ xyz4, size
   return r;
 }
 
+// ---- TMA bulk staging (cp.async.bulk + mbarrier): one elected thread streams a whole tile of vertices into
+// shared memory; the loads in flight no longer cost registers or depend on occupancy ----
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// wait for phase `parity` of the barrier; a copy that never lands traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+  for(int spin = 0; spin < (1 << 24); spin++)
+  {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    if(ok)
+      return;
+  }
+  __trap();
+}
+
+// predicated shared-memory reduction (no branch around it): [addr] += v if pred
+__device__ __forceinline__ void red_shared_add_if(unsigned addr, unsigned v, bool pred)
+{
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q red.shared.add.u32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"((unsigned)pred) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // k_transform_bin: PointsExtraction::extract + HeightsHistogram::calcHist
 // (pointcloud.cpp:122-178, 194-204). grid = (tiles_per_frame, frames), block = 256.
@@ -45,33 +86,59 @@ __device__ __forceinline__ Quad4 load_quad(const float4 *__restrict__ xyz4, size
 // Histogram: each thread run-length merges its own codes (neighbouring pixels mostly share a bin) and adds
 // the runs to one shared-memory histogram per block; one global atomic per non-empty bin per block.
 // ---------------------------------------------------------------------------------------------
+#define SSD_TB_STAGE_BYTES (SSD_PT_THREADS * 48) // one iteration of the block: 256 threads x 4 vertices x 12 B
 template<int ITERS>
 __global__ void __launch_bounds__(SSD_PT_THREADS) k_transform_bin(const __grid_constant__ DevParams p, const float *__restrict__ xyz,
                                                                    unsigned char *__restrict__ codes, FrameDev *__restrict__ frames)
 {
+  extern __shared__ __align__(128) unsigned char s_dyn[]; // ITERS stages of SSD_TB_STAGE_BYTES
+  __shared__ __align__(8) unsigned long long s_bar[ITERS];
   __shared__ unsigned s_hist[SSD_BINS_PAD];
   __shared__ unsigned s_exact;
   const int tid = threadIdx.x;
   const int frame = blockIdx.y;
-  s_hist[tid] = 0; // SSD_PT_THREADS == SSD_BINS_PAD
-  if(tid == 0)
-    s_exact = 0;
-  __syncthreads();
-
   const size_t fbase = (size_t)frame * p.N;
   const int nquads = p.N >> 2;
-  const int q0 = blockIdx.x * (ITERS * SSD_PT_THREADS) + tid;
-  const float4 *src = reinterpret_cast<const float4 *>(xyz + fbase * 3) + (size_t)q0 * 3;
+  const int qb = blockIdx.x * (ITERS * SSD_PT_THREADS); // first quad (4 vertices) of the block
+  const unsigned stage_sa = (unsigned)__cvta_generic_to_shared(s_dyn);
+  const unsigned bar_sa = (unsigned)__cvta_generic_to_shared(s_bar);
+  if(tid == 0)
+  {
+#pragma unroll
+    for(int it = 0; it < ITERS; it++)
+      mbar_init(bar_sa + it * 8, 1);
+    mbar_fence_init();
+    // the whole tile is requested at once: ITERS bulk copies of up to 12 KB, each signalling its own barrier
+    const unsigned char *gsrc = reinterpret_cast<const unsigned char *>(xyz + fbase * 3) + (size_t)qb * 48;
+#pragma unroll
+    for(int it = 0; it < ITERS; it++)
+    {
+      const int nq = min(SSD_PT_THREADS, nquads - (qb + it * SSD_PT_THREADS));
+      if(nq > 0)
+      {
+        mbar_expect_tx(bar_sa + it * 8, (unsigned)nq * 48u);
+        bulk_g2s(stage_sa + it * SSD_TB_STAGE_BYTES, gsrc + (size_t)it * SSD_TB_STAGE_BYTES, (unsigned)nq * 48u, bar_sa + it * 8);
+      }
+    }
+    s_exact = 0;
+  }
+  s_hist[tid] = 0; // SSD_PT_THREADS == SSD_BINS_PAD
+  __syncthreads();
+
+  const int q0 = qb + tid;
   unsigned *dst = reinterpret_cast<unsigned *>(codes + fbase) + q0;
   unsigned run_code = SSD_CODE_INVALID, run_n = 0, exact = 0; // an empty run of a valid code: no sentinel pattern to collide with
+  const unsigned hist_sa = (unsigned)__cvta_generic_to_shared(s_hist);
 
 #pragma unroll
   for(int it = 0; it < ITERS; it++)
   {
+    if(qb + it * SSD_PT_THREADS < nquads) // block-uniform: the stage was requested
+      mbar_wait(bar_sa + it * 8, 0);
     if(q0 + it * SSD_PT_THREADS < nquads)
     {
-      const float4 *s4 = src + it * (SSD_PT_THREADS * 3);
-      const float4 v0 = __ldg(s4), v1 = __ldg(s4 + 1), v2 = __ldg(s4 + 2);
+      const float4 *s4 = reinterpret_cast<const float4 *>(s_dyn + it * SSD_TB_STAGE_BYTES) + tid * 3;
+      const float4 v0 = s4[0], v1 = s4[1], v2 = s4[2];
       const float vx[4] = { v0.x, v0.w, v1.z, v2.y }, vy[4] = { v0.y, v1.x, v1.w, v2.z }, vz[4] = { v0.z, v1.y, v2.x, v2.w };
       unsigned c[4];
       bool unc[4];
@@ -91,22 +158,18 @@ __global__ void __launch_bounds__(SSD_PT_THREADS) k_transform_bin(const __grid_c
       }
       const unsigned cw = c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24);
       dst[it * SSD_PT_THREADS] = cw;
-      if(cw == run_code * 0x01010101u)
-        run_n += 4; // all four in the current run (neighbouring pixels mostly share a bin)
+      if(__all_sync(0xffffffffu, cw == run_code * 0x01010101u))
+        run_n += 4; // warp-uniform: every lane's four codes continue its run (invalid / out-of-range areas, flat surfaces)
       else
       {
+        // branch-free run-length merge: a run that ends is added to the block histogram by a predicated reduction
 #pragma unroll
         for(int j = 0; j < 4; j++)
         {
-          if(c[j] == run_code)
-            run_n++;
-          else
-          {
-            if(run_n)
-              atomicAdd(&s_hist[run_code], run_n);
-            run_code = c[j];
-            run_n = 1;
-          }
+          const bool same = c[j] == run_code;
+          red_shared_add_if(hist_sa + run_code * 4u, run_n, !same);
+          run_n = same ? run_n + 1u : 1u;
+          run_code = c[j];
         }
       }
     }
