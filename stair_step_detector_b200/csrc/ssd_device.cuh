@@ -702,7 +702,7 @@ __device__ __forceinline__ bool quadtest_cell_pred(const QuadTestDev &t, int r, 
 }
 
 // Inner box for the fast accept. Candidate: the middle interval of the sorted corner coordinates, shrunk by
-// 2 %. It is accepted only if, for every map cell it overlaps, the cell's predicate holds at the four corners
+// 0.1 % .. 8 %. It is accepted only if, for every map cell it overlaps, the cell's predicate holds at the four corners
 // of (box intersect cell): each half-plane value fl(fl(x*k)+y)+c is monotone in x and in y (IEEE operations
 // are monotone), so its minimum over a rectangle is attained at a corner -- the predicate then holds on the
 // whole intersection, hence isPointWithin() is true for every point of the box.
@@ -729,31 +729,45 @@ __device__ inline void quadtest_inner_box(QuadTestDev &t, const P2d q[4])
         ys[j - 1] = tmp;
       }
     }
-  const double sx = 0.02 * (xs[2] - xs[1]) + 1e-6, sy = 0.02 * (ys[2] - ys[1]) + 1e-6;
-  const double bx0 = xs[1] + sx, bx1 = xs[2] - sx, by0 = ys[1] + sy, by1 = ys[2] - sy;
-  if(!(bx0 < bx1 && by0 < by1))
-    return;
-  if(!(t.tb_lo_x < bx0 && bx1 < t.tb_hi_x && t.tb_lo_y < by0 && by1 < t.tb_hi_y))
-    return;
-  for(int r = 0; r < t.nrow; r++)
+  // the smallest shrink whose box verifies (a near-rectangle passes with the first; every percent of shrink sends
+  // that share of the step's points to the slower filtered test)
+  double bx0 = 0, bx1 = 0, by0 = 0, by1 = 0;
+  bool found = false;
+  for(int attempt = 0; attempt < 4 && !found; attempt++)
   {
-    const double ry0 = r == 0 ? t.tb_lo_y : t.row_upper_y[r - 1];
-    const double ry1 = r == t.nrow - 1 ? t.tb_hi_y : t.row_upper_y[r];
-    const double ay = by0 > ry0 ? by0 : ry0, cy = by1 < ry1 ? by1 : ry1;
-    if(!(ay <= cy))
+    const double fr = attempt == 0 ? 0.001 : (attempt == 1 ? 0.005 : (attempt == 2 ? 0.02 : 0.08));
+    const double sx = fr * (xs[2] - xs[1]) + 1e-6, sy = fr * (ys[2] - ys[1]) + 1e-6;
+    bx0 = xs[1] + sx;
+    bx1 = xs[2] - sx;
+    by0 = ys[1] + sy;
+    by1 = ys[2] - sy;
+    if(!(bx0 < bx1 && by0 < by1))
+      return;
+    if(!(t.tb_lo_x < bx0 && bx1 < t.tb_hi_x && t.tb_lo_y < by0 && by1 < t.tb_hi_y))
       continue;
-    for(int c = 0; c < t.ncell[r]; c++)
+    bool ok = true;
+    for(int r = 0; r < t.nrow && ok; r++)
     {
-      const double rx0 = c == 0 ? t.tb_lo_x : t.cell_upper_x[r][c - 1];
-      const double rx1 = c == t.ncell[r] - 1 ? t.tb_hi_x : t.cell_upper_x[r][c];
-      const double ax = bx0 > rx0 ? bx0 : rx0, cx = bx1 < rx1 ? bx1 : rx1;
-      if(!(ax <= cx))
+      const double ry0 = r == 0 ? t.tb_lo_y : t.row_upper_y[r - 1];
+      const double ry1 = r == t.nrow - 1 ? t.tb_hi_y : t.row_upper_y[r];
+      const double ay = by0 > ry0 ? by0 : ry0, cy = by1 < ry1 ? by1 : ry1;
+      if(!(ay <= cy))
         continue;
-      if(!(quadtest_cell_pred(t, r, c, ax, ay) && quadtest_cell_pred(t, r, c, cx, ay) && quadtest_cell_pred(t, r, c, ax, cy) &&
-           quadtest_cell_pred(t, r, c, cx, cy)))
-        return;
+      for(int c = 0; c < t.ncell[r] && ok; c++)
+      {
+        const double rx0 = c == 0 ? t.tb_lo_x : t.cell_upper_x[r][c - 1];
+        const double rx1 = c == t.ncell[r] - 1 ? t.tb_hi_x : t.cell_upper_x[r][c];
+        const double ax = bx0 > rx0 ? bx0 : rx0, cx = bx1 < rx1 ? bx1 : rx1;
+        if(!(ax <= cx))
+          continue;
+        ok = quadtest_cell_pred(t, r, c, ax, ay) && quadtest_cell_pred(t, r, c, cx, ay) && quadtest_cell_pred(t, r, c, ax, cy) &&
+             quadtest_cell_pred(t, r, c, cx, cy);
+      }
     }
+    found = ok;
   }
+  if(!found)
+    return;
   // single-precision centre / half width, rounded so the f32 box lies inside the verified box
   const double u = 1.0 / 16777216.0;
   const double mx = fmax(fabs(bx0), fabs(bx1)), my = fmax(fabs(by0), fabs(by1));

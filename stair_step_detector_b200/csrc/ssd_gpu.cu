@@ -15,6 +15,7 @@
 
 #define SSD_PT_ITERS 4   // k_transform_bin: 4096 points per block
 #define SSD_TILE_POINTS (SSD_PT_THREADS * 4 * SSD_PT_ITERS)
+#define SSD_MAX_STREAMS 4
 
 static thread_local std::string g_create_error;
 
@@ -29,16 +30,17 @@ struct ssd_gpu_ctx
   size_t bm_words = 0;        // words per BEV bitmap
   size_t smem_cap_words = 0;  // dynamic shared memory available to the band (words)
   size_t ol_dyn_smem = 0;
-  cudaStream_t stream[2]{};
+  int n_streams = 3;
+  cudaStream_t stream[SSD_MAX_STREAMS]{};
   cudaStream_t copy_stream{};
   cudaEvent_t ev_start{}, ev_stop{}, ev_h2d0{}, ev_h2d1{};
-  cudaEvent_t ev_in_ready[2]{}, ev_in_free[2]{}, ev_chunk_done[2]{};
+  cudaEvent_t ev_in_ready[SSD_MAX_STREAMS]{}, ev_in_free[SSD_MAX_STREAMS]{}, ev_chunk_done[SSD_MAX_STREAMS]{};
   FrameDev *d_frames = nullptr;   // max_frames
   FrameOut *d_out = nullptr;      // max_frames
   FrameOut *h_out = nullptr;      // pinned
   unsigned char *d_labels = nullptr; // max_frames * N
   unsigned *d_bev = nullptr; // 2 x chunk_frames * MAX_PLATEAUS * bm_words (per stream)
-  float *d_stage[2]{};            // host-input staging, chunk_frames frames each
+  float *d_stage[SSD_MAX_STREAMS]{};            // host-input staging, chunk_frames frames each
   int pt_blocks_target = 0;       // blocks per launch of the tile-looping point kernels
   int n_frames_last = 0;
   int flags_last = 0;
@@ -443,11 +445,10 @@ void ssd_gpu_destroy(ssd_gpu_ctx *ctx)
   cudaFreeHost(ctx->h_out);
   cudaFree(ctx->d_labels);
   cudaFree(ctx->d_bev);
-  cudaFree(ctx->d_stage[0]);
-  cudaFree(ctx->d_stage[1]);
   cudaFree(ctx->d_img);
-  for(int i = 0; i < 2; i++)
+  for(int i = 0; i < SSD_MAX_STREAMS; i++)
   {
+    cudaFree(ctx->d_stage[i]);
     if(ctx->stream[i])
       cudaStreamDestroy(ctx->stream[i]);
     if(ctx->ev_in_ready[i])
@@ -506,8 +507,10 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
     int cf = 256;
     if(const char *e = getenv("SSD_GPU_CHUNK_FRAMES"))
       cf = atoi(e);
+    if(const char *e = getenv("SSD_GPU_STREAMS"))
+      ctx->n_streams = std::max(1, std::min(SSD_MAX_STREAMS, atoi(e)));
     // the BEV bitmaps (2 streams x chunk x 32 slots) must stay a small part of HBM
-    const size_t per_frame = (size_t)2 * SSD_GPU_MAX_PLATEAUS * ctx->bm_words * 4;
+    const size_t per_frame = (size_t)ctx->n_streams * SSD_GPU_MAX_PLATEAUS * ctx->bm_words * 4;
     const size_t budget = (size_t)8 << 30;
     if((size_t)cf * per_frame > budget)
       cf = (int)(budget / per_frame);
@@ -560,7 +563,7 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
       return bail(#call, e_ == cudaErrorMemoryAllocation ? SSD_E_NOMEM : SSD_E_CUDA); \
     }                                                                        \
   } while(0)
-  for(int i = 0; i < 2; i++)
+  for(int i = 0; i < ctx->n_streams; i++)
   {
     CKC(cudaStreamCreateWithFlags(&ctx->stream[i], cudaStreamNonBlocking));
     CKC(cudaEventCreateWithFlags(&ctx->ev_in_ready[i], cudaEventDisableTiming));
@@ -576,7 +579,7 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
   CKC(cudaMalloc(&ctx->d_out, sizeof(FrameOut) * (size_t)max_frames));
   CKC(cudaMallocHost(&ctx->h_out, sizeof(FrameOut) * (size_t)max_frames));
   CKC(cudaMalloc(&ctx->d_labels, (size_t)max_frames * dp.N));
-  const size_t bev_bytes = (size_t)2 * ctx->chunk_frames * SSD_GPU_MAX_PLATEAUS * ctx->bm_words * 4;
+  const size_t bev_bytes = (size_t)ctx->n_streams * ctx->chunk_frames * SSD_GPU_MAX_PLATEAUS * ctx->bm_words * 4;
   CKC(cudaMalloc(&ctx->d_bev, bev_bytes));
   CKC(cudaMemset(ctx->d_bev, 0, bev_bytes)); // bitmaps are self-cleaning afterwards
   CKC(cudaMemset(ctx->d_frames, 0, sizeof(FrameDev) * (size_t)max_frames));
@@ -599,7 +602,7 @@ static int process_common(ssd_gpu_ctx *ctx, const float *xyz, bool host_input, i
   const size_t frame_floats = (size_t)p.N * 3;
   const int cf = ctx->chunk_frames;
   if(host_input)
-    for(int i = 0; i < 2; i++)
+    for(int i = 0; i < ctx->n_streams; i++)
       if(!ctx->d_stage[i])
         CK(cudaMalloc(&ctx->d_stage[i], (size_t)cf * frame_floats * sizeof(float)));
 
@@ -621,23 +624,25 @@ static int process_common(ssd_gpu_ctx *ctx, const float *xyz, bool host_input, i
   ctx->flags_last = flags;
   // the whole call is ordered after ev_start on stream 0; stream 1 joins via events
   CK(cudaEventRecord(ctx->ev_start, ctx->stream[0]));
-  CK(cudaStreamWaitEvent(ctx->stream[1], ctx->ev_start, 0));
+  for(int i = 1; i < ctx->n_streams; i++)
+    CK(cudaStreamWaitEvent(ctx->stream[i], ctx->ev_start, 0));
   CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_start, 0));
   // per-frame state: histogram must start at zero
   CK(cudaMemsetAsync(ctx->d_frames, 0, sizeof(FrameDev) * (size_t)n_frames, ctx->stream[0]));
   CK(cudaEventRecord(ctx->ev_chunk_done[0], ctx->stream[0]));
-  CK(cudaStreamWaitEvent(ctx->stream[1], ctx->ev_chunk_done[0], 0));
+  for(int i = 1; i < ctx->n_streams; i++)
+    CK(cudaStreamWaitEvent(ctx->stream[i], ctx->ev_chunk_done[0], 0));
 
   int chunk = 0;
   for(int f0 = 0; f0 < n_frames; f0 += cf, chunk++)
   {
     const int nf = std::min(cf, n_frames - f0);
-    const int s = chunk & 1;
+    const int s = chunk % ctx->n_streams;
     const float *src = xyz + (size_t)f0 * frame_floats;
     if(host_input)
     {
       // stage s may be overwritten once the chunk that last used it has finished
-      if(chunk >= 2)
+      if(chunk >= ctx->n_streams)
         CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_in_free[s], 0));
       CK(cudaMemcpyAsync(ctx->d_stage[s], src, (size_t)nf * frame_floats * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
       CK(cudaEventRecord(ctx->ev_in_ready[s], ctx->copy_stream));
@@ -651,8 +656,11 @@ static int process_common(ssd_gpu_ctx *ctx, const float *xyz, bool host_input, i
       CK(cudaEventRecord(ctx->ev_in_free[s], ctx->stream[s]));
   }
   // join stream 1 into stream 0, then bring the compact results home
-  CK(cudaEventRecord(ctx->ev_chunk_done[1], ctx->stream[1]));
-  CK(cudaStreamWaitEvent(ctx->stream[0], ctx->ev_chunk_done[1], 0));
+  for(int i = 1; i < ctx->n_streams; i++)
+  {
+    CK(cudaEventRecord(ctx->ev_chunk_done[i], ctx->stream[i]));
+    CK(cudaStreamWaitEvent(ctx->stream[0], ctx->ev_chunk_done[i], 0));
+  }
   CK(cudaMemcpyAsync(ctx->h_out, ctx->d_out, sizeof(FrameOut) * (size_t)n_frames, cudaMemcpyDeviceToHost, ctx->stream[0]));
   CK(cudaEventRecord(ctx->ev_stop, ctx->stream[0]));
   CK(cudaEventSynchronize(ctx->ev_stop));

@@ -23,7 +23,7 @@ struct Band
 __device__ __forceinline__ unsigned raw_word(const Band &bd, int r, int w, int wpr)
 {
   // r is band-relative; caller guarantees 0 <= r < nb
-  return (w >= 0 && w < wpr) ? bd.A[(size_t)r * bd.rs + w] : 0u;
+  return (w >= 0 && w < wpr) ? bd.A[(unsigned)(r * bd.rs + w)] : 0u;
 }
 
 // 64-bit window of raw row r: bit p <-> image column 32*w - 16 + p
@@ -100,23 +100,47 @@ __device__ inline void band_stage(const DevParams &p, unsigned *sm, const Band &
 }
 
 // first / last set row of column x of the closed image within rows [ylo, yhi]
-// (Scanner::probeVertical, segmentation.cpp:85-111; BottomScanner::probeBottomUp :225-240); one warp per column
+// (Scanner::probeVertical, segmentation.cpp:85-111; BottomScanner::probeBottomUp :225-240); one warp per column.
+// Only ONE bit per row is wanted, so the 3x3 close is evaluated for that column alone, one image row per lane:
+//   f   = raw bits of columns x-2 .. x+2 of the lane's row (0 outside the image / band)
+//   hd  = horizontal dilation at columns x-1, x, x+1              (3 bits, from f)
+//   D   = hd of rows y-1, y, y+1 OR-ed (warp shuffles)            = dilated image at (x-1..x+1, y)
+//   E   = D with out-of-image columns forced to 1; rows outside the image count as all ones (erosion ignores them)
+//   closed(x, y) = E(y-1) == E(y) == E(y+1) == 111b
+// A warp pass covers 28 rows (lanes 2..29) plus a two-row halo on either side.
 __device__ __forceinline__ bool probe_column(const DevParams &p, const Band &bd, int x, int ylo, int yhi, int lane, int &yFirst, int &ySecond)
 {
   int first = 0x7fffffff, last = -1;
   // the closed image can only be set within one row of the raw band
   const int lo = max(ylo, bd.b0), hi = min(yhi, bd.b0 + bd.nb - 1);
-  const int w = x >> 5, sh = x & 31;
-  for(int base = lo; base <= hi; base += 32)
+  const int xl = x - 2;
+  const int wA = xl >> 5, sh = xl & 31; // arithmetic shift: xl < 0 -> word -1 (reads as 0)
+  // columns x-1, x, x+1 that lie outside the image
+  const unsigned colout = (x - 1 < 0 ? 1u : 0u) | (x + 1 >= p.W ? 4u : 0u);
+  for(int base = lo; base <= hi; base += 28)
   {
-    const int y = base + lane;
-    const unsigned bit = y <= hi ? (closed_word(p, bd, y, w) >> sh) & 1u : 0u;
-    const unsigned m = __ballot_sync(0xffffffffu, bit);
+    const int y = base - 2 + lane;
+    const int r = y - bd.b0;
+    unsigned hd = 0;
+    if(r >= 0 && r < bd.nb) // (band rows are image rows)
+    {
+      const unsigned w0 = raw_word(bd, r, wA, p.wpr), w1 = raw_word(bd, r, wA + 1, p.wpr);
+      const unsigned f = __funnelshift_r(w0, w1, sh) & 31u;
+      hd = (f | (f >> 1) | (f >> 2)) & 7u;
+    }
+    const unsigned up = __shfl_up_sync(0xffffffffu, hd, 1), dn = __shfl_down_sync(0xffffffffu, hd, 1);
+    const bool inimg = y >= 0 && y < p.H;
+    // lanes 0 and 31 lack one neighbour: their E is never used for a reported row (lanes 2..29 read lanes 1..30)
+    const unsigned E = inimg ? (hd | up | dn | colout) : 7u;
+    const unsigned full = E == 7u ? 1u : 0u;
+    const unsigned fu = __shfl_up_sync(0xffffffffu, full, 1), fd = __shfl_down_sync(0xffffffffu, full, 1);
+    const bool set = (full & fu & fd) != 0u && lane >= 2 && lane < 30 && y >= lo && y <= hi;
+    const unsigned m = __ballot_sync(0xffffffffu, set);
     if(m)
     {
       if(first == 0x7fffffff)
-        first = base + __ffs(m) - 1;
-      last = base + 31 - __clz(m);
+        first = base - 2 + __ffs(m) - 1;
+      last = base - 2 + 31 - __clz(m);
     }
   }
   yFirst = first;
