@@ -351,6 +351,8 @@ struct WarpLists
   unsigned short act[SSD_PT_WARPS][SSD_WT_PX / 4];  // word index << 4 | mask of the pixels that matter
   unsigned short def[SSD_PT_WARPS][SSD_WT_PX];      // flag | word index << 2 | pixel of the word
   unsigned ndef[SSD_PT_WARPS];
+  unsigned short gb[SSD_PT_WARPS][SSD_WT_PX / 4];   // k_quad_reduce: words with ground points whose BEV pixel is wanted (index << 4 | mask)
+  unsigned ngb[SSD_PT_WARPS];
 };
 
 // Append word (it*32+lane) with pixel mask am4 to the warp's list (length n, warp-uniform); returns the new
@@ -705,7 +707,10 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, 3) k_quad_reduce(const __grid_
       S.fast[tid].rj = live ? make_float2(rj.x, rj.y) : make_float2(-1.f, -1.f);
     }
     if(tid < SSD_PT_WARPS)
+    {
       S.L.ndef[tid] = 0;
+      S.L.ngb[tid] = 0;
+    }
     if(tid == 0)
     {
       S.rmin = 0x7fffffff;
@@ -819,29 +824,21 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, 3) k_quad_reduce(const __grid_
           seg_n += (unsigned)cnt;
           if((int)l0 == ground)
           {
+            // Ground BEV image: only the pixel columns detectFrontEdge can see are written. Cheap column pre-filter
+            // (f32, conservative margin): t = ((wx - x_min) sx - (W/2 - 2)) / 50, the column is needed iff frac(t) in
+            // [0, 0.1). The few points that pass are queued per word; their pixels are computed densely at the end of
+            // the warp-tile (one point per lane) instead of diverging every step here.
+            unsigned gm = 0;
 #pragma unroll
             for(int j = 0; j < 4; j++)
             {
-              // cheap column pre-filter (f32, conservative margin) before the pixel is computed:
-              // t = ((wx - x_min) sx - (W/2 - 2)) / 50; the column is needed iff frac(t) in [0, 0.1)
               const float t = fmaf(wxs[j], p.gcol_a, p.gcol_b);
               const float fr = t - floorf(t);
-              if(inm[j] && (fr < p.gcol_lo || fr > p.gcol_hi || t > p.gcol_tmax))
-              {
-                int ix, iy;
-                if(fast_pixel2(p, vx[j], vy[j], vz[j], ix, iy))
-                {
-                  if(ground_col_needed(p, ix))
-                  {
-                    atomicOr(gbev + (unsigned)iy * (unsigned)p.wpr + (unsigned)(ix >> 5), 1u << (ix & 31));
-                    rmin = min(rmin, iy);
-                    rmax = max(rmax, iy);
-                  }
-                }
-                else
-                  defer_push(S.L, warp, SSD_DEF_BEVONLY | ((e >> 4) << 2) | (unsigned)j);
-              }
+              gm |= (fr < p.gcol_lo || fr > p.gcol_hi || t > p.gcol_tmax) ? (1u << j) : 0u;
             }
+            gm &= (unsigned)(inm[0] & 1) | (unsigned)(inm[1] & 2) | (unsigned)(inm[2] & 4) | (unsigned)(inm[3] & 8);
+            if(gm)
+              S.L.gb[warp][atomicAdd(&S.L.ngb[warp], 1u)] = (unsigned short)((e & 0xff0u) | gm);
           }
         }
       }
@@ -906,6 +903,42 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, 3) k_quad_reduce(const __grid_
       n_def += nd;
       if(lane == 0)
         S.L.ndef[warp] = 0;
+    }
+    {
+      // ---- dense pass over the queued ground points: BEV pixel, one queued word per lane ----
+      const unsigned ng = S.L.ngb[warp];
+      if(ng)
+      {
+        const float *tile = reinterpret_cast<const float *>(tile4);
+        for(unsigned i = lane; i < ng; i += 32)
+        {
+          const unsigned d = S.L.gb[warp][i];
+          const unsigned w = (d >> 4) & 0xffu;
+          unsigned mask = d & 15u;
+#pragma unroll 1
+          while(mask)
+          {
+            const unsigned j = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            const float *v = tile + (w * 4 + j) * 3;
+            int ix, iy;
+            if(fast_pixel2(p, __ldg(v), __ldg(v + 1), __ldg(v + 2), ix, iy))
+            {
+              if(ground_col_needed(p, ix))
+              {
+                atomicOr(gbev + (unsigned)iy * (unsigned)p.wpr + (unsigned)(ix >> 5), 1u << (ix & 31));
+                rmin = min(rmin, iy);
+                rmax = max(rmax, iy);
+              }
+            }
+            else
+              quad_reduce_exact_point(p, v, (unsigned)ground, true, F, amask, ground, gbev, S);
+          }
+        }
+        __syncwarp();
+        if(lane == 0)
+          S.L.ngb[warp] = 0;
+      }
     }
     {
       // end of the warp-tile: combine the warp's 32 open segments (single-pass segmented reduce: lanes grouped by
