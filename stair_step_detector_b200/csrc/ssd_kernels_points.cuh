@@ -381,6 +381,14 @@ __device__ __forceinline__ void warp_tile_range(int n_wt, int warp, int &first, 
   end = n_wt;
 }
 
+// request the 48 bytes of one 4-vertex word into L2 (both 32-byte sectors it can touch): issued in phase A, as soon as a
+// word is known to matter, so that phase B finds its vertices at L2 rather than DRAM latency
+__device__ __forceinline__ void prefetch_word_l2(const float4 *w)
+{
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(w));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(w + 2));
+}
+
 __device__ __forceinline__ void load3(const float4 *__restrict__ src, float4 &a, float4 &b, float4 &c)
 {
   a = __ldg(src);
@@ -730,6 +738,7 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, 3) k_quad_reduce(const __grid_
 
   for(; wt < wt_end; wt += wt_stride)
   {
+    const float4 *tile4 = frame4 + (size_t)wt * (SSD_WT_PX / 4 * 3);
     // ---- phase A: compaction of the words holding plateau labels (bit 7 of a label byte clear <=> label < 128) ----
     unsigned n = 0;
 #pragma unroll
@@ -740,7 +749,10 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, 3) k_quad_reduce(const __grid_
       if(__any_sync(0xffffffffu, am4 != 0u))
       {
         if(am4)
+        {
           labs[it * 32 + lane] = lw;
+          prefetch_word_l2(tile4 + (it * 32 + lane) * 3);
+        }
         n = compact_append(act, n, am4, it, lane);
       }
     }
@@ -755,7 +767,6 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, 3) k_quad_reduce(const __grid_
     __syncwarp();
 
     // ---- phase B: dense walk over the compacted words ----
-    const float4 *tile4 = frame4 + (size_t)wt * (SSD_WT_PX / 4 * 3);
     unsigned e = lane < n ? act[lane] : 0u;
     float4 c0, c1, c2, n0, n1, n2;
     c0 = c1 = c2 = n0 = n1 = n2 = make_float4(0.f, 0.f, 0.f, 0.f);
