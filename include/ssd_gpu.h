@@ -157,6 +157,8 @@ int ssd_gpu_process_device(ssd_gpu_ctx *ctx, const float *xyz_dev, int n_frames)
 #define SSD_FLAG_NO_LABELS 0x1
 /* Record CUDA events around every kernel of the chain (on the launching streams); read with ssd_gpu_get_stage_times. */
 #define SSD_FLAG_STAGE_TIMING 0x2
+/* Run every chunk on one stream (no overlap between chunks): with STAGE_TIMING the event brackets are then the kernels' own durations. */
+#define SSD_FLAG_SINGLE_STREAM 0x4
 int ssd_gpu_process_device_ex(ssd_gpu_ctx *ctx, const float *xyz_dev, int n_frames, int flags);
 
 /* ---- results of the last process call ---- */

@@ -27,6 +27,7 @@ STATUS_HMIN_WRAP = 0x40
 
 FLAG_NO_LABELS = 0x1
 FLAG_STAGE_TIMING = 0x2
+FLAG_SINGLE_STREAM = 0x4
 N_STAGES = 7
 
 

@@ -637,12 +637,12 @@ static int process_common(ssd_gpu_ctx *ctx, const float *xyz, bool host_input, i
   for(int f0 = 0; f0 < n_frames; f0 += cf, chunk++)
   {
     const int nf = std::min(cf, n_frames - f0);
-    const int s = chunk % ctx->n_streams;
+    const int s = (flags & SSD_FLAG_SINGLE_STREAM) ? 0 : chunk % ctx->n_streams;
     const float *src = xyz + (size_t)f0 * frame_floats;
     if(host_input)
     {
       // stage s may be overwritten once the chunk that last used it has finished
-      if(chunk >= ctx->n_streams)
+      if(chunk >= ((flags & SSD_FLAG_SINGLE_STREAM) ? 1 : ctx->n_streams))
         CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_in_free[s], 0));
       CK(cudaMemcpyAsync(ctx->d_stage[s], src, (size_t)nf * frame_floats * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
       CK(cudaEventRecord(ctx->ev_in_ready[s], ctx->copy_stream));
