@@ -228,25 +228,46 @@ def run_ours(args):
     det.process_device(d_xyz, frames, flags=A.FLAG_STAGE_TIMING)
     stages_overlapped = det.stage_times()
 
-    # ---- e2e: the same call with HOST buffers (pinned), H2D of the vertices + D2H of the results inside ----
+    # ---- e2e: the reference-facing call with HOST buffers (pinned), host->device copies and the device->host read of the
+    # results inside the timed region. The reference's process() receives the z16 DEPTH FRAME (Camera::DepthFrame,
+    # pointcloud.cpp:608,138), so that is the host buffer of the headline e2e: 2 bytes per pixel cross PCIe and the
+    # deprojection runs on the GPU (ssd_gpu_process_depth_host). The same through the packed-vertex entry point
+    # (12 bytes per pixel, ssd_gpu_process_host) is reported next to it.
+    intr = S.scene_intrinsics(base)
     e2e_frames = min(args.e2e_frames, frames)
-    h_xyz, h_handle = S.pinned_empty((e2e_frames, N, 3), np.float32)
-    det.d2h(h_xyz, d_xyz)
+    d_depth = det.malloc(e2e_frames * N * 2)
+    d_tmp = det.malloc(e2e_frames * N * 12)
+    det.synth_frames(base, BASE_SEED, rank * frames, e2e_frames, 3, 8, d_tmp, d_depth)  # same frames as the device-resident batch
+    det.free(d_tmp)
+    h_depth, h_depth_handle = S.pinned_empty((e2e_frames, N), np.uint16)
+    det.d2h(h_depth, d_depth)
+    det.free(d_depth)
     for _ in range(2):
-        det.process_host_ptr(h_handle, e2e_frames)
+        det.process_depth_host_ptr(h_depth_handle, intr, e2e_frames)
+    e2e_steps_found = int(det.n_steps_all(e2e_frames).sum())
     barrier_sync()
     e2e_ms = []
     for _ in range(max(3, args.steps // 2)):
-        det.process_host_ptr(h_handle, e2e_frames)
+        det.process_depth_host_ptr(h_depth_handle, intr, e2e_frames)
         e2e_ms.append(det.timing().total_ms)
     barrier_sync()
     my_e2e = sum(e2e_ms) / len(e2e_ms)
+    # packed vertices through PCIe
+    v_frames = min(256, e2e_frames)
+    h_xyz, h_handle = S.pinned_empty((v_frames, N, 3), np.float32)
+    det.d2h(h_xyz, d_xyz)
+    det.process_host_ptr(h_handle, v_frames)
+    v_ms = []
+    for _ in range(3):
+        det.process_host_ptr(h_handle, v_frames)
+        v_ms.append(det.timing().total_ms)
+    my_e2e_v = sum(v_ms) / len(v_ms)
 
     # ---- max over ranks ----
     if dist is not None:
         from stair_step_detector_b200 import sharding
-        (my_ms, my_e2e, wall_ms), (launches, n_steps_found) = sharding.reduce_timing(
-            dist, [my_ms, my_e2e, wall_ms], [launches, n_steps_found], device=f"cuda:{local}")
+        (my_ms, my_e2e, wall_ms, my_e2e_v), (launches, n_steps_found) = sharding.reduce_timing(
+            dist, [my_ms, my_e2e, wall_ms, my_e2e_v], [launches, n_steps_found], device=f"cuda:{local}")
 
     if rank == 0:
         ms_per_step = my_ms / args.steps
@@ -289,17 +310,24 @@ def run_ours(args):
                            "stairs_found": n_steps_found},
                 "clocks": clocks,
                 "e2e": {"value": e2e_fps * N / 1e6, "unit": "Mpoints/s", "frames_per_s": e2e_fps, "frames_per_step": e2e_frames * world,
-                        "ms_per_step": my_e2e, "h2d_bytes_per_step": e2e_frames * N * 12,
-                        "d2h_bytes_per_step": e2e_frames * (32 + 72 * A.MAX_STEPS + 16),
-                        "note": "ssd_gpu_process_host on pinned host vertices; PCIe-bound"},
+                        "ms_per_step": my_e2e, "h2d_bytes_per_step": e2e_frames * N * 2,
+                        "d2h_bytes_per_step": e2e_frames * (32 + 72 * A.MAX_STEPS + 16), "stairs_found_per_gpu": e2e_steps_found,
+                        "input": "z16 depth frames in pinned host memory (what the reference's Pointcloud::process receives), "
+                                 "deprojected on the GPU",
+                        "call": "ssd_gpu_process_depth_host",
+                        "vertices": {"value": v_frames * world / (my_e2e_v * 1e-3) * N / 1e6, "unit": "Mpoints/s",
+                                     "frames_per_s": v_frames * world / (my_e2e_v * 1e-3), "frames_per_step": v_frames * world,
+                                     "ms_per_step": my_e2e_v, "h2d_bytes_per_step": v_frames * N * 12,
+                                     "call": "ssd_gpu_process_host (packed f32 vertices in pinned host memory; PCIe-bound)"}},
                 "gpu_launches": launches,
                 "roofline": roofline}
         if world == 1 and not args.no_cpu_baseline:
-            sample = np.ascontiguousarray(h_xyz[:min(32, e2e_frames)])
+            sample = np.ascontiguousarray(h_xyz[:min(32, v_frames)])
             line["cpu_baseline"] = cpu_reference_leg(S, sample, xf, os.cpu_count() or 1, target_cpu_seconds=20.0)
         print(json.dumps(line), flush=True)
 
     S.free_pinned(h_handle)
+    S.free_pinned(h_depth_handle)
     det.free(d_xyz)
     det.close()
     if dist is not None:
@@ -313,7 +341,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=4096, help="frames per GPU per step (BASELINE config: 4096)")
-    ap.add_argument("--e2e-frames", type=int, default=256)
+    ap.add_argument("--e2e-frames", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -125,6 +125,7 @@ typedef struct ssd_gpu_frame_info
 } ssd_gpu_frame_info;
 
 typedef struct ssd_gpu_ctx ssd_gpu_ctx;
+struct ssd_scene;
 
 /* Timing of the last ssd_gpu_process_* call, CUDA events on the ctx stream (milliseconds). */
 typedef struct ssd_gpu_timing
@@ -153,6 +154,28 @@ const char *ssd_gpu_last_error(const ssd_gpu_ctx *ctx); /* ctx may be NULL: last
  * row-major pixel order, invalid pixel = (0,0,0). Results stay in the ctx until the next call. */
 int ssd_gpu_process_host(ssd_gpu_ctx *ctx, const float *xyz_host, int n_frames);
 int ssd_gpu_process_device(ssd_gpu_ctx *ctx, const float *xyz_dev, int n_frames);
+/*
+ * The same call one step further upstream: the input is the z16 DEPTH FRAME the reference's process() receives
+ * (Camera::DepthFrame, camera.h:58-118) and the library performs the deprojection the reference delegates to
+ * rs2::pointcloud::calculate (pointcloud.cpp:138), pin-hole model without distortion as in
+ * rs2_deproject_pixel_to_point / DepthFrame::deproject (camera.h:99-116):
+ *     z = depth * depth_unit,  x = z * ((u - ppx) / fx),  y = z * ((v - ppy) / fy),   depth 0 -> invalid vertex (0,0,0)
+ * single-rounded f32 operations in exactly this order. 2 bytes per pixel cross PCIe / HBM instead of 12.
+ * depth: n_frames * width*height uint16, row-major.
+ */
+typedef struct ssd_gpu_intrinsics
+{
+  float fx, fy, ppx, ppy; /* rs2_intrinsics of the depth stream */
+  float depth_unit;       /* metres per count (rs2::depth_sensor::get_depth_scale; L515: 0.00025) */
+  int32_t reserved[3];
+} ssd_gpu_intrinsics;
+int ssd_gpu_process_depth_host(ssd_gpu_ctx *ctx, const uint16_t *z16_host, const ssd_gpu_intrinsics *intr, int n_frames);
+int ssd_gpu_process_depth_device(ssd_gpu_ctx *ctx, const uint16_t *z16_dev, const ssd_gpu_intrinsics *intr, int n_frames);
+/* Deprojection alone: n_frames depth frames (device) -> packed vertices (device), for parity checks. */
+int ssd_gpu_deproject_device(ssd_gpu_ctx *ctx, const uint16_t *z16_dev, const ssd_gpu_intrinsics *intr, int n_frames, float *xyz_dev);
+/* intrinsics of a synthetic scene */
+void ssd_scene_intrinsics(const struct ssd_scene *s, ssd_gpu_intrinsics *out);
+
 /* Same, but skips the per-point label store (labels are still computed; results identical). */
 #define SSD_FLAG_NO_LABELS 0x1
 /* Record CUDA events around every kernel of the chain (on the launching streams); read with ssd_gpu_get_stage_times. */

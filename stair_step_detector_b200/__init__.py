@@ -94,6 +94,13 @@ def deproject_host(scene, depth):
     return xyz
 
 
+def scene_intrinsics(scene):
+    """Pin-hole intrinsics + depth unit of a synthetic scene (what rs2 would report for the depth stream)."""
+    k = A.Intrinsics()
+    lib().ssd_scene_intrinsics(C.byref(scene), C.byref(k))
+    return k
+
+
 def serialize(steps):
     """Stairs::serialize (reference stairs.cpp:55-70) of a list of (height, 4x2 quad)."""
     arr = (Step * max(1, len(steps)))()
@@ -149,6 +156,22 @@ class Detector:
 
     def process_host_ptr(self, ptr, n_frames):
         self._ck(self._l.ssd_gpu_process_host(self._h, ptr, n_frames), "ssd_gpu_process_host")
+
+    def process_depth_host(self, depth, intrinsics):
+        """depth: (n_frames, H, W) uint16 z16 depth frames in host memory -- what the reference's process() receives."""
+        depth = np.ascontiguousarray(depth, np.uint16)
+        n = depth.size // self.n_points
+        self._ck(self._l.ssd_gpu_process_depth_host(self._h, _ptr(depth), C.byref(intrinsics), n), "ssd_gpu_process_depth_host")
+        return n
+
+    def process_depth_host_ptr(self, ptr, intrinsics, n_frames):
+        self._ck(self._l.ssd_gpu_process_depth_host(self._h, ptr, C.byref(intrinsics), n_frames), "ssd_gpu_process_depth_host")
+
+    def process_depth_device(self, dev_ptr, intrinsics, n_frames):
+        self._ck(self._l.ssd_gpu_process_depth_device(self._h, dev_ptr, C.byref(intrinsics), n_frames), "ssd_gpu_process_depth_device")
+
+    def deproject_device(self, depth_dev, intrinsics, n_frames, xyz_dev):
+        self._ck(self._l.ssd_gpu_deproject_device(self._h, depth_dev, C.byref(intrinsics), n_frames, xyz_dev), "ssd_gpu_deproject_device")
 
     def process_device(self, dev_ptr, n_frames, flags=0):
         self._ck(self._l.ssd_gpu_process_device_ex(self._h, dev_ptr, n_frames, flags), "ssd_gpu_process_device")

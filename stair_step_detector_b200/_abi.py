@@ -46,6 +46,11 @@ class Transform(C.Structure):
                 ("ext_a", C.c_double * 4), ("ext_b", C.c_double * 2), ("ext_z", C.c_double)]
 
 
+class Intrinsics(C.Structure):
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("ppx", C.c_float), ("ppy", C.c_float),
+                ("depth_unit", C.c_float), ("reserved", C.c_int32 * 3)]
+
+
 class Step(C.Structure):
     _fields_ = [("height", C.c_double), ("quad", (C.c_double * 2) * 4)]
 
@@ -99,6 +104,10 @@ PROTOTYPES = {
     "ssd_gpu_process_host": (C.c_int, [_vp, _vp, C.c_int]),
     "ssd_gpu_process_device": (C.c_int, [_vp, _vp, C.c_int]),
     "ssd_gpu_process_device_ex": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+    "ssd_gpu_process_depth_host": (C.c_int, [_vp, _vp, _P(Intrinsics), C.c_int]),
+    "ssd_gpu_process_depth_device": (C.c_int, [_vp, _vp, _P(Intrinsics), C.c_int]),
+    "ssd_gpu_deproject_device": (C.c_int, [_vp, _vp, _P(Intrinsics), C.c_int, _vp]),
+    "ssd_scene_intrinsics": (None, [_P(Scene), _P(Intrinsics)]),
     "ssd_gpu_get_steps": (C.c_int, [_vp, C.c_int, _P(Step), C.c_int, _P(C.c_int), _P(C.c_uint32)]),
     "ssd_gpu_get_frame_info": (C.c_int, [_vp, C.c_int, _P(FrameInfo)]),
     "ssd_gpu_get_plateaus": (C.c_int, [_vp, C.c_int, _P(Plateau), C.c_int, _P(C.c_int)]),

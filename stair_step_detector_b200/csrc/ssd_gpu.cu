@@ -40,7 +40,10 @@ struct ssd_gpu_ctx
   FrameOut *h_out = nullptr;      // pinned
   unsigned char *d_labels = nullptr; // max_frames * N
   unsigned *d_bev = nullptr; // 2 x chunk_frames * MAX_PLATEAUS * bm_words (per stream)
-  float *d_stage[SSD_MAX_STREAMS]{};            // host-input staging, chunk_frames frames each
+  float *d_stage[SSD_MAX_STREAMS]{};            // vertex staging (host input / deprojected depth), chunk_frames frames each
+  uint16_t *d_depth[SSD_MAX_STREAMS]{};         // z16 staging of the host depth-frame path
+  float *d_xn = nullptr, *d_yn = nullptr;       // deprojection tables: (u - ppx) / fx per column, (v - ppy) / fy per row
+  ssd_gpu_intrinsics intr{};                    // intrinsics the tables were built for
   int pt_blocks_target = 0;       // blocks per launch of the tile-looping point kernels
   int n_frames_last = 0;
   int flags_last = 0;
@@ -278,6 +281,40 @@ __global__ void k_synth_frames(ssd_scene base, uint64_t base_seed, long long fir
 }
 
 // ---------------------------------------------------------------------------------------------
+// depth frame -> vertices: the deprojection the reference delegates to rs2::pointcloud::calculate
+// (pointcloud.cpp:138; pin-hole model of rs2_deproject_pixel_to_point / camera.h:99-116). Single-rounded f32
+// operations in the order of ssd_deproject_pixel (scene_model.h), so the vertices are bit-identical to the host's.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_deproject_tables(int W, int H, ssd_gpu_intrinsics in, float *__restrict__ xn, float *__restrict__ yn)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < W)
+    xn[i] = __fdiv_rn(__fsub_rn((float)i, in.ppx), in.fx);
+  if(i < H)
+    yn[i] = __fdiv_rn(__fsub_rn((float)i, in.ppy), in.fy);
+}
+
+// 4 consecutive pixels per thread: one 8-byte load, three 16-byte stores. grid = (ceil(N/4/256), frames). W % 4 == 0.
+__global__ void __launch_bounds__(256) k_deproject(int W, int N, float depth_unit, const float *__restrict__ xn, const float *__restrict__ yn,
+                                                   const uint16_t *__restrict__ depth, float *__restrict__ xyz)
+{
+  const int q = blockIdx.x * blockDim.x + threadIdx.x; // quad of pixels within the frame
+  if(q * 4 >= N)
+    return;
+  const size_t fbase = (size_t)blockIdx.y * N;
+  const uint2 d = __ldg(reinterpret_cast<const uint2 *>(depth + fbase) + q);
+  const int i0 = q * 4, v = i0 / W, u = i0 - v * W;
+  const float4 x4 = __ldg(reinterpret_cast<const float4 *>(xn + u));
+  const float y = __ldg(yn + v);
+  const float z0 = __fmul_rn((float)(d.x & 0xffffu), depth_unit), z1 = __fmul_rn((float)(d.x >> 16), depth_unit);
+  const float z2 = __fmul_rn((float)(d.y & 0xffffu), depth_unit), z3 = __fmul_rn((float)(d.y >> 16), depth_unit);
+  float4 *dst = reinterpret_cast<float4 *>(xyz + (fbase + (size_t)i0) * 3);
+  dst[0] = make_float4(__fmul_rn(z0, x4.x), __fmul_rn(z0, y), z0, __fmul_rn(z1, x4.y));
+  dst[1] = make_float4(__fmul_rn(z1, y), z1, __fmul_rn(z2, x4.z), __fmul_rn(z2, y));
+  dst[2] = make_float4(z2, __fmul_rn(z3, x4.w), __fmul_rn(z3, y), z3);
+}
+
+// ---------------------------------------------------------------------------------------------
 // single-stage kernels (same device functions as the chain)
 // ---------------------------------------------------------------------------------------------
 __global__ void k_pack_bitmap(const __grid_constant__ DevParams p, const unsigned char *__restrict__ img, unsigned *__restrict__ bm)
@@ -446,9 +483,12 @@ void ssd_gpu_destroy(ssd_gpu_ctx *ctx)
   cudaFree(ctx->d_labels);
   cudaFree(ctx->d_bev);
   cudaFree(ctx->d_img);
+  cudaFree(ctx->d_xn);
+  cudaFree(ctx->d_yn);
   for(int i = 0; i < SSD_MAX_STREAMS; i++)
   {
     cudaFree(ctx->d_stage[i]);
+    cudaFree(ctx->d_depth[i]);
     if(ctx->stream[i])
       cudaStreamDestroy(ctx->stream[i]);
     if(ctx->ev_in_ready[i])
@@ -591,9 +631,36 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
   return SSD_OK;
 }
 
-static int process_common(ssd_gpu_ctx *ctx, const float *xyz, bool host_input, int n_frames, int flags)
+// (re)build the deprojection tables when the intrinsics change
+static int ensure_deproject_tables(ssd_gpu_ctx *ctx, const ssd_gpu_intrinsics &in)
 {
-  if(!ctx || !xyz || n_frames <= 0)
+  const DevParams &p = ctx->dp;
+  if(!(in.fx != 0.f) || !(in.fy != 0.f) || !(in.depth_unit > 0.f))
+    return fail(ctx, SSD_E_INVALID_ARG, "depth input: fx, fy must be non-zero and depth_unit positive");
+  if(p.W % 4 != 0)
+    return fail(ctx, SSD_E_INVALID_ARG, "depth input: the frame width must be a multiple of 4");
+  if(!ctx->d_xn)
+  {
+    CK(cudaMalloc(&ctx->d_xn, sizeof(float) * (size_t)p.W));
+    CK(cudaMalloc(&ctx->d_yn, sizeof(float) * (size_t)p.H));
+    memset(&ctx->intr, 0, sizeof(ctx->intr));
+  }
+  if(memcmp(&ctx->intr, &in, sizeof(float) * 5) != 0)
+  {
+    const int n = std::max(p.W, p.H);
+    k_deproject_tables<<<(n + 255) / 256, 256, 0, ctx->stream[0]>>>(p.W, p.H, in, ctx->d_xn, ctx->d_yn);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream[0])); // every stream reads the tables
+    ctx->intr = in;
+  }
+  return SSD_OK;
+}
+
+// xyz != nullptr: packed vertices; else z16 depth frames + intrinsics (deprojected chunk by chunk into the vertex staging)
+static int process_common(ssd_gpu_ctx *ctx, const float *xyz, const uint16_t *z16, const ssd_gpu_intrinsics *intr, bool host_input, int n_frames,
+                          int flags)
+{
+  if(!ctx || (!xyz && !(z16 && intr)) || n_frames <= 0)
     return fail(ctx, SSD_E_INVALID_ARG, "process: bad argument");
   if(n_frames > ctx->max_frames)
     return fail(ctx, SSD_E_RANGE, "process: n_frames exceeds max_frames of the context");
@@ -601,10 +668,21 @@ static int process_common(ssd_gpu_ctx *ctx, const float *xyz, bool host_input, i
   const DevParams &p = ctx->dp;
   const size_t frame_floats = (size_t)p.N * 3;
   const int cf = ctx->chunk_frames;
-  if(host_input)
+  const bool depth_input = xyz == nullptr;
+  if(depth_input)
+  {
+    const int rc = ensure_deproject_tables(ctx, *intr);
+    if(rc)
+      return rc;
+  }
+  if(host_input || depth_input)
     for(int i = 0; i < ctx->n_streams; i++)
+    {
       if(!ctx->d_stage[i])
         CK(cudaMalloc(&ctx->d_stage[i], (size_t)cf * frame_floats * sizeof(float)));
+      if(depth_input && host_input && !ctx->d_depth[i])
+        CK(cudaMalloc(&ctx->d_depth[i], (size_t)cf * p.N * sizeof(uint16_t)));
+    }
 
   int launches = 0;
   const bool stage_timing = (flags & SSD_FLAG_STAGE_TIMING) != 0;
@@ -638,21 +716,39 @@ static int process_common(ssd_gpu_ctx *ctx, const float *xyz, bool host_input, i
   {
     const int nf = std::min(cf, n_frames - f0);
     const int s = (flags & SSD_FLAG_SINGLE_STREAM) ? 0 : chunk % ctx->n_streams;
-    const float *src = xyz + (size_t)f0 * frame_floats;
+    const float *src = depth_input ? nullptr : xyz + (size_t)f0 * frame_floats;
+    const uint16_t *dsrc = depth_input ? z16 + (size_t)f0 * p.N : nullptr;
     if(host_input)
     {
-      // stage s may be overwritten once the chunk that last used it has finished
+      // staging buffer s may be overwritten once the chunk that last used it has consumed it
       if(chunk >= ((flags & SSD_FLAG_SINGLE_STREAM) ? 1 : ctx->n_streams))
         CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_in_free[s], 0));
-      CK(cudaMemcpyAsync(ctx->d_stage[s], src, (size_t)nf * frame_floats * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
+      if(depth_input)
+      {
+        CK(cudaMemcpyAsync(ctx->d_depth[s], dsrc, (size_t)nf * p.N * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->copy_stream));
+        dsrc = ctx->d_depth[s];
+      }
+      else
+      {
+        CK(cudaMemcpyAsync(ctx->d_stage[s], src, (size_t)nf * frame_floats * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
+        src = ctx->d_stage[s];
+      }
       CK(cudaEventRecord(ctx->ev_in_ready[s], ctx->copy_stream));
       CK(cudaStreamWaitEvent(ctx->stream[s], ctx->ev_in_ready[s], 0));
+    }
+    if(depth_input)
+    {
+      // (the vertex staging of stream s is free: the chunk that used it last ran on this very stream)
+      k_deproject<<<dim3((p.N / 4 + 255) / 256, nf), 256, 0, ctx->stream[s]>>>(p.W, p.N, intr->depth_unit, ctx->d_xn, ctx->d_yn, dsrc, ctx->d_stage[s]);
+      launches++;
       src = ctx->d_stage[s];
+      if(host_input)
+        CK(cudaEventRecord(ctx->ev_in_free[s], ctx->stream[s])); // the z16 staging is consumed
     }
     const int rc = launch_chunk(ctx, s, src, f0, nf, &launches, stage_timing ? &ctx->stage_ev[(size_t)chunk * (SSD_GPU_N_STAGES + 1)] : nullptr);
     if(rc)
       return rc;
-    if(host_input)
+    if(host_input && !depth_input)
       CK(cudaEventRecord(ctx->ev_in_free[s], ctx->stream[s]));
   }
   // join stream 1 into stream 0, then bring the compact results home
@@ -695,17 +791,51 @@ static int process_common(ssd_gpu_ctx *ctx, const float *xyz, bool host_input, i
 
 int ssd_gpu_process_host(ssd_gpu_ctx *ctx, const float *xyz_host, int n_frames)
 {
-  return process_common(ctx, xyz_host, true, n_frames, 0);
+  return process_common(ctx, xyz_host, nullptr, nullptr, true, n_frames, 0);
 }
 
 int ssd_gpu_process_device(ssd_gpu_ctx *ctx, const float *xyz_dev, int n_frames)
 {
-  return process_common(ctx, xyz_dev, false, n_frames, 0);
+  return process_common(ctx, xyz_dev, nullptr, nullptr, false, n_frames, 0);
 }
 
 int ssd_gpu_process_device_ex(ssd_gpu_ctx *ctx, const float *xyz_dev, int n_frames, int flags)
 {
-  return process_common(ctx, xyz_dev, false, n_frames, flags);
+  return process_common(ctx, xyz_dev, nullptr, nullptr, false, n_frames, flags);
+}
+
+int ssd_gpu_process_depth_host(ssd_gpu_ctx *ctx, const uint16_t *z16_host, const ssd_gpu_intrinsics *intr, int n_frames)
+{
+  if(!z16_host || !intr)
+    return fail(ctx, SSD_E_INVALID_ARG, "process_depth: bad argument");
+  return process_common(ctx, nullptr, z16_host, intr, true, n_frames, 0);
+}
+
+int ssd_gpu_process_depth_device(ssd_gpu_ctx *ctx, const uint16_t *z16_dev, const ssd_gpu_intrinsics *intr, int n_frames)
+{
+  if(!z16_dev || !intr)
+    return fail(ctx, SSD_E_INVALID_ARG, "process_depth: bad argument");
+  return process_common(ctx, nullptr, z16_dev, intr, false, n_frames, 0);
+}
+
+int ssd_gpu_deproject_device(ssd_gpu_ctx *ctx, const uint16_t *z16_dev, const ssd_gpu_intrinsics *intr, int n_frames, float *xyz_dev)
+{
+  if(!ctx || !z16_dev || !intr || !xyz_dev || n_frames <= 0)
+    return fail(ctx, SSD_E_INVALID_ARG, "deproject: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  const int rc = ensure_deproject_tables(ctx, *intr);
+  if(rc)
+    return rc;
+  const DevParams &p = ctx->dp;
+  for(int f0 = 0; f0 < n_frames; f0 += 32768)
+  {
+    const int nf = std::min(32768, n_frames - f0);
+    k_deproject<<<dim3((p.N / 4 + 255) / 256, nf), 256, 0, ctx->stream[0]>>>(p.W, p.N, intr->depth_unit, ctx->d_xn, ctx->d_yn, z16_dev + (size_t)f0 * p.N,
+                                                                            xyz_dev + (size_t)f0 * p.N * 3);
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream[0]));
+  return SSD_OK;
 }
 
 static int check_frame(ssd_gpu_ctx *ctx, int frame)

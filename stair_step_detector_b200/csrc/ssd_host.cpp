@@ -1,5 +1,6 @@
 // ssd_host.cpp -- host-only entry points of the C ABI (no GPU needed): default configuration,
 // transformation builder, synthetic scene generator (host leg).
+#include <cstring>
 #include "../../include/ssd_gpu.h"
 #include "host/transformation.h"
 #include "scene_model.h"
@@ -77,6 +78,16 @@ void ssd_scene_calibration_points(const ssd_scene *s, double world_pts[9], doubl
       world_pts[i * 3 + j] = marks[i][j];
     ssd_scene_to_camera(&rt, marks[i], camera_pts + i * 3);
   }
+}
+
+void ssd_scene_intrinsics(const ssd_scene *s, ssd_gpu_intrinsics *out)
+{
+  memset(out, 0, sizeof(*out));
+  out->fx = s->fx;
+  out->fy = s->fy;
+  out->ppx = s->ppx;
+  out->ppy = s->ppy;
+  out->depth_unit = s->depth_unit;
 }
 
 int ssd_synth_depth_host(const ssd_scene *s, uint16_t *depth_out)

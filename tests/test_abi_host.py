@@ -36,6 +36,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(A.Step) == 72
     assert C.sizeof(A.FrameInfo) == 32
     assert C.sizeof(A.Plateau) == 32 + 64 + 8
+    assert C.sizeof(A.Intrinsics) == 32
     assert A.Scene.seed.offset % 8 == 0
 
 

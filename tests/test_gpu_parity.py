@@ -96,6 +96,47 @@ def test_empty_and_garbage_frames(S, oracle):
             assert g.info["status"] == o.info["status"]
 
 
+def test_depth_frame_input(S, oracle):
+    """The z16 depth-frame entry points (what the reference's process() receives): on-device deprojection is bit-identical
+    to the host's, and host / device depth input give exactly the results of the vertex path -- which is checked
+    against the oracle."""
+    w, h = 640, 480
+    cfg = S.default_config(w, h)
+    base = S.default_scene(w, h, **NOISY)
+    scenes = [S.randomize_scene(base, 77, i, 3, 6) for i in range(5)]
+    xf = S.scene_transform(base)
+    k = S.scene_intrinsics(base)
+    depth = np.stack([S.synth_depth_host(sc) for sc in scenes])
+    xyz = np.stack([S.deproject_host(sc, d) for sc, d in zip(scenes, depth)])
+    n = len(scenes)
+    with S.Detector(cfg, xf, max_frames=n) as det:
+        # deprojection alone
+        d_depth = det.malloc(depth.nbytes)
+        d_xyz = det.malloc(xyz.nbytes)
+        det.h2d(d_depth, depth)
+        det.deproject_device(d_depth, k, n, d_xyz)
+        got = np.empty_like(xyz)
+        det.d2h(got, d_xyz)
+        assert np.array_equal(got.view(np.uint32), xyz.view(np.uint32)), "device deprojection differs from the host's"
+        # vertex path = reference results
+        det.process_host(xyz)
+        ref = [(det.labels(f), det.histogram(f), det.line(f)) for f in range(n)]
+        for f in range(n):
+            o = H.oracle_process(oracle, cfg, xf, xyz[f])
+            assert not H.compare_results(o, gpu_result(S, det, f), tol=TOL), f
+        for run in ("host", "device"):
+            if run == "host":
+                det.process_depth_host(depth, k)
+            else:
+                det.process_depth_device(d_depth, k, n)
+            for f in range(n):
+                assert np.array_equal(det.labels(f), ref[f][0]), (run, f)
+                assert np.array_equal(det.histogram(f), ref[f][1]), (run, f)
+                assert det.line(f) == ref[f][2], (run, f)
+        det.free(d_depth)
+        det.free(d_xyz)
+
+
 def test_hires_extended_range(S, oracle):
     cfg = S.default_config(4096, 3072, y_max=3.7, z_max=2.3)
     sc = S.default_scene(4096, 3072, n_steps=12, riser=0.17, tread=0.26, cam_height=3.2, cam_pitch_deg=48.0,
