@@ -33,15 +33,17 @@ int main(int argc, char **argv)
   const GeometricTransformation trans(wp, cp);
   const Pointcloud pointcloud(app, trans);
 
+  // like the reference's loop (frames.depthFrame() -> process): the frame handed over is the z16 depth image;
+  // the deprojection the reference leaves to rs2::pointcloud::calculate runs on the GPU
   std::vector<uint16_t> depth(size_t(w) * h);
-  std::vector<float> xyz(size_t(w) * h * 3);
+  ssd_gpu_intrinsics intr;
+  ssd_scene_intrinsics(&base, &intr);
   for(int f = 0; f < nFrames && app; f++)
   {
     ssd_scene sc;
     ssd_scene_randomize(&sc, &base, 2026, f, 3, 8);
     ssd_synth_depth_host(&sc, depth.data());
-    ssd_deproject_host(&sc, depth.data(), xyz.data());
-    pointcloud.process(Camera::DepthFrame(xyz.data(), w, h));
+    pointcloud.process(Camera::DepthFrame(depth.data(), intr, w, h));
   }
   return 0;
 }

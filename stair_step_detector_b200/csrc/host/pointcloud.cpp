@@ -42,7 +42,12 @@ void Pointcloud::ensureContext(int width, int height) const
 std::vector<Stairs> Pointcloud::processBatch(const Camera::DepthFrame &frames, int nFrames, std::vector<unsigned> *status) const
 {
   ensureContext(frames.width(), frames.height());
-  const int rc = frames.onDevice ? ssd_gpu_process_device(_ctx, frames.vertices, nFrames) : ssd_gpu_process_host(_ctx, frames.vertices, nFrames);
+  int rc;
+  if(frames.z16)
+    rc = frames.onDevice ? ssd_gpu_process_depth_device(_ctx, frames.z16, &frames.intrinsics, nFrames)
+                         : ssd_gpu_process_depth_host(_ctx, frames.z16, &frames.intrinsics, nFrames);
+  else
+    rc = frames.onDevice ? ssd_gpu_process_device(_ctx, frames.vertices, nFrames) : ssd_gpu_process_host(_ctx, frames.vertices, nFrames);
   if(rc != SSD_OK)
     throw std::runtime_error(std::string("ssd_gpu_process: ") + ssd_gpu_last_error(_ctx));
   std::vector<Stairs> out(static_cast<size_t>(nFrames));
