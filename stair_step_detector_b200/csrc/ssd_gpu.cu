@@ -432,20 +432,25 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, int frame
   // k_label_bev / k_quad_reduce: each block loops over tiles of its frame; enough blocks for ~6 waves of the GPU
   const int tiles2 = (p.N + SSD_WT_PX * SSD_PT_WARPS - 1) / (SSD_WT_PX * SSD_PT_WARPS); // at least one warp-tile per warp
   const int bpf = std::max(1, std::min(tiles2, (ctx->pt_blocks_target + nf - 1) / nf));
-  const dim3 gpt2(bpf, nf);
+  int bpf_l = bpf, bpf_q = bpf;
+  if(const char *e = getenv("SSD_GPU_L_BPF"))
+    bpf_l = std::max(1, std::min(tiles2, atoi(e)));
+  if(const char *e = getenv("SSD_GPU_Q_BPF"))
+    bpf_q = std::max(1, std::min(tiles2, atoi(e)));
+  const dim3 gpt2l(bpf_l, nf), gpt2q(bpf_q, nf);
 
   STAGE_EV(0);
   k_transform_bin<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, SSD_PT_ITERS * SSD_TB_STAGE_BYTES, st>>>(p, xyz_dev, labels, frames);
   STAGE_EV(1);
   k_peaks<<<nf, 32, 0, st>>>(p, frames, nf);
   STAGE_EV(2);
-  k_label_bev<<<gpt2, SSD_PT_THREADS, 0, st>>>(p, xyz_dev, labels, frames, bev, ctx->bm_words);
+  k_label_bev<<<gpt2l, SSD_PT_THREADS, 0, st>>>(p, xyz_dev, labels, frames, bev, ctx->bm_words);
   STAGE_EV(3);
   k_outline<<<dim3(SSD_GPU_MAX_PLATEAUS, nf), SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, bev, ctx->bm_words, ctx->smem_cap_words);
   STAGE_EV(4);
   k_frame_logic<<<nf, 32, 0, st>>>(p, frames, nf);
   STAGE_EV(5);
-  k_quad_reduce<<<gpt2, SSD_PT_THREADS, 0, st>>>(p, xyz_dev, labels, frames, bev, ctx->bm_words);
+  k_quad_reduce<<<gpt2q, SSD_PT_THREADS, 0, st>>>(p, xyz_dev, labels, frames, bev, ctx->bm_words);
   STAGE_EV(6);
   k_finalize<<<nf, SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, ctx->d_out + frame0, bev, ctx->bm_words, ctx->smem_cap_words);
   STAGE_EV(7);
@@ -561,7 +566,7 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
   {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    int bt = sms * 4 * 6;
+    int bt = sms * 4 * 5;
     if(const char *e = getenv("SSD_GPU_PT_BLOCKS"))
       bt = atoi(e);
     ctx->pt_blocks_target = std::max(1, bt);

@@ -262,6 +262,73 @@ def test_device_input_and_determinism(S, oracle):
         det.free(d_xyz)
 
 
+def _all_lines(det, n):
+    return [det.line(f) for f in range(n)]
+
+
+def test_batch_properties_at_scale(S, oracle, monkeypatch):
+    """Size-independent properties on a batch the oracle cannot afford (config 3 shape: 600 device-generated 1024x768
+    frames, several chunks and streams): the result of a frame does not depend on the batch it travels in -- chunk
+    size, stream count and batch position change nothing, bit for bit; label counts equal the plateau sizes;
+    spot frames agree with the oracle."""
+    W, Hh = 1024, 768
+    N = W * Hh
+    cfg = S.default_config(W, Hh)
+    base = S.default_scene(W, Hh, **NOISY)
+    xf = S.scene_transform(base)
+    nF = 600
+    ref_lines = None
+    keep = {}
+    for chunk, streams in ((256, 3), (37, 2), (600, 1)):
+        monkeypatch.setenv("SSD_GPU_CHUNK_FRAMES", str(chunk))
+        monkeypatch.setenv("SSD_GPU_STREAMS", str(streams))
+        with S.Detector(cfg, xf, max_frames=nF) as det:
+            d_xyz = det.malloc(nF * N * 12)
+            det.synth_frames(base, 4242, 0, nF, 3, 8, d_xyz)
+            det.process_device(d_xyz, nF)
+            lines = _all_lines(det, nF)
+            if ref_lines is None:
+                ref_lines = lines
+                assert sum(l.count("height") for l in lines) > 3 * nF  # stairs were found nearly everywhere
+                for f in (0, 255, 256, 511, 599):
+                    lab = det.labels(f)
+                    hist = det.histogram(f)
+                    info = det.frame_info(f)
+                    plats, K = det.plateaus(f)
+                    keep[f] = lab.copy()
+                    # label counts == plateau sizes (sums of their histogram bands); invalid / out-of-range / remainder counts
+                    in_plateaus = 0
+                    for k in range(K):
+                        assert int((lab == k).sum()) == plats[k].n_points, (f, k)
+                        in_plateaus += plats[k].n_points
+                    assert int((lab == 253).sum()) == info.n_in_range - in_plateaus
+                    assert int((lab == 255).sum()) == N - info.n_nonzero
+                    assert int((lab == 254).sum()) == info.n_nonzero - info.n_in_range
+                    assert int(hist.sum()) == info.n_in_range
+                    xyz = np.empty((N, 3), np.float32)
+                    det.d2h(xyz, C.c_void_p(d_xyz.value + f * N * 12))
+                    o = H.oracle_process(oracle, cfg, xf, xyz)
+                    assert not H.compare_results(o, gpu_result(S, det, f), tol=TOL), f
+                # a frame alone == the same frame inside the batch
+                det.process_device(C.c_void_p(d_xyz.value + 300 * N * 12), 1)
+                assert det.line(0) == ref_lines[300]
+            else:
+                assert lines == ref_lines, (chunk, streams)
+                for f, lab in keep.items():
+                    assert np.array_equal(det.labels(f), lab), (chunk, streams, f)
+            det.free(d_xyz)
+
+
+def test_descending_batch(S, oracle):
+    """config 4 shape: upside-down camera (image rotated 180 degrees), occluders, a batch of frames; every frame against
+    the oracle."""
+    cfg = S.default_config(1024, 768)
+    base = S.default_scene(1024, 768, rotate180=1, n_occluders=2, **NOISY)
+    scenes = [S.randomize_scene(base, 515, i, 3, 8) for i in range(12)]
+    res = run_frames(S, oracle, cfg, scenes)
+    assert sum(g.info["n_steps"] for g, _ in res) > 12 * 2
+
+
 def test_cpp_host_classes_main_loop(S, oracle, tmp_path):
     """the reference's main loop on the kept class surface (examples/detect_stairs_synthetic.cpp): same lines
     as the oracle for the same synthetic frames"""
