@@ -194,9 +194,10 @@ int ssd_gpu_get_labels(ssd_gpu_ctx *ctx, int frame, uint8_t *out_host);
 /* Height histogram, HeightsHistogram::calcHist (pointcloud.cpp:194-204). */
 int ssd_gpu_get_histogram(ssd_gpu_ctx *ctx, int frame, uint32_t *out, int cap, int *n_bins);
 int ssd_gpu_get_timing(ssd_gpu_ctx *ctx, ssd_gpu_timing *out);
-/* Counters of the last call. n_exact_fallback: points whose single-precision transform lay within the proven
- * f32 error bound (eps = filter_eps1 * max|x,y,z| + filter_eps0 metres) of a range / height-bin threshold, so the
- * decision was taken by the exact double-precision chain instead (results are bit-identical either way). */
+/* Counters of the last call. n_exact_fallback: points whose single-precision, range-normalised transform
+ * v = (w - range centre) / half range lay within the proven f32 error bound eps = filter_eps1 * max|x,y,z| + filter_eps0
+ * of a range / height-bin threshold, so the decision was taken by the exact double-precision chain instead (results
+ * are bit-identical either way). */
 typedef struct ssd_gpu_stats
 {
   uint64_t n_points;

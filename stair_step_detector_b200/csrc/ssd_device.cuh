@@ -14,7 +14,6 @@
 #define SSD_MAX_LINE_PTS 192        // points per edge list (W/25 + 2 scans split in overlapping halves)
 #define SSD_MAX_SCANS 384
 #define SSD_MAX_VPTS 512            // vertical-edge probe rows (H/10 + 1)
-#define SSD_FIX_SHIFT 36            // fixed-point fraction bits of the per-step z accumulator
 
 // Constant per-context parameters, passed to every kernel by value (__grid_constant__).
 struct DevParams
@@ -33,13 +32,11 @@ struct DevParams
   double x_min, x_max, y_min, y_max, z_min, z_max;
   double hir;              // heightIntervalReciprocal (pointcloud.cpp:101)
   double x_to_image, y_to_image, x_to_world, y_to_world, xy_ratio; // Projection2D (pointcloud.cpp:73-76,95)
-  // single-precision filter of k_transform_bin (see point_code_filtered): f32-rounded transform, range
-  // centres / half widths, and the coefficients of the rigorous error bound eps = E1 * max|p| + E0
+  // single-precision world coordinates of a vertex: f32-rounded CameraToWorld rows and the coefficients of the rigorous
+  // error bound eps = E1 * max|p| + E0 on them (derive_params); used through the packed pairs axy2 / bxy2 below
   float af[9], bf[3];
-  float cf[3], hf[3];
-  float hirf, k0f;         // t = wz * hirf + k0f ~ (wz - z_min) * hir
-  float E0, E1, dbin0;
-  // single-precision BEV pixel (fast_pixel): u = au . p + bu ~ (wx - x_min) * x_to_image, v = av . p + bv ~
+  float E0, E1;
+  // single-precision BEV pixel (fast_pixel2): u = au . p + bu ~ (wx - x_min) * x_to_image, v = av . p + bv ~
   // (y_max - wy) * y_to_image, with the error bounds |u^ - u_ref| <= Eu1 * max|p| + Eu0 (same for v)
   float au[3], bu, av[3], bv;
   float Eu0, Eu1, Ev0, Ev1;
@@ -113,7 +110,7 @@ struct PlateauDev
   double quad_px[4][2];
   double quad_world[4][2];
   double mean_z;
-  unsigned long long sum_fix; // sum of z in 2^-36 m units (two's complement)
+  unsigned long long sum_fix; // sum of z_fix_u() over the points inside the quadrilateral
   int row_min, row_max;       // BEV rows touched by this plateau's bitmap
   int front_valid;
   int pad;
@@ -243,38 +240,6 @@ __device__ __noinline__ unsigned point_code_slow(const DevParams &p, float fx, f
   return point_code(p, fx, fy, fz);
 }
 
-// The same decision from single-precision arithmetic plus a rigorous error bound; `uncertain` is set when the
-// f32 value is within the bound of any threshold, and only then the exact double path above has to run.
-//   w^ = fma chain with f32-rounded coefficients:  |w^_i - w_ref,i| <= 5u (|b_i| + sum_j |a_ij| |p_j|),  u = 2^-24
-//   (coefficient rounding u*M, three fma roundings ~3u*M, the reference's own f64 roundings ~2^-51*M), and the
-//   f32 range centre / half width / bin arithmetic add <= 8u * max|threshold| and 4u * n_bins.
-// derive_params() sets E0, E1, dbin0 with a factor 2 of slack on top of these bounds.
-__device__ __forceinline__ unsigned point_code_filtered(const DevParams &p, float x, float y, float z, bool &uncertain)
-{
-  const float m = fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z));
-  const float eps = fmaf(p.E1, m, p.E0);
-  const float wx = fmaf(p.af[2], z, fmaf(p.af[1], y, fmaf(p.af[0], x, p.bf[0])));
-  const float wy = fmaf(p.af[5], z, fmaf(p.af[4], y, fmaf(p.af[3], x, p.bf[1])));
-  const float wz = fmaf(p.af[8], z, fmaf(p.af[7], y, fmaf(p.af[6], x, p.bf[2])));
-  // r_i < 0 inside the open range, > 0 outside
-  const float rx = fabsf(wx - p.cf[0]) - p.hf[0];
-  const float ry = fabsf(wy - p.cf[1]) - p.hf[1];
-  const float rz = fabsf(wz - p.cf[2]) - p.hf[2];
-  const float rmax = fmaxf(rx, fmaxf(ry, rz));
-  const bool out = rmax > eps, in = rmax < -eps;
-  // floor(t) without a conversion instruction: adding 1.5*2^23 rounds t to the nearest integer in the mantissa
-  const float t = fmaf(wz, p.hirf, p.k0f);
-  const float MAGIC = 12582912.0f;
-  const float s = t + MAGIC;
-  const float d = t - (s - MAGIC); // in [-0.5, 0.5]: distance to the nearest integer
-  const int k = __float_as_int(s) - 0x4B400000;
-  const unsigned bin = (unsigned)(k - (d < 0.f ? 1 : 0));
-  const bool bin_ok = fabsf(d) > fmaf(eps, p.hirf, p.dbin0);
-  const bool valid = z > 0.f;
-  uncertain = valid && !(out || (in && bin_ok));
-  return valid ? (out ? SSD_CODE_OUT_OF_RANGE : bin) : SSD_CODE_INVALID;
-}
-
 // 3-input maximum of absolute values, NaN-propagating (one FMNMX3.NAN): a NaN coordinate must not be dropped
 __device__ __forceinline__ float max3abs_nan(float a, float b, float c)
 {
@@ -312,7 +277,10 @@ __device__ __forceinline__ unsigned point_code_scaled(const DevParams &p, float 
   return valid ? c : SSD_CODE_INVALID;
 }
 
-// fast_pixel with the constant error bounds euc / evc and packed arithmetic (for points known to be in range)
+// Single-precision BEV pixel of an in-range point with the constant error bounds euc / evc (packed arithmetic). Returns
+// true when (ix, iy) is certainly the pixel the exact double chain (camera_to_world_xy + bev_pixel) produces: u^, v^ are
+// further than their error bound from every integer boundary and from the image edges (so neither the x == W wrap nor an
+// out-of-image pixel can occur). floor() via the 1.5*2^23 trick (no conversion instruction).
 __device__ __forceinline__ bool fast_pixel2(const DevParams &p, float x, float y, float z, int &ix, int &iy)
 {
   const float MAGIC = 12582912.0f;
@@ -871,34 +839,6 @@ __device__ __forceinline__ bool quadfilter_eval(const QuadFilterDev &f, float x,
   return cin;
 }
 
-// Single-precision BEV pixel of an in-range point. Returns true when (ix, iy) is certainly the pixel the exact
-// double chain (camera_to_world_xy + bev_pixel) produces: u^, v^ are further than their error bound from every
-// integer boundary and from the image edges (so neither the x == W wrap nor an out-of-image pixel can occur).
-// m = max(|x|,|y|,|z|). floor() via the 1.5*2^23 trick (no conversion instruction).
-__device__ __forceinline__ bool fast_pixel(const DevParams &p, float x, float y, float z, float m, int &ix, int &iy)
-{
-  const float MAGIC = 12582912.0f;
-  const float uu = fmaf(p.au[2], z, fmaf(p.au[1], y, fmaf(p.au[0], x, p.bu)));
-  const float vv = fmaf(p.av[2], z, fmaf(p.av[1], y, fmaf(p.av[0], x, p.bv)));
-  const float eu = fmaf(p.Eu1, m, p.Eu0), ev = fmaf(p.Ev1, m, p.Ev0);
-  const float su = uu + MAGIC, sv = vv + MAGIC;
-  const float du = uu - (su - MAGIC), dv = vv - (sv - MAGIC); // signed distance to the nearest integer
-  ix = __float_as_int(su) - 0x4B400000 - (du < 0.f ? 1 : 0);
-  iy = __float_as_int(sv) - 0x4B400000 - (dv < 0.f ? 1 : 0);
-  const bool ok_u = fabsf(du) > eu && uu > eu && uu < (float)p.W - eu;
-  const bool ok_v = fabsf(dv) > ev && vv > ev && vv < (float)p.H - ev;
-  return ok_u && ok_v;
-}
-
-// world z of a vertex in 2^-36 m fixed point, straight from the f32 camera coordinates: three fused multiply-adds
-// with the coefficients pre-scaled by 2^36 (exact), one conversion. Differs from rounding the reference's
-// double wz by < 2^-37 m + 4 ulp(double): far inside the error the fixed-point sum itself allows.
-__device__ __forceinline__ long long z_to_fix_fused(const DevParams &p, float fx, float fy, float fz)
-{
-  const double S = (double)(1ull << SSD_FIX_SHIFT);
-  return __double2ll_rn(__fma_rn(p.a[8] * S, (double)fz, __fma_rn(p.a[7] * S, (double)fy, __fma_rn(p.a[6] * S, (double)fx, p.b[2] * S))));
-}
-
 // World z for the per-step mean (calcAverageZ, pointcloud.cpp:574-581) as an unsigned integer: single-precision
 // fma chain on coefficients pre-scaled by 2^zshift (|error| <= 4u (S_z m + |b_z|) ~ 1e-6 m worst case, random sign),
 // rounded to the nearest integer by adding 1.5*2^23; the 23 mantissa bits are k + 2^22 with k = round(wz * 2^zshift),
@@ -909,10 +849,4 @@ __device__ __forceinline__ unsigned z_fix_u(const DevParams &p, float x, float y
 {
   const float zq = fmaf(p.azf[2], z, fmaf(p.azf[1], y, fmaf(p.azf[0], x, p.bzf)));
   return (unsigned)__float_as_int(zq + 12582912.0f) & 0x7fffffu;
-}
-
-// fixed-point z for the order-independent (deterministic) per-step sum
-__device__ __forceinline__ long long z_to_fix(double z)
-{
-  return __double2ll_rn(z * (double)(1ull << SSD_FIX_SHIFT));
 }

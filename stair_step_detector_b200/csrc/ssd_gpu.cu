@@ -111,7 +111,7 @@ static int derive_params(const ssd_gpu_config &c, const ssd_gpu_transform &t, De
   d.y_max = c.y_max;
   d.z_min = c.z_min;
   d.z_max = c.z_max;
-  // single-precision filter constants (point_code_filtered): everything rounded so the bound stays an upper bound
+  // single-precision world coordinates (k_label_bev / k_quad_reduce): everything rounded so the bound stays an upper bound
   {
     const double u = 1.0 / 16777216.0; // 2^-24
     double e0 = 0, e1 = 0, T = 0;
@@ -125,16 +125,10 @@ static int derive_params(const ssd_gpu_config &c, const ssd_gpu_transform &t, De
       for(int j = 0; j < 3; j++)
         d.af[i * 3 + j] = (float)t.a[i * 3 + j];
       d.bf[i] = (float)t.b[i];
-      d.cf[i] = (float)((lo[i] + hi[i]) * 0.5);
-      d.hf[i] = (float)((hi[i] - lo[i]) * 0.5);
     }
     // proven bound: 5u*(|b| + S*m) + 8u*T ; used: twice that, rounded up
     d.E0 = (float)((10.0 * u * e0 + 16.0 * u * T) * 1.001) + 1e-12f;
     d.E1 = (float)(10.0 * u * e1 * 1.001);
-    d.hirf = (float)d.hir;
-    d.k0f = (float)(-c.z_min * d.hir);
-    // bin arithmetic: |t^ - t_ref| <= hir*eps + 4u*(n_bins + |z_min|*hir) (+ f32 rounding of hir itself)
-    d.dbin0 = (float)(16.0 * u * (d.n_bins + std::fabs(c.z_min) * d.hir + 1.0) + 1e-6);
     // range-scaled rows for point_code_scaled: v_i = (w_i - c_i)/h_i
     {
       double S1 = 0, B1 = 0, X1 = 0;
@@ -549,7 +543,7 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
   // per-plateau kernels overlap the other's HBM-bound point kernels. Measured on B200 (tools/sweep.py):
   // throughput grows with the chunk size up to ~256 frames. SSD_GPU_CHUNK_FRAMES overrides.
   {
-    int cf = 256;
+    int cf = 512;
     if(const char *e = getenv("SSD_GPU_CHUNK_FRAMES"))
       cf = atoi(e);
     if(const char *e = getenv("SSD_GPU_STREAMS"))
@@ -963,8 +957,8 @@ int ssd_gpu_get_stats(ssd_gpu_ctx *ctx, ssd_gpu_stats *out)
   out->n_quad_fast = c[1] - c[2];
   out->n_quad_exact = c[2];
   out->n_bev_exact = c[3];
-  out->filter_eps0 = ctx->dp.E0;
-  out->filter_eps1 = ctx->dp.E1;
+  out->filter_eps0 = ctx->dp.E0s;
+  out->filter_eps1 = ctx->dp.E1s;
   return SSD_OK;
 }
 

@@ -11,30 +11,6 @@
 #define SSD_PT_THREADS 256
 #define SSD_PT_WARPS (SSD_PT_THREADS / 32)
 
-// 4 consecutive packed {x,y,z} vertices = 3 float4
-struct Quad4
-{
-  float x[4], y[4], z[4];
-};
-
-__device__ __forceinline__ float4 ldg_stream(const float4 *p)
-{
-  float4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-  return r;
-}
-
-__device__ __forceinline__ Quad4 load_quad(const float4 *__restrict__ xyz4, size_t q)
-{
-  const float4 v0 = __ldg(xyz4 + q * 3), v1 = __ldg(xyz4 + q * 3 + 1), v2 = __ldg(xyz4 + q * 3 + 2);
-  Quad4 r;
-  r.x[0] = v0.x; r.y[0] = v0.y; r.z[0] = v0.z;
-  r.x[1] = v0.w; r.y[1] = v1.x; r.z[1] = v1.y;
-  r.x[2] = v1.z; r.y[2] = v1.w; r.z[2] = v2.x;
-  r.x[3] = v2.y; r.y[3] = v2.z; r.z[3] = v2.w;
-  return r;
-}
-
 // ---- TMA bulk staging (cp.async.bulk + mbarrier): one elected thread streams a whole tile of vertices into
 // shared memory; the loads in flight no longer cost registers or depend on occupancy ----
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
