@@ -167,7 +167,7 @@ def run_reference(args):
             "cpu_baseline": cb,
             "e2e": {"value": val, "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -324,7 +324,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             sample = np.ascontiguousarray(h_xyz[:min(32, v_frames)])
             line["cpu_baseline"] = cpu_reference_leg(S, sample, xf, os.cpu_count() or 1, target_cpu_seconds=20.0)
-        print(json.dumps(line), flush=True)
+        emit(line)
 
     S.free_pinned(h_handle)
     S.free_pinned(h_depth_handle)
@@ -334,7 +334,26 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout. Libraries write there too (NCCL prints its version banner on stdout at
+    communicator creation): point fd 1 at stderr for the duration of the run and keep the real stdout for emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
