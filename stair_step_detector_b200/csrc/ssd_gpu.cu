@@ -24,6 +24,7 @@ struct ssd_gpu_ctx
   int device = 0;
   int max_frames = 0;
   int chunk_frames = 0;
+  int host_chunk_frames = 0;  // chunk of the host-input entry points: small enough that PCIe copies and kernels pipeline
   ssd_gpu_config cfg{};
   ssd_gpu_transform xf{};
   DevParams dp{};
@@ -33,6 +34,11 @@ struct ssd_gpu_ctx
   int n_streams = 3;
   cudaStream_t stream[SSD_MAX_STREAMS]{};
   cudaStream_t copy_stream{};
+  // optional lead stream: k_transform_bin of every chunk runs here (low priority), the rest of the chain on stream[s]
+  cudaStream_t p1_stream{};
+  cudaEvent_t ev_pre[SSD_MAX_STREAMS]{}, ev_p1[SSD_MAX_STREAMS]{};
+  int split = 0;
+  size_t pad_tb = 0, pad_l = 0, pad_q = 0; // extra dynamic shared memory per block: caps the resident blocks per SM
   cudaEvent_t ev_start{}, ev_stop{}, ev_h2d0{}, ev_h2d1{};
   cudaEvent_t ev_in_ready[SSD_MAX_STREAMS]{}, ev_in_free[SSD_MAX_STREAMS]{}, ev_chunk_done[SSD_MAX_STREAMS]{};
   FrameDev *d_frames = nullptr;   // max_frames
@@ -40,7 +46,8 @@ struct ssd_gpu_ctx
   FrameOut *h_out = nullptr;      // pinned
   unsigned char *d_labels = nullptr; // max_frames * N
   unsigned *d_bev = nullptr; // 2 x chunk_frames * MAX_PLATEAUS * bm_words (per stream)
-  float *d_stage[SSD_MAX_STREAMS]{};            // vertex staging (host input / deprojected depth), chunk_frames frames each
+  float *d_stage[SSD_MAX_STREAMS]{};            // vertex staging (host input / deprojected depth)
+  int stage_frames[SSD_MAX_STREAMS]{};          // ... and its capacity in frames
   uint16_t *d_depth[SSD_MAX_STREAMS]{};         // z16 staging of the host depth-frame path
   float *d_xn = nullptr, *d_yn = nullptr;       // deprojection tables: (u - ppx) / fx per column, (v - ppy) / fy per row
   ssd_gpu_intrinsics intr{};                    // intrinsics the tables were built for
@@ -409,7 +416,7 @@ __global__ void k_test_camera_to_world(const __grid_constant__ DevParams p, cons
 // ---------------------------------------------------------------------------------------------
 // the launch chain for one chunk of frames on one stream
 // ---------------------------------------------------------------------------------------------
-static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, int frame0, int nf, int *launches, cudaEvent_t *ev)
+static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, int frame0, int nf, int *launches, cudaEvent_t *ev, bool single = false)
 {
 #define STAGE_EV(i)                         \
   do                                        \
@@ -433,18 +440,33 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, int frame
     bpf_q = std::max(1, std::min(tiles2, atoi(e)));
   const dim3 gpt2l(bpf_l, nf), gpt2q(bpf_q, nf);
 
-  STAGE_EV(0);
-  k_transform_bin<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, SSD_PT_ITERS * SSD_TB_STAGE_BYTES, st>>>(p, xyz_dev, labels, frames);
+  if(ctx->split && !single)
+  {
+    // everything already queued on stream s (input copy / deprojection, the previous chunk of this stream) first
+    cudaStream_t p1 = ctx->p1_stream;
+    CK(cudaEventRecord(ctx->ev_pre[s], st));
+    CK(cudaStreamWaitEvent(p1, ctx->ev_pre[s], 0));
+    if(ev)
+      CK(cudaEventRecord(ev[0], p1));
+    k_transform_bin<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, SSD_PT_ITERS * SSD_TB_STAGE_BYTES + ctx->pad_tb, p1>>>(p, xyz_dev, labels, frames);
+    CK(cudaEventRecord(ctx->ev_p1[s], p1));
+    CK(cudaStreamWaitEvent(st, ctx->ev_p1[s], 0));
+  }
+  else
+  {
+    STAGE_EV(0);
+    k_transform_bin<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, SSD_PT_ITERS * SSD_TB_STAGE_BYTES + ctx->pad_tb, st>>>(p, xyz_dev, labels, frames);
+  }
   STAGE_EV(1);
   k_peaks<<<nf, 32, 0, st>>>(p, frames, nf);
   STAGE_EV(2);
-  k_label_bev<<<gpt2l, SSD_PT_THREADS, 0, st>>>(p, xyz_dev, labels, frames, bev, ctx->bm_words);
+  k_label_bev<<<gpt2l, SSD_PT_THREADS, ctx->pad_l, st>>>(p, xyz_dev, labels, frames, bev, ctx->bm_words);
   STAGE_EV(3);
   k_outline<<<dim3(SSD_GPU_MAX_PLATEAUS, nf), SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, bev, ctx->bm_words, ctx->smem_cap_words);
   STAGE_EV(4);
   k_frame_logic<<<nf, 32, 0, st>>>(p, frames, nf);
   STAGE_EV(5);
-  k_quad_reduce<<<gpt2q, SSD_PT_THREADS, 0, st>>>(p, xyz_dev, labels, frames, bev, ctx->bm_words);
+  k_quad_reduce<<<gpt2q, SSD_PT_THREADS, ctx->pad_q, st>>>(p, xyz_dev, labels, frames, bev, ctx->bm_words);
   STAGE_EV(6);
   k_finalize<<<nf, SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, ctx->d_out + frame0, bev, ctx->bm_words, ctx->smem_cap_words);
   STAGE_EV(7);
@@ -496,7 +518,13 @@ void ssd_gpu_destroy(ssd_gpu_ctx *ctx)
       cudaEventDestroy(ctx->ev_in_free[i]);
     if(ctx->ev_chunk_done[i])
       cudaEventDestroy(ctx->ev_chunk_done[i]);
+    if(ctx->ev_pre[i])
+      cudaEventDestroy(ctx->ev_pre[i]);
+    if(ctx->ev_p1[i])
+      cudaEventDestroy(ctx->ev_p1[i]);
   }
+  if(ctx->p1_stream)
+    cudaStreamDestroy(ctx->p1_stream);
   if(ctx->copy_stream)
     cudaStreamDestroy(ctx->copy_stream);
   for(cudaEvent_t e : { ctx->ev_start, ctx->ev_stop, ctx->ev_h2d0, ctx->ev_h2d1 })
@@ -555,6 +583,10 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
       cf = (int)(budget / per_frame);
     cf = std::max(1, std::min(cf, max_frames));
     ctx->chunk_frames = cf;
+    int hc = 32; // measured on B200 (tools/e2e_sweep.py): 16..64 frames reach 54.4 GB/s of H2D, 512 only 49.5
+    if(const char *e = getenv("SSD_GPU_HOST_CHUNK_FRAMES"))
+      hc = atoi(e);
+    ctx->host_chunk_frames = std::max(1, std::min(hc, cf));
   }
 
   {
@@ -585,7 +617,17 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
   dyn &= ~(size_t)15;
   ctx->ol_dyn_smem = dyn;
   ctx->smem_cap_words = dyn / 4;
-  if(cudaFuncSetAttribute(k_transform_bin<SSD_PT_ITERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SSD_PT_ITERS * SSD_TB_STAGE_BYTES) != cudaSuccess)
+  if(const char *e = getenv("SSD_GPU_TB_PAD_KB"))
+    ctx->pad_tb = (size_t)atoi(e) * 1024;
+  if(const char *e = getenv("SSD_GPU_L_PAD_KB"))
+    ctx->pad_l = (size_t)atoi(e) * 1024;
+  if(const char *e = getenv("SSD_GPU_Q_PAD_KB"))
+    ctx->pad_q = (size_t)atoi(e) * 1024;
+  if(ctx->pad_l)
+    cudaFuncSetAttribute(k_label_bev, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->pad_l);
+  if(ctx->pad_q)
+    cudaFuncSetAttribute(k_quad_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->pad_q);
+  if(cudaFuncSetAttribute(k_transform_bin<SSD_PT_ITERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SSD_PT_ITERS * SSD_TB_STAGE_BYTES + (int)ctx->pad_tb) != cudaSuccess)
     return bail("cudaFuncSetAttribute(k_transform_bin) failed", SSD_E_CUDA);
   cudaFuncSetAttribute(k_outline, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
   cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
@@ -602,9 +644,26 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
       return bail(#call, e_ == cudaErrorMemoryAllocation ? SSD_E_NOMEM : SSD_E_CUDA); \
     }                                                                        \
   } while(0)
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  int use_prio = 0;
+  if(const char *e = getenv("SSD_GPU_SPLIT"))
+    ctx->split = atoi(e);
+  if(const char *e = getenv("SSD_GPU_PRIO"))
+    use_prio = atoi(e);
+  if(const char *e = getenv("SSD_GPU_TB_PAD_KB"))
+    ctx->pad_tb = (size_t)atoi(e) * 1024;
+  if(const char *e = getenv("SSD_GPU_L_PAD_KB"))
+    ctx->pad_l = (size_t)atoi(e) * 1024;
+  if(const char *e = getenv("SSD_GPU_Q_PAD_KB"))
+    ctx->pad_q = (size_t)atoi(e) * 1024;
+  if(ctx->split)
+    CKC(cudaStreamCreateWithPriority(&ctx->p1_stream, cudaStreamNonBlocking, use_prio ? prio_lo : 0));
   for(int i = 0; i < ctx->n_streams; i++)
   {
-    CKC(cudaStreamCreateWithFlags(&ctx->stream[i], cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithPriority(&ctx->stream[i], cudaStreamNonBlocking, (use_prio && ctx->split) ? prio_hi : 0));
+    CKC(cudaEventCreateWithFlags(&ctx->ev_pre[i], cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&ctx->ev_p1[i], cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->ev_in_ready[i], cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->ev_in_free[i], cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->ev_chunk_done[i], cudaEventDisableTiming));
@@ -666,7 +725,9 @@ static int process_common(ssd_gpu_ctx *ctx, const float *xyz, const uint16_t *z1
   CK(cudaSetDevice(ctx->device));
   const DevParams &p = ctx->dp;
   const size_t frame_floats = (size_t)p.N * 3;
-  const int cf = ctx->chunk_frames;
+  // host input: every byte crosses PCIe, the copy of chunk i+1 overlaps the kernels of chunk i and only the last
+  // chunk's kernels stay exposed -- small chunks. Device input: large chunks (the per-frame kernels need the parallelism).
+  const int cf = host_input ? ctx->host_chunk_frames : ctx->chunk_frames;
   const bool depth_input = xyz == nullptr;
   if(depth_input)
   {
@@ -677,10 +738,17 @@ static int process_common(ssd_gpu_ctx *ctx, const float *xyz, const uint16_t *z1
   if(host_input || depth_input)
     for(int i = 0; i < ctx->n_streams; i++)
     {
-      if(!ctx->d_stage[i])
+      if(ctx->stage_frames[i] < cf) // grows once when a device-depth call follows host-input calls
+      {
+        CK(cudaDeviceSynchronize());
+        if(ctx->d_stage[i])
+          CK(cudaFree(ctx->d_stage[i]));
+        ctx->d_stage[i] = nullptr;
         CK(cudaMalloc(&ctx->d_stage[i], (size_t)cf * frame_floats * sizeof(float)));
+        ctx->stage_frames[i] = cf;
+      }
       if(depth_input && host_input && !ctx->d_depth[i])
-        CK(cudaMalloc(&ctx->d_depth[i], (size_t)cf * p.N * sizeof(uint16_t)));
+        CK(cudaMalloc(&ctx->d_depth[i], (size_t)ctx->host_chunk_frames * p.N * sizeof(uint16_t)));
     }
 
   int launches = 0;
@@ -744,7 +812,8 @@ static int process_common(ssd_gpu_ctx *ctx, const float *xyz, const uint16_t *z1
       if(host_input)
         CK(cudaEventRecord(ctx->ev_in_free[s], ctx->stream[s])); // the z16 staging is consumed
     }
-    const int rc = launch_chunk(ctx, s, src, f0, nf, &launches, stage_timing ? &ctx->stage_ev[(size_t)chunk * (SSD_GPU_N_STAGES + 1)] : nullptr);
+    const int rc = launch_chunk(ctx, s, src, f0, nf, &launches, stage_timing ? &ctx->stage_ev[(size_t)chunk * (SSD_GPU_N_STAGES + 1)] : nullptr,
+                                (flags & SSD_FLAG_SINGLE_STREAM) != 0);
     if(rc)
       return rc;
     if(host_input && !depth_input)

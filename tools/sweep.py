@@ -33,6 +33,8 @@ for ns, cf in [(int(n), int(c)) for n in args.streams.split(",") for c in args.c
     for _ in range(args.reps):
         det.process_device(d, args.frames)
         ts.append(det.timing().total_ms)
+    det.process_device(d, args.frames, flags=A.FLAG_STAGE_TIMING | A.FLAG_SINGLE_STREAM)
+    st_serial = det.stage_times()
     det.process_device(d, args.frames, flags=A.FLAG_STAGE_TIMING)
     st = det.stage_times()
     tot = det.timing().total_ms
@@ -40,6 +42,7 @@ for ns, cf in [(int(n), int(c)) for n in args.streams.split(",") for c in args.c
     fps = args.frames / (ms * 1e-3)
     print(json.dumps({"streams": ns, "chunk": det.chunk_frames, "ms_best": round(ms, 3), "ms_med": round(float(np.median(ts)), 3), "kfps": round(fps / 1e3, 1),
                       "Gpts": round(fps * N / 1e9, 1), "chain_GBs": round(13 * fps * N / 1e9, 0), "staged_total": round(tot, 3),
-                      "stages": {k: round(v[0], 3) for k, v in st.items()}, "steps": int(det.n_steps_all(args.frames).sum()), "exact_frac": det.stats().n_exact_fallback / max(1, det.stats().n_points), "quad_fast": det.stats().n_quad_fast, "quad_exact": det.stats().n_quad_exact}), flush=True)
+                      "stages": {k: round(v[0], 3) for k, v in st.items()},
+                      "serial": {k: round(v[0], 3) for k, v in st_serial.items()}, "steps": int(det.n_steps_all(args.frames).sum()), "exact_frac": det.stats().n_exact_fallback / max(1, det.stats().n_points), "quad_fast": det.stats().n_quad_fast, "quad_exact": det.stats().n_quad_exact}), flush=True)
     det.free(d)
     det.close()
