@@ -139,7 +139,8 @@ PROTOTYPES = {
     "ssd_gpu_free_host": (C.c_int, [_vp]),
 }
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libssd_gpu.so")
+# SSD_GPU_LIB: developer override (A/B builds of the same library on the GPU box); never a different implementation
+LIB_PATH = os.environ.get("SSD_GPU_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libssd_gpu.so")
 
 
 def bind(lib, prototypes=PROTOTYPES):

@@ -55,6 +55,8 @@ struct DevParams
   float gcol_a, gcol_b, gcol_lo, gcol_hi, gcol_tmax, pad3;
   // packed pairs for the f32x2 pipes: {af[j], af[3+j]}, {bf[0], bf[1]} (world x,y) and {au[j], av[j]}, {bu, bv} (BEV pixel)
   unsigned long long axy2[3], bxy2, auv2[3], buv2;
+  // {sa[j], sa[3+j]}, {sb[0], sb[1]}: the x and y rows of the range-scaled transform (point_code_scaled)
+  unsigned long long sxy2[3], sbxy2;
 };
 
 struct SegmentDev
@@ -260,8 +262,9 @@ __device__ __forceinline__ unsigned point_code_scaled(const DevParams &p, float 
 {
   const float m = max3abs_nan(x, y, z);
   const float eps = fmaf(p.E1s, m, p.E0s);
-  const float vx = fmaf(p.sa[2], z, fmaf(p.sa[1], y, fmaf(p.sa[0], x, p.sb[0])));
-  const float vy = fmaf(p.sa[5], z, fmaf(p.sa[4], y, fmaf(p.sa[3], x, p.sb[1])));
+  // x and y rows as one packed chain (same fma order and roundings as the scalar chains)
+  float vx, vy;
+  f2_unpack(f2_affine(p.sxy2, p.sbxy2, x, y, z), vx, vy);
   const float vz = fmaf(p.sa[8], z, fmaf(p.sa[7], y, fmaf(p.sa[6], x, p.sb[2])));
   const float e1 = max3abs_nan(vx, vy, vz) - 1.0f;
   const float MAGIC = 12582912.0f;

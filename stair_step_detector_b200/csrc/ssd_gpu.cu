@@ -31,7 +31,8 @@ struct ssd_gpu_ctx
   size_t bm_words = 0;        // words per BEV bitmap
   size_t smem_cap_words = 0;  // dynamic shared memory available to the band (words)
   size_t ol_dyn_smem = 0;
-  int n_streams = 3;
+  bool outline_small = false; // frame size admits the small work area of k_outline (OutlineSharedSmall)
+  int n_streams = 2;
   cudaStream_t stream[SSD_MAX_STREAMS]{};
   cudaStream_t copy_stream{};
   // optional lead stream: k_transform_bin of every chunk runs here (low priority), the rest of the chain on stream[s]
@@ -233,9 +234,11 @@ static int derive_params(const ssd_gpu_config &c, const ssd_gpu_transform &t, De
     for(int j = 0; j < 3; j++)
     {
       d.axy2[j] = f2_pack_bits(d.af[j], d.af[3 + j]);
+      d.sxy2[j] = f2_pack_bits(d.sa[j], d.sa[3 + j]);
       d.auv2[j] = f2_pack_bits(d.au[j], d.av[j]);
     }
     d.bxy2 = f2_pack_bits(d.bf[0], d.bf[1]);
+    d.sbxy2 = f2_pack_bits(d.sb[0], d.sb[1]);
     d.buv2 = f2_pack_bits(d.bu, d.bv);
   }
   if(d.n_bins < 3 || d.n_bins > SSD_GPU_MAX_BINS)
@@ -462,7 +465,10 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, int frame
   STAGE_EV(2);
   k_label_bev<<<gpt2l, SSD_PT_THREADS, ctx->pad_l, st>>>(p, xyz_dev, labels, frames, bev, ctx->bm_words);
   STAGE_EV(3);
-  k_outline<<<dim3(SSD_GPU_MAX_PLATEAUS, nf), SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, bev, ctx->bm_words, ctx->smem_cap_words);
+  if(ctx->outline_small)
+    k_outline<OutlineSharedSmall><<<dim3(SSD_GPU_MAX_PLATEAUS, nf), SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, bev, ctx->bm_words, ctx->smem_cap_words);
+  else
+    k_outline<OutlineShared><<<dim3(SSD_GPU_MAX_PLATEAUS, nf), SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, bev, ctx->bm_words, ctx->smem_cap_words);
   STAGE_EV(4);
   k_frame_logic<<<nf, 32, 0, st>>>(p, frames, nf);
   STAGE_EV(5);
@@ -571,7 +577,7 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
   // per-plateau kernels overlap the other's HBM-bound point kernels. Measured on B200 (tools/sweep.py):
   // throughput grows with the chunk size up to ~256 frames. SSD_GPU_CHUNK_FRAMES overrides.
   {
-    int cf = 512;
+    int cf = 1024;
     if(const char *e = getenv("SSD_GPU_CHUNK_FRAMES"))
       cf = atoi(e);
     if(const char *e = getenv("SSD_GPU_STREAMS"))
@@ -600,7 +606,8 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
   int max_optin = 0;
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   cudaFuncAttributes fa{};
-  if(cudaFuncGetAttributes(&fa, k_outline) != cudaSuccess)
+  ctx->outline_small = dp.W / 25 + 4 <= 64 && dp.W / 50 + 6 <= 32 && dp.H / 10 + 2 <= 112;
+  if(cudaFuncGetAttributes(&fa, k_outline<OutlineShared>) != cudaSuccess)
     return bail("cudaFuncGetAttributes(k_outline) failed: was the library built for this GPU (sm_100a)?", SSD_E_CUDA);
   cudaFuncAttributes fb{}, fc{};
   cudaFuncGetAttributes(&fb, k_finalize);
@@ -610,7 +617,7 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
   // raw band only (the close is evaluated on the fly); no more than the full image needs, and by default
   // small enough for three resident blocks per SM (larger bands fall back to probing global memory)
   const size_t full = (size_t)dp.H * (dp.wpr + 1) * 4;
-  size_t want = 48 * 1024;
+  size_t want = 32 * 1024; // measured on B200 (tools/knobs.sh): 32 KB beats 24 / 40 / 48 KB at 1024x768
   if(const char *e = getenv("SSD_GPU_OUTLINE_SMEM_KB"))
     want = (size_t)atoi(e) * 1024;
   dyn = std::min(dyn, std::min(full, want));
@@ -629,7 +636,8 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
     cudaFuncSetAttribute(k_quad_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->pad_q);
   if(cudaFuncSetAttribute(k_transform_bin<SSD_PT_ITERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SSD_PT_ITERS * SSD_TB_STAGE_BYTES + (int)ctx->pad_tb) != cudaSuccess)
     return bail("cudaFuncSetAttribute(k_transform_bin) failed", SSD_E_CUDA);
-  cudaFuncSetAttribute(k_outline, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  cudaFuncSetAttribute(k_outline<OutlineShared>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  cudaFuncSetAttribute(k_outline<OutlineSharedSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
   cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
   cudaFuncSetAttribute(k_test_front_edge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
 
@@ -1088,7 +1096,10 @@ int ssd_gpu_detect_outline(ssd_gpu_ctx *ctx, const uint8_t *image_host, int min_
   p.xy_ratio = xy_ratio;
   cudaStream_t st = ctx->stream[0];
   k_test_setup_plateau<<<1, 1, 0, st>>>(ctx->d_frames, p.H);
-  k_outline<<<dim3(1, 1), SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, ctx->d_frames, ctx->d_bev, ctx->bm_words, ctx->smem_cap_words);
+  if(ctx->outline_small)
+    k_outline<OutlineSharedSmall><<<dim3(1, 1), SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, ctx->d_frames, ctx->d_bev, ctx->bm_words, ctx->smem_cap_words);
+  else
+    k_outline<OutlineShared><<<dim3(1, 1), SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, ctx->d_frames, ctx->d_bev, ctx->bm_words, ctx->smem_cap_words);
   CK(cudaGetLastError());
   PlateauDev P;
   CK(cudaMemcpyAsync(&P, &ctx->d_frames[0].plat[0], sizeof(P), cudaMemcpyDeviceToHost, st));

@@ -360,30 +360,38 @@ __device__ inline P2d boundary_outer(const P2id *pts, int n, FlatLineD line)
   return r;
 }
 
-struct OutlineShared
+// Work area of one outline block. Sized per frame-size class (the launch picks it from W x H): the small class keeps
+// the block under 40 KB of shared memory with a 32 KB band, so five to six blocks are resident per SM -- the kernel is a
+// chain of short latency-bound phases and lives on resident blocks, not on issue slots.
+template<int MAX_SCANS, int MAX_LINE_PTS, int MAX_VPTS_>
+struct OutlineSharedT
 {
+  static constexpr int MAX_VPTS = MAX_VPTS_;
   // column scans
-  int scan_found[SSD_MAX_SCANS];
-  int scan_yf[SSD_MAX_SCANS];
-  int scan_ys[SSD_MAX_SCANS];
+  int scan_found[MAX_SCANS];
+  int scan_yf[MAX_SCANS];
+  int scan_ys[MAX_SCANS];
   // the four edge point lists (segmentation.cpp:557-567)
-  P2id frontLeft[SSD_MAX_LINE_PTS], backLeft[SSD_MAX_LINE_PTS], frontRight[SSD_MAX_LINE_PTS], backRight[SSD_MAX_LINE_PTS];
+  P2id frontLeft[MAX_LINE_PTS], backLeft[MAX_LINE_PTS], frontRight[MAX_LINE_PTS], backRight[MAX_LINE_PTS];
   int nLeft, nRight, ok;
   LineId line[4]; // frontLeft, frontRight, backLeft, backRight
   BestLineWork wk;
   // vertical edge probing
-  P2id vpts[SSD_MAX_VPTS];
-  int vfound[SSD_MAX_VPTS];
-  double vdist[SSD_MAX_VPTS];
+  P2id vpts[MAX_VPTS_];
+  int vfound[MAX_VPTS_];
+  double vdist[MAX_VPTS_];
   int vn;
   int ve_left, ve_right, ve_ystart, ve_yend, ve_go;
   LineDd base;
   P2d outer[4];
   int best_pt;
 };
+typedef OutlineSharedT<SSD_MAX_SCANS, SSD_MAX_LINE_PTS, SSD_MAX_VPTS> OutlineShared; // any supported frame size
+typedef OutlineSharedT<64, 32, 112> OutlineSharedSmall;                              // W <= 1280, H <= 1100
 
 // Segmentation::detectOutline after the close (segmentation.cpp:930-946). Block-cooperative.
 // Thread 0 ends up with the quadrilateral (image pixels) and the valid flag.
+template<class OutlineShared>
 __device__ inline void detect_outline_block(const DevParams &p, const Band &bd, OutlineShared &S, int min_img_y_extent, double xy_ratio,
                                             P2d quad[4], int &valid, int tid, int nthreads)
 {
@@ -540,7 +548,7 @@ __device__ inline void detect_outline_block(const DevParams &p, const Band &bd, 
       // (VerticalEdgePointsDetector, :243-312)
       const int x0 = e == 0 ? left : left + 1, x1 = e == 0 ? right - 1 : right;
       const int w0 = x0 >> 5, w1 = x1 >> 5;
-      for(int r = warp; r < nrows && r < SSD_MAX_VPTS; r += nwarps)
+      for(int r = warp; r < nrows && r < OutlineShared::MAX_VPTS; r += nwarps)
       {
         const int y = yStart - r * 10;
         int fx = -1;
@@ -594,7 +602,7 @@ __device__ inline void detect_outline_block(const DevParams &p, const Band &bd, 
       {
         // compact in probing order (top of the list = yStart)
         int n = 0;
-        const int lim = nrows < SSD_MAX_VPTS ? nrows : SSD_MAX_VPTS;
+        const int lim = nrows < OutlineShared::MAX_VPTS ? nrows : OutlineShared::MAX_VPTS;
         for(int r = 0; r < lim; r++)
           if(S.vfound[r])
           {
@@ -649,6 +657,7 @@ __device__ inline void detect_outline_block(const DevParams &p, const Band &bd, 
 
 // BottomScanner::scan + detectFrontEdge after the close (segmentation.cpp:169-241, 890-904). Block-cooperative;
 // thread 0 gets the result.
+template<class OutlineShared>
 __device__ inline void detect_front_edge_block(const DevParams &p, const Band &bd, OutlineShared &S, P2d &left, P2d &right, int &valid, int tid,
                                                int nthreads)
 {
@@ -763,7 +772,11 @@ __device__ inline void band_clear_global(const DevParams &p, const Band &bd, uns
 // k_outline: grid = (SSD_GPU_MAX_PLATEAUS, frames); one block per outlined plateau
 // (loop B of detectStairSteps, pointcloud.cpp:419-429, incl. imgPointsToWorld :476-487)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SSD_OL_THREADS) k_outline(const __grid_constant__ DevParams p, FrameDev *__restrict__ frames,
+#ifndef SSD_OL_MINB
+#define SSD_OL_MINB 6
+#endif
+template<class OutlineShared>
+__global__ void __launch_bounds__(SSD_OL_THREADS, SSD_OL_MINB) k_outline(const __grid_constant__ DevParams p, FrameDev *__restrict__ frames,
                                                              unsigned *__restrict__ bev, size_t bm_words, size_t smem_cap_words)
 {
   extern __shared__ __align__(16) unsigned s_words[];

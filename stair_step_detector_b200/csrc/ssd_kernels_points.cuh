@@ -138,15 +138,19 @@ __global__ void __launch_bounds__(SSD_PT_THREADS) k_transform_bin(const __grid_c
         run_n += 4; // warp-uniform: every lane's four codes continue its run (invalid / out-of-range areas, flat surfaces)
       else
       {
-        // branch-free run-length merge: a run that ends is added to the block histogram by a predicated reduction
+        // Branch-free: the lane's run follows the first code of each word. A run that ends is added to the block
+        // histogram by a predicated reduction; the word's points equal to its first code extend the (new) run, the
+        // others (height noise flips neighbouring pixels between two bins) are added one by one.
+        const bool sw = c[0] != run_code;
+        red_shared_add_if(hist_sa + run_code * 4u, run_n, sw);
+        run_n = sw ? 0u : run_n;
+        run_code = c[0];
+        const unsigned x = cw ^ (c[0] * 0x01010101u);                                   // zero bytes <=> code == c[0]
+        const unsigned nz = (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;       // bit 7 of every non-zero byte
+        run_n += 4u - __popc(nz);
 #pragma unroll
-        for(int j = 0; j < 4; j++)
-        {
-          const bool same = c[j] == run_code;
-          red_shared_add_if(hist_sa + run_code * 4u, run_n, !same);
-          run_n = same ? run_n + 1u : 1u;
-          run_code = c[j];
-        }
+        for(int j = 1; j < 4; j++)
+          red_shared_add_if(hist_sa + c[j] * 4u, 1u, (nz >> (8 * j + 7)) & 1u);
       }
     }
   }
