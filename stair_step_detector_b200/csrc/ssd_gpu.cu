@@ -474,7 +474,10 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, int frame
   STAGE_EV(5);
   k_quad_reduce<<<gpt2q, SSD_PT_THREADS, ctx->pad_q, st>>>(p, xyz_dev, labels, frames, bev, ctx->bm_words);
   STAGE_EV(6);
-  k_finalize<<<nf, SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, ctx->d_out + frame0, bev, ctx->bm_words, ctx->smem_cap_words);
+  if(ctx->outline_small)
+    k_finalize<OutlineSharedSmall><<<nf, SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, ctx->d_out + frame0, bev, ctx->bm_words, ctx->smem_cap_words);
+  else
+    k_finalize<OutlineShared><<<nf, SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, ctx->d_out + frame0, bev, ctx->bm_words, ctx->smem_cap_words);
   STAGE_EV(7);
 #undef STAGE_EV
   *launches += SSD_GPU_N_STAGES;
@@ -610,7 +613,7 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
   if(cudaFuncGetAttributes(&fa, k_outline<OutlineShared>) != cudaSuccess)
     return bail("cudaFuncGetAttributes(k_outline) failed: was the library built for this GPU (sm_100a)?", SSD_E_CUDA);
   cudaFuncAttributes fb{}, fc{};
-  cudaFuncGetAttributes(&fb, k_finalize);
+  cudaFuncGetAttributes(&fb, k_finalize<OutlineShared>);
   cudaFuncGetAttributes(&fc, k_test_front_edge);
   const size_t stat = std::max({ fa.sharedSizeBytes, fb.sharedSizeBytes, fc.sharedSizeBytes });
   size_t dyn = (size_t)max_optin > stat + 1024 ? (size_t)max_optin - stat - 1024 : 0;
@@ -638,7 +641,8 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
     return bail("cudaFuncSetAttribute(k_transform_bin) failed", SSD_E_CUDA);
   cudaFuncSetAttribute(k_outline<OutlineShared>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
   cudaFuncSetAttribute(k_outline<OutlineSharedSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-  cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  cudaFuncSetAttribute(k_finalize<OutlineShared>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  cudaFuncSetAttribute(k_finalize<OutlineSharedSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
   cudaFuncSetAttribute(k_test_front_edge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
 
 

@@ -916,7 +916,8 @@ __global__ void __launch_bounds__(32) k_frame_logic(const __grid_constant__ DevP
 // assembly of detectStairs with ToExternalWorld (:370-383, transformation.cpp:190-194).
 // grid = frames, one block per frame.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SSD_OL_THREADS) k_finalize(const __grid_constant__ DevParams p, FrameDev *__restrict__ frames,
+template<class OutlineShared>
+__global__ void __launch_bounds__(SSD_OL_THREADS, SSD_OL_MINB) k_finalize(const __grid_constant__ DevParams p, FrameDev *__restrict__ frames,
                                                               FrameOut *__restrict__ out, unsigned *__restrict__ bev, size_t bm_words,
                                                               size_t smem_cap_words)
 {

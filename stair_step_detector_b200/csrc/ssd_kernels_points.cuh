@@ -406,7 +406,10 @@ __device__ __forceinline__ void label_bev_exact_point(const DevParams &p, const 
     S.oob = 1;
 }
 
-__global__ void __launch_bounds__(SSD_PT_THREADS) k_label_bev(const __grid_constant__ DevParams p, const float *__restrict__ xyz,
+#ifndef SSD_LB_MINB
+#define SSD_LB_MINB 4
+#endif
+__global__ void __launch_bounds__(SSD_PT_THREADS, SSD_LB_MINB) k_label_bev(const __grid_constant__ DevParams p, const float *__restrict__ xyz,
                                                                unsigned char *__restrict__ labels, FrameDev *__restrict__ frames,
                                                                unsigned *__restrict__ bev, size_t bm_words)
 {
@@ -651,7 +654,10 @@ __device__ __forceinline__ void quad_reduce_exact_point(const DevParams &p, cons
 #define SSD_DEF_MID 0x2000u     // deferred point between inner and reject box: f32 image of the test first
 #define SSD_DEF_GENERIC 0x4000u // deferred point of a word with mixed labels: not yet checked against amask
 
-__global__ void __launch_bounds__(SSD_PT_THREADS, 3) k_quad_reduce(const __grid_constant__ DevParams p, const float *__restrict__ xyz,
+#ifndef SSD_QR_MINB
+#define SSD_QR_MINB 3
+#endif
+__global__ void __launch_bounds__(SSD_PT_THREADS, SSD_QR_MINB) k_quad_reduce(const __grid_constant__ DevParams p, const float *__restrict__ xyz,
                                                                  const unsigned char *__restrict__ labels, FrameDev *__restrict__ frames,
                                                                  unsigned *__restrict__ bev, size_t bm_words)
 {

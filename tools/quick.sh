@@ -4,7 +4,7 @@
 TAG=${1:-q}; KR=${2:-k_label_bev|k_quad_reduce}
 mkdir -p gpurun_out/$TAG
 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python tools/sweep.py --frames 2048 --chunks 512 --streams 2 --reps 4 2>&1 | tee gpurun_out/$TAG/sweep.jsonl | python -c "
+python tools/sweep.py --frames 2048 --chunks 1024 --streams 2 --reps 4 2>&1 | tee gpurun_out/$TAG/sweep.jsonl | python -c "
 import sys, json
 for l in sys.stdin:
     try: d = json.loads(l)
