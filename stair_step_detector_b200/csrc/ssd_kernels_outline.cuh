@@ -158,6 +158,35 @@ struct BestLineWork
   int idx[SSD_OL_THREADS / 32][4];
 };
 
+// Sum of the cnt (<= S) smallest distances of the other points to line l: insertion into a sorted register array
+// (one min / max pair per slot, no branches). Ties need no order: only the sum of the values is used.
+template<int S>
+__device__ __forceinline__ long long sum_smallest(const P2id *pts, int n, int pi, int qi, LineId l, int cnt)
+{
+  int a[S];
+#pragma unroll
+  for(int k = 0; k < S; k++)
+    a[k] = 0x7fffffff;
+  for(int i = 0; i < n; i++)
+  {
+    if(i == pi || i == qi)
+      continue;
+    int d = abs(pts[i].x * l.a + pts[i].y * l.b + l.c);
+#pragma unroll
+    for(int k = 0; k < S; k++)
+    {
+      const int lo = min(a[k], d);
+      d = max(a[k], d);
+      a[k] = lo;
+    }
+  }
+  long long sum = 0;
+#pragma unroll
+  for(int k = 0; k < S; k++)
+    sum += k < cnt ? a[k] : 0;
+  return sum;
+}
+
 __device__ inline double pair_residual(const P2id *pts, int n, int pi, int qi, LineId l)
 {
   if(n <= 2)
@@ -165,7 +194,13 @@ __device__ inline double pair_residual(const P2id *pts, int n, int pi, int qi, L
   const int m = n - 2;
   const int cnt = m > 4 ? (m - 1) / 2 : 1;
   long long sum = 0;
-  if(cnt <= 24)
+  if(cnt <= 4)
+    sum = sum_smallest<4>(pts, n, pi, qi, l, cnt);
+  else if(cnt <= 8)
+    sum = sum_smallest<8>(pts, n, pi, qi, l, cnt);
+  else if(cnt <= 12)
+    sum = sum_smallest<12>(pts, n, pi, qi, l, cnt);
+  else if(cnt <= 24)
   {
     // repeated minimum extraction without materialising the list: extract in (value, index) order
     int lastv = -1, lasti = -1;
