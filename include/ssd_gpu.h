@@ -239,6 +239,17 @@ int ssd_gpu_camera_to_world(ssd_gpu_ctx *ctx, const float *xyz_host, int n, doub
 /* ---- host-side transformation builders (transformation.cpp), no GPU needed ---- */
 /* GeometricTransformation(worldPoints, cameraPoints) (transformation.cpp:196-215): 3 points each, xyz. */
 int ssd_make_transform(const double world_pts[9], const double camera_pts[9], ssd_gpu_transform *out);
+/* GeometricCalibration::load() (geometricCalibration.cpp:185-203): reads "<directory>/calibration-triangle"
+ * (CalibrationTriangle::load, calibrationTriangle.cpp:97-125; validity :148-168) and "<directory>/calibration-points"
+ * (loadPoints, geometricCalibration.cpp:73-98: header + ten rows of three "x, y, z" float triples), averages the rows
+ * (calcAverageRefPointSet, :127-141) and builds the transformation. directory NULL or "": current directory, as the
+ * reference. Returns SSD_OK, or SSD_CAL_* > 0 when a file is missing / malformed -- then *out is the identity
+ * transformation the reference silently falls back to (geometricCalibration.cpp:199-202); world_pts / camera_pts
+ * (may be NULL) receive the six reference points. */
+#define SSD_CAL_TRIANGLE_MISSING 1
+#define SSD_CAL_TRIANGLE_INVALID 2
+#define SSD_CAL_POINTS_MISSING 3
+int ssd_load_calibration(const char *directory, ssd_gpu_transform *out, double world_pts[9], double camera_pts[9]);
 
 /* ---- synthetic input source (stands in for the stubbed RealSense capture) ---- */
 typedef struct ssd_scene

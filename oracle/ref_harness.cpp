@@ -44,6 +44,8 @@
 #include SSD_REF_FILE(pointcloud.cpp)
 #undef private
 #undef protected
+#include SSD_REF_FILE(geometricCalibration.h) // GeometricCalibration::load (the TU itself is compiled by path, see Makefile)
+#include SSD_REF_FILE(calibrationMark.h)
 
 // assert() in the reference aborts the process; turn it into an exception the harness can report.
 struct ssd_ref_assert_failure : std::runtime_error
@@ -59,6 +61,13 @@ namespace stairs
 {
 // GL overlay is stubbed (drawing.h:57)
 void drawQuadrilateral(const Quadrilateralf_t &, const Quadrilateral_t &, Coordinate_t) {}
+// The mark-detection half of geometricCalibration.cpp (calibration tool, never called here) refers to these:
+void setDrawOffset(int, int) {}
+void resetDrawOffset() {}
+void drawSubframeRect(const Rect2i &, Rgb) {}
+void drawMarker(const Point2 &, const Contour_t &) {}
+void drawMarker(const Point2 &, const Point3f &) {}
+CalibrationMark::Detections CalibrationMark::detect(const Image &) { throw std::logic_error("CalibrationMark::detect is outside the oracle"); }
 }
 
 namespace
@@ -214,6 +223,18 @@ SSD_API int ssd_ref_make_transform(const double world_pts[9], const double camer
                      c[i] = Point3(camera_pts[i * 3], camera_pts[i * 3 + 1], camera_pts[i * 3 + 2]);
                    }
                    const GeometricTransformation t(w, c);
+                   getTransform(t, *out);
+                   return SSD_OK;
+                 });
+}
+
+// GeometricCalibration::load() (geometricCalibration.cpp:185-203) on the files "calibration-triangle" and
+// "calibration-points" of the CURRENT DIRECTORY (the reference resolves them there; the caller chdir()s).
+SSD_API int ssd_ref_load_calibration(ssd_gpu_transform *out)
+{
+  return guarded([&]
+                 {
+                   const GeometricTransformation t = GeometricCalibration::load();
                    getTransform(t, *out);
                    return SSD_OK;
                  });

@@ -8,6 +8,7 @@ There is no CPU fallback: the shared library must have been built (``__graft_ent
 ``Detector`` needs a CUDA device.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -50,6 +51,19 @@ def make_transform(world_pts, camera_pts):
     if rc:
         raise SsdError(f"ssd_make_transform failed ({rc})")
     return xf
+
+
+def load_calibration(directory=""):
+    """GeometricCalibration::load() (reference geometricCalibration.cpp:185-203): the transformation from the text files
+    ``calibration-triangle`` and ``calibration-points`` in ``directory``. Returns (Transform, status, world_pts, camera_pts);
+    status != 0 (SSD_CAL_*) means a file was missing or malformed and the transform is the identity, as in the reference."""
+    xf = Transform()
+    w = (C.c_double * 9)()
+    c = (C.c_double * 9)()
+    rc = lib().ssd_load_calibration(os.fsencode(directory), C.byref(xf), w, c)
+    if rc < 0:
+        raise SsdError(f"ssd_load_calibration failed ({rc})")
+    return xf, rc, np.array(w).reshape(3, 3), np.array(c).reshape(3, 3)
 
 
 def default_scene(width, height, **overrides):

@@ -135,6 +135,7 @@ PROTOTYPES = {
     "ssd_gpu_free": (C.c_int, [_vp, _vp]),
     "ssd_gpu_memcpy_h2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
     "ssd_gpu_memcpy_d2h": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+    "ssd_load_calibration": (C.c_int, [C.c_char_p, _P(Transform), _P(C.c_double), _P(C.c_double)]),
     "ssd_gpu_malloc_host": (C.c_int, [C.c_size_t, _P(_vp)]),
     "ssd_gpu_free_host": (C.c_int, [_vp]),
 }

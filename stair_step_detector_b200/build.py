@@ -22,6 +22,8 @@ SOURCES = [
     "host/pointcloud.cpp",
     "host/segmentation.cpp",
     "host/quadrilateralTest.cpp",
+    "host/calibrationTriangle.cpp",
+    "host/geometricCalibration.cpp",
 ]
 
 NVCC_FLAGS = [

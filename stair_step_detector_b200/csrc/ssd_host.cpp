@@ -3,6 +3,7 @@
 #include <cstring>
 #include "../../include/ssd_gpu.h"
 #include "host/transformation.h"
+#include "host/geometricCalibration.h"
 #include "scene_model.h"
 #include <exception>
 
@@ -44,6 +45,38 @@ int ssd_make_transform(const double world_pts[9], const double camera_pts[9], ss
       w[i] = stairs::Point3(world_pts[i * 3], world_pts[i * 3 + 1], world_pts[i * 3 + 2]);
       c[i] = stairs::Point3(camera_pts[i * 3], camera_pts[i * 3 + 1], camera_pts[i * 3 + 2]);
     }
+    const stairs::GeometricTransformation t(w, c);
+    *out = t.abi();
+    return SSD_OK;
+  }
+  catch(const std::exception &)
+  {
+    return SSD_E_INVALID_ARG;
+  }
+}
+
+int ssd_load_calibration(const char *directory, ssd_gpu_transform *out, double world_pts[9], double camera_pts[9])
+{
+  if(!out)
+    return SSD_E_INVALID_ARG;
+  try
+  {
+    stairs::GeometricTransformation::RefPoints w, c;
+    const int st = (int)stairs::GeometricCalibration::loadPoints(directory ? directory : "", w, c);
+    if(st != 0)
+    {
+      const stairs::GeometricTransformation identity;
+      *out = identity.abi();
+      return st;
+    }
+    for(int i = 0; i < 3; i++)
+      for(int j = 0; j < 3; j++)
+      {
+        if(world_pts)
+          world_pts[i * 3 + j] = w[i][j];
+        if(camera_pts)
+          camera_pts[i * 3 + j] = c[i][j];
+      }
     const stairs::GeometricTransformation t(w, c);
     *out = t.abi();
     return SSD_OK;

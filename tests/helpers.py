@@ -84,6 +84,7 @@ def load_ref(cfg):
     lib.ssd_ref_points_in_quad.argtypes = [_P(C.c_double), _vp, C.c_int, _vp, _P(C.c_int)]
     lib.ssd_ref_camera_to_world.argtypes = [_P(A.Transform), _vp, C.c_int, _vp]
     lib.ssd_ref_serialize.argtypes = [_P(A.Step), C.c_int, C.c_char_p, C.c_size_t]
+    lib.ssd_ref_load_calibration.argtypes = [_P(A.Transform)]
     got = A.Config()
     lib.ssd_ref_config(C.byref(got))
     for f, _ in A.Config._fields_:

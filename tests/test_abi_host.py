@@ -85,6 +85,25 @@ def test_serialize_wire_format(S):
     assert j[1][1] == 1 and j[2][0][0][1] == 0.25 and j[2][0][1][1] == [-0.45, 0.279]
 
 
+def test_wire_format_through_the_consumers_index_paths(S):
+    """The line protocol as its two consumers read it: print-stairs.py:54-72 (jdata[0], jdata[1][1], jdata[2][i],
+    step[1][1..4]) and the ROS publisher stair_step_detector.py:33-57 (step[0][1], step[1][1..4] -> Point2 x, y)."""
+    import json
+    rng = np.random.default_rng(3)
+    steps = [(float(h), rng.uniform(-0.6, 1.3, (4, 2))) for h in (0.004, 0.177, 0.35)]
+    jdata = json.loads(S.serialize(steps))
+    assert jdata[0] == "stairs" and jdata[1][0] == "stairSteps" and jdata[1][1] == len(steps) == len(jdata[2])
+    for (h, q), step in zip(steps, jdata[2]):
+        assert step[0][0] == "height" and step[1][0] == "quadrilateral"
+        msg = dict(height=step[0][1], quadrilateral=[dict(x=step[1][k][0], y=step[1][k][1]) for k in (1, 2, 3, 4)])
+        assert abs(msg["height"] - h) <= 0.0005 + 1e-12  # three decimals (stairs.cpp:58)
+        for k in range(4):
+            assert abs(msg["quadrilateral"][k]["x"] - q[k, 0]) <= 0.0005 + 1e-12
+            assert abs(msg["quadrilateral"][k]["y"] - q[k, 1]) <= 0.0005 + 1e-12
+    empty = json.loads(S.serialize([]))
+    assert empty[1][1] == 0 and len(empty) == 2  # print-stairs.py:60 / stair_step_detector.py:38 never index jdata[2] then
+
+
 def test_scene_source_geometry(S):
     sc = S.default_scene(320, 240)
     d = S.synth_depth_host(sc)
