@@ -43,6 +43,7 @@ struct DevParams
   float Tf;                // max |x|, |y| of an in-range world point (quadfilter margins)
   // the same bounds for ANY in-range point: max|p| <= Mmax (derive_params), so eps <= epsc etc. are constants
   float epsc, euc, evc;
+  float hu, hv;            // fast_pixel2: 1/2 - euc - 2^-20, 1/2 - evc - 2^-20 (negative: never certain)
   // k_transform_bin (point_code_scaled): rows of the transform scaled to the measuring range, v_i = (w_i - c_i) / h_i,
   // so "in range" is max|v_i| < 1; height bin t = G * (v_z + 1) with G = h_z * hir; eps = E1s * max|p| + E0s bounds
   // |v^_i - v_i| (8u (S_i m + B_i), derive_params); bin certain iff |frac distance| < thr0 - Gup * eps
@@ -281,24 +282,38 @@ __device__ __forceinline__ unsigned point_code_scaled(const DevParams &p, float 
 }
 
 // Single-precision BEV pixel of an in-range point with the constant error bounds euc / evc (packed arithmetic). Returns
-// true when (ix, iy) is certainly the pixel the exact double chain (camera_to_world_xy + bev_pixel) produces: u^, v^ are
-// further than their error bound from every integer boundary and from the image edges (so neither the x == W wrap nor an
-// out-of-image pixel can occur). floor() via the 1.5*2^23 trick (no conversion instruction).
+// true when (ix, iy) is certainly the pixel the exact double chain (camera_to_world_xy + bev_pixel) produces.
+//   s = RD(u^ + 1.5*2^23): the sum rounded towards -inf lands on the integer grid, so its mantissa holds floor(u^)
+//   (no conversion instruction, no correction step); k = s - 1.5*2^23 and d = u^ - k in [0, 1) are exact.
+//   floor(u_ref) == floor(u^) is certain when d is further than the error bound from both ends: |d - 1/2| < hu with
+//   hu = 1/2 - euc - 2^-20 (the slack covers the rounding of d - 1/2). A certain pixel with 0 <= ix < W, 0 <= iy < H
+//   lies inside the image, so neither the x == W wrap nor an out-of-image write (pointcloud.cpp:468) can occur.
+__device__ __forceinline__ f32x2_t f2_sub(f32x2_t a, f32x2_t b)
+{
+  f32x2_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t f2_add_rm(f32x2_t a, f32x2_t b)
+{
+  f32x2_t r;
+  asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
 __device__ __forceinline__ bool fast_pixel2(const DevParams &p, float x, float y, float z, int &ix, int &iy)
 {
   const float MAGIC = 12582912.0f;
   const f32x2_t uv = f2_affine(p.auv2, p.buv2, x, y, z);
-  const f32x2_t s = f2_add(uv, f2_pack(MAGIC, MAGIC));
-  const f32x2_t d = f2_add(uv, f2_add(f2_pack(MAGIC, MAGIC), s ^ 0x8000000080000000ull)); // uv - (s - MAGIC), exact inner difference
-  float uu, vv, su, sv, du, dv;
-  f2_unpack(uv, uu, vv);
+  const f32x2_t s = f2_add_rm(uv, f2_pack(MAGIC, MAGIC));
+  const f32x2_t k = f2_add(s, f2_pack(-MAGIC, -MAGIC));                 // exact
+  const f32x2_t d = f2_sub(uv, k);                                      // exact, in [0, 1)
+  const f32x2_t t = f2_add(d, f2_pack(-0.5f, -0.5f));
+  float su, sv, tu, tv;
   f2_unpack(s, su, sv);
-  f2_unpack(d, du, dv);
-  ix = __float_as_int(su) - 0x4B400000 - (du < 0.f ? 1 : 0);
-  iy = __float_as_int(sv) - 0x4B400000 - (dv < 0.f ? 1 : 0);
-  const bool ok_u = fabsf(du) > p.euc && uu > p.euc && uu < (float)p.W - p.euc;
-  const bool ok_v = fabsf(dv) > p.evc && vv > p.evc && vv < (float)p.H - p.evc;
-  return ok_u && ok_v;
+  f2_unpack(t, tu, tv);
+  ix = __float_as_int(su) - 0x4B400000;
+  iy = __float_as_int(sv) - 0x4B400000;
+  return fabsf(tu) < p.hu && fabsf(tv) < p.hv && (unsigned)ix < (unsigned)p.W && (unsigned)iy < (unsigned)p.H;
 }
 
 // Projection2D::worldToImage (pointcloud.cpp:79-83)

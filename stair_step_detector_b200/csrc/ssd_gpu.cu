@@ -177,7 +177,8 @@ static int derive_params(const ssd_gpu_config &c, const ssd_gpu_transform &t, De
     }
     // BEV pixel in single precision (fast_pixel): u = sx*(wx - x_min), v = sy*(y_max - wy) folded into one fma chain.
     // |u^ - u_ref| <= 4u (S'm + |b'|) (coefficient rounding + three fma roundings; the reference's own f64
-    // roundings are ~2^-50 of that); used: 10u, i.e. a factor 2.5 of slack, plus an absolute 1e-6 px.
+    // roundings are ~2^-50 of that); used: 6u, i.e. a factor 1.5 of slack, plus an absolute 1e-6 px. (Half of all
+    // phase-B warp steps of k_label_bev see an uncertain pixel at 10u: the bound's slack is paid in divergence.)
     const double sx = d.x_to_image, sy = d.y_to_image;
     double Su = 0, Sv = 0;
     for(int j = 0; j < 3; j++)
@@ -190,10 +191,10 @@ static int derive_params(const ssd_gpu_config &c, const ssd_gpu_transform &t, De
     const double bu = (t.b[0] - c.x_min) * sx, bv = (c.y_max - t.b[1]) * sy;
     d.bu = (float)bu;
     d.bv = (float)bv;
-    d.Eu1 = (float)(10.0 * u * Su * 1.001);
-    d.Eu0 = (float)(10.0 * u * std::fabs(bu) * 1.001 + 1e-6);
-    d.Ev1 = (float)(10.0 * u * Sv * 1.001);
-    d.Ev0 = (float)(10.0 * u * std::fabs(bv) * 1.001 + 1e-6);
+    d.Eu1 = (float)(6.0 * u * Su * 1.001);
+    d.Eu0 = (float)(6.0 * u * std::fabs(bu) * 1.001 + 1e-6);
+    d.Ev1 = (float)(6.0 * u * Sv * 1.001);
+    d.Ev0 = (float)(6.0 * u * std::fabs(bv) * 1.001 + 1e-6);
     d.Tf = (float)(std::max({ std::fabs(c.x_min), std::fabs(c.x_max), std::fabs(c.y_min), std::fabs(c.y_max) }) * 1.001 + 1e-3);
     // Constant bounds for points that are known to be in range (everything k_label_bev / k_quad_reduce touch):
     // p = A^-1 (w - b), so max|p| <= max_i sum_j |A^-1_ij| (T_j + |b_j|) =: Mmax (1 % slack). A singular A gives
@@ -220,6 +221,8 @@ static int derive_params(const ssd_gpu_config &c, const ssd_gpu_transform &t, De
       d.epsc = (float)((double)d.E1 * Mmax * 1.0001) + d.E0;
       d.euc = (float)((double)d.Eu1 * Mmax * 1.0001) + d.Eu0;
       d.evc = (float)((double)d.Ev1 * Mmax * 1.0001) + d.Ev0;
+      d.hu = 0.5f - d.euc - 9.5367431640625e-07f; // infinite / NaN bounds make every comparison false: exact pass
+      d.hv = 0.5f - d.evc - 9.5367431640625e-07f;
     }
     {
       // ground BEV columns W/2 - 2 + 50 j + {0..4}: f32 pre-filter with a conservative margin (pixel error of the f32

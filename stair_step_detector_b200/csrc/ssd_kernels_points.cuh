@@ -500,34 +500,68 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_LB_MINB) k_label_bev(const
       if(e1)
         load3(tile4 + (e1 >> 4) * 3, n0, n1, n2);
       const unsigned lab = labs[e >> 4];
+      const unsigned m4 = e & 15u;
       const float vx[4] = { c0.x, c0.w, c1.z, c2.y }, vy[4] = { c0.y, c1.x, c1.w, c2.z }, vz[4] = { c0.z, c1.y, c2.x, c2.w };
+      // the four pixels in straight-line code (the chains of the four points interleave); inactive lanes (e == 0) and
+      // inactive points compute on whatever the registers hold and are masked out by m4
+      int ix[4], iy[4];
+      unsigned okm = 0;
 #pragma unroll
       for(int j = 0; j < 4; j++)
+        okm |= fast_pixel2(p, vx[j], vy[j], vz[j], ix[j], iy[j]) ? (1u << j) : 0u;
+      const unsigned good = okm & m4, bad = ~okm & m4;
+      // label of the word's first point of an outlined plateau; the word is "uniform" when all such points carry it
+      // (image rows are iso-height: almost every word is)
+      const unsigned l0 = (lab >> (8 * (__ffs(m4 | 16u) - 1) & 31)) & 0xffu;
+      const unsigned bytes = ((m4 * 0x00204081u) & 0x01010101u) * 0xffu;
+      if(((lab ^ (l0 * 0x01010101u)) & bytes) == 0u)
       {
-        if((e >> j) & 1u)
-        {
-          const unsigned l = (lab >> (8 * j)) & 0xffu;
-          int ix, iy;
-          if(fast_pixel2(p, vx[j], vy[j], vz[j], ix, iy))
+        const unsigned lbase = l0 * bmw;
+        int ylo = 0x7fffffff, yhi = -1;
+#pragma unroll
+        for(int j = 0; j < 4; j++)
+          if((good >> j) & 1u)
           {
-            atomicOr(fbev + (l * bmw + (unsigned)iy * wpr + (unsigned)(ix >> 5)), 1u << (ix & 31));
-            if(l != rl)
-            {
-              if(rhi >= 0)
-              {
-                atomicMin(&S.rmin[rl], rlo);
-                atomicMax(&S.rmax[rl], rhi);
-              }
-              rl = l;
-              rlo = 0x7fffffff;
-              rhi = -1;
-            }
-            rlo = min(rlo, iy);
-            rhi = max(rhi, iy);
+            atomicOr(fbev + (lbase + (unsigned)iy[j] * wpr + ((unsigned)ix[j] >> 5)), 1u << (ix[j] & 31));
+            ylo = min(ylo, iy[j]);
+            yhi = max(yhi, iy[j]);
           }
-          else
-            defer_push(S.L, warp, ((e >> 4) << 2) | (unsigned)j);
+        if(yhi >= 0)
+        {
+          if(l0 != rl)
+          {
+            if(rhi >= 0)
+            {
+              atomicMin(&S.rmin[rl], rlo);
+              atomicMax(&S.rmax[rl], rhi);
+            }
+            rl = l0;
+            rlo = 0x7fffffff;
+            rhi = -1;
+          }
+          rlo = min(rlo, ylo);
+          rhi = max(rhi, yhi);
         }
+      }
+      else
+      {
+        // two plateaus meet inside the word: per point
+#pragma unroll
+        for(int j = 0; j < 4; j++)
+          if((good >> j) & 1u)
+          {
+            const unsigned l = (lab >> (8 * j)) & 0xffu;
+            atomicOr(fbev + (l * bmw + (unsigned)iy[j] * wpr + ((unsigned)ix[j] >> 5)), 1u << (ix[j] & 31));
+            atomicMin(&S.rmin[l], iy[j]);
+            atomicMax(&S.rmax[l], iy[j]);
+          }
+      }
+      if(bad)
+      {
+#pragma unroll
+        for(int j = 0; j < 4; j++)
+          if((bad >> j) & 1u)
+            defer_push(S.L, warp, ((e >> 4) << 2) | (unsigned)j);
       }
       e = e1;
       c0 = n0;
