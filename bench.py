@@ -294,10 +294,16 @@ def run_ours(args):
             try:
                 with open(traffic_file) as f:
                     tj = json.load(f)
-                roofline["traffic"] = tj.get("k_transform_bin_bytes_per_launch")
+                per = tj["per_kernel"]
+                # measured DRAM bytes per frame (one ncu --set full launch) scaled to this run's launch size
+                roofline["traffic"] = per["k_transform_bin"]["bytes_per_frame"] * det.chunk_frames
                 roofline["traffic_source"] = tj.get("source")
+                roofline["chain"]["traffic_bytes_per_frame"] = {k: v["bytes_per_frame"] for k, v in per.items()}
             except Exception:
                 pass
+        if roofline["frac"] and roofline["frac"] > 1.0:
+            roofline["note"] += ("; frac > 1: the peak is the driver's COPY bandwidth (equal read and write streams), "
+                                 "this kernel reads 12 bytes for every byte it writes and a read-dominated stream runs faster than a copy")
         e2e_fps = e2e_frames * world / (my_e2e * 1e-3)
         line = {"metric": "Mpoints/s", "value": mpts, "unit": "Mpoints/s", "frames_per_s": fps, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "wall_ms_per_step": wall_ms / args.steps,

@@ -51,6 +51,28 @@ def full(rep, dst):
             w.writerow([r[idx["Kernel Name"]].split("(")[0].replace("void ", "")] + [r[idx[m]] for m in METRICS if m in idx])
 
 
+def traffic(rep, dst, tag):
+    """profiles/traffic_latest.json: measured DRAM bytes per FRAME of every point kernel (dram__bytes_read.sum +
+    dram__bytes_write.sum of one `ncu --set full` launch / frames of that launch); bench.py scales it to its chunk."""
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per = {}
+    for r in rows[2:]:
+        name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").split("<")[0]
+        grid = [int(x) for x in r[idx["launch__grid_size"]].replace(",", "").split()] if False else None
+        frames = int(r[idx["Grid Size"]].strip("()").split(",")[1]) if "Grid Size" in idx else None
+        b = sum(float(r[idx[m]]) * scale[units[idx[m]]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        if frames:
+            per[name] = {"bytes_per_frame": b / frames, "frames_per_launch": frames, "us": float(r[idx["gpu__time_duration.sum"]]) *
+                         {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(units[idx["gpu__time_duration.sum"]], 1.0)}
+    with open(dst, "w") as f:
+        json.dump({"source": f"profiles/{tag}_ncu_full.csv (ncu --set full --clock-control none; dram__bytes_read.sum + dram__bytes_write.sum per launch / frames per launch)",
+                   "per_kernel": per}, f, indent=1)
+
+
 def main():
     src, name = sys.argv[1], sys.argv[2]
     os.makedirs(os.path.dirname(name) or ".", exist_ok=True)
@@ -58,6 +80,7 @@ def main():
         launches(f"{src}/launches.csv", f"{name}_launches.csv")
     if os.path.exists(f"{src}/prof.ncu-rep"):
         full(f"{src}/prof.ncu-rep", f"{name}_ncu_full.csv")
+        traffic(f"{src}/prof.ncu-rep", os.path.join(os.path.dirname(name) or ".", "traffic_latest.json"), os.path.basename(name))
     for fn in ("bench.json", "sweep.jsonl"):
         if os.path.exists(f"{src}/{fn}") and os.path.getsize(f"{src}/{fn}"):
             shutil.copy(f"{src}/{fn}", f"{name}_{fn}")
