@@ -422,7 +422,10 @@ __global__ void k_test_camera_to_world(const __grid_constant__ DevParams p, cons
 // ---------------------------------------------------------------------------------------------
 // the launch chain for one chunk of frames on one stream
 // ---------------------------------------------------------------------------------------------
-static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, int frame0, int nf, int *launches, cudaEvent_t *ev, bool single = false)
+// xyz_dev: packed vertices of the chunk, or nullptr with z16_dev: the chunk's depth frames, deprojected inside the
+// three point kernels (SrcDepth)
+static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, const uint16_t *z16_dev, float depth_unit, int frame0, int nf, int *launches,
+                        cudaEvent_t *ev, bool single = false)
 {
 #define STAGE_EV(i)                         \
   do                                        \
@@ -445,6 +448,15 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, int frame
   if(const char *e = getenv("SSD_GPU_Q_BPF"))
     bpf_q = std::max(1, std::min(tiles2, atoi(e)));
   const dim3 gpt2l(bpf_l, nf), gpt2q(bpf_q, nf);
+  const bool depth = xyz_dev == nullptr;
+  SrcVertices sv;
+  sv.xyz = xyz_dev;
+  SrcDepth sd;
+  sd.z16 = z16_dev;
+  sd.xn = ctx->d_xn;
+  sd.yn = ctx->d_yn;
+  sd.unit = depth_unit;
+  sd.wmagic = (((unsigned long long)1 << 40) + (unsigned long long)p.W - 1) / (unsigned long long)p.W;
 
   if(ctx->split && !single)
   {
@@ -454,19 +466,28 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, int frame
     CK(cudaStreamWaitEvent(p1, ctx->ev_pre[s], 0));
     if(ev)
       CK(cudaEventRecord(ev[0], p1));
-    k_transform_bin<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, SSD_PT_ITERS * SSD_TB_STAGE_BYTES + ctx->pad_tb, p1>>>(p, xyz_dev, labels, frames);
+    if(depth)
+      k_transform_bin_depth<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, 0, p1>>>(p, sd, labels, frames);
+    else
+      k_transform_bin<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, SSD_PT_ITERS * SSD_TB_STAGE_BYTES + ctx->pad_tb, p1>>>(p, xyz_dev, labels, frames);
     CK(cudaEventRecord(ctx->ev_p1[s], p1));
     CK(cudaStreamWaitEvent(st, ctx->ev_p1[s], 0));
   }
   else
   {
     STAGE_EV(0);
-    k_transform_bin<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, SSD_PT_ITERS * SSD_TB_STAGE_BYTES + ctx->pad_tb, st>>>(p, xyz_dev, labels, frames);
+    if(depth)
+      k_transform_bin_depth<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, 0, st>>>(p, sd, labels, frames);
+    else
+      k_transform_bin<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, SSD_PT_ITERS * SSD_TB_STAGE_BYTES + ctx->pad_tb, st>>>(p, xyz_dev, labels, frames);
   }
   STAGE_EV(1);
   k_peaks<<<nf, 32, 0, st>>>(p, frames, nf);
   STAGE_EV(2);
-  k_label_bev<<<gpt2l, SSD_PT_THREADS, ctx->pad_l, st>>>(p, xyz_dev, labels, frames, bev, ctx->bm_words);
+  if(depth)
+    k_label_bev<SrcDepth><<<gpt2l, SSD_PT_THREADS, ctx->pad_l, st>>>(p, sd, labels, frames, bev, ctx->bm_words);
+  else
+    k_label_bev<SrcVertices><<<gpt2l, SSD_PT_THREADS, ctx->pad_l, st>>>(p, sv, labels, frames, bev, ctx->bm_words);
   STAGE_EV(3);
   if(ctx->outline_small)
     k_outline<OutlineSharedSmall><<<dim3(SSD_GPU_MAX_PLATEAUS, nf), SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, bev, ctx->bm_words, ctx->smem_cap_words);
@@ -475,7 +496,10 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, int frame
   STAGE_EV(4);
   k_frame_logic<<<nf, 32, 0, st>>>(p, frames, nf);
   STAGE_EV(5);
-  k_quad_reduce<<<gpt2q, SSD_PT_THREADS, ctx->pad_q, st>>>(p, xyz_dev, labels, frames, bev, ctx->bm_words);
+  if(depth)
+    k_quad_reduce<SrcDepth><<<gpt2q, SSD_PT_THREADS, ctx->pad_q, st>>>(p, sd, labels, frames, bev, ctx->bm_words);
+  else
+    k_quad_reduce<SrcVertices><<<gpt2q, SSD_PT_THREADS, ctx->pad_q, st>>>(p, sv, labels, frames, bev, ctx->bm_words);
   STAGE_EV(6);
   if(ctx->outline_small)
     k_finalize<OutlineSharedSmall><<<nf, SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, ctx->d_out + frame0, bev, ctx->bm_words, ctx->smem_cap_words);
@@ -637,9 +661,15 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
   if(const char *e = getenv("SSD_GPU_Q_PAD_KB"))
     ctx->pad_q = (size_t)atoi(e) * 1024;
   if(ctx->pad_l)
-    cudaFuncSetAttribute(k_label_bev, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->pad_l);
+  {
+    cudaFuncSetAttribute(k_label_bev<SrcVertices>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->pad_l);
+    cudaFuncSetAttribute(k_label_bev<SrcDepth>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->pad_l);
+  }
   if(ctx->pad_q)
-    cudaFuncSetAttribute(k_quad_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->pad_q);
+  {
+    cudaFuncSetAttribute(k_quad_reduce<SrcVertices>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->pad_q);
+    cudaFuncSetAttribute(k_quad_reduce<SrcDepth>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->pad_q);
+  }
   if(cudaFuncSetAttribute(k_transform_bin<SSD_PT_ITERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SSD_PT_ITERS * SSD_TB_STAGE_BYTES + (int)ctx->pad_tb) != cudaSuccess)
     return bail("cudaFuncSetAttribute(k_transform_bin) failed", SSD_E_CUDA);
   cudaFuncSetAttribute(k_outline<OutlineShared>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
@@ -750,9 +780,18 @@ static int process_common(ssd_gpu_ctx *ctx, const float *xyz, const uint16_t *z1
     if(rc)
       return rc;
   }
+  // depth frames are deprojected inside the point kernels (SrcDepth): no vertex array is ever written.
+  const char *unfused_env = getenv("SSD_GPU_DEPTH_UNFUSED"); // A/B switch, read per call
+  const bool unfused = unfused_env && atoi(unfused_env) != 0;
   if(host_input || depth_input)
     for(int i = 0; i < ctx->n_streams; i++)
     {
+      if(depth_input && !unfused)
+      {
+        if(host_input && !ctx->d_depth[i])
+          CK(cudaMalloc(&ctx->d_depth[i], (size_t)ctx->host_chunk_frames * p.N * sizeof(uint16_t)));
+        continue;
+      }
       if(ctx->stage_frames[i] < cf) // grows once when a device-depth call follows host-input calls
       {
         CK(cudaDeviceSynchronize());
@@ -818,8 +857,9 @@ static int process_common(ssd_gpu_ctx *ctx, const float *xyz, const uint16_t *z1
       CK(cudaEventRecord(ctx->ev_in_ready[s], ctx->copy_stream));
       CK(cudaStreamWaitEvent(ctx->stream[s], ctx->ev_in_ready[s], 0));
     }
-    if(depth_input)
+    if(depth_input && unfused)
     {
+      // A/B path (SSD_GPU_DEPTH_UNFUSED=1): materialise the vertices, then the vertex kernels
       // (the vertex staging of stream s is free: the chunk that used it last ran on this very stream)
       k_deproject<<<dim3((p.N / 4 + 255) / 256, nf), 256, 0, ctx->stream[s]>>>(p.W, p.N, intr->depth_unit, ctx->d_xn, ctx->d_yn, dsrc, ctx->d_stage[s]);
       launches++;
@@ -827,12 +867,13 @@ static int process_common(ssd_gpu_ctx *ctx, const float *xyz, const uint16_t *z1
       if(host_input)
         CK(cudaEventRecord(ctx->ev_in_free[s], ctx->stream[s])); // the z16 staging is consumed
     }
-    const int rc = launch_chunk(ctx, s, src, f0, nf, &launches, stage_timing ? &ctx->stage_ev[(size_t)chunk * (SSD_GPU_N_STAGES + 1)] : nullptr,
-                                (flags & SSD_FLAG_SINGLE_STREAM) != 0);
+    const bool fused = depth_input && !unfused;
+    const int rc = launch_chunk(ctx, s, fused ? nullptr : src, fused ? dsrc : nullptr, fused ? intr->depth_unit : 0.f, f0, nf, &launches,
+                                stage_timing ? &ctx->stage_ev[(size_t)chunk * (SSD_GPU_N_STAGES + 1)] : nullptr, (flags & SSD_FLAG_SINGLE_STREAM) != 0);
     if(rc)
       return rc;
-    if(host_input && !depth_input)
-      CK(cudaEventRecord(ctx->ev_in_free[s], ctx->stream[s]));
+    if(host_input && (!depth_input || fused))
+      CK(cudaEventRecord(ctx->ev_in_free[s], ctx->stream[s])); // all three passes have read the staging
   }
   // join stream 1 into stream 0, then bring the compact results home
   for(int i = 1; i < ctx->n_streams; i++)

@@ -53,6 +53,157 @@ __device__ __forceinline__ void red_shared_add_if(unsigned addr, unsigned v, boo
 }
 
 // ---------------------------------------------------------------------------------------------
+// Where the point kernels read their vertices from. Two sources, chosen at launch (template parameter):
+//   SrcVertices : the packed rs2::vertex array (12 B/point) -- what rs2::pointcloud::calculate returns
+//                 (pointcloud.cpp:138-147);
+//   SrcDepth    : the z16 depth frame itself (2 B/point) -- what Pointcloud::process receives (pointcloud.cpp:608).
+//                 The deprojection the reference delegates to rs2::pointcloud::calculate (pin-hole model of
+//                 rs2_deproject_pixel_to_point / camera.h:99-116) is evaluated in registers, with the single-rounded f32
+//                 operations of ssd_deproject_pixel (scene_model.h) / k_deproject: the vertices never exist in memory
+//                 and all three passes move 2 bytes per point instead of 12.
+// A kernel derives a frame cursor once (src_frame), then loads 4-point words (word_load: issued one step ahead, so the
+// registers of a word in flight are the raw loads) and unpacks them where they are consumed (word_unpack).
+// ---------------------------------------------------------------------------------------------
+struct SrcVertices
+{
+  const float *xyz; // n_frames x N x {x, y, z}
+};
+struct SrcDepth
+{
+  const uint16_t *z16;         // n_frames x N
+  const float *xn, *yn;        // (u - ppx) / fx per column, (v - ppy) / fy per row (k_deproject_tables)
+  float unit;                  // metres per depth unit
+  unsigned long long wmagic;   // ceil(2^40 / W): row of pixel i = (i * wmagic) >> 40, exact for i * W < 2^40
+};
+struct FrameV
+{
+  const float4 *f4;
+};
+struct FrameD
+{
+  const uint2 *d2; // four z16 pixels per element
+  const float *xn, *yn;
+  float unit;
+  unsigned long long wmagic;
+  unsigned W;
+};
+struct WordV
+{
+  float4 a, b, c;
+};
+struct WordD
+{
+  uint2 d;
+  float4 x4;
+  float y;
+};
+template<class SRC>
+struct SrcTraits;
+template<>
+struct SrcTraits<SrcVertices>
+{
+  typedef FrameV Frame;
+  typedef WordV Word;
+};
+template<>
+struct SrcTraits<SrcDepth>
+{
+  typedef FrameD Frame;
+  typedef WordD Word;
+};
+__device__ __forceinline__ FrameV src_frame(const SrcVertices &s, const DevParams &p, size_t fbase)
+{
+  FrameV f;
+  f.f4 = reinterpret_cast<const float4 *>(s.xyz + fbase * 3);
+  return f;
+}
+__device__ __forceinline__ FrameD src_frame(const SrcDepth &s, const DevParams &p, size_t fbase)
+{
+  FrameD f;
+  f.d2 = reinterpret_cast<const uint2 *>(s.z16 + fbase);
+  f.xn = s.xn;
+  f.yn = s.yn;
+  f.unit = s.unit;
+  f.wmagic = s.wmagic;
+  f.W = (unsigned)p.W;
+  return f;
+}
+__device__ __forceinline__ void word_zero(WordV &r)
+{
+  r.a = r.b = r.c = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ void word_zero(WordD &r)
+{
+  r.d = make_uint2(0u, 0u);
+  r.x4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  r.y = 0.f;
+}
+// w: index of the 4-point word within the frame
+__device__ __forceinline__ void word_load(const FrameV &f, unsigned w, WordV &r)
+{
+  const float4 *src = f.f4 + (size_t)w * 3;
+  r.a = __ldg(src);
+  r.b = __ldg(src + 1);
+  r.c = __ldg(src + 2);
+}
+__device__ __forceinline__ void word_load(const FrameD &f, unsigned w, WordD &r)
+{
+  r.d = __ldg(f.d2 + w);
+  const unsigned i0 = w * 4u;
+  const unsigned v = (unsigned)(((unsigned long long)i0 * f.wmagic) >> 40), u = i0 - v * f.W; // W % 4 == 0: one row per word
+  r.x4 = __ldg(reinterpret_cast<const float4 *>(f.xn + u));
+  r.y = __ldg(f.yn + v);
+}
+__device__ __forceinline__ void word_unpack(const FrameV &, const WordV &r, float vx[4], float vy[4], float vz[4])
+{
+  vx[0] = r.a.x, vy[0] = r.a.y, vz[0] = r.a.z;
+  vx[1] = r.a.w, vy[1] = r.b.x, vz[1] = r.b.y;
+  vx[2] = r.b.z, vy[2] = r.b.w, vz[2] = r.c.x;
+  vx[3] = r.c.y, vy[3] = r.c.z, vz[3] = r.c.w;
+}
+__device__ __forceinline__ void word_unpack(const FrameD &f, const WordD &r, float vx[4], float vy[4], float vz[4])
+{
+  vz[0] = __fmul_rn((float)(r.d.x & 0xffffu), f.unit);
+  vz[1] = __fmul_rn((float)(r.d.x >> 16), f.unit);
+  vz[2] = __fmul_rn((float)(r.d.y & 0xffffu), f.unit);
+  vz[3] = __fmul_rn((float)(r.d.y >> 16), f.unit);
+  const float xn[4] = { r.x4.x, r.x4.y, r.x4.z, r.x4.w };
+#pragma unroll
+  for(int j = 0; j < 4; j++)
+  {
+    vx[j] = __fmul_rn(vz[j], xn[j]);
+    vy[j] = __fmul_rn(vz[j], r.y);
+  }
+}
+// request a word into L2 (issued as soon as it is known to matter, a phase ahead of its use)
+__device__ __forceinline__ void word_prefetch_l2(const FrameV &f, unsigned w)
+{
+  const float4 *src = f.f4 + (size_t)w * 3;
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(src));     // both 32-byte sectors the 48 bytes can touch
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 2));
+}
+__device__ __forceinline__ void word_prefetch_l2(const FrameD &f, unsigned w)
+{
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(f.d2 + w));
+}
+// one point by its index within the frame (the compacted exact passes)
+__device__ __forceinline__ void point_load(const FrameV &f, unsigned pt, float &x, float &y, float &z)
+{
+  const float *v = reinterpret_cast<const float *>(f.f4) + (size_t)pt * 3;
+  x = __ldg(v);
+  y = __ldg(v + 1);
+  z = __ldg(v + 2);
+}
+__device__ __forceinline__ void point_load(const FrameD &f, unsigned pt, float &x, float &y, float &z)
+{
+  const unsigned d = __ldg(reinterpret_cast<const unsigned short *>(f.d2) + pt);
+  const unsigned v = (unsigned)(((unsigned long long)pt * f.wmagic) >> 40), u = pt - v * f.W;
+  z = __fmul_rn((float)d, f.unit);
+  x = __fmul_rn(z, __ldg(f.xn + u));
+  y = __fmul_rn(z, __ldg(f.yn + v));
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_transform_bin: PointsExtraction::extract + HeightsHistogram::calcHist
 // (pointcloud.cpp:122-178, 194-204). grid = (tiles_per_frame, frames), block = 256.
 // Each thread handles 4 consecutive points per iteration: three 16 B loads, one 4 B store.
@@ -62,6 +213,49 @@ __device__ __forceinline__ void red_shared_add_if(unsigned addr, unsigned v, boo
 // Histogram: each thread run-length merges its own codes (neighbouring pixels mostly share a bin) and adds
 // the runs to one shared-memory histogram per block; one global atomic per non-empty bin per block.
 // ---------------------------------------------------------------------------------------------
+// One 4-point word of k_transform_bin: codes (filtered decision, exact fallback), the 4-byte code store, the lane's
+// run-length histogram update. Shared by the vertex and the depth-frame variant of the kernel.
+__device__ __forceinline__ void tb_word(const DevParams &p, const float vx[4], const float vy[4], const float vz[4], unsigned *__restrict__ dst_word,
+                                    unsigned hist_sa, unsigned &run_code, unsigned &run_n, unsigned &exact)
+{
+  unsigned c[4];
+  bool unc[4];
+#pragma unroll
+  for(int j = 0; j < 4; j++)
+    c[j] = point_code_scaled(p, vx[j], vy[j], vz[j], unc[j]);
+  if(unc[0] || unc[1] || unc[2] || unc[3])
+  {
+    // rare: one out-of-line exact evaluation per uncertain point
+#pragma unroll
+    for(int j = 0; j < 4; j++)
+      if(unc[j])
+      {
+        c[j] = point_code_slow(p, vx[j], vy[j], vz[j]);
+        exact++;
+      }
+  }
+  const unsigned cw = c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24);
+  *dst_word = cw;
+  if(__all_sync(0xffffffffu, cw == run_code * 0x01010101u))
+    run_n += 4; // warp-uniform: every lane's four codes continue its run (invalid / out-of-range areas, flat surfaces)
+  else
+  {
+    // Branch-free: the lane's run follows the first code of each word. A run that ends is added to the block
+    // histogram by a predicated reduction; the word's points equal to its first code extend the (new) run, the
+    // others (height noise flips neighbouring pixels between two bins) are added one by one.
+    const bool sw = c[0] != run_code;
+    red_shared_add_if(hist_sa + run_code * 4u, run_n, sw);
+    run_n = sw ? 0u : run_n;
+    run_code = c[0];
+    const unsigned x = cw ^ (c[0] * 0x01010101u);                                   // zero bytes <=> code == c[0]
+    const unsigned nz = (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;       // bit 7 of every non-zero byte
+    run_n += 4u - __popc(nz);
+#pragma unroll
+    for(int j = 1; j < 4; j++)
+      red_shared_add_if(hist_sa + c[j] * 4u, 1u, (nz >> (8 * j + 7)) & 1u);
+  }
+}
+
 #define SSD_TB_STAGE_BYTES (SSD_PT_THREADS * 48) // one iteration of the block: 256 threads x 4 vertices x 12 B
 template<int ITERS>
 __global__ void __launch_bounds__(SSD_PT_THREADS) k_transform_bin(const __grid_constant__ DevParams p, const float *__restrict__ xyz,
@@ -116,44 +310,61 @@ __global__ void __launch_bounds__(SSD_PT_THREADS) k_transform_bin(const __grid_c
       const float4 *s4 = reinterpret_cast<const float4 *>(s_dyn + it * SSD_TB_STAGE_BYTES) + tid * 3;
       const float4 v0 = s4[0], v1 = s4[1], v2 = s4[2];
       const float vx[4] = { v0.x, v0.w, v1.z, v2.y }, vy[4] = { v0.y, v1.x, v1.w, v2.z }, vz[4] = { v0.z, v1.y, v2.x, v2.w };
-      unsigned c[4];
-      bool unc[4];
-#pragma unroll
-      for(int j = 0; j < 4; j++)
-        c[j] = point_code_scaled(p, vx[j], vy[j], vz[j], unc[j]);
-      if(unc[0] || unc[1] || unc[2] || unc[3])
-      {
-        // rare: one out-of-line exact evaluation per uncertain point
-#pragma unroll
-        for(int j = 0; j < 4; j++)
-          if(unc[j])
-          {
-            c[j] = point_code_slow(p, vx[j], vy[j], vz[j]);
-            exact++;
-          }
-      }
-      const unsigned cw = c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24);
-      dst[it * SSD_PT_THREADS] = cw;
-      if(__all_sync(0xffffffffu, cw == run_code * 0x01010101u))
-        run_n += 4; // warp-uniform: every lane's four codes continue its run (invalid / out-of-range areas, flat surfaces)
-      else
-      {
-        // Branch-free: the lane's run follows the first code of each word. A run that ends is added to the block
-        // histogram by a predicated reduction; the word's points equal to its first code extend the (new) run, the
-        // others (height noise flips neighbouring pixels between two bins) are added one by one.
-        const bool sw = c[0] != run_code;
-        red_shared_add_if(hist_sa + run_code * 4u, run_n, sw);
-        run_n = sw ? 0u : run_n;
-        run_code = c[0];
-        const unsigned x = cw ^ (c[0] * 0x01010101u);                                   // zero bytes <=> code == c[0]
-        const unsigned nz = (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;       // bit 7 of every non-zero byte
-        run_n += 4u - __popc(nz);
-#pragma unroll
-        for(int j = 1; j < 4; j++)
-          red_shared_add_if(hist_sa + c[j] * 4u, 1u, (nz >> (8 * j + 7)) & 1u);
-      }
+      tb_word(p, vx, vy, vz, dst + it * SSD_PT_THREADS, hist_sa, run_code, run_n, exact);
     }
   }
+  if(run_n)
+    atomicAdd(&s_hist[run_code], run_n);
+  if(exact)
+    atomicAdd(&s_exact, exact);
+  __syncthreads();
+  const unsigned sum = s_hist[tid];
+  if(sum)
+    atomicAdd(&frames[frame].hist[tid], sum);
+  if(tid == 0 && s_exact)
+    atomicAdd(&frames[frame].n_exact_bin, s_exact);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_transform_bin_depth: the same pass on a z16 depth frame (SrcDepth): 2 bytes per point come in, 1 goes out, the
+// deprojected vertices live in registers only. No staging: the loads are 8 bytes per lane (256 B per warp, coalesced) and
+// all ITERS words of a thread are requested before the first is consumed. Not HBM-bound (3 B/point): issue-bound.
+// ---------------------------------------------------------------------------------------------
+template<int ITERS>
+__global__ void __launch_bounds__(SSD_PT_THREADS) k_transform_bin_depth(const __grid_constant__ DevParams p, const SrcDepth src,
+                                                                         unsigned char *__restrict__ codes, FrameDev *__restrict__ frames)
+{
+  __shared__ unsigned s_hist[SSD_BINS_PAD];
+  __shared__ unsigned s_exact;
+  const int tid = threadIdx.x;
+  const int frame = blockIdx.y;
+  const size_t fbase = (size_t)frame * p.N;
+  const int nquads = p.N >> 2;
+  const int q0 = blockIdx.x * (ITERS * SSD_PT_THREADS) + tid;
+  const FrameD F = src_frame(src, p, fbase);
+  WordD w[ITERS];
+#pragma unroll
+  for(int it = 0; it < ITERS; it++)
+  {
+    word_zero(w[it]);
+    if(q0 + it * SSD_PT_THREADS < nquads)
+      word_load(F, (unsigned)(q0 + it * SSD_PT_THREADS), w[it]);
+  }
+  s_hist[tid] = 0; // SSD_PT_THREADS == SSD_BINS_PAD
+  if(tid == 0)
+    s_exact = 0;
+  __syncthreads();
+  unsigned *dst = reinterpret_cast<unsigned *>(codes + fbase) + q0;
+  unsigned run_code = SSD_CODE_INVALID, run_n = 0, exact = 0;
+  const unsigned hist_sa = (unsigned)__cvta_generic_to_shared(s_hist);
+#pragma unroll
+  for(int it = 0; it < ITERS; it++)
+    if(q0 + it * SSD_PT_THREADS < nquads)
+    {
+      float vx[4], vy[4], vz[4];
+      word_unpack(F, w[it], vx, vy, vz);
+      tb_word(p, vx, vy, vz, dst + it * SSD_PT_THREADS, hist_sa, run_code, run_n, exact);
+    }
   if(run_n)
     atomicAdd(&s_hist[run_code], run_n);
   if(exact)
@@ -361,21 +572,6 @@ __device__ __forceinline__ void warp_tile_range(int n_wt, int warp, int &first, 
   end = n_wt;
 }
 
-// request the 48 bytes of one 4-vertex word into L2 (both 32-byte sectors it can touch): issued in phase A, as soon as a
-// word is known to matter, so that phase B finds its vertices at L2 rather than DRAM latency
-__device__ __forceinline__ void prefetch_word_l2(const float4 *w)
-{
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(w));
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(w + 2));
-}
-
-__device__ __forceinline__ void load3(const float4 *__restrict__ src, float4 &a, float4 &b, float4 &c)
-{
-  a = __ldg(src);
-  b = __ldg(src + 1);
-  c = __ldg(src + 2);
-}
-
 // ---------------------------------------------------------------------------------------------
 // k_label_bev: the per-point segment label (PlateausExtraction::extractPlateaus, pointcloud.cpp:280-343,
 // as a LUT lookup) and StairsDetector::projectToBinaryImage (:458-471) for every outlined plateau.
@@ -390,11 +586,11 @@ struct LabelBevShared
   WarpLists L;
 };
 
-__device__ __forceinline__ void label_bev_exact_point(const DevParams &p, const float *__restrict__ v, unsigned l, unsigned *__restrict__ fbev,
+__device__ __forceinline__ void label_bev_exact_point(const DevParams &p, float fx, float fy, float fz, unsigned l, unsigned *__restrict__ fbev,
                                                       size_t bm_words, LabelBevShared &S)
 {
   double wx, wy;
-  camera_to_world_xy(p, __ldg(v), __ldg(v + 1), __ldg(v + 2), wx, wy);
+  camera_to_world_xy(p, fx, fy, fz, wx, wy);
   int x, y;
   if(bev_pixel(p, wx, wy, x, y))
   {
@@ -409,7 +605,8 @@ __device__ __forceinline__ void label_bev_exact_point(const DevParams &p, const 
 #ifndef SSD_LB_MINB
 #define SSD_LB_MINB 4
 #endif
-__global__ void __launch_bounds__(SSD_PT_THREADS, SSD_LB_MINB) k_label_bev(const __grid_constant__ DevParams p, const float *__restrict__ xyz,
+template<class SRC>
+__global__ void __launch_bounds__(SSD_PT_THREADS, SSD_LB_MINB) k_label_bev(const __grid_constant__ DevParams p, const SRC src,
                                                                unsigned char *__restrict__ labels, FrameDev *__restrict__ frames,
                                                                unsigned *__restrict__ bev, size_t bm_words)
 {
@@ -420,6 +617,7 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_LB_MINB) k_label_bev(const
   const size_t fbase = (size_t)frame * p.N;
   unsigned *lab32 = reinterpret_cast<unsigned *>(labels + fbase);
   unsigned *fbev = bev + (size_t)frame * SSD_GPU_MAX_PLATEAUS * bm_words;
+  const typename SrcTraits<SRC>::Frame FR = src_frame(src, p, fbase);
   const int nquads = p.N >> 2;
   int wt, wt_end, wt_stride;
   warp_tile_range((p.N + SSD_WT_PX - 1) / SSD_WT_PX, warp, wt, wt_end, wt_stride);
@@ -487,21 +685,23 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_LB_MINB) k_label_bev(const
     __syncwarp();
 
     // ---- phase B: dense walk over the compacted words ----
-    const float4 *tile4 = reinterpret_cast<const float4 *>(xyz + (fbase + (size_t)wt * SSD_WT_PX) * 3);
+    const unsigned wbase = (unsigned)wt * (SSD_WT_PX / 4); // first word of the warp-tile within the frame
     unsigned e = lane < n ? act[lane] : 0u;
-    float4 c0, c1, c2, n0, n1, n2;
-    c0 = c1 = c2 = n0 = n1 = n2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    typename SrcTraits<SRC>::Word wc, wn;
+    word_zero(wc);
+    word_zero(wn);
     if(e)
-      load3(tile4 + (e >> 4) * 3, c0, c1, c2);
+      word_load(FR, wbase + (e >> 4), wc);
     for(unsigned s0 = 0; s0 < n; s0 += 32)
     {
       const unsigned i1 = s0 + 32 + lane;
       const unsigned e1 = i1 < n ? act[i1] : 0u;
       if(e1)
-        load3(tile4 + (e1 >> 4) * 3, n0, n1, n2);
+        word_load(FR, wbase + (e1 >> 4), wn);
       const unsigned lab = labs[e >> 4];
       const unsigned m4 = e & 15u;
-      const float vx[4] = { c0.x, c0.w, c1.z, c2.y }, vy[4] = { c0.y, c1.x, c1.w, c2.z }, vz[4] = { c0.z, c1.y, c2.x, c2.w };
+      float vx[4], vy[4], vz[4];
+      word_unpack(FR, wc, vx, vy, vz);
       // the four pixels in straight-line code (the chains of the four points interleave); inactive lanes (e == 0) and
       // inactive points compute on whatever the registers hold and are masked out by m4
       int ix[4], iy[4];
@@ -564,21 +764,20 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_LB_MINB) k_label_bev(const
             defer_push(S.L, warp, ((e >> 4) << 2) | (unsigned)j);
       }
       e = e1;
-      c0 = n0;
-      c1 = n1;
-      c2 = n2;
+      wc = wn;
     }
     // ---- dense exact pass over the warp's compacted uncertain points ----
     __syncwarp();
     const unsigned nd = S.L.ndef[warp];
     if(nd)
     {
-      const float *tile = reinterpret_cast<const float *>(tile4);
       for(unsigned i = lane; i < nd; i += 32)
       {
         const unsigned d = S.L.def[warp][i];
         const unsigned w = (d >> 2) & 0xffu, j = d & 3u;
-        label_bev_exact_point(p, tile + (w * 4 + j) * 3, (labs[w] >> (8 * j)) & 0xffu, fbev, bm_words, S);
+        float fx, fy, fz;
+        point_load(FR, (wbase + w) * 4u + j, fx, fy, fz);
+        label_bev_exact_point(p, fx, fy, fz, (labs[w] >> (8 * j)) & 0xffu, fbev, bm_words, S);
       }
       __syncwarp();
       n_def += nd;
@@ -657,12 +856,11 @@ __device__ __forceinline__ void seg_flush(QuadReduceShared &S, unsigned l, unsig
 }
 
 // one point of the compacted exact pass: the reference's own double-precision test
-__device__ __forceinline__ void quad_reduce_exact_point(const DevParams &p, const float *__restrict__ v, unsigned l, bool bevonly, const FrameDev &F,
+__device__ __forceinline__ void quad_reduce_exact_point(const DevParams &p, float fx, float fy, float fz, unsigned l, bool bevonly, const FrameDev &F,
                                                         unsigned amask, int ground, unsigned *__restrict__ gbev, QuadReduceShared &S)
 {
   if(l >= SSD_GPU_MAX_PLATEAUS || !((amask >> l) & 1u))
     return;
-  const float fx = __ldg(v), fy = __ldg(v + 1), fz = __ldg(v + 2);
   double wx, wy;
   camera_to_world_xy(p, fx, fy, fz, wx, wy);
   if(!bevonly)
@@ -691,7 +889,8 @@ __device__ __forceinline__ void quad_reduce_exact_point(const DevParams &p, cons
 #ifndef SSD_QR_MINB
 #define SSD_QR_MINB 3
 #endif
-__global__ void __launch_bounds__(SSD_PT_THREADS, SSD_QR_MINB) k_quad_reduce(const __grid_constant__ DevParams p, const float *__restrict__ xyz,
+template<class SRC>
+__global__ void __launch_bounds__(SSD_PT_THREADS, SSD_QR_MINB) k_quad_reduce(const __grid_constant__ DevParams p, const SRC src,
                                                                  const unsigned char *__restrict__ labels, FrameDev *__restrict__ frames,
                                                                  unsigned *__restrict__ bev, size_t bm_words)
 {
@@ -754,11 +953,11 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_QR_MINB) k_quad_reduce(con
   unsigned seg_l = 0xffu, seg_n = 0, n_def = 0, n_mid = 0;
   unsigned long long seg_sum = 0;
   int rmin = 0x7fffffff, rmax = -1;
-  const float4 *frame4 = reinterpret_cast<const float4 *>(xyz + fbase * 3);
+  const typename SrcTraits<SRC>::Frame FR = src_frame(src, p, fbase);
 
   for(; wt < wt_end; wt += wt_stride)
   {
-    const float4 *tile4 = frame4 + (size_t)wt * (SSD_WT_PX / 4 * 3);
+    const unsigned wbase = (unsigned)wt * (SSD_WT_PX / 4); // first word of the warp-tile within the frame
     // ---- phase A: compaction of the words holding plateau labels (bit 7 of a label byte clear <=> label < 128) ----
     unsigned n = 0;
 #pragma unroll
@@ -771,7 +970,7 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_QR_MINB) k_quad_reduce(con
         if(am4)
         {
           labs[it * 32 + lane] = lw;
-          prefetch_word_l2(tile4 + (it * 32 + lane) * 3);
+          word_prefetch_l2(FR, wbase + (unsigned)(it * 32 + lane));
         }
         n = compact_append(act, n, am4, it, lane);
       }
@@ -788,23 +987,25 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_QR_MINB) k_quad_reduce(con
 
     // ---- phase B: dense walk over the compacted words ----
     unsigned e = lane < n ? act[lane] : 0u;
-    float4 c0, c1, c2, n0, n1, n2;
-    c0 = c1 = c2 = n0 = n1 = n2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    typename SrcTraits<SRC>::Word wc, wn;
+    word_zero(wc);
+    word_zero(wn);
     if(e)
-      load3(tile4 + (e >> 4) * 3, c0, c1, c2);
+      word_load(FR, wbase + (e >> 4), wc);
     for(unsigned s0 = 0; s0 < n; s0 += 32)
     {
       const unsigned i1 = s0 + 32 + lane;
       const unsigned e1 = i1 < n ? act[i1] : 0u;
       if(e1)
-        load3(tile4 + (e1 >> 4) * 3, n0, n1, n2);
+        word_load(FR, wbase + (e1 >> 4), wn);
       const unsigned m4 = e & 15u;
       const unsigned lw = labs[e >> 4];
       // label of the word's first plateau point; the word is "uniform" when all its plateau points carry it
       const unsigned l0 = (lw >> (8 * (__ffs(m4 | 16u) - 1) & 31)) & 0x1fu;
       const unsigned bytes = ((m4 * 0x00204081u) & 0x01010101u) * 0xffu;
       const bool uniform = ((lw ^ (l0 * 0x01010101u)) & bytes) == 0u;
-      const float vx[4] = { c0.x, c0.w, c1.z, c2.y }, vy[4] = { c0.y, c1.x, c1.w, c2.z }, vz[4] = { c0.z, c1.y, c2.x, c2.w };
+      float vx[4], vy[4], vz[4];
+      word_unpack(FR, wc, vx, vy, vz);
       if(uniform)
       {
         // Branch-free on sign bits (every operand is finite here: plateau points are valid and in range, the tables
@@ -882,26 +1083,23 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_QR_MINB) k_quad_reduce(con
             defer_push(S.L, warp, SSD_DEF_GENERIC | ((e >> 4) << 2) | (unsigned)j);
       }
       e = e1;
-      c0 = n0;
-      c1 = n1;
-      c2 = n2;
+      wc = wn;
     }
     // ---- dense exact pass over the warp's compacted uncertain points ----
     __syncwarp();
     const unsigned nd = S.L.ndef[warp];
     if(nd)
     {
-      const float *tile = reinterpret_cast<const float *>(tile4);
       for(unsigned i = lane; i < nd; i += 32)
       {
         const unsigned d = S.L.def[warp][i];
         const unsigned w = (d >> 2) & 0xffu, j = d & 3u;
         const unsigned l = (labs[w] >> (8 * j)) & 0xffu;
-        const float *v = tile + (w * 4 + j) * 3;
+        float fx, fy, fz;
+        point_load(FR, (wbase + w) * 4u + j, fx, fy, fz);
         bool exact = true, bevonly = (d & SSD_DEF_BEVONLY) != 0u;
         if(d & SSD_DEF_MID)
         {
-          const float fx = __ldg(v), fy = __ldg(v + 1), fz = __ldg(v + 2);
           float wxf, wyf;
           f2_unpack(f2_affine(p.axy2, p.bxy2, fx, fy, fz), wxf, wyf);
           bool unc;
@@ -928,7 +1126,7 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_QR_MINB) k_quad_reduce(con
           }
         }
         if(exact)
-          quad_reduce_exact_point(p, v, l, bevonly, F, amask, ground, gbev, S);
+          quad_reduce_exact_point(p, fx, fy, fz, l, bevonly, F, amask, ground, gbev, S);
       }
       __syncwarp();
       n_def += nd;
@@ -940,7 +1138,6 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_QR_MINB) k_quad_reduce(con
       const unsigned ng = S.L.ngb[warp];
       if(ng)
       {
-        const float *tile = reinterpret_cast<const float *>(tile4);
         for(unsigned i = lane; i < ng; i += 32)
         {
           const unsigned d = S.L.gb[warp][i];
@@ -951,9 +1148,10 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_QR_MINB) k_quad_reduce(con
           {
             const unsigned j = __ffs(mask) - 1;
             mask &= mask - 1u;
-            const float *v = tile + (w * 4 + j) * 3;
+            float fx, fy, fz;
+            point_load(FR, (wbase + w) * 4u + j, fx, fy, fz);
             int ix, iy;
-            if(fast_pixel2(p, __ldg(v), __ldg(v + 1), __ldg(v + 2), ix, iy))
+            if(fast_pixel2(p, fx, fy, fz, ix, iy))
             {
               if(ground_col_needed(p, ix))
               {
@@ -963,7 +1161,7 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_QR_MINB) k_quad_reduce(con
               }
             }
             else
-              quad_reduce_exact_point(p, v, (unsigned)ground, true, F, amask, ground, gbev, S);
+              quad_reduce_exact_point(p, fx, fy, fz, (unsigned)ground, true, F, amask, ground, gbev, S);
           }
         }
         __syncwarp();

@@ -96,11 +96,12 @@ def test_empty_and_garbage_frames(S, oracle):
             assert g.info["status"] == o.info["status"]
 
 
-def test_depth_frame_input(S, oracle):
+@pytest.mark.parametrize("w,h", [(640, 480), (1024, 768)])
+def test_depth_frame_input(S, oracle, monkeypatch, w, h):
     """The z16 depth-frame entry points (what the reference's process() receives): on-device deprojection is bit-identical
-    to the host's, and host / device depth input give exactly the results of the vertex path -- which is checked
-    against the oracle."""
-    w, h = 640, 480
+    to the host's, and host / device depth input -- deprojected inside the three point kernels, no vertex array in
+    memory -- give exactly the results of the vertex path, which is checked against the oracle. The unfused A/B path
+    (separate deprojection kernel) must agree too."""
     cfg = S.default_config(w, h)
     base = S.default_scene(w, h, **NOISY)
     scenes = [S.randomize_scene(base, 77, i, 3, 6) for i in range(5)]
@@ -120,12 +121,17 @@ def test_depth_frame_input(S, oracle):
         assert np.array_equal(got.view(np.uint32), xyz.view(np.uint32)), "device deprojection differs from the host's"
         # vertex path = reference results
         det.process_host(xyz)
-        ref = [(det.labels(f), det.histogram(f), det.line(f)) for f in range(n)]
+        def exact_steps(f):
+            st, status = det.steps(f)
+            return [(float(hh).hex(), np.asarray(q, np.float64).tobytes()) for hh, q in st], status
+
+        ref = [(det.labels(f), det.histogram(f), det.line(f), exact_steps(f)) for f in range(n)]
         for f in range(n):
             o = H.oracle_process(oracle, cfg, xf, xyz[f])
             assert not H.compare_results(o, gpu_result(S, det, f), tol=TOL), f
-        for run in ("host", "device"):
-            if run == "host":
+        for run in ("host", "device", "device-unfused", "host-unfused"):
+            monkeypatch.setenv("SSD_GPU_DEPTH_UNFUSED", "1" if run.endswith("unfused") else "0")
+            if run.startswith("host"):
                 det.process_depth_host(depth, k)
             else:
                 det.process_depth_device(d_depth, k, n)
@@ -133,6 +139,7 @@ def test_depth_frame_input(S, oracle):
                 assert np.array_equal(det.labels(f), ref[f][0]), (run, f)
                 assert np.array_equal(det.histogram(f), ref[f][1]), (run, f)
                 assert det.line(f) == ref[f][2], (run, f)
+                assert exact_steps(f) == ref[f][3], (run, f)  # same vertices, same arithmetic: bit-identical doubles
         det.free(d_depth)
         det.free(d_xyz)
 
