@@ -44,14 +44,42 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / power / throttle reasons DURING the timed region (B200_PROFILING.md recipe). NVML in a sampling thread
+    (every 5 ms: the timed region is a few hundred ms); `nvidia-smi -lms` as the fallback when pynvml is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, device):
-        self.device, self.proc, self.path = device, None, None
+        self.device, self.proc, self.path, self.thread = device, None, None, None
+        self.sm, self.power, self.bits, self.smax = [], [], 0, None
+
+    def _nvml_loop(self):
+        import pynvml as nv
+        h = self.handle
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1e3)
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                self.bits |= int(get(h))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            self.handle = nv.nvmlDeviceGetHandleByIndex(self.device)
+            self.smax = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+            self.stop_flag = False
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
@@ -62,6 +90,13 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        if self.thread:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            if not self.sm:
+                return {"sm_mhz": None, "sm_max_mhz": self.smax, "reasons": ["no samples"]}
+            return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.smax, "power_w_max": max(self.power), "samples": len(self.sm),
+                    "source": "nvml", "reasons": sorted(name for bit, name in self.REASONS if self.bits & bit)}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -89,7 +124,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power), "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "source": "nvidia-smi", "reasons": sorted(reasons)}
 
 
 def dist_env():
