@@ -213,7 +213,7 @@ def blob_image(rng, w, h, kind):
     return img
 
 
-@pytest.mark.parametrize("w,h", [(320, 240), (1024, 768)])
+@pytest.mark.parametrize("w,h", [(320, 240), (1024, 768), (2560, 1920)])  # the last: > 12 "smallest distances" per line fit
 def test_outline_and_front_edge_images(S, oracle, w, h):
     cfg = S.default_config(w, h)
     xf = S.scene_transform(S.default_scene(w, h))
@@ -222,7 +222,7 @@ def test_outline_and_front_edge_images(S, oracle, w, h):
     oracle.ssd_oracle_derive(C.byref(cfg), C.byref(der))
     n_valid = 0
     with S.Detector(cfg, xf) as det:
-        for i in range(24):
+        for i in range(24 if w <= 1024 else 12):
             img = blob_image(rng, w, h, i % 4)
             gq, gv = det.detect_outline(img, der.min_img_y_extent, der.xy_ratio)
             oq = (C.c_double * 8)()
