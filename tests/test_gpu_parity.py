@@ -151,6 +151,23 @@ def test_hires_extended_range(S, oracle):
     run_frames(S, oracle, cfg, [sc])
 
 
+def test_hires_depth_input_equals_vertex_input(S):
+    """4096x3072 z16 frame through the fused depth kernels (row / column of a pixel by the 2^40 magic multiply, 12.6 M
+    pixels per frame) against the same frame as packed vertices: labels, histogram and steps identical."""
+    w, h = 4096, 3072
+    cfg = S.default_config(w, h, y_max=3.7, z_max=2.3)
+    sc = S.default_scene(w, h, n_steps=12, riser=0.17, tread=0.26, cam_height=3.2, cam_pitch_deg=48.0, first_riser_y=0.5, **NOISY)
+    xf = S.scene_transform(sc)
+    depth = S.synth_depth_host(sc)
+    xyz = S.deproject_host(sc, depth)
+    with S.Detector(cfg, xf, max_frames=1) as det:
+        det.process_host(xyz[None])
+        ref = (det.labels(0), det.histogram(0), det.line(0))
+        assert len(det.steps(0)[0]) >= 5
+        det.process_depth_host(depth[None], S.scene_intrinsics(sc))
+        assert np.array_equal(det.labels(0), ref[0]) and np.array_equal(det.histogram(0), ref[1]) and det.line(0) == ref[2]
+
+
 def test_camera_to_world_exact(S, oracle):
     cfg = S.default_config(320, 240)
     sc = S.default_scene(320, 240, cam_roll_deg=3.0, cam_yaw_deg=-7.0)
