@@ -9,6 +9,6 @@ import sys, json
 for l in sys.stdin:
     try: d = json.loads(l)
     except Exception: print('  ?', l[:160].rstrip()); continue
-    print('%-70s s=%d c=%d  %.3f ms  %.1f kfps  %s' % ('''$line''', d['streams'], d['chunk'], d['ms_best'], d['kfps'], {k: round(v, 2) for k, v in d['stages'].items() if k in ('transform_bin', 'label_bev', 'outline', 'quad_reduce')}))
+    print('%-70s s=%d c=%d  %.3f ms  %.1f kfps  %s' % ('''$line''', d['streams'], d['chunk'], d['ms_best'], d['kfps'], {k: round(v, 2) for k, v in d['serial'].items() if k in ('transform_bin', 'label_bev', 'outline', 'quad_reduce')}))
 "
 done
