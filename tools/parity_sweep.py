@@ -1,0 +1,54 @@
+"""GPU box: one-off wide parity sweep -- many random scenes (camera pose jitter, yaw / roll, rotate180, occluders, noise levels)
+through the CUDA path (vertex input AND fused depth input) against the C oracle. Everything must match exactly (labels,
+histogram) / within 1e-7 m (steps).   python tools/parity_sweep.py --frames 1200"""
+import argparse, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import helpers as H
+import stair_step_detector_b200 as S
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--frames", type=int, default=1200)
+ap.add_argument("--w", type=int, default=640)
+ap.add_argument("--h", type=int, default=480)
+args = ap.parse_args()
+W, Hh = args.w, args.h
+rng = np.random.default_rng(2026)
+orc = H.load_oracle()
+cfg = S.default_config(W, Hh)
+t0 = time.time()
+bad = 0
+done = 0
+B = 24
+while done < args.frames:
+    # one camera / calibration per group of B frames (the transform is per context)
+    kw = dict(noise_sigma=float(rng.choice([0.0, 0.001, 0.0025, 0.004])), dropout=float(rng.choice([0.0, 0.03, 0.08])), n_holes=int(rng.integers(0, 5)),
+              cam_yaw_deg=float(rng.uniform(-8, 8)), cam_roll_deg=float(rng.uniform(-4, 4)), cam_pitch_deg=float(rng.uniform(42, 58)),
+              cam_height=float(rng.uniform(1.05, 1.5)), rotate180=int(rng.integers(0, 2)), n_occluders=int(rng.integers(0, 3)))
+    base = S.default_scene(W, Hh, **kw)
+    xf = S.scene_transform(base)
+    intr = S.scene_intrinsics(base)
+    scenes = [S.randomize_scene(base, int(rng.integers(1, 1 << 30)), i, 0 if rng.random() < 0.05 else 3, 8) for i in range(B)]
+    depth = np.stack([S.synth_depth_host(sc) for sc in scenes])
+    xyz = np.stack([S.deproject_host(sc, d) for sc, d in zip(scenes, depth)])
+    with S.Detector(cfg, xf, max_frames=B) as det:
+        det.process_host(xyz)
+        a = [(det.labels(f), det.histogram(f), det.steps(f), det.line(f)) for f in range(B)]
+        det.process_depth_host(depth, intr)
+        b = [(det.labels(f), det.histogram(f), det.steps(f), det.line(f)) for f in range(B)]
+    for f in range(B):
+        o = H.oracle_process(orc, cfg, xf, xyz[f])
+        ok = np.array_equal(a[f][0], o.labels) and np.array_equal(a[f][1], o.hist) and len(a[f][2][0]) == len(o.steps)
+        ok = ok and a[f][2][1] == o.info["status"]
+        if ok:
+            for (hh, q), s in zip(a[f][2][0], o.steps):
+                same = (hh == s["height"] or (np.isnan(hh) and np.isnan(s["height"])) or abs(hh - s["height"]) < 1e-7)
+                ok = ok and same and np.abs(q - s["quad"]).max() < 1e-7
+        ok = ok and np.array_equal(b[f][0], a[f][0]) and np.array_equal(b[f][1], a[f][1]) and b[f][3] == a[f][3]
+        if not ok:
+            bad += 1
+            print("MISMATCH group", done // B, "frame", f, kw, flush=True)
+    done += B
+print(json.dumps({"frames": done, "mismatches": bad, "size": [W, Hh], "seconds": round(time.time() - t0, 1)}))
+sys.exit(1 if bad else 0)
