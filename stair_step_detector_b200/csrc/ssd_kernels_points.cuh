@@ -693,13 +693,16 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_LB_MINB) k_label_bev(const
       const unsigned bytes = ((m4 * 0x00204081u) & 0x01010101u) * 0xffu;
       if(((lab ^ (l0 * 0x01010101u)) & bytes) == 0u)
       {
-        const unsigned lbase = l0 * bmw;
+        // word index of the plateau's bitmap within the stream's BEV buffer: 32-bit (the buffer holds < 2^32 words, see
+        // ssd_gpu_create), so a reduction's address is one widening multiply-add on the kernel's base pointer
+        unsigned lidx = ((unsigned)frame * SSD_GPU_MAX_PLATEAUS + l0) * bmw;
+        asm volatile("" : "+r"(lidx)); // keep it in a register: the compiler otherwise recomputes it inside every predicated reduction
         int ylo = 0x7fffffff, yhi = -1;
 #pragma unroll
         for(int j = 0; j < 4; j++)
           if((good >> j) & 1u)
           {
-            atomicOr(fbev + (lbase + (unsigned)iy[j] * wpr + ((unsigned)ix[j] >> 5)), 1u << (ix[j] & 31));
+            atomicOr(bev + (lidx + (unsigned)iy[j] * wpr + ((unsigned)ix[j] >> 5)), 1u << (ix[j] & 31));
             ylo = min(ylo, iy[j]);
             yhi = max(yhi, iy[j]);
           }
