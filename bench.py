@@ -223,6 +223,15 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    if world > 1:
+        # one process per GPU: run on the CPUs (and allocate the pinned host buffers on the memory) next to that GPU
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            nv.nvmlDeviceSetCpuAffinity(nv.nvmlDeviceGetHandleByIndex(local))
+        except Exception:
+            pass
+
     frames = args.frames
     cfg = S.default_config(W, H)
     base = base_scene(S)
