@@ -599,14 +599,6 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_LB_MINB) k_label_bev(const
   int wt, wt_end, wt_stride;
   warp_tile_range((p.N + SSD_WT_PX - 1) / SSD_WT_PX, warp, wt, wt_end, wt_stride);
 
-  // the first warp-tile's code words are requested before the tables arrive
-  unsigned labw[SSD_WT_WORDS];
-#pragma unroll
-  for(int it = 0; it < SSD_WT_WORDS; it++)
-  {
-    const int q = wt * (SSD_WT_PX / 4) + it * 32 + lane;
-    labw[it] = (wt < wt_end && q < nquads) ? lab32[q] : 0xffffffffu;
-  }
   S.lut[tid] = F.lut16[tid]; // SSD_PT_THREADS == SSD_BINS_PAD
   if(tid < SSD_GPU_MAX_PLATEAUS)
   {
@@ -633,6 +625,17 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_LB_MINB) k_label_bev(const
   {
     // ---- phase A: codes -> labels, compaction of the words with pixels of outlined plateaus ----
     unsigned n = 0;
+    // the tile's eight code words per lane, live in registers during phase A only; the next tile's 1 KB line is requested
+    // into L2 now (keeping it in registers across phase B cost more in occupancy than it hid in latency)
+    unsigned labw[SSD_WT_WORDS];
+#pragma unroll
+    for(int it = 0; it < SSD_WT_WORDS; it++)
+    {
+      const int q = wt * (SSD_WT_PX / 4) + it * 32 + lane;
+      labw[it] = q < nquads ? lab32[q] : 0xffffffffu;
+    }
+    if(wt + wt_stride < wt_end)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(lab32 + (size_t)(wt + wt_stride) * (SSD_WT_PX / 4) + lane * 8));
 #pragma unroll
     for(int it = 0; it < SSD_WT_WORDS; it++)
     {
@@ -649,13 +652,6 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_LB_MINB) k_label_bev(const
       }
       if(__any_sync(0xffffffffu, am4 != 0u))
         n = compact_append(act, n, am4, it, lane);
-    }
-    // next warp-tile's code words
-#pragma unroll
-    for(int it = 0; it < SSD_WT_WORDS; it++)
-    {
-      const int q = (wt + wt_stride) * (SSD_WT_PX / 4) + it * 32 + lane;
-      labw[it] = (wt + wt_stride < wt_end && q < nquads) ? lab32[q] : 0xffffffffu;
     }
     if(n == 0)
       continue;
@@ -867,7 +863,7 @@ __device__ __forceinline__ void quad_reduce_exact_point(const DevParams &p, floa
 #define SSD_DEF_GENERIC 0x4000u // deferred point of a word with mixed labels: not yet checked against amask
 
 #ifndef SSD_QR_MINB
-#define SSD_QR_MINB 3
+#define SSD_QR_MINB 4
 #endif
 template<class SRC>
 __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_QR_MINB) k_quad_reduce(const __grid_constant__ DevParams p, const SRC src,
@@ -889,13 +885,6 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_QR_MINB) k_quad_reduce(con
   int wt, wt_end, wt_stride;
   warp_tile_range((p.N + SSD_WT_PX - 1) / SSD_WT_PX, warp, wt, wt_end, wt_stride);
 
-  unsigned labw[SSD_WT_WORDS];
-#pragma unroll
-  for(int it = 0; it < SSD_WT_WORDS; it++)
-  {
-    const int q = wt * (SSD_WT_PX / 4) + it * 32 + lane;
-    labw[it] = (wt < wt_end && q < nquads) ? __ldg(lab32 + q) : 0xffffffffu;
-  }
   {
     // the frame's filter tables: one coalesced copy, independent of anything else
     const unsigned *src = reinterpret_cast<const unsigned *>(F.qf);
@@ -940,6 +929,15 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_QR_MINB) k_quad_reduce(con
     const unsigned wbase = (unsigned)wt * (SSD_WT_PX / 4); // first word of the warp-tile within the frame
     // ---- phase A: compaction of the words holding plateau labels (bit 7 of a label byte clear <=> label < 128) ----
     unsigned n = 0;
+    unsigned labw[SSD_WT_WORDS];
+#pragma unroll
+    for(int it = 0; it < SSD_WT_WORDS; it++)
+    {
+      const int q = wt * (SSD_WT_PX / 4) + it * 32 + lane;
+      labw[it] = q < nquads ? __ldg(lab32 + q) : 0xffffffffu;
+    }
+    if(wt + wt_stride < wt_end)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(lab32 + (size_t)(wt + wt_stride) * (SSD_WT_PX / 4) + lane * 8));
 #pragma unroll
     for(int it = 0; it < SSD_WT_WORDS; it++)
     {
@@ -955,29 +953,27 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_QR_MINB) k_quad_reduce(con
         n = compact_append(act, n, am4, it, lane);
       }
     }
-#pragma unroll
-    for(int it = 0; it < SSD_WT_WORDS; it++)
-    {
-      const int q = (wt + wt_stride) * (SSD_WT_PX / 4) + it * 32 + lane;
-      labw[it] = (wt + wt_stride < wt_end && q < nquads) ? __ldg(lab32 + q) : 0xffffffffu;
-    }
     if(n == 0)
       continue;
     __syncwarp();
 
     // ---- phase B: dense walk over the compacted words ----
     unsigned e = lane < n ? act[lane] : 0u;
-    typename SrcTraits<SRC>::Word wc, wn;
+    typename SrcTraits<SRC>::Word wc;
     word_zero(wc);
-    word_zero(wn);
     if(e)
       word_load(FR, wbase + (e >> 4), wc);
     for(unsigned s0 = 0; s0 < n; s0 += 32)
     {
-      const unsigned i1 = s0 + 32 + lane;
-      const unsigned e1 = i1 < n ? act[i1] : 0u;
-      if(e1)
-        word_load(FR, wbase + (e1 >> 4), wn);
+      // (no software prefetch of the next step's words: the L2 prefetch of phase A and four resident blocks per SM hide the
+      //  latency better than twelve more registers per thread did -- measured 2.51 -> 2.28 ms per 2048 frames)
+      if(s0)
+      {
+        const unsigned i0 = s0 + lane;
+        e = i0 < n ? act[i0] : 0u;
+        if(e)
+          word_load(FR, wbase + (e >> 4), wc);
+      }
       const unsigned m4 = e & 15u;
       const unsigned lw = labs[e >> 4];
       // label of the word's first plateau point; the word is "uniform" when all its plateau points carry it
@@ -1062,8 +1058,6 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_QR_MINB) k_quad_reduce(con
           if((m4 >> j) & 1u)
             defer_push(S.L, warp, SSD_DEF_GENERIC | ((e >> 4) << 2) | (unsigned)j);
       }
-      e = e1;
-      wc = wn;
     }
     // ---- dense exact pass over the warp's compacted uncertain points ----
     __syncwarp();
