@@ -13,7 +13,9 @@
 #include <string>
 #include <vector>
 
-#define SSD_PT_ITERS 4   // k_transform_bin: 4096 points per block
+#ifndef SSD_PT_ITERS
+#define SSD_PT_ITERS 4 // k_transform_bin: 4096 points per block
+#endif
 #define SSD_TILE_POINTS (SSD_PT_THREADS * 4 * SSD_PT_ITERS)
 #define SSD_MAX_STREAMS 4
 
