@@ -151,6 +151,34 @@ def test_hires_extended_range(S, oracle):
     run_frames(S, oracle, cfg, [sc])
 
 
+def test_depth_input_edge_cases(S):
+    """Depth frames that are not scenes -- all zero (every pixel invalid), all 65535, white noise, a constant plane -- and a
+    batch that is not a multiple of the host chunk (33 frames, chunk 32): the fused depth kernels must give exactly what
+    the vertex path gives on the host-deprojected vertices, frame by frame."""
+    w, h = 320, 240
+    cfg = S.default_config(w, h)
+    base = S.default_scene(w, h, **NOISY)
+    xf = S.scene_transform(base)
+    k = S.scene_intrinsics(base)
+    rng = np.random.default_rng(5)
+    frames = [np.zeros((h, w), np.uint16), np.full((h, w), 65535, np.uint16), rng.integers(0, 65536, (h, w), dtype=np.uint16),
+              np.full((h, w), 4000, np.uint16)]
+    frames += [S.synth_depth_host(S.randomize_scene(base, 9, i, 3, 6)).reshape(h, w) for i in range(29)]
+    depth = np.stack(frames).reshape(len(frames), -1)
+    xyz = np.stack([S.deproject_host(base, d) for d in depth])
+    n = len(frames)
+    assert n == 33
+    with S.Detector(cfg, xf, max_frames=n) as det:
+        det.process_host(xyz)
+        ref = [(det.labels(f), det.histogram(f), det.line(f), det.steps(f)[1]) for f in range(n)]
+        assert ref[0][2] == '["stairs",["stairSteps",0]]' and (ref[0][0] == 255).all()
+        det.process_depth_host(depth, k)
+        for f in range(n):
+            assert np.array_equal(det.labels(f), ref[f][0]) and np.array_equal(det.histogram(f), ref[f][1]), f
+            assert det.line(f) == ref[f][2] and det.steps(f)[1] == ref[f][3], f
+        assert sum(len(det.steps(f)[0]) > 0 for f in range(n)) >= 20
+
+
 def test_hires_depth_input_equals_vertex_input(S):
     """4096x3072 z16 frame through the fused depth kernels (row / column of a pixel by the 2^40 magic multiply, 12.6 M
     pixels per frame) against the same frame as packed vertices: labels, histogram and steps identical."""
