@@ -187,6 +187,7 @@ __device__ __forceinline__ long long sum_smallest(const P2id *pts, int n, int pi
   return sum;
 }
 
+template<int MAXPTS>
 __device__ inline double pair_residual(const P2id *pts, int n, int pi, int qi, LineId l)
 {
   if(n <= 2)
@@ -200,7 +201,7 @@ __device__ inline double pair_residual(const P2id *pts, int n, int pi, int qi, L
     sum = sum_smallest<8>(pts, n, pi, qi, l, cnt);
   else if(cnt <= 12)
     sum = sum_smallest<12>(pts, n, pi, qi, l, cnt);
-  else if(cnt <= 24)
+  else if(cnt <= 24 && MAXPTS <= 64)
   {
     // repeated minimum extraction without materialising the list: extract in (value, index) order
     int lastv = -1, lasti = -1;
@@ -223,9 +224,45 @@ __device__ inline double pair_residual(const P2id *pts, int n, int pi, int qi, L
       lasti = besti;
     }
   }
+  else if(MAXPTS > 64)
+  {
+    // many points per list (high-resolution frames): value bisection for T = the cnt-th smallest distance, i.e. the
+    // smallest T with count(d <= T) >= cnt; sum = sum(d < T) + (cnt - count(d < T)) * T. The distances are computed once
+    // into a per-thread array (local memory: interleaved per thread, so a warp's accesses coalesce and stay in L1) and
+    // each of the ~22 bisection passes is a load, a compare and an add per point.
+    int d[MAXPTS]; // the list capacity of the frame-size class
+    int k = 0, hi = 0, lo = 0;
+    for(int i = 0; i < n; i++)
+      if(i != pi && i != qi)
+      {
+        const int v = abs(pts[i].x * l.a + pts[i].y * l.b + l.c);
+        d[k++] = v;
+        hi = max(hi, v);
+      }
+    while(lo < hi)
+    {
+      const int mid = lo + ((hi - lo) >> 1);
+      int c = 0;
+      for(int i = 0; i < k; i++)
+        c += d[i] <= mid;
+      if(c >= cnt)
+        hi = mid;
+      else
+        lo = mid + 1;
+    }
+    int below = 0;
+    for(int i = 0; i < k; i++)
+      if(d[i] < lo)
+      {
+        sum += d[i];
+        below++;
+      }
+    sum += (long long)(cnt - below) * lo;
+  }
   else
   {
-    // value bisection: smallest T with count(d <= T) >= cnt; sum = sum(d < T) + (cnt - count(d < T)) * T
+    // the same value bisection for the few such fits of a small frame (n <= 32 points): distances recomputed per pass,
+    // no per-thread array (it would cost every thread of the kernel its local-memory frame)
     int lo = 0, hi = 0;
     for(int i = 0; i < n; i++)
       if(i != pi && i != qi)
@@ -246,10 +283,10 @@ __device__ inline double pair_residual(const P2id *pts, int n, int pi, int qi, L
     for(int i = 0; i < n; i++)
       if(i != pi && i != qi)
       {
-        const int d = abs(pts[i].x * l.a + pts[i].y * l.b + l.c);
-        if(d < lo)
+        const int v = abs(pts[i].x * l.a + pts[i].y * l.b + l.c);
+        if(v < lo)
         {
-          sum += d;
+          sum += v;
           below++;
         }
       }
@@ -263,6 +300,7 @@ __device__ inline double pair_residual(const P2id *pts, int n, int pi, int qi, L
 }
 
 // all threads of the block must call. lists[e] with n[e] points (n[e] < 2: skipped); out[e] = winning line.
+template<int MAXPTS>
 __device__ inline void best_lines_block(const P2id *const lists[4], const int n[4], BestLineWork &wk, LineId *out, int tid, int nthreads)
 {
   int off[5];
@@ -293,7 +331,7 @@ __device__ inline void best_lines_block(const P2id *const lists[4], const int n[
     const int qI = local - rowStart + pI + 1;
     const P2id *pts = lists[e];
     const LineId l = linei_from(pts[pI], pts[qI]);
-    const double r = pair_residual(pts, ne, pI, qI, l);
+    const double r = pair_residual<MAXPTS>(pts, ne, pI, qI, l);
 #pragma unroll
     for(int k = 0; k < 4; k++)
       if(k == e && (bidx[k] == 0x7fffffff || r < bres[k])) // local ascends per thread: first of equals kept
@@ -402,6 +440,7 @@ template<int MAX_SCANS, int MAX_LINE_PTS, int MAX_VPTS_>
 struct OutlineSharedT
 {
   static constexpr int MAX_VPTS = MAX_VPTS_;
+  static constexpr int MAX_LPTS = MAX_LINE_PTS;
   // column scans
   int scan_found[MAX_SCANS];
   int scan_yf[MAX_SCANS];
@@ -514,7 +553,7 @@ __device__ inline void detect_outline_block(const DevParams &p, const Band &bd, 
   {
     const P2id *const lists[4] = { S.frontLeft, S.frontRight, S.backLeft, S.backRight };
     const int ns[4] = { S.nLeft, S.nRight, S.nLeft, S.nRight };
-    best_lines_block(lists, ns, S.wk, S.line, tid, nthreads);
+    best_lines_block<OutlineShared::MAX_LPTS>(lists, ns, S.wk, S.line, tid, nthreads);
   }
 
   if(tid == 0)
@@ -758,7 +797,7 @@ __device__ inline void detect_front_edge_block(const DevParams &p, const Band &b
   {
     const P2id *const lists[4] = { S.frontLeft, S.frontLeft, S.frontLeft, S.frontLeft };
     const int ns[4] = { n, 0, 0, 0 };
-    best_lines_block(lists, ns, S.wk, S.line, tid, nthreads);
+    best_lines_block<OutlineShared::MAX_LPTS>(lists, ns, S.wk, S.line, tid, nthreads);
   }
   if(tid == 0)
   {
