@@ -55,7 +55,7 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
 //                 rs2_deproject_pixel_to_point / camera.h:99-116) is evaluated in registers, with the single-rounded f32
 //                 operations of ssd_deproject_pixel (scene_model.h) / k_deproject: the vertices never exist in memory
 //                 and all three passes move 2 bytes per point instead of 12.
-// A kernel derives a frame cursor once (src_frame), then loads 4-point words (word_load: issued one step ahead, so the
+// A kernel derives a frame cursor once (src_frame), then loads 4-point words (word_load: where a kernel issues it ahead of use, the
 // registers of a word in flight are the raw loads) and unpacks them where they are consumed (word_unpack).
 // ---------------------------------------------------------------------------------------------
 struct SrcVertices
@@ -500,10 +500,11 @@ __global__ void __launch_bounds__(32) k_peaks(const __grid_constant__ DevParams 
 // i.e. eight coalesced 128 B label loads per warp), with no block-level barrier until the very end.
 //   Phase A (all pixels, a handful of instructions per 4-pixel word): label word -> which of its pixels matter
 //     -> the warp compacts the words with at least one such pixel into its private list in shared memory
-//     (ballot + popc prefix, no atomics). The next warp-tile's label words are requested as soon as the
-//     current ones are consumed.
+//     (ballot + popc prefix, no atomics). The next warp-tile's line of label words is requested into L2 as soon as the
+//     current one has been read (keeping it in registers across phase B cost more in occupancy than it hid).
 //   Phase B (dense): the warp walks the compacted list 32 words = 128 pixels at a time: three aligned 16 B
-//     vertex loads per lane, issued one step ahead; only words that matter are ever fetched.
+//     vertex loads per lane (or 8 B of depth); only words that matter are ever fetched. k_quad_reduce requests
+//     them into L2 during phase A and loads them where they are consumed; k_label_bev issues the loads one step ahead.
 // Every per-point decision in phase B is first taken in single precision with a rigorous error bound
 // (fast_pixel, quadfilter_eval). The few points that come within the bound of a threshold are appended to a
 // second compacted list and re-decided by the exact double-precision chain in a dense pass at the end of the
