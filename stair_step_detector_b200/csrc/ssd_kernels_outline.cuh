@@ -117,8 +117,8 @@ __device__ __forceinline__ bool probe_column(const DevParams &p, const Band &bd,
   const int wA = xl >> 5, sh = xl & 31; // arithmetic shift: xl < 0 -> word -1 (reads as 0)
   // columns x-1, x, x+1 that lie outside the image
   const unsigned colout = (x - 1 < 0 ? 1u : 0u) | (x + 1 >= p.W ? 4u : 0u);
-  for(int base = lo; base <= hi; base += 28)
-  {
+  // rows base .. base + 27 of the column as a ballot mask (bit = lane = row base - 2 + lane)
+  auto chunk = [&](int base) -> unsigned {
     const int y = base - 2 + lane;
     const int r = y - bd.b0;
     unsigned hd = 0;
@@ -135,14 +135,31 @@ __device__ __forceinline__ bool probe_column(const DevParams &p, const Band &bd,
     const unsigned full = E == 7u ? 1u : 0u;
     const unsigned fu = __shfl_up_sync(0xffffffffu, full, 1), fd = __shfl_down_sync(0xffffffffu, full, 1);
     const bool set = (full & fu & fd) != 0u && lane >= 2 && lane < 30 && y >= lo && y <= hi;
-    const unsigned m = __ballot_sync(0xffffffffu, set);
+    return __ballot_sync(0xffffffffu, set);
+  };
+  // top-down to the first set row, then bottom-up to the last one: a plateau's column is set near both ends of its band,
+  // so two passes usually do where a full scan of the band took nine
+  int bf = lo;
+  for(; bf <= hi; bf += 28)
+  {
+    const unsigned m = chunk(bf);
     if(m)
     {
-      if(first == 0x7fffffff)
-        first = base - 2 + __ffs(m) - 1;
-      last = base - 2 + 31 - __clz(m);
+      first = bf - 2 + __ffs(m) - 1;
+      last = bf - 2 + 31 - __clz(m);
+      break;
     }
   }
+  if(last >= 0)
+    for(int b2 = hi - 27; b2 > bf; b2 -= 28)
+    {
+      const unsigned m = chunk(b2);
+      if(m)
+      {
+        last = max(last, b2 - 2 + 31 - __clz(m));
+        break;
+      }
+    }
   yFirst = first;
   ySecond = last;
   return last >= 0;
