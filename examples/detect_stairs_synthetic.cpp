@@ -2,7 +2,8 @@
 // with the RealSense capture replaced by the synthetic scene source and the GL window stubbed:
 //   Window app; GeometricTransformation trans(world, camera); Pointcloud pointcloud(app, trans);
 //   for each frame: pointcloud.process(frame)   -> one result line per frame on stdout
-// Usage: detect_stairs_synthetic [width height n_frames]
+// Usage: detect_stairs_synthetic [width height n_frames [overlay]]   (overlay: the step quadrilaterals projected into the
+//        camera image, what the reference draws over the depth view, one line per step on stderr)
 #include "../stair_step_detector_b200/csrc/host/pointcloud.h"
 #include "../stair_step_detector_b200/csrc/host/transformation.h"
 #include "../stair_step_detector_b200/csrc/host/window.h"
@@ -38,12 +39,22 @@ int main(int argc, char **argv)
   std::vector<uint16_t> depth(size_t(w) * h);
   ssd_gpu_intrinsics intr;
   ssd_scene_intrinsics(&base, &intr);
+  if(argc > 4)
+    pointcloud.enableOverlay(intr);
   for(int f = 0; f < nFrames && app; f++)
   {
     ssd_scene sc;
     ssd_scene_randomize(&sc, &base, 2026, f, 3, 8);
     ssd_synth_depth_host(&sc, depth.data());
     pointcloud.process(Camera::DepthFrame(depth.data(), intr, w, h));
+    if(argc > 4)
+      for(const Quadrilateralf_t &q : pointcloud.overlay())
+      {
+        std::cerr << "overlay " << f;
+        for(const Point2f &p : q)
+          std::cerr << ' ' << p.x << ' ' << p.y;
+        std::cerr << std::endl;
+      }
   }
   return 0;
 }

@@ -189,6 +189,27 @@ int ssd_gpu_process_device_ex(ssd_gpu_ctx *ctx, const float *xyz_dev, int n_fram
 int ssd_gpu_get_steps(ssd_gpu_ctx *ctx, int frame, ssd_gpu_step *out, int cap, int *n, uint32_t *status);
 int ssd_gpu_get_frame_info(ssd_gpu_ctx *ctx, int frame, ssd_gpu_frame_info *out);
 int ssd_gpu_get_plateaus(ssd_gpu_ctx *ctx, int frame, ssd_gpu_plateau *out, int cap, int *n);
+/*
+ * Overlay of the detected steps in the camera image: replaces drawStairStep (pointcloud.cpp:583-597) up to the GL
+ * call it ends in. Every corner {x, y, averageZ} of a step (the world quadrilateral BEFORE ToExternalWorld) goes
+ * through WorldToCamera (transformation.h:90-94, transformation.cpp:185-188 = Transformation_::transformInv,
+ * transformation.h:66-69: a_inv * (p - b), Boost.QVM mat*vec order, no FMA), is narrowed to f32 and projected by
+ * DepthFrame::project (camera.h:80-97) = rs2_project_point_to_pixel without distortion:
+ *     x = X / Z, y = Y / Z, u = x * fx + ppx, v = y * fy + ppy     (single-rounded f32 operations, this order).
+ * The result is the Quadrilateralf_t handed to drawQuadrilateral (drawing.h:57), corners in the order of
+ * ssd_gpu_step.quad. detectStairs draws every step twice (depth and infrared viewport, pointcloud.cpp:367-368,
+ * 388-392) with the same corners; one record per step is kept. A rejected ground front edge ("return{}",
+ * pointcloud.cpp:546) projects the all-zero quadrilateral like the reference does.
+ * a_inv: the reference's Transformation_<3>::_aInv, row-major (GeometricTransformation::abiInverse() on the host
+ * side). intr: depth_unit is not used. Off until set; a_inv == NULL switches it off again.
+ */
+typedef struct ssd_gpu_overlay
+{
+  float px[4][2];
+} ssd_gpu_overlay;
+int ssd_gpu_set_overlay(ssd_gpu_ctx *ctx, const double a_inv[9], const ssd_gpu_intrinsics *intr);
+/* out[0..min(*n, cap)): one projected quadrilateral per step of ssd_gpu_get_steps, same order. */
+int ssd_gpu_get_overlay(ssd_gpu_ctx *ctx, int frame, ssd_gpu_overlay *out, int cap, int *n);
 /* Per-pixel segment labels (device -> host copy of width*height bytes). */
 int ssd_gpu_get_labels(ssd_gpu_ctx *ctx, int frame, uint8_t *out_host);
 /* Height histogram, HeightsHistogram::calcHist (pointcloud.cpp:194-204). */
@@ -239,6 +260,11 @@ int ssd_gpu_camera_to_world(ssd_gpu_ctx *ctx, const float *xyz_host, int n, doub
 /* ---- host-side transformation builders (transformation.cpp), no GPU needed ---- */
 /* GeometricTransformation(worldPoints, cameraPoints) (transformation.cpp:196-215): 3 points each, xyz. */
 int ssd_make_transform(const double world_pts[9], const double camera_pts[9], ssd_gpu_transform *out);
+/* The same, and the camera transformation's _aInv (row-major) exactly as the reference holds it: the triangle ctor
+ * (transformation.cpp:108-157) sets _aInv from the plane's base vectors and _a = transposed(_aInv). For ssd_gpu_set_overlay. */
+int ssd_make_transform_ex(const double world_pts[9], const double camera_pts[9], ssd_gpu_transform *out, double a_inv[9]);
+/* boost::qvm::inverse of a 3x3 as the (rp, rpMapping) ctor computes _aInv = inverse(_a) (transformation.cpp:175-178). */
+int ssd_inverse3(const double a[9], double a_inv[9]);
 /* GeometricCalibration::load() (geometricCalibration.cpp:185-203): reads "<directory>/calibration-triangle"
  * (CalibrationTriangle::load, calibrationTriangle.cpp:97-125; validity :148-168) and "<directory>/calibration-points"
  * (loadPoints, geometricCalibration.cpp:73-98: header + ten rows of three "x, y, z" float triples), averages the rows

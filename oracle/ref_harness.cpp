@@ -59,8 +59,31 @@ extern "C" __attribute__((visibility("hidden"))) void __assert_fail(const char *
 
 namespace stairs
 {
-// GL overlay is stubbed (drawing.h:57)
-void drawQuadrilateral(const Quadrilateralf_t &, const Quadrilateral_t &, Coordinate_t) {}
+// GL overlay (drawing.h:57): the GL calls are stubbed; the arguments drawStairStep (pointcloud.cpp:588-597) hands
+// over -- the projected quadrilateral, the labelling corners and the z label -- are recorded per thread.
+struct ssd_ref_overlay_call
+{
+  float px[4][2];
+  double label[2][2];
+  double z_label;
+};
+thread_local std::vector<ssd_ref_overlay_call> g_overlay_calls;
+void drawQuadrilateral(const Quadrilateralf_t &q, const Quadrilateral_t &labeling, Coordinate_t zLabel)
+{
+  ssd_ref_overlay_call c{};
+  for(int i = 0; i < 4; i++)
+  {
+    c.px[i][0] = q[i].x;
+    c.px[i][1] = q[i].y;
+  }
+  for(int i = 0; i < 2; i++)
+  {
+    c.label[i][0] = labeling[i].x;
+    c.label[i][1] = labeling[i].y;
+  }
+  c.z_label = zLabel;
+  g_overlay_calls.push_back(c);
+}
 // The mark-detection half of geometricCalibration.cpp (calibration tool, never called here) refers to these:
 void setDrawOffset(int, int) {}
 void resetDrawOffset() {}
@@ -119,6 +142,10 @@ void getTransform(const GeometricTransformation &t, ssd_gpu_transform &xf)
   xf.ext_z = t._toExternalWorld._worldZ;
 }
 
+// intrinsics of the stub depth frame (only DepthFrame::project reads them): default fx = fy = width, centre principal point
+thread_local bool g_intr_set = false;
+thread_local float g_intr[4];
+
 Camera::DepthFrame makeFrame(const float *xyz)
 {
   auto d = std::make_shared<rs2::frame_data>();
@@ -127,9 +154,19 @@ Camera::DepthFrame makeFrame(const float *xyz)
   d->vertices = reinterpret_cast<const rs2::vertex *>(xyz);
   d->intr.width = d->width;
   d->intr.height = d->height;
-  d->intr.fx = d->intr.fy = float(d->width);
-  d->intr.ppx = d->width * 0.5f;
-  d->intr.ppy = d->height * 0.5f;
+  if(g_intr_set)
+  {
+    d->intr.fx = g_intr[0];
+    d->intr.fy = g_intr[1];
+    d->intr.ppx = g_intr[2];
+    d->intr.ppy = g_intr[3];
+  }
+  else
+  {
+    d->intr.fx = d->intr.fy = float(d->width);
+    d->intr.ppx = d->width * 0.5f;
+    d->intr.ppy = d->height * 0.5f;
+  }
   return Camera::DepthFrame(rs2::depth_frame(rs2::frame(d)));
 }
 
@@ -251,6 +288,7 @@ SSD_API int ssd_ref_process(const ssd_gpu_transform *xf, const float *xyz, uint8
                    setTransform(w.trans, *xf);
                    const Camera::DepthFrame frame = makeFrame(xyz);
                    const rs2::pointcloud pc;
+                   stairs::g_overlay_calls.clear();
                    const int W = cfg().streams.depth.width, H = cfg().streams.depth.height;
                    const size_t N = size_t(W) * H;
                    std::memset(info, 0, sizeof(*info));
@@ -405,6 +443,53 @@ SSD_API int ssd_ref_process(const ssd_gpu_transform *xf, const float *xyz, uint8
                      const std::string s = stairs.serialize();
                      std::snprintf(line, line_cap, "%s", s.c_str());
                    }
+                   return SSD_OK;
+                 });
+}
+
+// The drawQuadrilateral calls of the last ssd_ref_process on this thread (detectStairs draws every step twice:
+// depth viewport with {corner 0, corner 1, z} of the world quadrilateral as the label, then infrared viewport with the
+// external-world corners and height, pointcloud.cpp:367-368,388-392). px: n x 8 floats, label: n x 4 doubles, z: n.
+SSD_API int ssd_ref_last_overlay(float *px, double *label, double *z_label, int cap, int *n)
+{
+  const auto &v = stairs::g_overlay_calls;
+  *n = int(v.size());
+  for(int i = 0; i < *n && i < cap; i++)
+  {
+    if(px)
+      std::memcpy(px + 8 * i, v[i].px, sizeof(v[i].px));
+    if(label)
+      std::memcpy(label + 4 * i, v[i].label, sizeof(v[i].label));
+    if(z_label)
+      z_label[i] = v[i].z_label;
+  }
+  return SSD_OK;
+}
+
+// Intrinsics of the stub depth frame for the following calls on this thread (NULL: back to the default).
+SSD_API int ssd_ref_set_intrinsics(const ssd_gpu_intrinsics *intr)
+{
+  g_intr_set = intr != nullptr;
+  if(intr)
+  {
+    g_intr[0] = intr->fx;
+    g_intr[1] = intr->fy;
+    g_intr[2] = intr->ppx;
+    g_intr[3] = intr->ppy;
+  }
+  return SSD_OK;
+}
+
+// Transformation_<3>::_aInv as the reference holds it for this transform (setTransform: boost::qvm::inverse(_a))
+SSD_API int ssd_ref_a_inv(const ssd_gpu_transform *xf, double a_inv[9])
+{
+  return guarded([&]
+                 {
+                   RefWorld w;
+                   setTransform(w.trans, *xf);
+                   for(int i = 0; i < 3; i++)
+                     for(int j = 0; j < 3; j++)
+                       a_inv[i * 3 + j] = w.trans._camera._aInv.a[i][j];
                    return SSD_OK;
                  });
 }

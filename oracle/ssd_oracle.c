@@ -1156,6 +1156,11 @@ static P2 line_intersection_plain(LineD t, LineD o)
   return r;
 }
 
+/* world quadrilaterals {x, y, averageZ} of the steps of the last ssd_oracle_process on this thread, before
+ * ToExternalWorld: what detectStairs hands to drawStairStep (pointcloud.cpp:367-368) */
+static __thread double g_last_step_quads[SSD_GPU_MAX_STEPS][4][3];
+static __thread int g_last_n_steps;
+
 int ssd_oracle_process(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, const float *xyz, uint8_t *labels, uint32_t *hist_out,
                        int hist_cap, ssd_gpu_frame_info *info, ssd_gpu_plateau *plats, ssd_gpu_step *steps)
 {
@@ -1436,12 +1441,19 @@ int ssd_oracle_process(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, c
   {
     for(int c = 0; c < 4; c++)
     {
+      g_last_step_quads[s][c][0] = stepQuads[s][c].x;
+      g_last_step_quads[s][c][1] = stepQuads[s][c].y;
+      g_last_step_quads[s][c][2] = stepQuads[s][c].z;
+    }
+    for(int c = 0; c < 4; c++)
+    {
       const double x = stepQuads[s][c].x, y = stepQuads[s][c].y;
       steps[s].quad[c][0] = (xf->ext_a[0] * x + xf->ext_a[1] * y) + xf->ext_b[0];
       steps[s].quad[c][1] = (xf->ext_a[2] * x + xf->ext_a[3] * y) + xf->ext_b[1];
     }
     steps[s].height = xf->ext_z + stepQuads[s][0].z;
   }
+  g_last_n_steps = nSteps;
   if(nSteps == 0)
     info->status |= SSD_STATUS_NO_STEPS;
 
@@ -1455,6 +1467,48 @@ done:
   free(sel);
   free(img);
   return rc;
+}
+
+/* boost::qvm::inverse of a 3x3 (Transformation_<3>::_aInv = inverse(_a), transformation.cpp:178): adjugate times
+ * 1/det, determinant by cofactor expansion along the first row. */
+int ssd_oracle_inverse3(const double m[9], double r[9])
+{
+  const double det = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+  if(det == 0)
+    return SSD_E_INVALID_ARG;
+  const double f = 1 / det;
+  r[0] = f * (m[4] * m[8] - m[5] * m[7]);
+  r[1] = f * (m[2] * m[7] - m[1] * m[8]);
+  r[2] = f * (m[1] * m[5] - m[2] * m[4]);
+  r[3] = f * (m[5] * m[6] - m[3] * m[8]);
+  r[4] = f * (m[0] * m[8] - m[2] * m[6]);
+  r[5] = f * (m[2] * m[3] - m[0] * m[5]);
+  r[6] = f * (m[3] * m[7] - m[4] * m[6]);
+  r[7] = f * (m[1] * m[6] - m[0] * m[7]);
+  r[8] = f * (m[0] * m[4] - m[1] * m[3]);
+  return SSD_OK;
+}
+
+/* drawStairStep (pointcloud.cpp:588-597) on the steps of the last ssd_oracle_process of this thread:
+ * WorldToCamera = transformInv (transformation.h:66-69: _aInv * (x - _b), QVM mat*vec left to right), narrowing to
+ * float and rs2_project_point_to_pixel without distortion (camera.h:80-97). */
+int ssd_oracle_last_overlay(const ssd_gpu_transform *xf, const double a_inv[9], const ssd_gpu_intrinsics *intr, ssd_gpu_overlay *out,
+                            int cap, int *n)
+{
+  *n = g_last_n_steps;
+  for(int s = 0; s < g_last_n_steps && s < cap; s++)
+    for(int c = 0; c < 4; c++)
+    {
+      const double dx = g_last_step_quads[s][c][0] - xf->b[0], dy = g_last_step_quads[s][c][1] - xf->b[1],
+                   dz = g_last_step_quads[s][c][2] - xf->b[2];
+      const float X = (float)((a_inv[0] * dx + a_inv[1] * dy) + a_inv[2] * dz);
+      const float Y = (float)((a_inv[3] * dx + a_inv[4] * dy) + a_inv[5] * dz);
+      const float Z = (float)((a_inv[6] * dx + a_inv[7] * dy) + a_inv[8] * dz);
+      const float x = X / Z, y = Y / Z;
+      out[s].px[c][0] = x * intr->fx + intr->ppx;
+      out[s].px[c][1] = y * intr->fy + intr->ppy;
+    }
+  return SSD_OK;
 }
 
 int ssd_oracle_process_batch(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, const float *xyz, int n_frames, int *n_steps_out)

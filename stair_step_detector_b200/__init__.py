@@ -85,6 +85,30 @@ def scene_transform(scene):
     return xf
 
 
+def scene_transform_ex(scene):
+    """(Transform, a_inv): the camera transformation's _aInv (9 doubles, row-major) as the reference holds it,
+    for Detector.set_overlay."""
+    w = (C.c_double * 9)()
+    c = (C.c_double * 9)()
+    lib().ssd_scene_calibration_points(C.byref(scene), w, c)
+    xf = Transform()
+    a_inv = (C.c_double * 9)()
+    rc = lib().ssd_make_transform_ex(w, c, C.byref(xf), a_inv)
+    if rc:
+        raise SsdError(f"ssd_make_transform_ex failed ({rc})")
+    return xf, np.array(a_inv[:])
+
+
+def inverse3(a):
+    """boost::qvm::inverse of a 3x3 (row-major 9 doubles) as Transformation_<3>(rp, rpMapping) computes _aInv."""
+    src = (C.c_double * 9)(*[float(v) for v in np.asarray(a, np.float64).ravel()])
+    dst = (C.c_double * 9)()
+    rc = lib().ssd_inverse3(src, dst)
+    if rc:
+        raise SsdError(f"ssd_inverse3 failed ({rc})")
+    return np.array(dst[:])
+
+
 def randomize_scene(base, base_seed, index, min_steps, max_steps):
     s = Scene()
     lib().ssd_scene_randomize(C.byref(s), C.byref(base), base_seed, index, min_steps, max_steps)
@@ -197,6 +221,22 @@ class Detector:
         st = C.c_uint32()
         self._ck(self._l.ssd_gpu_get_steps(self._h, frame, out, A.MAX_STEPS, C.byref(n), C.byref(st)), "ssd_gpu_get_steps")
         return [(s.height, np.array([[s.quad[c][0], s.quad[c][1]] for c in range(4)])) for s in out[:n.value]], st.value
+
+    def set_overlay(self, a_inv, intrinsics):
+        """Enable drawStairStep's projection of the step corners into the camera image (pointcloud.cpp:583-597);
+        a_inv None switches it off."""
+        if a_inv is None:
+            self._ck(self._l.ssd_gpu_set_overlay(self._h, None, None), "ssd_gpu_set_overlay")
+            return
+        arr = (C.c_double * 9)(*[float(v) for v in np.asarray(a_inv, np.float64).ravel()])
+        self._ck(self._l.ssd_gpu_set_overlay(self._h, arr, C.byref(intrinsics)), "ssd_gpu_set_overlay")
+
+    def overlay(self, frame):
+        """(n_steps, 4, 2) float32 pixel coordinates, corner order of steps()."""
+        out = (A.Overlay * A.MAX_STEPS)()
+        n = C.c_int()
+        self._ck(self._l.ssd_gpu_get_overlay(self._h, frame, out, A.MAX_STEPS, C.byref(n)), "ssd_gpu_get_overlay")
+        return np.array([[[o.px[c][0], o.px[c][1]] for c in range(4)] for o in out[:n.value]], np.float32).reshape(n.value, 4, 2)
 
     def n_steps_all(self, n_frames):
         out = np.empty(n_frames, np.int32)

@@ -51,6 +51,10 @@ class Intrinsics(C.Structure):
                 ("depth_unit", C.c_float), ("reserved", C.c_int32 * 3)]
 
 
+class Overlay(C.Structure):
+    _fields_ = [("px", (C.c_float * 2) * 4)]
+
+
 class Step(C.Structure):
     _fields_ = [("height", C.c_double), ("quad", (C.c_double * 2) * 4)]
 
@@ -109,6 +113,8 @@ PROTOTYPES = {
     "ssd_gpu_deproject_device": (C.c_int, [_vp, _vp, _P(Intrinsics), C.c_int, _vp]),
     "ssd_scene_intrinsics": (None, [_P(Scene), _P(Intrinsics)]),
     "ssd_gpu_get_steps": (C.c_int, [_vp, C.c_int, _P(Step), C.c_int, _P(C.c_int), _P(C.c_uint32)]),
+    "ssd_gpu_set_overlay": (C.c_int, [_vp, _P(C.c_double), _P(Intrinsics)]),
+    "ssd_gpu_get_overlay": (C.c_int, [_vp, C.c_int, _P(Overlay), C.c_int, _P(C.c_int)]),
     "ssd_gpu_get_frame_info": (C.c_int, [_vp, C.c_int, _P(FrameInfo)]),
     "ssd_gpu_get_plateaus": (C.c_int, [_vp, C.c_int, _P(Plateau), C.c_int, _P(C.c_int)]),
     "ssd_gpu_get_labels": (C.c_int, [_vp, C.c_int, _vp]),
@@ -125,6 +131,8 @@ PROTOTYPES = {
     "ssd_gpu_points_in_quad": (C.c_int, [_vp, _P(C.c_double), _vp, C.c_int, _vp, _P(C.c_int)]),
     "ssd_gpu_camera_to_world": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "ssd_make_transform": (C.c_int, [_P(C.c_double), _P(C.c_double), _P(Transform)]),
+    "ssd_make_transform_ex": (C.c_int, [_P(C.c_double), _P(C.c_double), _P(Transform), _P(C.c_double)]),
+    "ssd_inverse3": (C.c_int, [_P(C.c_double), _P(C.c_double)]),
     "ssd_scene_default": (None, [_P(Scene), C.c_int32, C.c_int32]),
     "ssd_scene_randomize": (None, [_P(Scene), _P(Scene), C.c_uint64, C.c_int64, C.c_int, C.c_int]),
     "ssd_scene_calibration_points": (None, [_P(Scene), _P(C.c_double), _P(C.c_double)]),

@@ -39,9 +39,39 @@ void Pointcloud::ensureContext(int width, int height) const
     throw std::runtime_error(std::string("ssd_gpu_create: ") + ssd_gpu_last_error(nullptr)); // no CPU fallback
 }
 
+void Pointcloud::enableOverlay(const ssd_gpu_intrinsics &intrinsics) const
+{
+  _overlayIntrinsics = intrinsics;
+  _overlay = true;
+  _overlayApplied = false;
+}
+
+std::vector<Quadrilateralf_t> Pointcloud::overlay(int frame) const
+{
+  if(!_ctx)
+    throw std::logic_error("Pointcloud::overlay before any frame was processed");
+  ssd_gpu_overlay q[SSD_GPU_MAX_STEPS];
+  int n = 0;
+  if(ssd_gpu_get_overlay(_ctx, frame, q, SSD_GPU_MAX_STEPS, &n) != SSD_OK)
+    throw std::runtime_error(std::string("ssd_gpu_get_overlay: ") + ssd_gpu_last_error(_ctx));
+  std::vector<Quadrilateralf_t> out(static_cast<size_t>(n));
+  for(int i = 0; i < n; i++)
+    for(int c = 0; c < 4; c++)
+      out[static_cast<size_t>(i)][static_cast<size_t>(c)] = Point2f{ q[i].px[c][0], q[i].px[c][1] };
+  return out;
+}
+
 std::vector<Stairs> Pointcloud::processBatch(const Camera::DepthFrame &frames, int nFrames, std::vector<unsigned> *status) const
 {
   ensureContext(frames.width(), frames.height());
+  if(_overlay && !_overlayApplied)
+  {
+    double aInv[9];
+    _transformation.abiInverse(aInv);
+    if(ssd_gpu_set_overlay(_ctx, aInv, &_overlayIntrinsics) != SSD_OK)
+      throw std::runtime_error(std::string("ssd_gpu_set_overlay: ") + ssd_gpu_last_error(_ctx));
+    _overlayApplied = true;
+  }
   int rc;
   if(frames.z16)
     rc = frames.onDevice ? ssd_gpu_process_depth_device(_ctx, frames.z16, &frames.intrinsics, nFrames)

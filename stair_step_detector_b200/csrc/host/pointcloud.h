@@ -35,6 +35,11 @@ public:
   std::vector<Stairs> processBatch(const Camera::DepthFrame &frames, int nFrames, std::vector<unsigned> *status = nullptr) const;
   // per-pixel segment labels of frame `frame` of the last call (SSD_LABEL_* codes / plateau index)
   std::vector<uint8_t> labels(int frame = 0) const;
+  // drawStairStep (reference pointcloud.cpp:583-597): project the corners of every detected step into the camera image
+  // (WorldToCamera, then DepthFrame::project with these depth-stream intrinsics). The quadrilaterals the reference
+  // hands to drawQuadrilateral are then available per frame after process()/processBatch().
+  void enableOverlay(const ssd_gpu_intrinsics &intrinsics) const;
+  std::vector<Quadrilateralf_t> overlay(int frame = 0) const;
   ssd_gpu_ctx *context() const { return _ctx; }
 
 private:
@@ -45,6 +50,8 @@ private:
   int _device = 0, _maxFrames = 1;
   mutable ssd_gpu_ctx *_ctx = nullptr;
   mutable bool _explicitConfig = false;
+  mutable bool _overlay = false, _overlayApplied = false;
+  mutable ssd_gpu_intrinsics _overlayIntrinsics{};
 };
 
 } // namespace stairs

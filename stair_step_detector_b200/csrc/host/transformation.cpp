@@ -224,4 +224,16 @@ ssd_gpu_transform GeometricTransformation::abi() const
   return t;
 }
 
+Matrix_<3> inverseMatrix3(const Matrix_<3> &m)
+{
+  return inverse3(m);
+}
+
+void GeometricTransformation::abiInverse(double a_inv[9]) const
+{
+  for(int i = 0; i < 3; i++)
+    for(int j = 0; j < 3; j++)
+      a_inv[i * 3 + j] = _camera.inverseMatrix().a[i][j];
+}
+
 } // namespace stairs

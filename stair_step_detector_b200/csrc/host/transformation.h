@@ -53,6 +53,9 @@ private:
   Vec _b;
 };
 
+// boost::qvm::inverse of a 3x3 (adjugate times 1/det), as Transformation_<3>(rp, rpMapping) uses it; throws on det == 0
+Matrix_<3> inverseMatrix3(const Matrix_<3> &m);
+
 using Transformation = Transformation_<3>;
 using Transformation2D = Transformation_<2>;
 
@@ -109,6 +112,8 @@ public:
 
   // the doubles the GPU path binds at ssd_gpu_create()
   ssd_gpu_transform abi() const;
+  // Transformation_<3>::_aInv of the camera transformation, row-major: what WorldToCamera multiplies by (ssd_gpu_set_overlay)
+  void abiInverse(double a_inv[9]) const;
 
 private:
   GeometricTransformation(const GeometricTransformation &) = delete;

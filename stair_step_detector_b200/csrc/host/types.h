@@ -67,5 +67,6 @@ struct Size2i
 template<typename PointType>
 using Quadrilateral_ = std::array<PointType, 4>;
 using Quadrilateral_t = Quadrilateral_<Point2>;
+using Quadrilateralf_t = Quadrilateral_<Point2f>; // projected step corners (reference types.h:115)
 
 } // namespace stairs

@@ -148,6 +148,15 @@ struct FrameOut
   unsigned n_exact_bin, n_quad_pts, n_def_quad, n_def_bev;
 };
 
+// drawStairStep's projection of the step corners into the camera image (pointcloud.cpp:583-597): WorldToCamera
+// (transformation.h:66-69: a_inv * (p - b)) then rs2_project_point_to_pixel (camera.h:80-97). enabled = 0: off.
+struct OverlayDev
+{
+  double a_inv[9];
+  float fx, fy, ppx, ppy;
+  int enabled, pad;
+};
+
 struct P2d
 {
   double x, y;

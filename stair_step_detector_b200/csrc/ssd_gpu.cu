@@ -47,6 +47,8 @@ struct ssd_gpu_ctx
   FrameDev *d_frames = nullptr;   // max_frames
   FrameOut *d_out = nullptr;      // max_frames
   FrameOut *h_out = nullptr;      // pinned
+  OverlayDev ov{};                // drawStairStep projection (ssd_gpu_set_overlay); off by default
+  ssd_gpu_overlay *d_ovl = nullptr, *h_ovl = nullptr; // max_frames * SSD_GPU_MAX_STEPS, allocated by ssd_gpu_set_overlay
   unsigned char *d_labels = nullptr; // max_frames * N
   unsigned *d_bev = nullptr; // 2 x chunk_frames * MAX_PLATEAUS * bm_words (per stream)
   float *d_stage[SSD_MAX_STREAMS]{};            // vertex staging (host input / deprojected depth)
@@ -504,9 +506,11 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, const uin
     k_quad_reduce<SrcVertices><<<gpt2q, SSD_PT_THREADS, ctx->pad_q, st>>>(p, sv, labels, frames, bev, ctx->bm_words);
   STAGE_EV(6);
   if(ctx->outline_small)
-    k_finalize<OutlineSharedSmall><<<nf, SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, ctx->d_out + frame0, bev, ctx->bm_words, ctx->smem_cap_words);
+    k_finalize<OutlineSharedSmall><<<nf, SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, ctx->d_out + frame0, bev, ctx->bm_words, ctx->smem_cap_words, ctx->ov,
+                                                                          ctx->d_ovl ? ctx->d_ovl + (size_t)frame0 * SSD_GPU_MAX_STEPS : nullptr);
   else
-    k_finalize<OutlineShared><<<nf, SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, ctx->d_out + frame0, bev, ctx->bm_words, ctx->smem_cap_words);
+    k_finalize<OutlineShared><<<nf, SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, ctx->d_out + frame0, bev, ctx->bm_words, ctx->smem_cap_words, ctx->ov,
+                                                                          ctx->d_ovl ? ctx->d_ovl + (size_t)frame0 * SSD_GPU_MAX_STEPS : nullptr);
   STAGE_EV(7);
 #undef STAGE_EV
   *launches += SSD_GPU_N_STAGES;
@@ -539,6 +543,8 @@ void ssd_gpu_destroy(ssd_gpu_ctx *ctx)
   cudaFree(ctx->d_frames);
   cudaFree(ctx->d_out);
   cudaFreeHost(ctx->h_out);
+  cudaFree(ctx->d_ovl);
+  cudaFreeHost(ctx->h_ovl);
   cudaFree(ctx->d_labels);
   cudaFree(ctx->d_bev);
   cudaFree(ctx->d_img);
@@ -884,6 +890,8 @@ static int process_common(ssd_gpu_ctx *ctx, const float *xyz, const uint16_t *z1
     CK(cudaStreamWaitEvent(ctx->stream[0], ctx->ev_chunk_done[i], 0));
   }
   CK(cudaMemcpyAsync(ctx->h_out, ctx->d_out, sizeof(FrameOut) * (size_t)n_frames, cudaMemcpyDeviceToHost, ctx->stream[0]));
+  if(ctx->ov.enabled)
+    CK(cudaMemcpyAsync(ctx->h_ovl, ctx->d_ovl, sizeof(ssd_gpu_overlay) * SSD_GPU_MAX_STEPS * (size_t)n_frames, cudaMemcpyDeviceToHost, ctx->stream[0]));
   CK(cudaEventRecord(ctx->ev_stop, ctx->stream[0]));
   CK(cudaEventSynchronize(ctx->ev_stop));
   CK(cudaGetLastError());
@@ -988,6 +996,53 @@ int ssd_gpu_get_steps(ssd_gpu_ctx *ctx, int frame, ssd_gpu_step *out, int cap, i
   if(out)
     for(int i = 0; i < o.info.n_steps && i < cap; i++)
       out[i] = o.steps[i];
+  return SSD_OK;
+}
+
+int ssd_gpu_set_overlay(ssd_gpu_ctx *ctx, const double a_inv[9], const ssd_gpu_intrinsics *intr)
+{
+  if(!ctx)
+    return SSD_E_INVALID_ARG;
+  if(!a_inv)
+  {
+    ctx->ov.enabled = 0;
+    return SSD_OK;
+  }
+  if(!intr)
+    return fail(ctx, SSD_E_INVALID_ARG, "ssd_gpu_set_overlay: intrinsics missing");
+  CK(cudaSetDevice(ctx->device));
+  if(!ctx->d_ovl)
+  {
+    const size_t bytes = sizeof(ssd_gpu_overlay) * SSD_GPU_MAX_STEPS * (size_t)ctx->max_frames;
+    CK(cudaMalloc(&ctx->d_ovl, bytes));
+    CK(cudaMallocHost(&ctx->h_ovl, bytes));
+    CK(cudaMemset(ctx->d_ovl, 0, bytes));
+    memset(ctx->h_ovl, 0, bytes);
+  }
+  for(int i = 0; i < 9; i++)
+    ctx->ov.a_inv[i] = a_inv[i];
+  ctx->ov.fx = intr->fx;
+  ctx->ov.fy = intr->fy;
+  ctx->ov.ppx = intr->ppx;
+  ctx->ov.ppy = intr->ppy;
+  ctx->ov.enabled = 1;
+  ctx->n_frames_last = 0; // results of an earlier call carry no overlay
+  return SSD_OK;
+}
+
+int ssd_gpu_get_overlay(ssd_gpu_ctx *ctx, int frame, ssd_gpu_overlay *out, int cap, int *n)
+{
+  const int rc = check_frame(ctx, frame);
+  if(rc)
+    return rc;
+  if(!ctx->ov.enabled || !ctx->h_ovl)
+    return fail(ctx, SSD_E_STATE, "ssd_gpu_get_overlay: overlay not enabled (ssd_gpu_set_overlay)");
+  const int ns = ctx->h_out[frame].info.n_steps;
+  if(n)
+    *n = ns;
+  if(out)
+    for(int i = 0; i < ns && i < cap; i++)
+      out[i] = ctx->h_ovl[(size_t)frame * SSD_GPU_MAX_STEPS + i];
   return SSD_OK;
 }
 

@@ -55,6 +55,51 @@ int ssd_make_transform(const double world_pts[9], const double camera_pts[9], ss
   }
 }
 
+int ssd_make_transform_ex(const double world_pts[9], const double camera_pts[9], ssd_gpu_transform *out, double a_inv[9])
+{
+  if(!world_pts || !camera_pts || !out || !a_inv)
+    return SSD_E_INVALID_ARG;
+  try
+  {
+    stairs::GeometricTransformation::RefPoints w, c;
+    for(int i = 0; i < 3; i++)
+    {
+      w[i] = stairs::Point3(world_pts[i * 3], world_pts[i * 3 + 1], world_pts[i * 3 + 2]);
+      c[i] = stairs::Point3(camera_pts[i * 3], camera_pts[i * 3 + 1], camera_pts[i * 3 + 2]);
+    }
+    const stairs::GeometricTransformation t(w, c);
+    *out = t.abi();
+    t.abiInverse(a_inv);
+    return SSD_OK;
+  }
+  catch(const std::exception &)
+  {
+    return SSD_E_INVALID_ARG;
+  }
+}
+
+int ssd_inverse3(const double a[9], double a_inv[9])
+{
+  if(!a || !a_inv)
+    return SSD_E_INVALID_ARG;
+  try
+  {
+    stairs::Matrix_<3> m;
+    for(int i = 0; i < 3; i++)
+      for(int j = 0; j < 3; j++)
+        m.a[i][j] = a[i * 3 + j];
+    const stairs::Matrix_<3> r = stairs::inverseMatrix3(m);
+    for(int i = 0; i < 3; i++)
+      for(int j = 0; j < 3; j++)
+        a_inv[i * 3 + j] = r.a[i][j];
+    return SSD_OK;
+  }
+  catch(const std::exception &)
+  {
+    return SSD_E_INVALID_ARG;
+  }
+}
+
 int ssd_load_calibration(const char *directory, ssd_gpu_transform *out, double world_pts[9], double camera_pts[9])
 {
   if(!out)

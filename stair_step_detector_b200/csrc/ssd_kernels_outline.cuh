@@ -1010,7 +1010,8 @@ __global__ void __launch_bounds__(32) k_frame_logic(const __grid_constant__ DevP
 template<class OutlineShared>
 __global__ void __launch_bounds__(SSD_OL_THREADS, SSD_OL_MINB) k_finalize(const __grid_constant__ DevParams p, FrameDev *__restrict__ frames,
                                                               FrameOut *__restrict__ out, unsigned *__restrict__ bev, size_t bm_words,
-                                                              size_t smem_cap_words)
+                                                              size_t smem_cap_words, const __grid_constant__ OverlayDev ov,
+                                                              ssd_gpu_overlay *__restrict__ overlay)
 {
   extern __shared__ __align__(16) unsigned s_words[];
   __shared__ OutlineShared S;
@@ -1124,6 +1125,22 @@ __global__ void __launch_bounds__(SSD_OL_THREADS, SSD_OL_MINB) k_finalize(const 
       O.steps[s].quad[c][1] = (p.ext_a[2] * x + p.ext_a[3] * y) + p.ext_b[1];
     }
     O.steps[s].height = p.ext_z + sq[s][0][2];
+  }
+  if(ov.enabled)
+  {
+    // drawStairStep (pointcloud.cpp:588-597): quadriWorld -> worldToCamera -> DepthFrame::project
+    ssd_gpu_overlay *Q = overlay + (size_t)frame * SSD_GPU_MAX_STEPS;
+    for(int s = 0; s < nSteps; s++)
+      for(int c = 0; c < 4; c++)
+      {
+        const double dx = sq[s][c][0] - p.b[0], dy = sq[s][c][1] - p.b[1], dz = sq[s][c][2] - p.b[2];
+        const float X = (float)((ov.a_inv[0] * dx + ov.a_inv[1] * dy) + ov.a_inv[2] * dz);
+        const float Y = (float)((ov.a_inv[3] * dx + ov.a_inv[4] * dy) + ov.a_inv[5] * dz);
+        const float Z = (float)((ov.a_inv[6] * dx + ov.a_inv[7] * dy) + ov.a_inv[8] * dz);
+        const float x = __fdiv_rn(X, Z), y = __fdiv_rn(Y, Z);
+        Q[s].px[c][0] = __fadd_rn(__fmul_rn(x, ov.fx), ov.ppx);
+        Q[s].px[c][1] = __fadd_rn(__fmul_rn(y, ov.fy), ov.ppy);
+      }
   }
   F.n_steps = nSteps;
   F.status = status;

@@ -44,6 +44,8 @@ def load_oracle():
     lib.ssd_oracle_camera_to_world.argtypes = [_P(A.Transform), _vp, C.c_int, _vp]
     lib.ssd_oracle_make_transform.argtypes = [_P(C.c_double), _P(C.c_double), _P(A.Transform)]
     lib.ssd_oracle_serialize.argtypes = [_P(A.Step), C.c_int, C.c_char_p, C.c_size_t]
+    lib.ssd_oracle_inverse3.argtypes = [_P(C.c_double), _P(C.c_double)]
+    lib.ssd_oracle_last_overlay.argtypes = [_P(A.Transform), _P(C.c_double), _P(A.Intrinsics), _P(A.Overlay), C.c_int, _P(C.c_int)]
     return lib
 
 
@@ -85,6 +87,9 @@ def load_ref(cfg):
     lib.ssd_ref_camera_to_world.argtypes = [_P(A.Transform), _vp, C.c_int, _vp]
     lib.ssd_ref_serialize.argtypes = [_P(A.Step), C.c_int, C.c_char_p, C.c_size_t]
     lib.ssd_ref_load_calibration.argtypes = [_P(A.Transform)]
+    lib.ssd_ref_last_overlay.argtypes = [_vp, _vp, _vp, C.c_int, _P(C.c_int)]
+    lib.ssd_ref_set_intrinsics.argtypes = [_P(A.Intrinsics)]
+    lib.ssd_ref_a_inv.argtypes = [_P(A.Transform), _P(C.c_double)]
     got = A.Config()
     lib.ssd_ref_config(C.byref(got))
     for f, _ in A.Config._fields_:
@@ -140,6 +145,33 @@ def ref_process(lib, cfg, xf, xyz):
     rc = lib.ssd_ref_process(C.byref(xf), ptr(xyz), ptr(labels), ptr(hist), A.MAX_BINS, C.byref(info), plats, steps, line, len(line))
     assert rc == 0, (rc, lib.ssd_ref_last_error())
     return _collect(labels, hist, info, plats, steps, line.value.decode())
+
+
+def oracle_overlay(lib, xf, a_inv, intr):
+    """drawStairStep's projected quadrilaterals of the last oracle_process on this thread: (n_steps, 4, 2) float32."""
+    out = (A.Overlay * A.MAX_STEPS)()
+    n = C.c_int()
+    arr = (C.c_double * 9)(*[float(v) for v in np.asarray(a_inv, np.float64).ravel()])
+    assert lib.ssd_oracle_last_overlay(C.byref(xf), arr, C.byref(intr), out, A.MAX_STEPS, C.byref(n)) == 0
+    return np.array([[[o.px[c][0], o.px[c][1]] for c in range(4)] for o in out[:n.value]], np.float32).reshape(n.value, 4, 2)
+
+
+def ref_overlay(lib):
+    """The drawQuadrilateral calls of the last ref_process on this thread (the harness records the arguments the
+    reference's drawStairStep passes): px (n_calls, 4, 2) float32, label (n_calls, 2, 2), z_label (n_calls)."""
+    cap = 2 * A.MAX_STEPS
+    px = np.zeros((cap, 4, 2), np.float32)
+    label = np.zeros((cap, 2, 2), np.float64)
+    z = np.zeros(cap, np.float64)
+    n = C.c_int()
+    assert lib.ssd_ref_last_overlay(ptr(px), ptr(label), ptr(z), cap, C.byref(n)) == 0
+    return px[:n.value], label[:n.value], z[:n.value]
+
+
+def ref_a_inv(lib, xf):
+    out = (C.c_double * 9)()
+    assert lib.ssd_ref_a_inv(C.byref(xf), out) == 0
+    return np.array(out[:])
 
 
 def make_config(hostlib, width, height, **kw):

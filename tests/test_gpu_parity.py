@@ -196,6 +196,76 @@ def test_hires_depth_input_equals_vertex_input(S):
         assert np.array_equal(det.labels(0), ref[0]) and np.array_equal(det.histogram(0), ref[1]) and det.line(0) == ref[2]
 
 
+def test_overlay_projection_golden(S, oracle):
+    """drawStairStep (pointcloud.cpp:583-597) on the GPU against what the compiled reference handed to drawQuadrilateral
+    (tests/golden/overlay.json). The corners' x, y agree with the reference to ~1e-12 m, the step's mean z to ~1e-8 m
+    (k_quad_reduce sums z in fixed point; the bar on heights is 0.1 mm), so a pixel can differ in its last f32 bits:
+    the bar here is 2e-3 px (the consumer, drawQuadrilateral, rounds to whole pixels) and most values are bit-identical."""
+    import json
+    import os
+    from test_oracle_golden import GOLDEN, load_case, load_overlay_golden
+    gold = load_overlay_golden()
+    n_val = n_exact = 0
+    for path in GOLDEN:
+        z, meta, sc, xf = load_case(path)
+        g = gold[meta["name"]]
+        cfg = S.default_config(meta["width"], meta["height"])
+        fx, fy, ppx, ppy = g["intrinsics"]
+        intr = A.Intrinsics(fx=fx, fy=fy, ppx=ppx, ppy=ppy)
+        xyz = H.deproject_np(sc, z["depth"])
+        with S.Detector(cfg, xf, max_frames=1) as det:
+            with pytest.raises(S.SsdError):
+                det.process_host(xyz[None])
+                det.overlay(0)  # not enabled yet
+            det.set_overlay(S.inverse3(xf.a), intr)
+            det.process_host(xyz[None])
+            ov = det.overlay(0)
+            want = np.array(g["px_bits"], np.uint32).reshape(-1, 4, 2).view(np.float32)
+            assert ov.shape == want.shape, meta["name"]
+            assert len(ov) == len(det.steps(0)[0])
+            if len(ov):
+                assert np.abs(ov - want).max() < 0.01, meta["name"]
+                n_val += ov.size
+                n_exact += int((ov.view(np.uint32) == want.view(np.uint32)).sum())
+            det.set_overlay(None, None)
+            det.process_host(xyz[None])
+            with pytest.raises(S.SsdError):
+                det.overlay(0)
+    assert n_val >= 6 * 4 * 8 and n_exact >= 0.5 * n_val, (n_exact, n_val)
+
+
+def test_overlay_projection_batch(S, oracle):
+    """the same on a batch of random scenes, vertex and z16 depth input, against the oracle (itself bit-identical to the
+    compiled reference, tests/test_oracle_vs_ref.py::test_overlay_projection); a_inv as the reference's triangle ctor holds it"""
+    w, h = 1024, 768
+    cfg = S.default_config(w, h)
+    base = S.default_scene(w, h, **NOISY)
+    scenes = [S.randomize_scene(base, 31337, i, 3, 8) for i in range(12)]
+    scenes[5].rotate180, scenes[5].n_occluders = 1, 2
+    xf, a_inv = S.scene_transform_ex(scenes[0])
+    assert np.abs(a_inv.reshape(3, 3) - np.array(xf.a[:]).reshape(3, 3).T).max() == 0  # rotation: _a = transposed(_aInv)
+    intr = S.scene_intrinsics(scenes[0])
+    depth = np.stack([S.synth_depth_host(sc) for sc in scenes])
+    xyz = np.stack([S.deproject_host(sc, d) for sc, d in zip(scenes, depth)])
+    with S.Detector(cfg, xf, max_frames=len(scenes)) as det:
+        det.set_overlay(a_inv, intr)
+        det.process_host(xyz)
+        got_v = [det.overlay(f) for f in range(len(scenes))]
+        det.process_depth_host(depth, intr)
+        got_d = [det.overlay(f) for f in range(len(scenes))]
+    n_val = n_exact = 0
+    for f in range(len(scenes)):
+        H.oracle_process(oracle, cfg, xf, xyz[f])
+        want = H.oracle_overlay(oracle, xf, a_inv, intr)
+        assert got_v[f].shape == want.shape, f
+        assert np.array_equal(got_v[f].view(np.uint32), got_d[f].view(np.uint32)), f  # depth input: identical results
+        if len(want):
+            assert np.abs(got_v[f] - want).max() < 2e-3, f
+            n_val += want.size
+            n_exact += int((got_v[f].view(np.uint32) == want.view(np.uint32)).sum())
+    assert n_val >= 12 * 3 * 8 and n_exact >= 0.5 * n_val, (n_exact, n_val)
+
+
 def test_camera_to_world_exact(S, oracle):
     cfg = S.default_config(320, 240)
     sc = S.default_scene(320, 240, cam_roll_deg=3.0, cam_yaw_deg=-7.0)
@@ -393,14 +463,22 @@ def test_cpp_host_classes_main_loop(S, oracle, tmp_path):
     subprocess.run(["g++", "-std=c++17", "-O2", "-o", exe, os.path.join(root, "examples", "detect_stairs_synthetic.cpp"),
                     "-L" + libdir, "-lssd_gpu", "-Wl,-rpath," + libdir], check=True)
     w, h, n = 640, 480, 3
-    out = subprocess.run([exe, str(w), str(h), str(n)], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    run = subprocess.run([exe, str(w), str(h), str(n), "overlay"], capture_output=True, text=True, check=True)
+    out = run.stdout.strip().splitlines()
     assert len(out) == n
+    drawn = [[float(v) for v in l.split()[1:]] for l in run.stderr.splitlines() if l.startswith("overlay ")]
     cfg = S.default_config(w, h)
     base = S.default_scene(w, h, **NOISY)
-    xf = S.scene_transform(base)
+    xf, a_inv = S.scene_transform_ex(base)
+    intr = S.scene_intrinsics(base)
     for f in range(n):
         sc = S.randomize_scene(base, 2026, f, 3, 8)
         o = H.oracle_process(oracle, cfg, xf, S.deproject_host(sc, S.synth_depth_host(sc)))
+        # Pointcloud::overlay(): the quadrilaterals drawStairStep projects into the camera image (printed with 6 digits)
+        want = H.oracle_overlay(oracle, xf, a_inv, intr)
+        mine = np.array([d[1:] for d in drawn if d[0] == f]).reshape(-1, 4, 2)
+        assert mine.shape == want.shape and len(want) == len(o.steps)
+        assert np.abs(mine - want).max() < 2e-3
         got = json.loads(out[f])
         assert got[0] == "stairs" and got[1] == ["stairSteps", len(o.steps)]
         for s, g in zip(o.steps, got[2] if len(o.steps) else []):

@@ -36,6 +36,44 @@ def test_frames_random_scenes(S, oracle, w, h, n):
     assert oracle.ssd_oracle_sort_ties() == 0  # no rank tie that the reference's unstable sort could resolve differently
 
 
+@pytest.mark.parametrize("w,h,n", [(320, 240, 6), (640, 480, 4), (1024, 768, 2)])
+def test_overlay_projection(S, oracle, w, h, n):
+    """drawStairStep (pointcloud.cpp:583-597): the quadrilaterals the reference hands to drawQuadrilateral, recorded by
+    the harness' stub, against the oracle's restatement -- bit-exact f32 pixels; every step is drawn twice (depth and
+    infrared viewport) with the same corners; labelling arguments as detectStairs passes them."""
+    ref = get_ref(S, w, h)
+    cfg = S.default_config(w, h)
+    base = S.default_scene(w, h, randomize_camera=1, **NOISY)
+    try:
+        for i in range(n):
+            sc = S.randomize_scene(base, 777, i, 3, 8)
+            if i % 3 == 2:
+                sc.rotate180, sc.n_occluders = 1, 2
+            xf = S.scene_transform(sc)
+            intr = S.scene_intrinsics(sc) if i % 2 else None  # odd frames: the scene's intrinsics, even: the harness default
+            ref.ssd_ref_set_intrinsics(C.byref(intr) if intr is not None else None)
+            if intr is None:
+                intr = A.Intrinsics(fx=w, fy=w, ppx=w * 0.5, ppy=h * 0.5)
+            xyz = S.deproject_host(sc, S.synth_depth_host(sc))
+            o = H.oracle_process(oracle, cfg, xf, xyz)
+            a_inv = np.empty(9)
+            assert oracle.ssd_oracle_inverse3(xf.a, a_inv.ctypes.data_as(C.POINTER(C.c_double))) == 0
+            assert np.array_equal(a_inv, H.ref_a_inv(ref, xf))
+            assert np.array_equal(a_inv, S.inverse3(xf.a))  # host library: same inverse
+            ov = H.oracle_overlay(oracle, xf, a_inv, intr)
+            r = H.ref_process(ref, cfg, xf, xyz)
+            px, label, z = H.ref_overlay(ref)
+            ns = r.info["n_steps"]
+            assert ns > 0 and len(px) == 2 * ns and len(ov) == ns
+            assert np.array_equal(px[:ns].view(np.uint32), ov.view(np.uint32)), i
+            assert np.array_equal(px[ns:].view(np.uint32), ov.view(np.uint32)), i
+            assert np.isfinite(ov).all()
+            for k in range(ns):  # second pass labels: external-world corners and height (pointcloud.cpp:388-392)
+                assert np.array_equal(label[ns + k], r.steps[k]["quad"][:2]) and z[ns + k] == r.steps[k]["height"]
+    finally:
+        ref.ssd_ref_set_intrinsics(None)
+
+
 def test_derived_constants(S, oracle):
     for (w, h) in ((320, 240), (640, 480), (1024, 768)):
         ref = get_ref(S, w, h)
