@@ -62,8 +62,11 @@ def traffic(rep, dst, tag):
     per = {}
     for r in rows[2:]:
         name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").split("<")[0]
-        grid = [int(x) for x in r[idx["launch__grid_size"]].replace(",", "").split()] if False else None
-        frames = int(r[idx["Grid Size"]].strip("()").split(",")[1]) if "Grid Size" in idx else None
+        frames = None
+        if "Grid Size" in idx:
+            g = [int(x) for x in r[idx["Grid Size"]].strip("()").split(",")]
+            # point kernels and k_outline: grid = (blocks or plateaus, frames); the per-frame kernels: grid = (frames)
+            frames = g[0] if name in ("k_peaks", "k_frame_logic", "k_finalize") else g[1]
         b = sum(float(r[idx[m]]) * scale[units[idx[m]]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
         if frames:
             per[name] = {"bytes_per_frame": b / frames, "frames_per_launch": frames, "us": float(r[idx["gpu__time_duration.sum"]]) *
