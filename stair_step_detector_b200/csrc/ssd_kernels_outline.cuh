@@ -169,10 +169,12 @@ __device__ __forceinline__ bool probe_column(const DevParams &p, const Band &bd,
 // distances of the other points / hypot(a,b); winner = first minimal residual in (p,q) order.
 // Up to four point lists are fitted in one pass: one (list, pair) task per thread, warp-shuffle arg-min on
 // (residual, pair index) per list, one shared-memory round across the warps.
-struct BestLineWork
+template<int NWARPS>
+struct BestLineWorkT
 {
-  double res[SSD_OL_THREADS / 32][4];
-  int idx[SSD_OL_THREADS / 32][4];
+  double res[NWARPS][4];
+  int idx[NWARPS][4];
+  unsigned long long best[4]; // large frame-size class: bits of the smallest residual any thread has computed so far, per list
 };
 
 // Sum of the cnt (<= S) smallest distances of the other points to line l: insertion into a sorted register array
@@ -204,8 +206,11 @@ __device__ __forceinline__ long long sum_smallest(const P2id *pts, int n, int pi
   return sum;
 }
 
+// bound: a residual some line of this list is already known to reach (+inf: none). Only the large frame-size class
+// uses it: a line whose residual is certainly LARGER than bound is abandoned after one probe and reported as +inf
+// (it can neither be the minimum nor tie with it, so the winner -- first minimal residual in pair order -- is unchanged).
 template<int MAXPTS>
-__device__ inline double pair_residual(const P2id *pts, int n, int pi, int qi, LineId l)
+__device__ inline double pair_residual(const P2id *pts, int n, int pi, int qi, LineId l, double bound)
 {
   if(n <= 2)
     return 0.0;
@@ -256,6 +261,41 @@ __device__ inline double pair_residual(const P2id *pts, int n, int pi, int qi, L
         d[k++] = v;
         hi = max(hi, v);
       }
+    // Pruning probe. residual = isum / D with D = cnt * hypot (below). If isum >= B := floor(bound * D * (1 + 1e-12)) + 1 then
+    // isum / D exceeds bound by a relative 0.9e-12 >> 1 ulp, so the rounded residual is strictly larger than bound. With
+    // c = count(d <= mid) < cnt every one of the cnt smallest beyond those c is >= mid + 1, so
+    // sum >= sum(d <= mid) + (cnt - c) * (mid + 1): at mid = 2 B / cnt (twice the admissible mean) a line with fewer than
+    // cnt / 2 points that close is out after this single pass; otherwise the probe narrows the bisection interval.
+    // Only when the reference's int sum cannot wrap (cnt * hi < 2^31), so that isum == sum.
+    if(bound < 1e300 && (long long)cnt * hi < (1ll << 31))
+    {
+      const double Bf = bound * ((double)(size_t)cnt * sqrt((double)((long long)l.a * l.a + (long long)l.b * l.b))) * (1.0 + 1e-12);
+      if(Bf < 4e18)
+      {
+        const long long B = (long long)Bf + 1;
+        const long long th = 2 * B / cnt;
+        if(th < hi)
+        {
+          const int mid = (int)th;
+          int c = 0;
+          long long sb = 0;
+          for(int i = 0; i < k; i++)
+            if(d[i] <= mid)
+            {
+              c++;
+              sb += d[i];
+            }
+          if(c >= cnt)
+            hi = mid;
+          else
+          {
+            if(sb + (long long)(cnt - c) * ((long long)mid + 1) >= B)
+              return __longlong_as_double(0x7ff0000000000000ll);
+            lo = mid + 1;
+          }
+        }
+      }
+    }
     while(lo < hi)
     {
       const int mid = lo + ((hi - lo) >> 1);
@@ -317,7 +357,7 @@ __device__ inline double pair_residual(const P2id *pts, int n, int pi, int qi, L
 }
 
 // all threads of the block must call. lists[e] with n[e] points (n[e] < 2: skipped); out[e] = winning line.
-template<int MAXPTS>
+template<int MAXPTS, class BestLineWork>
 __device__ inline void best_lines_block(const P2id *const lists[4], const int n[4], BestLineWork &wk, LineId *out, int tid, int nthreads)
 {
   int off[5];
@@ -331,6 +371,12 @@ __device__ inline void best_lines_block(const P2id *const lists[4], const int n[
   {
     bres[e] = 0;
     bidx[e] = 0x7fffffff;
+  }
+  if(MAXPTS > 64)
+  {
+    if(tid < 4)
+      wk.best[tid] = 0x7ff0000000000000ull; // +inf
+    __syncthreads();
   }
   for(int t = tid; t < off[4]; t += nthreads)
   {
@@ -348,7 +394,12 @@ __device__ inline void best_lines_block(const P2id *const lists[4], const int n[
     const int qI = local - rowStart + pI + 1;
     const P2id *pts = lists[e];
     const LineId l = linei_from(pts[pI], pts[qI]);
-    const double r = pair_residual<MAXPTS>(pts, ne, pI, qI, l);
+    double bound = __longlong_as_double(0x7ff0000000000000ll);
+    if(MAXPTS > 64)
+      bound = __longlong_as_double((long long)*(volatile unsigned long long *)&wk.best[e]);
+    const double r = pair_residual<MAXPTS>(pts, ne, pI, qI, l, bound);
+    if(MAXPTS > 64 && r >= 0.0 && r < bound) // (false for NaN; non-negative doubles order like their bit patterns)
+      atomicMin(&wk.best[e], (unsigned long long)__double_as_longlong(r));
 #pragma unroll
     for(int k = 0; k < 4; k++)
       if(k == e && (bidx[k] == 0x7fffffff || r < bres[k])) // local ascends per thread: first of equals kept
@@ -453,9 +504,12 @@ __device__ inline P2d boundary_outer(const P2id *pts, int n, FlatLineD line)
 // Work area of one outline block. Sized per frame-size class (the launch picks it from W x H): the small class keeps
 // the block under 40 KB of shared memory with a 32 KB band, so five to six blocks are resident per SM -- the kernel is a
 // chain of short latency-bound phases and lives on resident blocks, not on issue slots.
-template<int MAX_SCANS, int MAX_LINE_PTS, int MAX_VPTS_>
+template<int MAX_SCANS, int MAX_LINE_PTS, int MAX_VPTS_, int THREADS_ = SSD_OL_THREADS, int MINB_ = 0>
 struct OutlineSharedT
 {
+  // block size / minimum resident blocks of k_outline for this class (MINB_ = 0: SSD_OL_MINB)
+  static constexpr int THREADS = THREADS_;
+  static constexpr int MINB = MINB_;
   static constexpr int MAX_VPTS = MAX_VPTS_;
   static constexpr int MAX_LPTS = MAX_LINE_PTS;
   // column scans
@@ -466,7 +520,7 @@ struct OutlineSharedT
   P2id frontLeft[MAX_LINE_PTS], backLeft[MAX_LINE_PTS], frontRight[MAX_LINE_PTS], backRight[MAX_LINE_PTS];
   int nLeft, nRight, ok;
   LineId line[4]; // frontLeft, frontRight, backLeft, backRight
-  BestLineWork wk;
+  BestLineWorkT<(THREADS_ > SSD_OL_THREADS ? THREADS_ : SSD_OL_THREADS) / 32> wk; // (k_finalize runs SSD_OL_THREADS on either class)
   // vertical edge probing
   P2id vpts[MAX_VPTS_];
   int vfound[MAX_VPTS_];
@@ -477,7 +531,10 @@ struct OutlineSharedT
   P2d outer[4];
   int best_pt;
 };
-typedef OutlineSharedT<SSD_MAX_SCANS, SSD_MAX_LINE_PTS, SSD_MAX_VPTS> OutlineShared; // any supported frame size
+// any supported frame size. 512 threads: the O(n^4) line fits are ~14 k tasks per block of long-latency (local-memory) work;
+// the larger block halves a block's run time (fewer, longer blocks left a 30 % tail on 148 SMs) and raises the resident
+// warps from 32 to 48 per SM (shared memory admits 4 blocks either way; registers admit 3 x 512 threads)
+typedef OutlineSharedT<SSD_MAX_SCANS, SSD_MAX_LINE_PTS, SSD_MAX_VPTS, 512, 3> OutlineShared;
 typedef OutlineSharedT<64, 32, 112> OutlineSharedSmall;                              // W <= 1280, H <= 1100
 
 // Segmentation::detectOutline after the close (segmentation.cpp:930-946). Block-cooperative.
@@ -867,7 +924,7 @@ __device__ inline void band_clear_global(const DevParams &p, const Band &bd, uns
 #define SSD_OL_MINB 6
 #endif
 template<class OutlineShared>
-__global__ void __launch_bounds__(SSD_OL_THREADS, SSD_OL_MINB) k_outline(const __grid_constant__ DevParams p, FrameDev *__restrict__ frames,
+__global__ void __launch_bounds__(OutlineShared::THREADS, OutlineShared::MINB ? OutlineShared::MINB : SSD_OL_MINB) k_outline(const __grid_constant__ DevParams p, FrameDev *__restrict__ frames,
                                                              unsigned *__restrict__ bev, size_t bm_words, size_t smem_cap_words)
 {
   extern __shared__ __align__(16) unsigned s_words[];
@@ -888,12 +945,12 @@ __global__ void __launch_bounds__(SSD_OL_THREADS, SSD_OL_MINB) k_outline(const _
       s_smem_path = band_setup(p, bd, P.row_min, P.row_max, s_words, smem_cap_words, gb);
     __syncthreads();
     if(s_smem_path)
-      band_stage(p, s_words, bd, gb, tid, SSD_OL_THREADS);
-    detect_outline_block(p, bd, S, p.min_img_y_extent, p.xy_ratio, quad, valid, tid, SSD_OL_THREADS);
+      band_stage(p, s_words, bd, gb, tid, OutlineShared::THREADS);
+    detect_outline_block(p, bd, S, p.min_img_y_extent, p.xy_ratio, quad, valid, tid, OutlineShared::THREADS);
     if(!s_smem_path)
     {
       __syncthreads();
-      band_clear_global(p, bd, gb, tid, SSD_OL_THREADS);
+      band_clear_global(p, bd, gb, tid, OutlineShared::THREADS);
     }
   }
   else if(tid == 0)

@@ -16,6 +16,8 @@ CASES = [
     ("configs[4] hi-res 4096x3072, 12 steps, range y<3.7 z<2.3", (4096, 3072), dict(y_max=3.7, z_max=2.3),
      dict(n_steps=12, riser=0.17, tread=0.26, cam_height=3.2, cam_pitch_deg=48.0, first_riser_y=0.5, **NOISY), 64, (12, 12)),
 ]
+if os.environ.get("CONFIGS_ONLY"):  # e.g. CONFIGS_ONLY=2: only the hi-res case (profiling)
+    CASES = [CASES[int(i)] for i in os.environ["CONFIGS_ONLY"].split(",")]
 for name, (w, h), ck, sk, frames, (smin, smax) in CASES:
     N = w * h
     cfg = S.default_config(w, h, **ck)

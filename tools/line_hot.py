@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-source-line executed warp-instructions of one kernel: joins `nvdisasm -g` (line info of the shipped cubin)
 with the SASS page of an ncu report (same instruction order).
-    python tools/line_hot.py <rep> <kernel-substring> [top]
+    python tools/line_hot.py <rep> <kernel-substring> [top]      (NCU_KERN=<base name> when the substring is a mangled template instance)
 The .so must be the one that was profiled."""
 import collections, csv, io, os, re, subprocess, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -28,7 +28,7 @@ for ln in dis.splitlines():
     m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(.*?);", ln)
     if m:
         lines_of.append((cur_line, m.group(1)))
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{kern}", "--print-source", "sass"],
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + os.environ.get("NCU_KERN", kern), "--print-source", "sass"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
