@@ -780,7 +780,16 @@ static int process_common(ssd_gpu_ctx *ctx, const float *xyz, const uint16_t *z1
   const size_t frame_floats = (size_t)p.N * 3;
   // host input: every byte crosses PCIe, the copy of chunk i+1 overlaps the kernels of chunk i and only the last
   // chunk's kernels stay exposed -- small chunks. Device input: large chunks (the per-frame kernels need the parallelism).
-  const int cf = host_input ? ctx->host_chunk_frames : ctx->chunk_frames;
+  int cf = host_input ? ctx->host_chunk_frames : ctx->chunk_frames;
+  // a device-resident batch that fits one chunk is still split over the streams, so that one half's latency-bound
+  // per-plateau kernels overlap the other half's point kernels (measured: 64 frames of 4096x3072 as 2 x 32: +5 %;
+  // below ~32 frames per chain the per-frame kernels lose more parallelism than the overlap returns)
+  if(!host_input && !(flags & SSD_FLAG_SINGLE_STREAM) && ctx->n_streams > 1 && n_frames <= cf && !getenv("SSD_GPU_NO_SPLIT_SMALL"))
+  {
+    const int half = (n_frames + ctx->n_streams - 1) / ctx->n_streams;
+    if(half >= 32)
+      cf = half;
+  }
   const bool depth_input = xyz == nullptr;
   if(depth_input)
   {
