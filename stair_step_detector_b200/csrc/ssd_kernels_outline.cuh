@@ -396,7 +396,7 @@ __device__ inline void best_lines_block(const P2id *const lists[4], const int n[
     const LineId l = linei_from(pts[pI], pts[qI]);
     double bound = __longlong_as_double(0x7ff0000000000000ll);
     if(MAXPTS > 64)
-      bound = __longlong_as_double((long long)*(volatile unsigned long long *)&wk.best[e]);
+      bound = __longlong_as_double((long long)atomicMin(&wk.best[e], ~0ull)); // atomic read (other threads lower it concurrently)
     const double r = pair_residual<MAXPTS>(pts, ne, pI, qI, l, bound);
     if(MAXPTS > 64 && r >= 0.0 && r < bound) // (false for NaN; non-negative doubles order like their bit patterns)
       atomicMin(&wk.best[e], (unsigned long long)__double_as_longlong(r));
