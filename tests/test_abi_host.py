@@ -37,7 +37,26 @@ def test_struct_layouts_match_header():
     assert C.sizeof(A.FrameInfo) == 32
     assert C.sizeof(A.Plateau) == 32 + 64 + 8
     assert C.sizeof(A.Intrinsics) == 32
+    assert C.sizeof(A.Overlay) == 32
     assert A.Scene.seed.offset % 8 == 0
+
+
+def test_inverse3_and_transform_ex(S):
+    """host side of the overlay projection: boost::qvm::inverse of a 3x3 (adjugate / determinant) and the camera
+    transformation's _aInv as the triangle ctor holds it (_a = transposed(_aInv), transformation.cpp:128-132)"""
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        a = rng.normal(size=(3, 3))
+        inv = S.inverse3(a).reshape(3, 3)
+        assert np.abs(inv @ a - np.eye(3)).max() < 1e-9
+    with pytest.raises(S.SsdError):
+        S.inverse3(np.zeros((3, 3)))
+    sc = S.default_scene(640, 480, cam_yaw_deg=5.0, cam_roll_deg=-2.0)
+    xf, a_inv = S.scene_transform_ex(sc)
+    xf0 = S.scene_transform(sc)
+    assert list(xf.a) == list(xf0.a) and list(xf.b) == list(xf0.b)
+    assert np.array_equal(a_inv.reshape(3, 3), np.array(xf.a[:]).reshape(3, 3).T)
+    assert np.abs(S.inverse3(xf.a) - a_inv).max() < 1e-12  # a rotation: inverse == transpose up to rounding
 
 
 def test_no_gpu_means_loud_failure(S):
