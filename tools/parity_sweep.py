@@ -20,6 +20,7 @@ cfg = S.default_config(W, Hh)
 t0 = time.time()
 bad = 0
 done = 0
+ov_max, ov_n, ov_exact = 0.0, 0, 0
 B = 24
 while done < args.frames:
     # one camera / calibration per group of B frames (the transform is per context)
@@ -27,16 +28,17 @@ while done < args.frames:
               cam_yaw_deg=float(rng.uniform(-8, 8)), cam_roll_deg=float(rng.uniform(-4, 4)), cam_pitch_deg=float(rng.uniform(42, 58)),
               cam_height=float(rng.uniform(1.05, 1.5)), rotate180=int(rng.integers(0, 2)), n_occluders=int(rng.integers(0, 3)))
     base = S.default_scene(W, Hh, **kw)
-    xf = S.scene_transform(base)
+    xf, a_inv = S.scene_transform_ex(base)
     intr = S.scene_intrinsics(base)
     scenes = [S.randomize_scene(base, int(rng.integers(1, 1 << 30)), i, 0 if rng.random() < 0.05 else 3, 8) for i in range(B)]
     depth = np.stack([S.synth_depth_host(sc) for sc in scenes])
     xyz = np.stack([S.deproject_host(sc, d) for sc, d in zip(scenes, depth)])
     with S.Detector(cfg, xf, max_frames=B) as det:
+        det.set_overlay(a_inv, intr)  # drawStairStep's projection of the step corners into the camera image
         det.process_host(xyz)
-        a = [(det.labels(f), det.histogram(f), det.steps(f), det.line(f)) for f in range(B)]
+        a = [(det.labels(f), det.histogram(f), det.steps(f), det.line(f), det.overlay(f)) for f in range(B)]
         det.process_depth_host(depth, intr)
-        b = [(det.labels(f), det.histogram(f), det.steps(f), det.line(f)) for f in range(B)]
+        b = [(det.labels(f), det.histogram(f), det.steps(f), det.line(f), det.overlay(f)) for f in range(B)]
     for f in range(B):
         o = H.oracle_process(orc, cfg, xf, xyz[f])
         ok = np.array_equal(a[f][0], o.labels) and np.array_equal(a[f][1], o.hist) and len(a[f][2][0]) == len(o.steps)
@@ -45,10 +47,21 @@ while done < args.frames:
             for (hh, q), s in zip(a[f][2][0], o.steps):
                 same = (hh == s["height"] or (np.isnan(hh) and np.isnan(s["height"])) or abs(hh - s["height"]) < 1e-7)
                 ok = ok and same and np.abs(q - s["quad"]).max() < 1e-7
+        if ok:
+            # overlay pixels: the oracle's f32 arithmetic (bit-identical to the compiled reference) on its own corners;
+            # ours can differ in the last bits through the fixed-point mean z -- bar 2e-3 px; NaN where the reference has NaN
+            want = H.oracle_overlay(orc, xf, a_inv, intr)
+            got = a[f][4]
+            ok = got.shape == want.shape and bool(np.all((np.abs(got - want) < 2e-3) | (np.isnan(got) & np.isnan(want)) | (got == want)))
+            ov_max = max(ov_max, float(np.nanmax(np.abs(got - want))) if want.size and np.isfinite(want).any() else 0.0)
+            ov_n += want.size
+            ov_exact += int((got.view(np.uint32) == want.view(np.uint32)).sum())
         ok = ok and np.array_equal(b[f][0], a[f][0]) and np.array_equal(b[f][1], a[f][1]) and b[f][3] == a[f][3]
+        ok = ok and np.array_equal(b[f][4].view(np.uint32), a[f][4].view(np.uint32))
         if not ok:
             bad += 1
             print("MISMATCH group", done // B, "frame", f, kw, flush=True)
     done += B
-print(json.dumps({"frames": done, "mismatches": bad, "size": [W, Hh], "seconds": round(time.time() - t0, 1)}))
+print(json.dumps({"frames": done, "mismatches": bad, "size": [W, Hh], "seconds": round(time.time() - t0, 1),
+                  "overlay": {"values": ov_n, "bit_identical": ov_exact, "max_abs_diff_px": ov_max}}))
 sys.exit(1 if bad else 0)
