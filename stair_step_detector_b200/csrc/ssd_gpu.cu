@@ -33,6 +33,10 @@ struct ssd_gpu_ctx
   size_t bm_words = 0;        // words per BEV bitmap
   size_t smem_cap_words = 0;  // dynamic shared memory available to the band (words)
   size_t ol_dyn_smem = 0;
+  // blocks per frame of k_outline; they loop over the frame's outlined plateaus. Measured (tools/configs_bench.py): 12 against one
+  // block per plateau slot (32): k_outline -7 % at 1024x768 (fewer empty blocks), unchanged at 4096x3072 with 13 outlined plateaus;
+  // 8 and 6 lose there (1.15 -> 1.45 / 1.77 ms per 64 frames). SSD_GPU_OUTLINE_GRIDX overrides.
+  int outline_gridx = 12;
   bool outline_small = false; // frame size admits the small work area of k_outline (OutlineSharedSmall)
   int n_streams = 2;
   cudaStream_t stream[SSD_MAX_STREAMS]{};
@@ -494,9 +498,9 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, const uin
     k_label_bev<SrcVertices><<<gpt2l, SSD_PT_THREADS, ctx->pad_l, st>>>(p, sv, labels, frames, bev, ctx->bm_words);
   STAGE_EV(3);
   if(ctx->outline_small)
-    k_outline<OutlineSharedSmall><<<dim3(SSD_GPU_MAX_PLATEAUS, nf), SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, bev, ctx->bm_words, ctx->smem_cap_words);
+    k_outline<OutlineSharedSmall><<<dim3(ctx->outline_gridx, nf), SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, bev, ctx->bm_words, ctx->smem_cap_words);
   else
-    k_outline<OutlineShared><<<dim3(SSD_GPU_MAX_PLATEAUS, nf), OutlineShared::THREADS, ctx->ol_dyn_smem, st>>>(p, frames, bev, ctx->bm_words, ctx->smem_cap_words);
+    k_outline<OutlineShared><<<dim3(ctx->outline_gridx, nf), OutlineShared::THREADS, ctx->ol_dyn_smem, st>>>(p, frames, bev, ctx->bm_words, ctx->smem_cap_words);
   STAGE_EV(4);
   k_frame_logic<<<nf, 32, 0, st>>>(p, frames, nf);
   STAGE_EV(5);
@@ -618,6 +622,8 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
     int cf = 1024;
     if(const char *e = getenv("SSD_GPU_CHUNK_FRAMES"))
       cf = atoi(e);
+    if(const char *e = getenv("SSD_GPU_OUTLINE_GRIDX"))
+      ctx->outline_gridx = std::max(1, std::min(SSD_GPU_MAX_PLATEAUS, atoi(e)));
     if(const char *e = getenv("SSD_GPU_STREAMS"))
       ctx->n_streams = std::max(1, std::min(SSD_MAX_STREAMS, atoi(e)));
     // the BEV bitmaps (2 streams x chunk x 32 slots) must stay a small part of HBM

@@ -931,10 +931,15 @@ __global__ void __launch_bounds__(OutlineShared::THREADS, OutlineShared::MINB ? 
   __shared__ OutlineShared S;
   __shared__ Band bd;
   __shared__ int s_smem_path;
-  const int k = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x;
+  const int frame = blockIdx.y, tid = threadIdx.x;
   FrameDev &F = frames[frame];
-  if(k >= F.n_plateaus || !F.plat[k].outlined)
-    return;
+  // grid.x blocks per frame walk the frame's outlined plateaus (first_outlined .. n_plateaus-1, k_peaks); grid.x is
+  // smaller than SSD_GPU_MAX_PLATEAUS because a frame rarely has more than a handful (ssd_gpu.cu, launch_chain)
+  const int n_plat = F.n_plateaus;
+  for(int k = max(F.first_outlined, 0) + (int)blockIdx.x; k < n_plat; k += (int)gridDim.x)
+  {
+  if(!F.plat[k].outlined)
+    continue;
   PlateauDev &P = F.plat[k];
   P2d quad[4];
   int valid = 0;
@@ -969,6 +974,8 @@ __global__ void __launch_bounds__(OutlineShared::THREADS, OutlineShared::MINB ? 
       P.quad_world[c][1] = w.y;
     }
     P.valid = valid;
+  }
+  __syncthreads(); // the shared band / work area is reused by the next plateau of this block
   }
 }
 
