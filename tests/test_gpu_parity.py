@@ -384,6 +384,34 @@ def test_device_input_and_determinism(S, oracle):
         det.free(d_xyz)
 
 
+@pytest.mark.parametrize("nF", [63, 64, 71])
+def test_small_device_batch_split_over_streams(S, monkeypatch, nF):
+    """a device-resident batch that fits one chunk is split over the two streams when each part keeps >= 32 frames
+    (64 -> 2 x 32, 71 -> 36 + 35; 63 stays one chain): results, labels and result lines are identical to the unsplit
+    run (SSD_GPU_NO_SPLIT_SMALL=1) and to the single-stream run"""
+    w, h = 320, 240
+    N = w * h
+    cfg = S.default_config(w, h)
+    base = S.default_scene(w, h, **NOISY)
+    xf = S.scene_transform(base)
+    with S.Detector(cfg, xf, max_frames=nF) as det:
+        d_xyz = det.malloc(nF * N * 12)
+        det.synth_frames(base, 5150, 0, nF, 3, 8, d_xyz)
+        det.process_device(d_xyz, nF)
+        split = [(det.line(f), det.labels(f).copy()) for f in range(nF)]
+        monkeypatch.setenv("SSD_GPU_NO_SPLIT_SMALL", "1")
+        det.process_device(d_xyz, nF)
+        whole = [(det.line(f), det.labels(f).copy()) for f in range(nF)]
+        monkeypatch.delenv("SSD_GPU_NO_SPLIT_SMALL")
+        det.process_device(d_xyz, nF, flags=A.FLAG_SINGLE_STREAM)
+        single = [(det.line(f), det.labels(f).copy()) for f in range(nF)]
+        det.free(d_xyz)
+    assert sum(l.count("height") for l, _ in split) > nF  # the frames do hold stairs
+    for f in range(nF):
+        assert split[f][0] == whole[f][0] == single[f][0], f
+        assert np.array_equal(split[f][1], whole[f][1]) and np.array_equal(split[f][1], single[f][1]), f
+
+
 def _all_lines(det, n):
     return [det.line(f) for f in range(n)]
 
