@@ -58,6 +58,15 @@ struct DevParams
   unsigned long long axy2[3], bxy2, auv2[3], buv2;
   // {sa[j], sa[3+j]}, {sb[0], sb[1]}: the x and y rows of the range-scaled transform (point_code_scaled)
   unsigned long long sxy2[3], sbxy2;
+  // resident-frame path (ssd_kernels_stream.cuh). Per-point record: ix | iy << rec_bx | d << (32 - rec_zbits), d = the point's
+  // height offset from the centre of its bin in units of 2^-rec_zshift m (rec_mf = height_interval * 2^rec_zshift,
+  // |d| <= rec_mf / 2 < 2^(rec_zbits - 1)); iy == H marks a pixel the f32 chain could not decide. rec_zbits == 0: the
+  // frame size does not admit the path.
+  int rec_bx, rec_by, rec_zbits, rec_zshift;
+  float rec_mf;
+  int gs_steps;            // 128-point steps per frame
+  // k_quad_sum: world rectangle of a BEV pixel box in single precision (x = ix * gs_xw + gs_x0, y = gs_y0 - iy * gs_yw)
+  float gs_xw, gs_x0, gs_yw, gs_y0, gs_margin, pad4;
 };
 
 struct SegmentDev
@@ -113,7 +122,11 @@ struct PlateauDev
   double quad_px[4][2];
   double quad_world[4][2];
   double mean_z;
-  unsigned long long sum_fix; // sum of z_fix_u() over the points inside the quadrilateral
+  unsigned long long sum_fix; // sum of z_fix_u() over the points inside the quadrilateral that were tested one by one
+  // ... and of the points taken in as whole 32-pixel summaries (k_quad_sum): height offsets, bin codes, how many
+  long long sum_d;
+  unsigned long long sum_c;
+  unsigned n_sum, pad_s;
   int row_min, row_max;       // BEV rows touched by this plateau's bitmap
   int front_valid;
   int pad;

@@ -3,6 +3,7 @@
 #include "ssd_device.cuh"
 #include "ssd_kernels_points.cuh"
 #include "ssd_kernels_outline.cuh"
+#include "ssd_kernels_stream.cuh"
 #include "scene_model.h"
 
 #include <algorithm>
@@ -60,6 +61,13 @@ struct ssd_gpu_ctx
   uint16_t *d_depth[SSD_MAX_STREAMS]{};         // z16 staging of the host depth-frame path
   float *d_xn = nullptr, *d_yn = nullptr;       // deprojection tables: (u - ppx) / fx per column, (v - ppy) / fy per row
   ssd_gpu_intrinsics intr{};                    // intrinsics the tables were built for
+  // resident-frame path (ssd_kernels_stream.cuh): one persistent kernel per chunk instead of the three point passes
+  bool resident = false;
+  int fs_grid = 0, fs_d_raw = 4, fs_d_rec = 6;
+  GroupSum *d_sums = nullptr;     // n_streams x chunk_frames x N/32 summaries
+  unsigned *d_done = nullptr;     // n_streams x chunk_frames frame counters (self-resetting)
+  cudaEvent_t ev_fs{};            // the persistent kernels of consecutive chunks never overlap (each wants every SM)
+  bool fs_pending = false;
   int pt_blocks_target = 0;       // blocks per launch of the tile-looping point kernels
   int n_frames_last = 0;
   int flags_last = 0;
@@ -251,6 +259,33 @@ static int derive_params(const ssd_gpu_config &c, const ssd_gpu_transform &t, De
     d.bxy2 = f2_pack_bits(d.bf[0], d.bf[1]);
     d.sbxy2 = f2_pack_bits(d.sb[0], d.sb[1]);
     d.buv2 = f2_pack_bits(d.bu, d.bv);
+  }
+  {
+    // resident-frame path: record layout and the summary -> world-rectangle map (ssd_kernels_stream.cuh)
+    int bx = 1, by = 1;
+    while((1 << bx) < c.width)
+      bx++;
+    while((1 << by) < c.height + 1)
+      by++;
+    const int zbits = std::min(12, 32 - bx - by);
+    d.rec_bx = bx;
+    d.rec_by = by;
+    d.rec_zbits = 0;
+    d.gs_steps = d.N / SSD_FS_STEP_PX;
+    if(zbits >= 10 && d.N % SSD_FS_STEP_PX == 0 && c.width <= 0xfffe && c.height <= 0xfffe)
+    {
+      int sh = 0;
+      while(sh < 24 && 0.5 * std::ldexp(c.height_interval, sh + 1) + 1.0 < std::ldexp(1.0, zbits - 1) - 1.0)
+        sh++;
+      d.rec_zbits = zbits;
+      d.rec_zshift = sh;
+      d.rec_mf = (float)std::ldexp(1.0 / d.hir, sh);
+    }
+    d.gs_xw = (float)d.x_to_world;
+    d.gs_x0 = (float)c.x_min;
+    d.gs_yw = (float)d.y_to_world;
+    d.gs_y0 = (float)c.y_max;
+    d.gs_margin = (float)(16.0 / 16777216.0 * (std::fabs(c.x_min) + std::fabs(c.x_max) + std::fabs(c.y_min) + std::fabs(c.y_max) + 1.0) + 1e-7);
   }
   if(d.n_bins < 3 || d.n_bins > SSD_GPU_MAX_BINS)
     return SSD_E_RANGE;
@@ -466,6 +501,61 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, const uin
   sd.unit = depth_unit;
   sd.wmagic = (((unsigned long long)1 << 40) + (unsigned long long)p.W - 1) / (unsigned long long)p.W;
 
+  if(ctx->resident)
+  {
+    // ---- resident-frame chain: k_frame_stream -> k_outline -> k_frame_logic -> k_quad_sum -> k_finalize ----
+    FsParams a;
+    a.n_frames = nf;
+    a.d_raw = ctx->fs_d_raw;
+    a.d_rec = ctx->fs_d_rec;
+    a.flags = 0;
+    a.done = ctx->d_done + (size_t)s * ctx->chunk_frames;
+    a.sums = ctx->d_sums + (size_t)s * ctx->chunk_frames * (size_t)(p.N / 32);
+    size_t bmw = ctx->bm_words;
+    DevParams pp = p;
+    if(ctx->fs_pending)
+      CK(cudaStreamWaitEvent(st, ctx->ev_fs, 0));
+    STAGE_EV(0);
+    if(depth)
+    {
+      void *args[] = { &pp, &sd, &a, &labels, &frames, &bev, &bmw };
+      CK(cudaLaunchCooperativeKernel((const void *)k_frame_stream<SrcDepth>, dim3(ctx->fs_grid), dim3(SSD_FS_THREADS), args,
+                                     fs_smem_bytes(FsSrc<SrcDepth>::STEP_BYTES, a.d_raw, a.d_rec), st));
+    }
+    else
+    {
+      void *args[] = { &pp, &sv, &a, &labels, &frames, &bev, &bmw };
+      CK(cudaLaunchCooperativeKernel((const void *)k_frame_stream<SrcVertices>, dim3(ctx->fs_grid), dim3(SSD_FS_THREADS), args,
+                                     fs_smem_bytes(FsSrc<SrcVertices>::STEP_BYTES, a.d_raw, a.d_rec), st));
+    }
+    CK(cudaEventRecord(ctx->ev_fs, st));
+    ctx->fs_pending = true;
+    STAGE_EV(1);
+    STAGE_EV(2);
+    STAGE_EV(3);
+    if(ctx->outline_small)
+      k_outline<OutlineSharedSmall><<<dim3(ctx->outline_gridx, nf), SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, bev, ctx->bm_words, ctx->smem_cap_words);
+    else
+      k_outline<OutlineShared><<<dim3(ctx->outline_gridx, nf), OutlineShared::THREADS, ctx->ol_dyn_smem, st>>>(p, frames, bev, ctx->bm_words, ctx->smem_cap_words);
+    STAGE_EV(4);
+    k_frame_logic<<<nf, 32, 0, st>>>(p, frames, nf);
+    STAGE_EV(5);
+    if(depth)
+      k_quad_sum<SrcDepth><<<gpt2q, SSD_PT_THREADS, 0, st>>>(p, sd, labels, frames, bev, ctx->bm_words, a.sums);
+    else
+      k_quad_sum<SrcVertices><<<gpt2q, SSD_PT_THREADS, 0, st>>>(p, sv, labels, frames, bev, ctx->bm_words, a.sums);
+    STAGE_EV(6);
+    if(ctx->outline_small)
+      k_finalize<OutlineSharedSmall><<<nf, SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, ctx->d_out + frame0, bev, ctx->bm_words, ctx->smem_cap_words, ctx->ov,
+                                                                            ctx->d_ovl ? ctx->d_ovl + (size_t)frame0 * SSD_GPU_MAX_STEPS : nullptr);
+    else
+      k_finalize<OutlineShared><<<nf, SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, ctx->d_out + frame0, bev, ctx->bm_words, ctx->smem_cap_words, ctx->ov,
+                                                                            ctx->d_ovl ? ctx->d_ovl + (size_t)frame0 * SSD_GPU_MAX_STEPS : nullptr);
+    STAGE_EV(7);
+    *launches += 5;
+    CK(cudaGetLastError());
+    return SSD_OK;
+  }
   if(ctx->split && !single)
   {
     // everything already queued on stream s (input copy / deprojection, the previous chunk of this stream) first
@@ -551,6 +641,10 @@ void ssd_gpu_destroy(ssd_gpu_ctx *ctx)
   cudaFreeHost(ctx->h_ovl);
   cudaFree(ctx->d_labels);
   cudaFree(ctx->d_bev);
+  cudaFree(ctx->d_sums);
+  cudaFree(ctx->d_done);
+  if(ctx->ev_fs)
+    cudaEventDestroy(ctx->ev_fs);
   cudaFree(ctx->d_img);
   cudaFree(ctx->d_xn);
   cudaFree(ctx->d_yn);
@@ -739,6 +833,47 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
   const size_t bev_bytes = (size_t)ctx->n_streams * ctx->chunk_frames * SSD_GPU_MAX_PLATEAUS * ctx->bm_words * 4;
   CKC(cudaMalloc(&ctx->d_bev, bev_bytes));
   CKC(cudaMemset(ctx->d_bev, 0, bev_bytes)); // bitmaps are self-cleaning afterwards
+  {
+    // Resident-frame path: used when a frame's records fit the shared memory of the GPU with room for the frame barrier's
+    // latency (every warp must hold all its steps of one frame, plus what it works ahead). SSD_GPU_PATH=classic|resident.
+    const char *pe = getenv("SSD_GPU_PATH");
+    const bool want = !(pe && !strcmp(pe, "classic"));
+    int sms = 148, coop = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+    if(const char *e = getenv("SSD_GPU_FS_RAW"))
+      ctx->fs_d_raw = std::max(2, atoi(e));
+    if(const char *e = getenv("SSD_GPU_FS_REC"))
+      ctx->fs_d_rec = std::max(2, atoi(e));
+    int grid = sms;
+    if(const char *e = getenv("SSD_GPU_FS_CTAS"))
+      grid = std::max(1, std::min(sms, atoi(e)));
+    if(want && coop && dp.rec_zbits > 0 && dp.gs_steps >= SSD_FS_WARPS)
+    {
+      grid = std::min(grid, dp.gs_steps / SSD_FS_WARPS); // at least one step per warp and frame
+      const int per_warp = (dp.gs_steps + grid * SSD_FS_WARPS - 1) / (grid * SSD_FS_WARPS);
+      ctx->fs_d_rec = std::max(ctx->fs_d_rec, per_warp + 2);
+      const size_t sm_v = fs_smem_bytes(FsSrc<SrcVertices>::STEP_BYTES, ctx->fs_d_raw, ctx->fs_d_rec);
+      const size_t sm_d = fs_smem_bytes(FsSrc<SrcDepth>::STEP_BYTES, ctx->fs_d_raw, ctx->fs_d_rec);
+      int occ = 0;
+      if(sm_v <= (size_t)max_optin && ctx->fs_d_rec <= 64 &&
+         cudaFuncSetAttribute(k_frame_stream<SrcVertices>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_v) == cudaSuccess &&
+         cudaFuncSetAttribute(k_frame_stream<SrcDepth>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_d) == cudaSuccess &&
+         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_frame_stream<SrcVertices>, SSD_FS_THREADS, sm_v) == cudaSuccess && occ >= 1)
+      {
+        ctx->resident = true;
+        ctx->fs_grid = grid;
+        const size_t n_sums = (size_t)ctx->n_streams * ctx->chunk_frames * (size_t)(dp.N / 32);
+        CKC(cudaMalloc(&ctx->d_sums, n_sums * sizeof(GroupSum)));
+        CKC(cudaMalloc(&ctx->d_done, (size_t)ctx->n_streams * ctx->chunk_frames * sizeof(unsigned)));
+        CKC(cudaMemset(ctx->d_done, 0, (size_t)ctx->n_streams * ctx->chunk_frames * sizeof(unsigned)));
+        CKC(cudaEventCreateWithFlags(&ctx->ev_fs, cudaEventDisableTiming));
+      }
+      cudaGetLastError();
+    }
+    if(pe && !strcmp(pe, "resident") && !ctx->resident)
+      return bail("SSD_GPU_PATH=resident: the frame size does not admit the resident-frame path", SSD_E_RANGE);
+  }
   CKC(cudaMemset(ctx->d_frames, 0, sizeof(FrameDev) * (size_t)max_frames));
   CKC(cudaMemset(ctx->d_out, 0, sizeof(FrameOut) * (size_t)max_frames));
   memset(ctx->h_out, 0, sizeof(FrameOut) * (size_t)max_frames);

@@ -485,6 +485,9 @@ __global__ void __launch_bounds__(32) k_peaks(const __grid_constant__ DevParams 
     P.quad_status = -1;
     P.mean_z = 0;
     P.sum_fix = 0;
+    P.sum_d = 0;
+    P.sum_c = 0;
+    P.n_sum = 0;
     P.row_min = 0x7fffffff;
     P.row_max = -1;
     P.front_valid = 0;
@@ -863,30 +866,231 @@ __device__ __forceinline__ void quad_reduce_exact_point(const DevParams &p, floa
 #define SSD_DEF_MID 0x2000u     // deferred point between inner and reject box: f32 image of the test first
 #define SSD_DEF_GENERIC 0x4000u // deferred point of a word with mixed labels: not yet checked against amask
 
-#ifndef SSD_QR_MINB
-#define SSD_QR_MINB 4
-#endif
-template<class SRC>
-__global__ void __launch_bounds__(SSD_PT_THREADS, SSD_QR_MINB) k_quad_reduce(const __grid_constant__ DevParams p, const SRC src,
-                                                                 const unsigned char *__restrict__ labels, FrameDev *__restrict__ frames,
-                                                                 unsigned *__restrict__ bev, size_t bm_words)
+// state a warp of k_quad_reduce / k_quad_sum carries across its warp-tiles
+struct QrWarp
 {
-  __shared__ QuadReduceShared S;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int frame = blockIdx.y;
-  FrameDev &F = frames[frame];
-  const unsigned amask = F.quad_amask;
-  if(amask == 0u)
-    return; // no valid plateau: nothing is emitted (pointcloud.cpp:434)
-  const int ground = F.ground_index;
-  const size_t fbase = (size_t)frame * p.N;
-  const unsigned *lab32 = reinterpret_cast<const unsigned *>(labels + fbase);
-  unsigned *gbev = ground >= 0 ? bev + ((size_t)frame * SSD_GPU_MAX_PLATEAUS + ground) * bm_words : nullptr;
-  const int nquads = p.N >> 2;
-  int wt, wt_end, wt_stride;
-  warp_tile_range((p.N + SSD_WT_PX - 1) / SSD_WT_PX, warp, wt, wt_end, wt_stride);
+  unsigned seg_l, seg_n, n_def, n_mid;
+  unsigned long long seg_sum;
+  int rmin, rmax;
+};
 
+// The dense part of one warp-tile: phase B over the n compacted words of the warp's list (S.L.act / S.L.lab), the exact
+// pass over the deferred points, the queued ground BEV pixels, and the warp's segmented reduce. wbase: first 4-point word
+// of the warp-tile within the frame.
+template<class SRC, class FRAME>
+__device__ __forceinline__ void qr_dense(const DevParams &p, const FRAME &FR, QuadReduceShared &S, QrWarp &W, const FrameDev &F, unsigned amask, int ground,
+                                         unsigned *__restrict__ gbev, unsigned wbase, unsigned n, int warp, int lane)
+{
+  unsigned short *act = S.L.act[warp];
+  unsigned *labs = S.L.lab[warp];
+  unsigned &seg_l = W.seg_l, &seg_n = W.seg_n, &n_def = W.n_def, &n_mid = W.n_mid;
+  unsigned long long &seg_sum = W.seg_sum;
+  int &rmin = W.rmin, &rmax = W.rmax;
+  // ---- phase B: dense walk over the compacted words ----
+  unsigned e = lane < n ? act[lane] : 0u;
+  typename SrcTraits<SRC>::Word wc;
+  word_zero(wc);
+  if(e)
+    word_load(FR, wbase + (e >> 4), wc);
+  for(unsigned s0 = 0; s0 < n; s0 += 32)
   {
+    // (no software prefetch of the next step's words: the L2 prefetch of phase A and four resident blocks per SM hide the
+    //  latency better than twelve more registers per thread did -- measured 2.51 -> 2.28 ms per 2048 frames)
+    if(s0)
+    {
+      const unsigned i0 = s0 + lane;
+      e = i0 < n ? act[i0] : 0u;
+      if(e)
+        word_load(FR, wbase + (e >> 4), wc);
+    }
+    const unsigned m4 = e & 15u;
+    const unsigned lw = labs[e >> 4];
+    // label of the word's first plateau point; the word is "uniform" when all its plateau points carry it
+    const unsigned l0 = (lw >> (8 * (__ffs(m4 | 16u) - 1) & 31)) & 0x1fu;
+    const unsigned bytes = ((m4 * 0x00204081u) & 0x01010101u) * 0xffu;
+    const bool uniform = ((lw ^ (l0 * 0x01010101u)) & bytes) == 0u;
+    float vx[4], vy[4], vz[4];
+    word_unpack(FR, wc, vx, vy, vz);
+    if(uniform)
+    {
+      // Branch-free on sign bits (every operand is finite here: plateau points are valid and in range, the tables
+      // hold finite numbers or +inf). Labels outside amask have an empty inner box and an empty reject box.
+      //   in  <=> active && |wx - cx| < hx && |wy - cy| < hy      (sign of |d| - h, both set)
+      //   rej <=> |wx - cx| > Rx || |wy - cy| > Ry                 (sign of R - |d|, either set)
+      //   mid <=> active && !in && !rej  -> deferred
+      const float4 ib = S.fast[l0].ibe;
+      const float2 rj = S.fast[l0].rj;
+      float wxs[4];
+      int inm[4], midm[4];
+      int cnt = 0;
+      unsigned zs = 0;
+#pragma unroll
+      for(int j = 0; j < 4; j++)
+      {
+        float wy;
+        f2_unpack(f2_affine(p.axy2, p.bxy2, vx[j], vy[j], vz[j]), wxs[j], wy);
+        const float dx = fabsf(wxs[j] - ib.x), dy = fabsf(wy - ib.y);
+        const int act = (int)(m4 << (31 - j));
+        const int ins = __float_as_int(dx - ib.z) & __float_as_int(dy - ib.w) & act;
+        const int rej = __float_as_int(rj.x - dx) | __float_as_int(rj.y - dy);
+        midm[j] = act & ~ins & ~rej;
+        inm[j] = ins >> 31; // all ones when inside
+        zs += z_fix_u(p, vx[j], vy[j], vz[j]) & (unsigned)inm[j];
+        cnt -= inm[j];
+      }
+      // between the inner box and the reject box (a few percent of the points, but in most warp steps): deferred to
+      // the dense pass at the end of the warp-tile, which evaluates the f32 image of the full test one point per lane
+      if((midm[0] | midm[1] | midm[2] | midm[3]) < 0)
+      {
+#pragma unroll
+        for(int j = 0; j < 4; j++)
+          if(midm[j] < 0)
+            defer_push(S.L, warp, SSD_DEF_MID | ((e >> 4) << 2) | (unsigned)j);
+      }
+      if(cnt)
+      {
+        if(l0 != seg_l)
+        {
+          if(seg_n)
+            seg_flush(S, seg_l, seg_sum, seg_n);
+          seg_l = l0;
+          seg_sum = 0;
+          seg_n = 0;
+        }
+        seg_sum += zs;
+        seg_n += (unsigned)cnt;
+        if((int)l0 == ground)
+        {
+          // Ground BEV image: only the pixel columns detectFrontEdge can see are written. Cheap column pre-filter
+          // (f32, conservative margin): t = ((wx - x_min) sx - (W/2 - 2)) / 50, the column is needed iff frac(t) in
+          // [0, 0.1). The few points that pass are queued per word; their pixels are computed densely at the end of
+          // the warp-tile (one point per lane) instead of diverging every step here.
+          unsigned gm = 0;
+#pragma unroll
+          for(int j = 0; j < 4; j++)
+          {
+            const float t = fmaf(wxs[j], p.gcol_a, p.gcol_b);
+            const float fr = t - floorf(t);
+            gm |= (fr < p.gcol_lo || fr > p.gcol_hi || t > p.gcol_tmax) ? (1u << j) : 0u;
+          }
+          gm &= (unsigned)(inm[0] & 1) | (unsigned)(inm[1] & 2) | (unsigned)(inm[2] & 4) | (unsigned)(inm[3] & 8);
+          if(gm)
+            S.L.gb[warp][atomicAdd(&S.L.ngb[warp], 1u)] = (unsigned short)((e & 0xff0u) | gm);
+        }
+      }
+    }
+    else
+    {
+      // mixed labels in one word (plateau boundaries in the image): every point goes to the exact pass
+#pragma unroll
+      for(int j = 0; j < 4; j++)
+        if((m4 >> j) & 1u)
+          defer_push(S.L, warp, SSD_DEF_GENERIC | ((e >> 4) << 2) | (unsigned)j);
+    }
+  }
+  // ---- dense exact pass over the warp's compacted uncertain points ----
+  __syncwarp();
+  const unsigned nd = S.L.ndef[warp];
+  if(nd)
+  {
+    for(unsigned i = lane; i < nd; i += 32)
+    {
+      const unsigned d = S.L.def[warp][i];
+      const unsigned w = (d >> 2) & 0xffu, j = d & 3u;
+      const unsigned l = (labs[w] >> (8 * j)) & 0xffu;
+      float fx, fy, fz;
+      point_load(FR, (wbase + w) * 4u + j, fx, fy, fz);
+      bool exact = true, bevonly = (d & SSD_DEF_BEVONLY) != 0u;
+      if(d & SSD_DEF_MID)
+      {
+        float wxf, wyf;
+        f2_unpack(f2_affine(p.axy2, p.bxy2, fx, fy, fz), wxf, wyf);
+        bool unc;
+        const bool in = quadfilter_eval(S.qf[l & 31u], wxf, wyf, p.epsc, unc);
+        if(!unc)
+        {
+          n_mid++;
+          exact = in && (int)l == ground; // certain: count it here; an inside ground point still needs its BEV pixel
+          bevonly = true;
+          if(in)
+          {
+            // into the lane's running segment (no shared-memory atomics: 64-bit ones are CAS loops)
+            if(l != seg_l)
+            {
+              if(seg_n)
+                seg_flush(S, seg_l, seg_sum, seg_n);
+              seg_l = l;
+              seg_sum = 0;
+              seg_n = 0;
+            }
+            seg_sum += z_fix_u(p, fx, fy, fz);
+            seg_n++;
+          }
+        }
+      }
+      if(exact)
+        quad_reduce_exact_point(p, fx, fy, fz, l, bevonly, F, amask, ground, gbev, S);
+    }
+    __syncwarp();
+    n_def += nd;
+    if(lane == 0)
+      S.L.ndef[warp] = 0;
+  }
+  {
+    // ---- dense pass over the queued ground points: BEV pixel, one queued word per lane ----
+    const unsigned ng = S.L.ngb[warp];
+    if(ng)
+    {
+      for(unsigned i = lane; i < ng; i += 32)
+      {
+        const unsigned d = S.L.gb[warp][i];
+        const unsigned w = (d >> 4) & 0xffu;
+        unsigned mask = d & 15u;
+#pragma unroll 1
+        while(mask)
+        {
+          const unsigned j = __ffs(mask) - 1;
+          mask &= mask - 1u;
+          float fx, fy, fz;
+          point_load(FR, (wbase + w) * 4u + j, fx, fy, fz);
+          int ix, iy;
+          if(fast_pixel2(p, fx, fy, fz, ix, iy))
+          {
+            if(ground_col_needed(p, ix))
+            {
+              atomicOr(gbev + (unsigned)iy * (unsigned)p.wpr + (unsigned)(ix >> 5), 1u << (ix & 31));
+              rmin = min(rmin, iy);
+              rmax = max(rmax, iy);
+            }
+          }
+          else
+            quad_reduce_exact_point(p, fx, fy, fz, (unsigned)ground, true, F, amask, ground, gbev, S);
+        }
+      }
+      __syncwarp();
+      if(lane == 0)
+        S.L.ngb[warp] = 0;
+    }
+  }
+  {
+    // end of the warp-tile: combine the warp's 32 open segments (single-pass segmented reduce: lanes grouped by
+    // label, 64-bit sums as 21 low bits + the rest), one set of shared-memory adds per distinct label
+    const unsigned key = seg_n ? seg_l : 0xffu;
+    const unsigned grp = __match_any_sync(0xffffffffu, key);
+    const unsigned lo = __reduce_add_sync(grp, (unsigned)seg_sum & 0x1fffffu);
+    const unsigned hi = __reduce_add_sync(grp, (unsigned)(seg_sum >> 21)); // a lane's sum < 2^23 * 2^10 points per tile
+    const unsigned cn = __reduce_add_sync(grp, seg_n);
+    if(key != 0xffu && lane == __ffs(grp) - 1)
+      seg_flush(S, key, ((unsigned long long)hi << 21) + (unsigned long long)lo, cn);
+    seg_l = 0xffu;
+    seg_sum = 0;
+    seg_n = 0;
+  }
+}
+
+// the frame's filter tables and the block's accumulators (k_quad_reduce / k_quad_sum)
+__device__ __forceinline__ void qr_init(QuadReduceShared &S, const FrameDev &F, unsigned amask, int tid)
+{
     // the frame's filter tables: one coalesced copy, independent of anything else
     const unsigned *src = reinterpret_cast<const unsigned *>(F.qf);
     unsigned *dst = reinterpret_cast<unsigned *>(S.qf);
@@ -915,14 +1119,75 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_QR_MINB) k_quad_reduce(con
       S.oob = 0;
       S.n_def = 0;
     }
+}
+
+// end of k_quad_reduce / k_quad_sum: the warps' leftovers into the block's accumulators, the block's into the frame's
+__device__ __forceinline__ void qr_epilogue(QuadReduceShared &S, QrWarp &W, FrameDev &F, int ground, int tid, int lane)
+{
+  unsigned n_def = W.n_def;
+  int rmin = W.rmin, rmax = W.rmax;
+  n_def -= __reduce_add_sync(0xffffffffu, W.n_mid); // deferred points settled by the f32 image of the test are not exact decisions
+  rmin = __reduce_min_sync(0xffffffffu, rmin);
+  rmax = __reduce_max_sync(0xffffffffu, rmax);
+  if(lane == 0)
+  {
+    if(rmax >= 0)
+    {
+      atomicMin(&S.rmin, rmin);
+      atomicMax(&S.rmax, rmax);
+    }
+    if(n_def)
+      atomicAdd(&S.n_def, n_def);
   }
+  __syncthreads();
+  if(tid < SSD_GPU_MAX_PLATEAUS && S.cnt[tid])
+  {
+    atomicAdd(&F.plat[tid].sum_fix, ((unsigned long long)S.shi[tid] << 16) + (unsigned long long)S.slo[tid]);
+    atomicAdd(&F.plat[tid].n_in_quad, S.cnt[tid]);
+  }
+  if(tid == 0)
+  {
+    if(S.rmax >= 0)
+    {
+      atomicMin(&F.plat[ground].row_min, S.rmin);
+      atomicMax(&F.plat[ground].row_max, S.rmax);
+    }
+    if(S.oob)
+      atomicOr(&F.status, SSD_STATUS_BEV_OOB);
+    if(S.n_def)
+      atomicAdd(&F.n_def_quad, S.n_def);
+  }
+}
+
+#ifndef SSD_QR_MINB
+#define SSD_QR_MINB 4
+#endif
+template<class SRC>
+__global__ void __launch_bounds__(SSD_PT_THREADS, SSD_QR_MINB) k_quad_reduce(const __grid_constant__ DevParams p, const SRC src,
+                                                                 const unsigned char *__restrict__ labels, FrameDev *__restrict__ frames,
+                                                                 unsigned *__restrict__ bev, size_t bm_words)
+{
+  __shared__ QuadReduceShared S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int frame = blockIdx.y;
+  FrameDev &F = frames[frame];
+  const unsigned amask = F.quad_amask;
+  if(amask == 0u)
+    return; // no valid plateau: nothing is emitted (pointcloud.cpp:434)
+  const int ground = F.ground_index;
+  const size_t fbase = (size_t)frame * p.N;
+  const unsigned *lab32 = reinterpret_cast<const unsigned *>(labels + fbase);
+  unsigned *gbev = ground >= 0 ? bev + ((size_t)frame * SSD_GPU_MAX_PLATEAUS + ground) * bm_words : nullptr;
+  const int nquads = p.N >> 2;
+  int wt, wt_end, wt_stride;
+  warp_tile_range((p.N + SSD_WT_PX - 1) / SSD_WT_PX, warp, wt, wt_end, wt_stride);
+
+  qr_init(S, F, amask, tid);
   __syncthreads();
 
   unsigned short *act = S.L.act[warp];
   unsigned *labs = S.L.lab[warp];
-  unsigned seg_l = 0xffu, seg_n = 0, n_def = 0, n_mid = 0;
-  unsigned long long seg_sum = 0;
-  int rmin = 0x7fffffff, rmax = -1;
+  QrWarp W = { 0xffu, 0u, 0u, 0u, 0ull, 0x7fffffff, -1 };
   const typename SrcTraits<SRC>::Frame FR = src_frame(src, p, fbase);
 
   for(; wt < wt_end; wt += wt_stride)
@@ -958,237 +1223,8 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_QR_MINB) k_quad_reduce(con
       continue;
     __syncwarp();
 
-    // ---- phase B: dense walk over the compacted words ----
-    unsigned e = lane < n ? act[lane] : 0u;
-    typename SrcTraits<SRC>::Word wc;
-    word_zero(wc);
-    if(e)
-      word_load(FR, wbase + (e >> 4), wc);
-    for(unsigned s0 = 0; s0 < n; s0 += 32)
-    {
-      // (no software prefetch of the next step's words: the L2 prefetch of phase A and four resident blocks per SM hide the
-      //  latency better than twelve more registers per thread did -- measured 2.51 -> 2.28 ms per 2048 frames)
-      if(s0)
-      {
-        const unsigned i0 = s0 + lane;
-        e = i0 < n ? act[i0] : 0u;
-        if(e)
-          word_load(FR, wbase + (e >> 4), wc);
-      }
-      const unsigned m4 = e & 15u;
-      const unsigned lw = labs[e >> 4];
-      // label of the word's first plateau point; the word is "uniform" when all its plateau points carry it
-      const unsigned l0 = (lw >> (8 * (__ffs(m4 | 16u) - 1) & 31)) & 0x1fu;
-      const unsigned bytes = ((m4 * 0x00204081u) & 0x01010101u) * 0xffu;
-      const bool uniform = ((lw ^ (l0 * 0x01010101u)) & bytes) == 0u;
-      float vx[4], vy[4], vz[4];
-      word_unpack(FR, wc, vx, vy, vz);
-      if(uniform)
-      {
-        // Branch-free on sign bits (every operand is finite here: plateau points are valid and in range, the tables
-        // hold finite numbers or +inf). Labels outside amask have an empty inner box and an empty reject box.
-        //   in  <=> active && |wx - cx| < hx && |wy - cy| < hy      (sign of |d| - h, both set)
-        //   rej <=> |wx - cx| > Rx || |wy - cy| > Ry                 (sign of R - |d|, either set)
-        //   mid <=> active && !in && !rej  -> deferred
-        const float4 ib = S.fast[l0].ibe;
-        const float2 rj = S.fast[l0].rj;
-        float wxs[4];
-        int inm[4], midm[4];
-        int cnt = 0;
-        unsigned zs = 0;
-#pragma unroll
-        for(int j = 0; j < 4; j++)
-        {
-          float wy;
-          f2_unpack(f2_affine(p.axy2, p.bxy2, vx[j], vy[j], vz[j]), wxs[j], wy);
-          const float dx = fabsf(wxs[j] - ib.x), dy = fabsf(wy - ib.y);
-          const int act = (int)(m4 << (31 - j));
-          const int ins = __float_as_int(dx - ib.z) & __float_as_int(dy - ib.w) & act;
-          const int rej = __float_as_int(rj.x - dx) | __float_as_int(rj.y - dy);
-          midm[j] = act & ~ins & ~rej;
-          inm[j] = ins >> 31; // all ones when inside
-          zs += z_fix_u(p, vx[j], vy[j], vz[j]) & (unsigned)inm[j];
-          cnt -= inm[j];
-        }
-        // between the inner box and the reject box (a few percent of the points, but in most warp steps): deferred to
-        // the dense pass at the end of the warp-tile, which evaluates the f32 image of the full test one point per lane
-        if((midm[0] | midm[1] | midm[2] | midm[3]) < 0)
-        {
-#pragma unroll
-          for(int j = 0; j < 4; j++)
-            if(midm[j] < 0)
-              defer_push(S.L, warp, SSD_DEF_MID | ((e >> 4) << 2) | (unsigned)j);
-        }
-        if(cnt)
-        {
-          if(l0 != seg_l)
-          {
-            if(seg_n)
-              seg_flush(S, seg_l, seg_sum, seg_n);
-            seg_l = l0;
-            seg_sum = 0;
-            seg_n = 0;
-          }
-          seg_sum += zs;
-          seg_n += (unsigned)cnt;
-          if((int)l0 == ground)
-          {
-            // Ground BEV image: only the pixel columns detectFrontEdge can see are written. Cheap column pre-filter
-            // (f32, conservative margin): t = ((wx - x_min) sx - (W/2 - 2)) / 50, the column is needed iff frac(t) in
-            // [0, 0.1). The few points that pass are queued per word; their pixels are computed densely at the end of
-            // the warp-tile (one point per lane) instead of diverging every step here.
-            unsigned gm = 0;
-#pragma unroll
-            for(int j = 0; j < 4; j++)
-            {
-              const float t = fmaf(wxs[j], p.gcol_a, p.gcol_b);
-              const float fr = t - floorf(t);
-              gm |= (fr < p.gcol_lo || fr > p.gcol_hi || t > p.gcol_tmax) ? (1u << j) : 0u;
-            }
-            gm &= (unsigned)(inm[0] & 1) | (unsigned)(inm[1] & 2) | (unsigned)(inm[2] & 4) | (unsigned)(inm[3] & 8);
-            if(gm)
-              S.L.gb[warp][atomicAdd(&S.L.ngb[warp], 1u)] = (unsigned short)((e & 0xff0u) | gm);
-          }
-        }
-      }
-      else
-      {
-        // mixed labels in one word (plateau boundaries in the image): every point goes to the exact pass
-#pragma unroll
-        for(int j = 0; j < 4; j++)
-          if((m4 >> j) & 1u)
-            defer_push(S.L, warp, SSD_DEF_GENERIC | ((e >> 4) << 2) | (unsigned)j);
-      }
-    }
-    // ---- dense exact pass over the warp's compacted uncertain points ----
-    __syncwarp();
-    const unsigned nd = S.L.ndef[warp];
-    if(nd)
-    {
-      for(unsigned i = lane; i < nd; i += 32)
-      {
-        const unsigned d = S.L.def[warp][i];
-        const unsigned w = (d >> 2) & 0xffu, j = d & 3u;
-        const unsigned l = (labs[w] >> (8 * j)) & 0xffu;
-        float fx, fy, fz;
-        point_load(FR, (wbase + w) * 4u + j, fx, fy, fz);
-        bool exact = true, bevonly = (d & SSD_DEF_BEVONLY) != 0u;
-        if(d & SSD_DEF_MID)
-        {
-          float wxf, wyf;
-          f2_unpack(f2_affine(p.axy2, p.bxy2, fx, fy, fz), wxf, wyf);
-          bool unc;
-          const bool in = quadfilter_eval(S.qf[l & 31u], wxf, wyf, p.epsc, unc);
-          if(!unc)
-          {
-            n_mid++;
-            exact = in && (int)l == ground; // certain: count it here; an inside ground point still needs its BEV pixel
-            bevonly = true;
-            if(in)
-            {
-              // into the lane's running segment (no shared-memory atomics: 64-bit ones are CAS loops)
-              if(l != seg_l)
-              {
-                if(seg_n)
-                  seg_flush(S, seg_l, seg_sum, seg_n);
-                seg_l = l;
-                seg_sum = 0;
-                seg_n = 0;
-              }
-              seg_sum += z_fix_u(p, fx, fy, fz);
-              seg_n++;
-            }
-          }
-        }
-        if(exact)
-          quad_reduce_exact_point(p, fx, fy, fz, l, bevonly, F, amask, ground, gbev, S);
-      }
-      __syncwarp();
-      n_def += nd;
-      if(lane == 0)
-        S.L.ndef[warp] = 0;
-    }
-    {
-      // ---- dense pass over the queued ground points: BEV pixel, one queued word per lane ----
-      const unsigned ng = S.L.ngb[warp];
-      if(ng)
-      {
-        for(unsigned i = lane; i < ng; i += 32)
-        {
-          const unsigned d = S.L.gb[warp][i];
-          const unsigned w = (d >> 4) & 0xffu;
-          unsigned mask = d & 15u;
-#pragma unroll 1
-          while(mask)
-          {
-            const unsigned j = __ffs(mask) - 1;
-            mask &= mask - 1u;
-            float fx, fy, fz;
-            point_load(FR, (wbase + w) * 4u + j, fx, fy, fz);
-            int ix, iy;
-            if(fast_pixel2(p, fx, fy, fz, ix, iy))
-            {
-              if(ground_col_needed(p, ix))
-              {
-                atomicOr(gbev + (unsigned)iy * (unsigned)p.wpr + (unsigned)(ix >> 5), 1u << (ix & 31));
-                rmin = min(rmin, iy);
-                rmax = max(rmax, iy);
-              }
-            }
-            else
-              quad_reduce_exact_point(p, fx, fy, fz, (unsigned)ground, true, F, amask, ground, gbev, S);
-          }
-        }
-        __syncwarp();
-        if(lane == 0)
-          S.L.ngb[warp] = 0;
-      }
-    }
-    {
-      // end of the warp-tile: combine the warp's 32 open segments (single-pass segmented reduce: lanes grouped by
-      // label, 64-bit sums as 21 low bits + the rest), one set of shared-memory adds per distinct label
-      const unsigned key = seg_n ? seg_l : 0xffu;
-      const unsigned grp = __match_any_sync(0xffffffffu, key);
-      const unsigned lo = __reduce_add_sync(grp, (unsigned)seg_sum & 0x1fffffu);
-      const unsigned hi = __reduce_add_sync(grp, (unsigned)(seg_sum >> 21)); // a lane's sum < 2^23 * 2^10 points per tile
-      const unsigned cn = __reduce_add_sync(grp, seg_n);
-      if(key != 0xffu && lane == __ffs(grp) - 1)
-        seg_flush(S, key, ((unsigned long long)hi << 21) + (unsigned long long)lo, cn);
-      seg_l = 0xffu;
-      seg_sum = 0;
-      seg_n = 0;
-    }
+    qr_dense<SRC>(p, FR, S, W, F, amask, ground, gbev, wbase, n, warp, lane);
     __syncwarp();
   }
-  n_def -= __reduce_add_sync(0xffffffffu, n_mid); // deferred points settled by the f32 image of the test are not exact decisions
-  rmin = __reduce_min_sync(0xffffffffu, rmin);
-  rmax = __reduce_max_sync(0xffffffffu, rmax);
-  if(lane == 0)
-  {
-    if(rmax >= 0)
-    {
-      atomicMin(&S.rmin, rmin);
-      atomicMax(&S.rmax, rmax);
-    }
-    if(n_def)
-      atomicAdd(&S.n_def, n_def);
-  }
-  __syncthreads();
-  if(tid < SSD_GPU_MAX_PLATEAUS && S.cnt[tid])
-  {
-    atomicAdd(&F.plat[tid].sum_fix, ((unsigned long long)S.shi[tid] << 16) + (unsigned long long)S.slo[tid]);
-    atomicAdd(&F.plat[tid].n_in_quad, S.cnt[tid]);
-  }
-  if(tid == 0)
-  {
-    if(S.rmax >= 0)
-    {
-      atomicMin(&F.plat[ground].row_min, S.rmin);
-      atomicMax(&F.plat[ground].row_max, S.rmax);
-    }
-    if(S.oob)
-      atomicOr(&F.status, SSD_STATUS_BEV_OOB);
-    if(S.n_def)
-      atomicAdd(&F.n_def_quad, S.n_def);
-  }
+  qr_epilogue(S, W, F, ground, tid, lane);
 }

@@ -1,0 +1,988 @@
+// ssd_kernels_stream.cuh -- the resident-frame path: ONE persistent kernel reads every vertex exactly once.
+//
+// Why: labels depend on the whole-frame height histogram (pointcloud.cpp:184-256 before :280-343), so the classic chain
+// (ssd_kernels_points.cuh) reads the plateau points of a frame three times from HBM (24 B/point of DRAM traffic against
+// 13 algorithmic). A 1024x768 frame is 9.4 MB of vertices -- the shared memory of the 148 SMs together holds three of them.
+// k_frame_stream keeps a frame on chip between the two phases that the histogram separates:
+//
+//   phase 1 (per 128-point step, one warp): TMA bulk copy of the step's 1536 B of vertices into the warp's raw ring ->
+//            z>0 / CameraToWorld / range filter / height bin (point_code_scaled, exact fallback: the same decisions as
+//            k_transform_bin, pointcloud.cpp:122-178) -> block histogram in shared memory (pointcloud.cpp:194-204) ->
+//            a 4-byte record per point {BEV pixel (pointcloud.cpp:79-83), height offset inside its bin} + the 1-byte bin
+//            code into the warp's record ring (5 B/point stay on chip instead of 12).
+//   frame barrier: the last warp of a CTA to leave a frame adds the CTA's histogram to the frame's (global atomics) and
+//            arrives on the frame's counter; the last CTA to arrive evaluates the peaks / plateau bands / bin->label LUT
+//            (pointcloud.cpp:214-256, 300-335, 402-418; warp-parallel) and publishes the LUT -- the LUT's valid bits are
+//            the "frame ready" flag the other warps poll.
+//   phase 2 (same warp, same step, from the record ring): bin code -> segment label (1 B/point, the only per-point
+//            output), BEV occupancy bit of every point of an outlined plateau (projectToBinaryImage, pointcloud.cpp:458-471),
+//            and one 16-byte summary per 32 points {label, count, sum of height offsets, BEV pixel box} for the per-step
+//            mean (calcAverageZ, pointcloud.cpp:574-581): k_quad_sum adds whole summaries whose pixel box lies inside the
+//            quadrilateral and re-reads only the points of the summaries an edge crosses.
+//
+// Every warp is its own little pipeline (TMA issue -> phase 1 -> phase 2 on its steps g = warp + k * total_warps of the
+// chunk's step stream); the only block-level state are the per-frame accumulators; the only grid-level synchronisation is
+// the per-frame counter. All CTAs must be co-resident (cooperative launch, one CTA per SM).
+// DRAM traffic: 12 B read + 1 B label + 0.5 B summaries per point.
+#pragma once
+#include "ssd_kernels_points.cuh"
+
+#define SSD_FS_WARPS 16
+#define SSD_FS_THREADS (SSD_FS_WARPS * 32)
+#define SSD_FS_NB 8              // frames a CTA can have in flight (accumulator slots)
+#define SSD_FS_STEP_PX 128       // points per step: 32 lanes x 4
+#define SSD_FS_REC_BYTES 640     // record-ring slot: 32 code words + 32 x 4 records
+#define SSD_LUT_OUTLINED 0x100u  // lut16 flags: the label gets a BEV image
+#define SSD_LUT_GROUND 0x200u    //              the label is the ground plateau
+#define SSD_LUT_VALID 0x8000u    //              entry written (a zero entry means "frame not ready")
+
+// One summary per 32 consecutive pixels (8 lanes x 4): the points of the ground / outlined plateaus among them.
+struct __align__(16) GroupSum
+{
+  unsigned short ixmin, ixmax, iymin, iymax; // BEV pixel box of those points
+  int ds;                                    // sum of their height offsets d (units of 2^-rec_zshift m, relative to the bin centre)
+  unsigned short cs;                         // sum of their bin codes
+  unsigned char label;                       // their (common) segment label
+  unsigned char count;                       // how many; 0: none; 0xff: mixed labels or an uncertain pixel -> per point in k_quad_sum
+};
+#define SSD_GS_COMPLEX 0xffu
+
+struct FsParams
+{
+  int n_frames;
+  int d_raw, d_rec;   // ring depths per warp (slots)
+  int flags;          // SSD_FLAG_NO_LABELS
+  unsigned *done;     // per frame: CTAs that have delivered their histogram (self-resetting)
+  GroupSum *sums;     // n_frames x steps x 4
+};
+
+struct FsAcc // per in-flight frame (slot f % SSD_FS_NB) of one CTA
+{
+  unsigned hist[SSD_BINS_PAD];
+  int rmin[SSD_GPU_MAX_PLATEAUS], rmax[SSD_GPU_MAX_PLATEAUS];
+  unsigned p1_left, p2_left, n_exact, oob, n_def, pad[3];
+};
+
+struct FsPeaks // scratch of the warp that completes a frame (one at a time per CTA: lock)
+{
+  unsigned hist[SSD_BINS_PAD + 8]; // bin b at [4 + b]; zeros either side
+  unsigned short lut[SSD_BINS_PAD];
+  unsigned P[10], BL[10];          // word r at [1 + r]; zeros either side
+  int height[SSD_GPU_MAX_PLATEAUS], hmin[SSD_GPU_MAX_PLATEAUS], hmax[SSD_GPU_MAX_PLATEAUS];
+  unsigned np[SSD_GPU_MAX_PLATEAUS];
+  unsigned lock, pad[3];
+};
+
+template<class SRC>
+struct FsSrc;
+template<>
+struct FsSrc<SrcVertices>
+{
+  static constexpr int STEP_BYTES = SSD_FS_STEP_PX * 12;
+};
+template<>
+struct FsSrc<SrcDepth>
+{
+  static constexpr int STEP_BYTES = SSD_FS_STEP_PX * 2;
+};
+
+__device__ __forceinline__ const void *fs_src_base(const SrcVertices &s) { return s.xyz; }
+__device__ __forceinline__ const void *fs_src_base(const SrcDepth &s) { return s.z16; }
+
+__host__ __device__ inline size_t fs_smem_bytes(int step_bytes, int d_raw, int d_rec)
+{
+  return (size_t)SSD_FS_WARPS * d_raw * step_bytes + (size_t)SSD_FS_WARPS * d_rec * SSD_FS_REC_BYTES + (size_t)SSD_FS_WARPS * SSD_BINS_PAD * 2 +
+         sizeof(FsAcc) * SSD_FS_NB + sizeof(FsPeaks) + (size_t)SSD_FS_WARPS * d_raw * 8 + 128;
+}
+
+// point_code_scaled (ssd_device.cuh) that also hands out the point's position inside its height bin:
+// dfrac = (t - 0.5) - floor(t) in [-0.5, 0.5), t = (wz - z_min) * hir, exact remainder of the f32 value the bin came from.
+__device__ __forceinline__ unsigned point_code_scaled_d(const DevParams &p, float x, float y, float z, bool &uncertain, float &dfrac)
+{
+  const float m = max3abs_nan(x, y, z);
+  const float eps = fmaf(p.E1s, m, p.E0s);
+  float vx, vy;
+  f2_unpack(f2_affine(p.sxy2, p.sbxy2, x, y, z), vx, vy);
+  const float vz = fmaf(p.sa[8], z, fmaf(p.sa[7], y, fmaf(p.sa[6], x, p.sb[2])));
+  const float e1 = max3abs_nan(vx, vy, vz) - 1.0f;
+  const float MAGIC = 12582912.0f;
+  const float uf = fmaf(vz, p.Gf, p.Gm);
+  const float s = uf + MAGIC;
+  const float d = uf - (s - MAGIC);
+  const float thr = fmaf(-p.Gup, eps, p.thr0);
+  const bool out = e1 > eps;
+  const bool in_bin = e1 < -eps && fabsf(d) < thr;
+  const bool valid = z > 0.f;
+  uncertain = valid && !(out || in_bin);
+  dfrac = d;
+  const unsigned c = out ? SSD_CODE_OUT_OF_RANGE : ((unsigned)__float_as_int(s) & 0xffu);
+  return valid ? c : SSD_CODE_INVALID;
+}
+
+// exact fallback: the code by the double chain, and the height offset relative to THAT bin
+__device__ __noinline__ unsigned point_code_slow_d(const DevParams &p, float fx, float fy, float fz, int &d)
+{
+  const unsigned c = point_code(p, fx, fy, fz);
+  d = 0;
+  if(c < SSD_CODE_OUT_OF_RANGE)
+  {
+    const double t = (camera_to_world_z(p, fx, fy, fz) - p.z_min) * p.hir;
+    d = (int)rint((t - (double)c - 0.5) * (double)p.rec_mf);
+  }
+  return c;
+}
+
+__device__ __forceinline__ uint4 ld_volatile_v4(const void *ptr)
+{
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr) : "memory");
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Peaks of one frame, one warp: HeightsHistogram::findPeaks / filterPeaks (pointcloud.cpp:214-256), the plateau bands of
+// extractPlateauPoints (:300-335) as a bin -> label LUT, ground / first-outlined bookkeeping (:402-418). Same results as
+// k_peaks (which walks the bins serially), evaluated bin-parallel:
+//   rise(i) = hist[i] < hist[i+1], fall(i) = hist[i] > hist[i+1]   (i < n_bins - 1)
+//   ascending before i  <=>  the nearest j < i with rise(j) or fall(j) is a rise      (equal neighbours keep the flag)
+//   peak(i) = fall(i) && ascending && hist[i] >= min_peak_points && (2 hist[i] - hist[i-1] - hist[i+1]) * 2 > hist[i]
+//   band(i) = [i-1, i] if hist[i-1] > hist[i+1] else [i, i+1]; a bin claimed by two bands goes to the lower peak
+//   (peaks are at least two bins apart, so only the bands of the peaks at b-1, b, b+1 can hold bin b).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned fs_bit(const unsigned *words1, int idx) // words1[1 + r]; idx may be -2 .. 257
+{
+  return (words1[1 + (idx >> 5)] >> (idx & 31)) & 1u;
+}
+
+__device__ inline void fs_peaks(const DevParams &p, FrameDev &F, FsPeaks &K, int lane)
+{
+  if(lane == 0)
+  {
+    unsigned spin = 0;
+    while(atomicCAS(&K.lock, 0u, 1u) != 0u)
+    {
+      __nanosleep(32);
+      if(++spin > (1u << 24))
+        __trap();
+    }
+  }
+  __syncwarp();
+  __threadfence_block();
+  {
+    // the frame's histogram as the global atomics left it (L2)
+    const uint4 *src = reinterpret_cast<const uint4 *>(F.hist) + lane * 2;
+    const uint4 h0 = __ldcg(src), h1 = __ldcg(src + 1);
+    unsigned *dst = K.hist + 4 + lane * 8;
+    dst[0] = h0.x, dst[1] = h0.y, dst[2] = h0.z, dst[3] = h0.w;
+    dst[4] = h1.x, dst[5] = h1.y, dst[6] = h1.z, dst[7] = h1.w;
+    if(lane < 4)
+    {
+      K.hist[lane] = 0;
+      K.hist[4 + SSD_BINS_PAD + lane] = 0;
+    }
+    if(lane < 10)
+      K.P[lane] = K.BL[lane] = 0;
+  }
+  __syncwarp();
+  const unsigned *H = K.hist + 4;
+  const int last = p.n_bins - 1;
+  const unsigned lt = (1u << lane) - 1u;
+  unsigned R[8], Fm[8];
+#pragma unroll
+  for(int r = 0; r < 8; r++)
+  {
+    const int b = 32 * r + lane;
+    const unsigned c = H[b], s = H[b + 1];
+    const bool v = b < last;
+    R[r] = __ballot_sync(0xffffffffu, v && c < s);
+    Fm[r] = __ballot_sync(0xffffffffu, v && c > s);
+  }
+  unsigned Pw[8];
+  {
+    bool carry = false; // ascending at the start of word r
+#pragma unroll
+    for(int r = 0; r < 8; r++)
+    {
+      const int b = 32 * r + lane;
+      const unsigned c = H[b];
+      const unsigned E = R[r] | Fm[r];
+      const unsigned m = E & lt;
+      const bool asc = m ? ((R[r] >> (31 - __clz(m))) & 1u) != 0u : carry;
+      const bool fall = (Fm[r] >> lane) & 1u;
+      const bool peak = fall && asc && !(c < p.min_peak_points) && (unsigned)((c * 2u - H[b - 1] - H[b + 1]) * 2u) > c;
+      Pw[r] = __ballot_sync(0xffffffffu, peak);
+      const unsigned bl = __ballot_sync(0xffffffffu, H[b - 1] > H[b + 1]);
+      if(lane == 0)
+      {
+        K.P[1 + r] = Pw[r];
+        K.BL[1 + r] = bl;
+      }
+      if(E)
+        carry = ((R[r] >> (31 - __clz(E))) & 1u) != 0u;
+    }
+  }
+  __syncwarp();
+  int n_all = 0;
+#pragma unroll
+  for(int r = 0; r < 8; r++)
+    n_all += __popc(Pw[r]);
+  const int Kn = min(n_all, SSD_GPU_MAX_PLATEAUS);
+  unsigned status = n_all > SSD_GPU_MAX_PLATEAUS ? SSD_STATUS_TOO_MANY_PLATEAUS : 0u;
+  // uint16 wrap of heightMin - 1 (pointcloud.cpp:324): a peak at bin 1 with band [0, 1] -- necessarily the first peak --
+  // sends every point to the remainder; that plateau and all later ones stay empty
+  const bool wrapped = fs_bit(K.P, 1) && fs_bit(K.BL, 1);
+  if(wrapped)
+    status |= SSD_STATUS_HMIN_WRAP;
+  {
+    int base = 0;
+#pragma unroll
+    for(int r = 0; r < 8; r++)
+    {
+      const int b = 32 * r + lane;
+      const int cntlt = base + __popc(Pw[r] & lt); // peaks at bins < b
+      const bool pk = (Pw[r] >> lane) & 1u;
+      unsigned l = SSD_LABEL_REMAINDER;
+      if(!wrapped)
+      {
+        int k = -1;
+        if(fs_bit(K.P, b - 1) && !fs_bit(K.BL, b - 1))
+          k = cntlt - 1;
+        else if(pk)
+          k = cntlt;
+        else if(fs_bit(K.P, b + 1) && fs_bit(K.BL, b + 1))
+          k = cntlt;
+        if(k >= 0 && k < SSD_GPU_MAX_PLATEAUS)
+          l = (unsigned)k;
+      }
+      if(b == (int)SSD_CODE_OUT_OF_RANGE)
+        l = SSD_LABEL_OUT_OF_RANGE;
+      if(b == (int)SSD_CODE_INVALID)
+        l = SSD_LABEL_INVALID;
+      K.lut[b] = (unsigned short)l;
+      if(pk && cntlt < SSD_GPU_MAX_PLATEAUS)
+      {
+        const bool lo = fs_bit(K.BL, b) != 0u;
+        unsigned np = H[b];
+        if(lo)
+          np += (fs_bit(K.P, b - 2) && !fs_bit(K.BL, b - 2)) ? 0u : H[b - 1];
+        else
+          np += H[b + 1];
+        K.height[cntlt] = b;
+        K.hmin[cntlt] = lo ? b - 1 : b;
+        K.hmax[cntlt] = lo ? b : b + 1;
+        K.np[cntlt] = wrapped ? 0u : np;
+      }
+      base += __popc(Pw[r]);
+    }
+  }
+  __syncwarp();
+  // ground = the largest of the leading plateaus below minHeight (first maximum), outlines from the first plateau at or above it
+  const bool mine = lane < Kn;
+  const int height = mine ? K.height[lane] : 0;
+  const unsigned np = mine ? K.np[lane] : 0u;
+  const unsigned hi = __ballot_sync(0xffffffffu, mine && height >= p.min_height);
+  const int fo = hi ? __ffs(hi) - 1 : Kn;
+  const unsigned gnp = (mine && lane < fo) ? np : 0u;
+  const unsigned gmax = __reduce_max_sync(0xffffffffu, gnp);
+  const unsigned gb = __ballot_sync(0xffffffffu, lane < fo && mine && gnp == gmax);
+  const int ground = gmax > 0u ? __ffs(gb) - 1 : -1;
+  if(lane == 0)
+  {
+    F.n_nonzero = (unsigned)p.N - H[SSD_CODE_INVALID];
+    F.n_in_range = (unsigned)p.N - H[SSD_CODE_INVALID] - H[SSD_CODE_OUT_OF_RANGE];
+    F.n_plateaus = Kn;
+    F.ground_index = ground;
+    F.first_outlined = fo;
+    F.first_valid = -1;
+    F.n_steps = 0;
+    F.status = status;
+  }
+  if(mine)
+  {
+    PlateauDev &P = F.plat[lane];
+    P.height = height;
+    P.hmin = K.hmin[lane];
+    P.hmax = K.hmax[lane];
+    P.n_points = np;
+    P.valid = 0;
+    P.outlined = lane >= fo;
+    P.n_in_quad = 0;
+    P.quad_status = -1;
+    P.mean_z = 0;
+    P.sum_fix = 0;
+    P.sum_d = 0;
+    P.sum_c = 0;
+    P.n_sum = 0;
+    P.row_min = 0x7fffffff;
+    P.row_max = -1;
+    P.front_valid = 0;
+    for(int c4 = 0; c4 < 4; c4++)
+      P.quad_px[c4][0] = P.quad_px[c4][1] = P.quad_world[c4][0] = P.quad_world[c4][1] = 0;
+  }
+  // the plateau records must be visible before the LUT that announces them
+  __threadfence();
+  __syncwarp();
+  {
+    unsigned w[4];
+#pragma unroll
+    for(int i = 0; i < 4; i++)
+    {
+      unsigned e2[2];
+#pragma unroll
+      for(int h = 0; h < 2; h++)
+      {
+        const unsigned l = K.lut[lane * 8 + i * 2 + h];
+        unsigned e = l | SSD_LUT_VALID;
+        if((int)l >= fo && (int)l < Kn)
+          e |= SSD_LUT_OUTLINED;
+        if((int)l == ground)
+          e |= SSD_LUT_GROUND;
+        e2[h] = e;
+      }
+      w[i] = e2[0] | (e2[1] << 16);
+    }
+    *(reinterpret_cast<uint4 *>(F.lut16) + lane) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  __syncwarp();
+  if(lane == 0)
+  {
+    __threadfence_block();
+    atomicExch(&K.lock, 0u);
+  }
+}
+
+// a warp leaves phase 1 of frame f: the last warp of the CTA delivers the CTA's histogram; the last CTA evaluates the peaks
+__device__ inline void fs_leave_p1(const DevParams &p, const FsParams &a, FrameDev *frames, FsAcc *acc, FsPeaks &pk, int f, int lane)
+{
+  FsAcc &A = acc[f & (SSD_FS_NB - 1)];
+  __syncwarp();
+  unsigned last = 0;
+  if(lane == 0)
+  {
+    __threadfence_block();
+    last = atomicAdd(&A.p1_left, 1u) == SSD_FS_WARPS - 1 ? 1u : 0u;
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if(!last)
+    return;
+  __threadfence_block();
+  volatile unsigned *vh = A.hist;
+  for(int b = lane; b < SSD_BINS_PAD; b += 32)
+  {
+    const unsigned v = vh[b];
+    if(v)
+    {
+      atomicAdd(&frames[f].hist[b], v);
+      vh[b] = 0u;
+    }
+  }
+  if(lane == 0)
+  {
+    const unsigned ne = *(volatile unsigned *)&A.n_exact;
+    if(ne)
+    {
+      atomicAdd(&frames[f].n_exact_bin, ne);
+      A.n_exact = 0;
+    }
+    *(volatile unsigned *)&A.p1_left = 0u;
+  }
+  __threadfence();
+  __syncwarp();
+  unsigned glast = 0;
+  if(lane == 0)
+    glast = atomicAdd(&a.done[f], 1u) == gridDim.x - 1 ? 1u : 0u;
+  glast = __shfl_sync(0xffffffffu, glast, 0);
+  if(!glast)
+    return;
+  if(lane == 0)
+    a.done[f] = 0u; // self-resetting: nobody reads the counter after the last arrival
+  __threadfence();
+  fs_peaks(p, frames[f], pk, lane);
+}
+
+// a warp leaves phase 2 of frame f: the last warp of the CTA delivers the CTA's per-plateau BEV row ranges and counters
+__device__ inline void fs_leave_p2(FrameDev *frames, FsAcc *acc, int f, int lane)
+{
+  FsAcc &A = acc[f & (SSD_FS_NB - 1)];
+  __syncwarp();
+  unsigned last = 0;
+  if(lane == 0)
+  {
+    __threadfence_block();
+    last = atomicAdd(&A.p2_left, 1u) == SSD_FS_WARPS - 1 ? 1u : 0u;
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if(!last)
+    return;
+  __threadfence_block();
+  FrameDev &F = frames[f];
+  {
+    volatile int *rmin = A.rmin, *rmax = A.rmax;
+    const int hi = rmax[lane];
+    if(hi >= 0)
+    {
+      atomicMin(&F.plat[lane].row_min, rmin[lane]);
+      atomicMax(&F.plat[lane].row_max, hi);
+      rmin[lane] = 0x7fffffff;
+      rmax[lane] = -1;
+    }
+  }
+  if(lane == 0)
+  {
+    if(*(volatile unsigned *)&A.oob)
+    {
+      atomicOr(&F.status, SSD_STATUS_BEV_OOB);
+      A.oob = 0;
+    }
+    const unsigned nd = *(volatile unsigned *)&A.n_def;
+    if(nd)
+    {
+      atomicAdd(&F.n_def_bev, nd);
+      A.n_def = 0;
+    }
+    *(volatile unsigned *)&A.p2_left = 0u;
+  }
+  __threadfence_block();
+}
+
+// ---- phase 1 of one step: raw slot -> codes, histogram, records ----
+__device__ __forceinline__ void fs_unpack_raw(const SrcVertices &, const DevParams &, const unsigned char *raw, unsigned, int lane, float vx[4],
+                                              float vy[4], float vz[4])
+{
+  const float4 *s4 = reinterpret_cast<const float4 *>(raw) + lane * 3;
+  const float4 v0 = s4[0], v1 = s4[1], v2 = s4[2];
+  vx[0] = v0.x, vy[0] = v0.y, vz[0] = v0.z;
+  vx[1] = v0.w, vy[1] = v1.x, vz[1] = v1.y;
+  vx[2] = v1.z, vy[2] = v1.w, vz[2] = v2.x;
+  vx[3] = v2.y, vy[3] = v2.z, vz[3] = v2.w;
+}
+__device__ __forceinline__ void fs_unpack_raw(const SrcDepth &src, const DevParams &p, const unsigned char *raw, unsigned step, int lane, float vx[4],
+                                              float vy[4], float vz[4])
+{
+  FrameD f;
+  f.d2 = nullptr;
+  f.xn = src.xn;
+  f.yn = src.yn;
+  f.unit = src.unit;
+  f.wmagic = src.wmagic;
+  f.W = (unsigned)p.W;
+  WordD w;
+  w.d = reinterpret_cast<const uint2 *>(raw)[lane];
+  const unsigned i0 = step * SSD_FS_STEP_PX + (unsigned)lane * 4u;
+  const unsigned v = (unsigned)(((unsigned long long)i0 * f.wmagic) >> 40), u = i0 - v * f.W;
+  w.x4 = __ldg(reinterpret_cast<const float4 *>(f.xn + u));
+  w.y = __ldg(f.yn + v);
+  word_unpack(f, w, vx, vy, vz);
+}
+
+template<class SRC>
+__device__ __forceinline__ void fs_phase1(const DevParams &p, const SRC &src, const unsigned char *raw, unsigned char *rec, FsAcc &A, unsigned step,
+                                          int lane)
+{
+  float vx[4], vy[4], vz[4];
+  fs_unpack_raw(src, p, raw, step, lane, vx, vy, vz);
+  const float MAGIC = 12582912.0f;
+  const int zsh = 32 - p.rec_zbits;
+  unsigned c[4], zp[4];
+  bool unc[4];
+#pragma unroll
+  for(int j = 0; j < 4; j++)
+  {
+    float df;
+    c[j] = point_code_scaled_d(p, vx[j], vy[j], vz[j], unc[j], df);
+    zp[j] = (unsigned)__float_as_int(fmaf(df, p.rec_mf, MAGIC)) << zsh;
+  }
+  if(unc[0] || unc[1] || unc[2] || unc[3])
+  {
+    unsigned ne = 0;
+#pragma unroll
+    for(int j = 0; j < 4; j++)
+      if(unc[j])
+      {
+        int d;
+        c[j] = point_code_slow_d(p, vx[j], vy[j], vz[j], d);
+        zp[j] = (unsigned)d << zsh;
+        ne++;
+      }
+    atomicAdd(&A.n_exact, ne);
+  }
+  const unsigned cw = c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24);
+#pragma unroll
+  for(int j = 0; j < 4; j++)
+    atomicAdd(A.hist + c[j], 1u);
+  reinterpret_cast<unsigned *>(rec)[lane] = cw;
+  // records of the lane's in-range points (codes 254 / 255: out of range / invalid)
+  if((cw & 0xfefefefeu) != 0xfefefefeu)
+  {
+    unsigned r[4];
+#pragma unroll
+    for(int j = 0; j < 4; j++)
+    {
+      int ix, iy;
+      const bool ok = fast_pixel2(p, vx[j], vy[j], vz[j], ix, iy);
+      r[j] = zp[j] | (ok ? (((unsigned)iy << p.rec_bx) | (unsigned)ix) : ((unsigned)p.H << p.rec_bx));
+    }
+    reinterpret_cast<uint4 *>(rec + 128)[lane] = make_uint4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+// ---- phase 2 of one step: record slot -> labels, BEV bits, summaries ----
+template<class SRC>
+__device__ __forceinline__ void fs_phase2(const DevParams &p, const SRC &src, const FsParams &a, const unsigned char *rec, const unsigned short *lut,
+                                          FsAcc &A, unsigned frame, unsigned step, unsigned char *labels, unsigned *bev, unsigned bmw, int lane)
+{
+  const unsigned cw = reinterpret_cast<const unsigned *>(rec)[lane];
+  const size_t word = (size_t)frame * (size_t)(p.N >> 2) + (size_t)step * 32u + (unsigned)lane;
+  GroupSum *gs = a.sums + (((size_t)frame * (size_t)p.gs_steps + step) * 4u + (unsigned)(lane >> 3));
+  unsigned lab = cw, fl = 0, ol = 0;
+  if((cw & 0xfefefefeu) != 0xfefefefeu)
+  {
+    const unsigned e0 = lut[cw & 0xffu], e1 = lut[(cw >> 8) & 0xffu], e2 = lut[(cw >> 16) & 0xffu], e3 = lut[cw >> 24];
+    lab = (e0 & 0xffu) | ((e1 & 0xffu) << 8) | ((e2 & 0xffu) << 16) | (e3 << 24);
+    const unsigned K = SSD_LUT_OUTLINED | SSD_LUT_GROUND;
+    fl = ((e0 & K) ? 1u : 0u) | ((e1 & K) ? 2u : 0u) | ((e2 & K) ? 4u : 0u) | ((e3 & K) ? 8u : 0u);
+    ol = ((e0 >> 8) & 1u) | ((e1 >> 7) & 2u) | ((e2 >> 6) & 4u) | ((e3 >> 5) & 8u);
+  }
+  if(!(a.flags & SSD_FLAG_NO_LABELS))
+    reinterpret_cast<unsigned *>(labels)[word] = lab;
+  if(!__any_sync(0xffffffffu, fl != 0u))
+  {
+    if((lane & 7) == 0)
+      *reinterpret_cast<uint4 *>(gs) = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
+  const int bx = p.rec_bx, zsh = 32 - p.rec_zbits;
+  const unsigned mx = (1u << bx) - 1u, my = (1u << p.rec_by) - 1u;
+  int ixmin = 0x7fff, ixmax = 0, iymin = 0x7fff, iymax = 0, dsum = 0;
+  unsigned csum = 0, bad = 0;
+  // label of the lane's first flagged point; the lane is "uniform" when all its flagged points carry it
+  const unsigned l0 = (lab >> (8 * (__ffs(fl | 16u) - 1) & 31)) & 0xffu;
+  if(fl)
+  {
+    const uint4 rv = reinterpret_cast<const uint4 *>(rec + 128)[lane];
+    const unsigned r[4] = { rv.x, rv.y, rv.z, rv.w };
+    const unsigned bytes = ((fl * 0x00204081u) & 0x01010101u) * 0xffu;
+    bad = ((lab ^ (l0 * 0x01010101u)) & bytes) != 0u;
+    unsigned lidx = (frame * SSD_GPU_MAX_PLATEAUS + l0) * bmw;
+#pragma unroll
+    for(int j = 0; j < 4; j++)
+      if((fl >> j) & 1u)
+      {
+        const int ix = (int)(r[j] & mx), iy = (int)((r[j] >> bx) & my);
+        const unsigned l = (lab >> (8 * j)) & 0xffu;
+        if(iy >= p.H)
+        {
+          // the single-precision pixel was not certain (fast_pixel2): the exact double chain decides, from the vertex itself
+          bad = 1;
+          if((ol >> j) & 1u)
+          {
+            const typename SrcTraits<SRC>::Frame FR = src_frame(src, p, (size_t)frame * p.N);
+            float fx, fy, fz;
+            point_load(FR, step * SSD_FS_STEP_PX + (unsigned)lane * 4u + (unsigned)j, fx, fy, fz);
+            double wx, wy;
+            camera_to_world_xy(p, fx, fy, fz, wx, wy);
+            int x, y;
+            if(bev_pixel(p, wx, wy, x, y))
+            {
+              atomicOr(bev + ((size_t)(frame * SSD_GPU_MAX_PLATEAUS + l) * bmw + (size_t)y * p.wpr + (x >> 5)), 1u << (x & 31));
+              atomicMin(&A.rmin[l], y);
+              atomicMax(&A.rmax[l], y);
+            }
+            else
+              A.oob = 1;
+            atomicAdd(&A.n_def, 1u);
+          }
+          continue;
+        }
+        if((ol >> j) & 1u)
+        {
+          const unsigned base = bad ? (frame * SSD_GPU_MAX_PLATEAUS + l) * bmw : lidx;
+          atomicOr(bev + (base + (unsigned)iy * (unsigned)p.wpr + ((unsigned)ix >> 5)), 1u << (ix & 31));
+        }
+        ixmin = min(ixmin, ix);
+        ixmax = max(ixmax, ix);
+        iymin = min(iymin, iy);
+        iymax = max(iymax, iy);
+        dsum += (int)r[j] >> zsh;
+        csum += (cw >> (8 * j)) & 0xffu;
+      }
+  }
+  // 8-lane summary: one reduction instruction per quantity (members = the lanes of the lane's group)
+  const unsigned gm = 0xffu << (lane & 24);
+  const unsigned cnt = (unsigned)__popc(fl);
+  const unsigned lmin = __reduce_min_sync(gm, bad ? 0u : (fl ? l0 : 0xffu));
+  const unsigned lmax = __reduce_max_sync(gm, bad ? 0xffu : (fl ? l0 : 0u));
+  const unsigned cc = __reduce_add_sync(gm, cnt | (csum << 8));
+  const int gxmin = __reduce_min_sync(gm, ixmin), gxmax = __reduce_max_sync(gm, ixmax);
+  const int gymin = __reduce_min_sync(gm, iymin), gymax = __reduce_max_sync(gm, iymax);
+  const int gds = __reduce_add_sync(gm, dsum);
+  const unsigned gcnt = cc & 0xffu;
+  const bool uniform = lmin == lmax;
+  if((lane & 7) == 0)
+  {
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if(gcnt)
+    {
+      if(uniform)
+      {
+        o.x = (unsigned)gxmin | ((unsigned)gxmax << 16);
+        o.y = (unsigned)gymin | ((unsigned)gymax << 16);
+        o.z = (unsigned)gds;
+        o.w = (cc >> 8) | (lmin << 16) | (gcnt << 24);
+      }
+      else
+        o.w = SSD_GS_COMPLEX << 24;
+    }
+    *reinterpret_cast<uint4 *>(gs) = o;
+  }
+  // BEV rows touched, per plateau (the outline stages only that band): one pair of shared-memory reductions per group
+  // (all flagged points of a uniform group share the label, so any lane's `ol` tells whether it is outlined)
+  const unsigned gol = __reduce_or_sync(gm, ol);
+  if(uniform && gol)
+  {
+    if((lane & 7) == 0 && gymax >= gymin && gcnt)
+    {
+      atomicMin(&A.rmin[lmin], gymin);
+      atomicMax(&A.rmax[lmin], gymax);
+    }
+  }
+  else if(ol && iymax >= iymin)
+  {
+    // mixed labels inside the group (plateau boundaries in the image): per point
+    const uint4 rv = reinterpret_cast<const uint4 *>(rec + 128)[lane];
+    const unsigned r[4] = { rv.x, rv.y, rv.z, rv.w };
+#pragma unroll
+    for(int j = 0; j < 4; j++)
+      if((ol >> j) & 1u)
+      {
+        const int iy = (int)((r[j] >> bx) & my);
+        if(iy < p.H)
+        {
+          const unsigned l = (lab >> (8 * j)) & 0xffu;
+          atomicMin(&A.rmin[l], iy);
+          atomicMax(&A.rmax[l], iy);
+        }
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_frame_stream. grid = one CTA per SM (cooperative launch: all CTAs co-resident), block = 16 warps.
+// ---------------------------------------------------------------------------------------------
+struct FsCur
+{
+  unsigned k, f, s;
+};
+
+template<class SRC>
+__global__ void __launch_bounds__(SSD_FS_THREADS, 1) k_frame_stream(const __grid_constant__ DevParams p, const SRC src, const __grid_constant__ FsParams a,
+                                                                    unsigned char *__restrict__ labels, FrameDev *__restrict__ frames,
+                                                                    unsigned *__restrict__ bev, size_t bm_words)
+{
+  extern __shared__ __align__(128) unsigned char fs_smem[];
+  constexpr int RAW = FsSrc<SRC>::STEP_BYTES;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int d_raw = a.d_raw, d_rec = a.d_rec;
+  unsigned char *raw_all = fs_smem;
+  unsigned char *rec_all = raw_all + (size_t)SSD_FS_WARPS * d_raw * RAW;
+  unsigned short *lut_all = reinterpret_cast<unsigned short *>(rec_all + (size_t)SSD_FS_WARPS * d_rec * SSD_FS_REC_BYTES);
+  FsAcc *acc = reinterpret_cast<FsAcc *>(lut_all + SSD_FS_WARPS * SSD_BINS_PAD);
+  FsPeaks *pk = reinterpret_cast<FsPeaks *>(acc + SSD_FS_NB);
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(pk + 1);
+
+  {
+    unsigned *z = reinterpret_cast<unsigned *>(acc);
+    for(int i = tid; i < (int)(sizeof(FsAcc) * SSD_FS_NB / 4); i += SSD_FS_THREADS)
+      z[i] = 0u;
+    __syncthreads();
+    for(int i = tid; i < SSD_FS_NB * SSD_GPU_MAX_PLATEAUS; i += SSD_FS_THREADS)
+    {
+      acc[i / SSD_GPU_MAX_PLATEAUS].rmin[i % SSD_GPU_MAX_PLATEAUS] = 0x7fffffff;
+      acc[i / SSD_GPU_MAX_PLATEAUS].rmax[i % SSD_GPU_MAX_PLATEAUS] = -1;
+    }
+    if(tid == 0)
+      pk->lock = 0u;
+    if(lane == 0)
+    {
+      for(int i = 0; i < d_raw; i++)
+        mbar_init((unsigned)__cvta_generic_to_shared(bars + warp * d_raw + i), 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+  }
+
+  unsigned char *raw = raw_all + (size_t)warp * d_raw * RAW;
+  unsigned char *rec = rec_all + (size_t)warp * d_rec * SSD_FS_REC_BYTES;
+  unsigned short *lut = lut_all + warp * SSD_BINS_PAD;
+  const unsigned raw_sa = (unsigned)__cvta_generic_to_shared(raw);
+  const unsigned bar_sa = (unsigned)__cvta_generic_to_shared(bars + warp * d_raw);
+
+  const unsigned S = (unsigned)p.gs_steps;
+  const unsigned TW = gridDim.x * SSD_FS_WARPS, gw = blockIdx.x * SSD_FS_WARPS + warp;
+  const unsigned long long G = (unsigned long long)a.n_frames * S;
+  const unsigned K_total = gw < G ? (unsigned)((G - gw + TW - 1) / TW) : 0u;
+  const unsigned df = TW / S, ds = TW % S;
+  const unsigned n_frames = (unsigned)a.n_frames;
+  FsCur ct, c1, c2;
+  ct.k = 0, ct.f = gw / S, ct.s = gw % S;
+  c1 = ct;
+  c2 = ct;
+#define FS_ADV(c)          \
+  do                       \
+  {                        \
+    (c).k++;               \
+    (c).s += ds;           \
+    (c).f += df;           \
+    if((c).s >= S)         \
+    {                      \
+      (c).s -= S;          \
+      (c).f++;             \
+    }                      \
+  } while(0)
+#define FS_FRAME(c) ((c).k < K_total ? (c).f : n_frames)
+  unsigned slot_t = 0, slot_1 = 0, phase_1 = 0, rslot_1 = 0, rslot_2 = 0;
+  unsigned left1 = 0, left2 = 0; // frames this warp has left (phase 1 / phase 2): [0, left)
+  int lut_f = -1;                // frame whose LUT the warp's copy holds
+  const unsigned bmw = (unsigned)bm_words;
+  const unsigned char *gsrc = reinterpret_cast<const unsigned char *>(fs_src_base(src));
+
+  // frames before the warp's first step
+  for(; left1 < FS_FRAME(c1); left1++)
+    fs_leave_p1(p, a, frames, acc, *pk, (int)left1, lane);
+  for(; left2 < FS_FRAME(c2); left2++)
+    fs_leave_p2(frames, acc, (int)left2, lane);
+
+  unsigned idle = 0;
+  while(c2.k < K_total)
+  {
+    // 1. keep the raw ring full
+    while(ct.k < K_total && ct.k - c1.k < (unsigned)d_raw)
+    {
+      if(lane == 0)
+      {
+        const unsigned bar = bar_sa + slot_t * 8u;
+        mbar_expect_tx(bar, (unsigned)RAW);
+        bulk_g2s(raw_sa + slot_t * (unsigned)RAW, gsrc + ((size_t)ct.f * S + ct.s) * (size_t)RAW, (unsigned)RAW, bar);
+      }
+      slot_t = slot_t + 1 == (unsigned)d_raw ? 0u : slot_t + 1;
+      FS_ADV(ct);
+    }
+    // 2. is the frame of the oldest pending phase-2 step ready? (asynchronous: the answer is looked at after phase 1)
+    const bool pending = c2.k < c1.k;
+    bool polled = false;
+    uint4 pv = make_uint4(0u, 0u, 0u, 0u);
+    if(pending && (int)c2.f != lut_f)
+    {
+      pv = ld_volatile_v4(reinterpret_cast<const uint4 *>(frames[c2.f].lut16) + lane);
+      polled = true;
+    }
+    bool did = false;
+    // 3. phase 1 of the next loaded step
+    if(c1.k < K_total && c1.k - c2.k < (unsigned)d_rec && c1.f - c2.f < (unsigned)(SSD_FS_NB - 1))
+    {
+      mbar_wait(bar_sa + slot_1 * 8u, phase_1);
+      fs_phase1(p, src, raw + (size_t)slot_1 * RAW, rec + (size_t)rslot_1 * SSD_FS_REC_BYTES, acc[c1.f & (SSD_FS_NB - 1)], c1.s, lane);
+      __syncwarp();
+      if(++slot_1 == (unsigned)d_raw)
+      {
+        slot_1 = 0;
+        phase_1 ^= 1u;
+      }
+      rslot_1 = rslot_1 + 1 == (unsigned)d_rec ? 0u : rslot_1 + 1;
+      FS_ADV(c1);
+      for(; left1 < FS_FRAME(c1); left1++)
+        fs_leave_p1(p, a, frames, acc, *pk, (int)left1, lane);
+      did = true;
+    }
+    // 4. the poll's answer
+    if(polled)
+    {
+      const unsigned ok = (pv.x & pv.y & pv.z & pv.w & 0x80008000u) == 0x80008000u;
+      if(__all_sync(0xffffffffu, ok))
+      {
+        __threadfence();
+        reinterpret_cast<uint4 *>(lut)[lane] = pv;
+        __syncwarp();
+        lut_f = (int)c2.f;
+      }
+    }
+    // 5. phase 2 of every pending step of that frame
+    while(c2.k < c1.k && (int)c2.f == lut_f)
+    {
+      fs_phase2(p, src, a, rec + (size_t)rslot_2 * SSD_FS_REC_BYTES, lut, acc[c2.f & (SSD_FS_NB - 1)], c2.f, c2.s, labels, bev, bmw, lane);
+      __syncwarp();
+      rslot_2 = rslot_2 + 1 == (unsigned)d_rec ? 0u : rslot_2 + 1;
+      FS_ADV(c2);
+      for(; left2 < FS_FRAME(c2); left2++)
+        fs_leave_p2(frames, acc, (int)left2, lane);
+      did = true;
+    }
+    if(did)
+      idle = 0;
+    else
+    {
+      if(++idle > (1u << 22))
+        __trap(); // a frame barrier that never completes (a CTA not resident?) traps instead of hanging the GPU
+      __nanosleep(100);
+    }
+  }
+#undef FS_ADV
+#undef FS_FRAME
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_quad_sum: getPointsInQuadrilateral + calcAverageZ (pointcloud.cpp:560-581) from the summaries k_frame_stream left.
+// One summary (32 pixels) per lane and warp-tile. A summary whose BEV pixel box -- widened to the world rectangle every
+// point with such a pixel can lie in -- sits inside the verified inner box of its step's QuadrilateralTest
+// (quadtest_inner_box: isPointWithin() is true on the whole box) contributes its count and height sums wholesale; one
+// entirely beyond the reject box contributes nothing; the rest (an edge of the quadrilateral crosses it, mixed labels, an
+// uncertain pixel, ground points whose BEV columns detectFrontEdge looks at) goes point by point through the same dense
+// pass as k_quad_reduce (qr_dense), re-reading those 32 vertices.
+// ---------------------------------------------------------------------------------------------
+struct QuadSumShared
+{
+  int sd[SSD_GPU_MAX_PLATEAUS];
+  unsigned sc[SSD_GPU_MAX_PLATEAUS], sn[SSD_GPU_MAX_PLATEAUS];
+};
+
+template<class SRC>
+__global__ void __launch_bounds__(SSD_PT_THREADS, SSD_QR_MINB) k_quad_sum(const __grid_constant__ DevParams p, const SRC src,
+                                                                          const unsigned char *__restrict__ labels, FrameDev *__restrict__ frames,
+                                                                          unsigned *__restrict__ bev, size_t bm_words, const GroupSum *__restrict__ sums)
+{
+  __shared__ QuadReduceShared S;
+  __shared__ QuadSumShared Q;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int frame = blockIdx.y;
+  FrameDev &F = frames[frame];
+  const unsigned amask = F.quad_amask;
+  if(amask == 0u)
+    return; // no valid plateau: nothing is emitted (pointcloud.cpp:434)
+  const int ground = F.ground_index;
+  const size_t fbase = (size_t)frame * p.N;
+  const unsigned *lab32 = reinterpret_cast<const unsigned *>(labels + fbase);
+  unsigned *gbev = ground >= 0 ? bev + ((size_t)frame * SSD_GPU_MAX_PLATEAUS + ground) * bm_words : nullptr;
+  const int ngroups = p.N >> 5;
+  const uint4 *gs = reinterpret_cast<const uint4 *>(sums) + (size_t)frame * ngroups;
+  int wt, wt_end, wt_stride;
+  warp_tile_range((p.N + SSD_WT_PX - 1) / SSD_WT_PX, warp, wt, wt_end, wt_stride);
+
+  qr_init(S, F, amask, tid);
+  if(tid < SSD_GPU_MAX_PLATEAUS)
+  {
+    Q.sd[tid] = 0;
+    Q.sc[tid] = 0;
+    Q.sn[tid] = 0;
+  }
+  __syncthreads();
+
+  unsigned short *act = S.L.act[warp];
+  unsigned *labs = S.L.lab[warp];
+  QrWarp W = { 0xffu, 0u, 0u, 0u, 0ull, 0x7fffffff, -1 };
+  const typename SrcTraits<SRC>::Frame FR = src_frame(src, p, fbase);
+  // the lane's running run of whole summaries (consecutive summaries of a lane mostly share the label)
+  unsigned run_l = 0xffu, run_n = 0, run_c = 0;
+  int run_d = 0;
+  const int c0 = p.W / 2 - 2;
+
+  for(; wt < wt_end; wt += wt_stride)
+  {
+    const unsigned wbase = (unsigned)wt * (SSD_WT_PX / 4);
+    const int g = wt * 32 + lane;
+    uint4 gv = make_uint4(0u, 0u, 0u, 0u);
+    if(g < ngroups)
+      gv = __ldg(gs + g);
+    if(wt + wt_stride < wt_end)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(gs + (size_t)(wt + wt_stride) * 32 + lane));
+    const unsigned count = gv.w >> 24, l = (gv.w >> 16) & 0xffu;
+    bool per_point = count == SSD_GS_COMPLEX;
+    if(count != 0u && !per_point && ((amask >> (l & 31u)) & 1u) && l < SSD_GPU_MAX_PLATEAUS)
+    {
+      const int ixmin = (int)(gv.x & 0xffffu), ixmax = (int)(gv.x >> 16), iymin = (int)(gv.y & 0xffffu), iymax = (int)(gv.y >> 16);
+      // world rectangle of the pixel box (f32; gs_margin covers the rounding of these four values and of the differences below)
+      const float x0 = fmaf((float)ixmin, p.gs_xw, p.gs_x0), x1 = fmaf((float)(ixmax + 1), p.gs_xw, p.gs_x0);
+      const float y1 = fmaf(-(float)iymin, p.gs_yw, p.gs_y0), y0 = fmaf(-(float)(iymax + 1), p.gs_yw, p.gs_y0);
+      const float4 ib = S.fast[l].ibe;
+      const float2 rj = S.fast[l].rj;
+      const float ax = fmaxf(fabsf(x0 - ib.x), fabsf(x1 - ib.x)), ay = fmaxf(fabsf(y0 - ib.y), fabsf(y1 - ib.y));
+      const bool inside = ax < ib.z - p.gs_margin && ay < ib.w - p.gs_margin;
+      const bool outside = x0 - ib.x > rj.x + p.gs_margin || ib.x - x1 > rj.x + p.gs_margin || y0 - ib.y > rj.y + p.gs_margin ||
+                           ib.y - y1 > rj.y + p.gs_margin;
+      bool whole = inside;
+      if(inside && (int)l == ground)
+      {
+        // ground points in the pixel columns detectFrontEdge probes need their BEV bit: point by point
+        const unsigned r = (unsigned)(ixmin - c0 + 50 * 128) % 50u;
+        if(r < 5u || r + (unsigned)(ixmax - ixmin) >= 50u)
+          whole = false;
+      }
+      if(whole)
+      {
+        if(l != run_l)
+        {
+          if(run_n)
+          {
+            atomicAdd(&Q.sd[run_l], run_d);
+            atomicAdd(&Q.sc[run_l], run_c);
+            atomicAdd(&Q.sn[run_l], run_n);
+          }
+          run_l = l;
+          run_d = 0;
+          run_c = 0;
+          run_n = 0;
+        }
+        run_d += (int)gv.z;
+        run_c += gv.w & 0xffffu;
+        run_n += count;
+      }
+      else if(!outside)
+        per_point = true;
+    }
+    if(!__any_sync(0xffffffffu, per_point))
+      continue;
+    // ---- compaction of the 4-point words of the per-point summaries (word index within the warp-tile: lane * 8 + it) ----
+    uint4 la = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu), lb = la;
+    if(per_point)
+    {
+      const uint4 *lp = reinterpret_cast<const uint4 *>(lab32 + (size_t)g * 8);
+      la = __ldg(lp);
+      lb = __ldg(lp + 1);
+    }
+    const unsigned lw8[8] = { la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w };
+    unsigned n = 0;
+#pragma unroll
+    for(int it = 0; it < 8; it++)
+    {
+      const unsigned lw = lw8[it];
+      const unsigned am4 = (((~lw >> 7) & 0x01010101u) * 0x10204080u) >> 28; // bit j <-> byte j < 128 (a plateau label)
+      const unsigned b = __ballot_sync(0xffffffffu, am4 != 0u);
+      if(am4)
+      {
+        const unsigned widx = (unsigned)(lane * 8 + it);
+        labs[widx] = lw;
+        word_prefetch_l2(FR, wbase + widx);
+        act[n + __popc(b & ((1u << lane) - 1u))] = (unsigned short)((widx << 4) | am4);
+      }
+      n += __popc(b);
+    }
+    if(n == 0)
+      continue;
+    __syncwarp();
+    qr_dense<SRC>(p, FR, S, W, F, amask, ground, gbev, wbase, n, warp, lane);
+    __syncwarp();
+  }
+  if(run_n)
+  {
+    atomicAdd(&Q.sd[run_l], run_d);
+    atomicAdd(&Q.sc[run_l], run_c);
+    atomicAdd(&Q.sn[run_l], run_n);
+  }
+  qr_epilogue(S, W, F, ground, tid, lane); // (contains the block barrier)
+  if(tid < SSD_GPU_MAX_PLATEAUS && Q.sn[tid])
+  {
+    atomicAdd(reinterpret_cast<unsigned long long *>(&F.plat[tid].sum_d), (unsigned long long)(long long)Q.sd[tid]);
+    atomicAdd(&F.plat[tid].sum_c, (unsigned long long)Q.sc[tid]);
+    atomicAdd(&F.plat[tid].n_sum, Q.sn[tid]);
+    atomicAdd(&F.plat[tid].n_in_quad, Q.sn[tid]);
+  }
+}
