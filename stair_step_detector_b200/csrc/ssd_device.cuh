@@ -138,7 +138,8 @@ struct FrameDev
   unsigned hist[SSD_BINS_PAD];
   unsigned short lut16[SSD_BINS_PAD]; // bin code -> segment label | 0x100 if that label gets a BEV image (k_peaks)
   unsigned quad_amask;                // labels k_quad_reduce reduces: ground + valid plateaus with a usable test (k_frame_logic)
-  unsigned pad_a[3];
+  unsigned ready;                     // k_frame_stream: plateau records and lut16 are written (the frame barrier's flag)
+  unsigned pad_a[2];
   QuadFilterDev qf[SSD_GPU_MAX_PLATEAUS]; // f32 image of each step's QuadrilateralTest (k_frame_logic)
   unsigned status;
   int n_plateaus;

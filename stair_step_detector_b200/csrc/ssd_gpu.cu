@@ -63,9 +63,11 @@ struct ssd_gpu_ctx
   ssd_gpu_intrinsics intr{};                    // intrinsics the tables were built for
   // resident-frame path (ssd_kernels_stream.cuh): one persistent kernel per chunk instead of the three point passes
   bool resident = false;
-  int fs_grid = 0, fs_d_raw = 4, fs_d_rec = 6;
+  int fs_grid = 0, fs_d_raw = 4, fs_d_rec = 0, fs_lag_frames = 8;
   GroupSum *d_sums = nullptr;     // n_streams x chunk_frames x N/32 summaries
   unsigned *d_done = nullptr;     // n_streams x chunk_frames frame counters (self-resetting)
+  unsigned char *d_recs = nullptr; // record ring of k_frame_stream (one kernel at a time uses it): grid x 16 warps x fs_d_rec slots, L2-resident
+  unsigned long long *d_prof = nullptr; // SSD_GPU_FS_PROF=1: cycle counters of k_frame_stream
   cudaEvent_t ev_fs{};            // the persistent kernels of consecutive chunks never overlap (each wants every SM)
   bool fs_pending = false;
   int pt_blocks_target = 0;       // blocks per launch of the tile-looping point kernels
@@ -511,6 +513,17 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, const uin
     a.flags = 0;
     a.done = ctx->d_done + (size_t)s * ctx->chunk_frames;
     a.sums = ctx->d_sums + (size_t)s * ctx->chunk_frames * (size_t)(p.N / 32);
+    a.recs = ctx->d_recs;
+    a.prof = ctx->d_prof;
+    a.prof_warp_off = FS_PROF_HDR + (size_t)FS_PROF_PER_FRAME * ctx->chunk_frames;
+    if(ctx->d_prof)
+    {
+      std::vector<unsigned long long> init(FS_PROF_HDR + (size_t)FS_PROF_PER_FRAME * ctx->chunk_frames + (size_t)8 * ctx->fs_grid * SSD_FS_WARPS, 0ull);
+      for(int f = 0; f < ctx->chunk_frames; f++)
+        init[FS_PROF_HDR + (size_t)f * FS_PROF_PER_FRAME + 0] = init[FS_PROF_HDR + (size_t)f * FS_PROF_PER_FRAME + 3] = ~0ull;
+      CK(cudaStreamSynchronize(st));
+      CK(cudaMemcpy(ctx->d_prof, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
+    }
     size_t bmw = ctx->bm_words;
     DevParams pp = p;
     if(ctx->fs_pending)
@@ -643,6 +656,8 @@ void ssd_gpu_destroy(ssd_gpu_ctx *ctx)
   cudaFree(ctx->d_bev);
   cudaFree(ctx->d_sums);
   cudaFree(ctx->d_done);
+  cudaFree(ctx->d_recs);
+  cudaFree(ctx->d_prof);
   if(ctx->ev_fs)
     cudaEventDestroy(ctx->ev_fs);
   cudaFree(ctx->d_img);
@@ -851,12 +866,18 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
     if(want && coop && dp.rec_zbits > 0 && dp.gs_steps >= SSD_FS_WARPS)
     {
       grid = std::min(grid, dp.gs_steps / SSD_FS_WARPS); // at least one step per warp and frame
+      // record ring: fs_lag_frames frames of a warp's steps (phase 2 may trail phase 1 by that much: the frame barrier's
+      // latency and the skew between the CTAs disappear in it); ~3.9 MB per frame at 1024x768, re-used before L2 evicts it
+      if(const char *e = getenv("SSD_GPU_FS_LAG"))
+        ctx->fs_lag_frames = std::max(1, std::min(SSD_FS_NB - 3, atoi(e)));
       const int per_warp = (dp.gs_steps + grid * SSD_FS_WARPS - 1) / (grid * SSD_FS_WARPS);
+      if(!ctx->fs_d_rec)
+        ctx->fs_d_rec = (int)(((long long)ctx->fs_lag_frames * dp.gs_steps + (long long)grid * SSD_FS_WARPS - 1) / ((long long)grid * SSD_FS_WARPS)) + 1;
       ctx->fs_d_rec = std::max(ctx->fs_d_rec, per_warp + 2);
       const size_t sm_v = fs_smem_bytes(FsSrc<SrcVertices>::STEP_BYTES, ctx->fs_d_raw, ctx->fs_d_rec);
       const size_t sm_d = fs_smem_bytes(FsSrc<SrcDepth>::STEP_BYTES, ctx->fs_d_raw, ctx->fs_d_rec);
       int occ = 0;
-      if(sm_v <= (size_t)max_optin && ctx->fs_d_rec <= 64 &&
+      if(sm_v <= (size_t)max_optin &&
          cudaFuncSetAttribute(k_frame_stream<SrcVertices>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_v) == cudaSuccess &&
          cudaFuncSetAttribute(k_frame_stream<SrcDepth>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_d) == cudaSuccess &&
          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_frame_stream<SrcVertices>, SSD_FS_THREADS, sm_v) == cudaSuccess && occ >= 1)
@@ -866,8 +887,13 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
         const size_t n_sums = (size_t)ctx->n_streams * ctx->chunk_frames * (size_t)(dp.N / 32);
         CKC(cudaMalloc(&ctx->d_sums, n_sums * sizeof(GroupSum)));
         CKC(cudaMalloc(&ctx->d_done, (size_t)ctx->n_streams * ctx->chunk_frames * sizeof(unsigned)));
+        CKC(cudaMalloc(&ctx->d_recs, (size_t)grid * SSD_FS_WARPS * ctx->fs_d_rec * SSD_FS_REC_BYTES));
         CKC(cudaMemset(ctx->d_done, 0, (size_t)ctx->n_streams * ctx->chunk_frames * sizeof(unsigned)));
         CKC(cudaEventCreateWithFlags(&ctx->ev_fs, cudaEventDisableTiming));
+        if(getenv("SSD_GPU_FS_PROF"))
+        {
+          CKC(cudaMalloc(&ctx->d_prof, 8 * (FS_PROF_HDR + (size_t)FS_PROF_PER_FRAME * ctx->chunk_frames + (size_t)8 * grid * SSD_FS_WARPS)));
+        }
       }
       cudaGetLastError();
     }
@@ -1045,6 +1071,73 @@ static int process_common(ssd_gpu_ctx *ctx, const float *xyz, const uint16_t *z1
   CK(cudaEventRecord(ctx->ev_stop, ctx->stream[0]));
   CK(cudaEventSynchronize(ctx->ev_stop));
   CK(cudaGetLastError());
+  if(ctx->d_prof)
+  {
+    // (profiling runs use one chunk per call: the buffer is reset before every launch)
+    const int nf = std::min(n_frames, ctx->chunk_frames);
+    const size_t woff = FS_PROF_HDR + (size_t)FS_PROF_PER_FRAME * ctx->chunk_frames;
+    std::vector<unsigned long long> h(woff + (size_t)8 * ctx->fs_grid * SSD_FS_WARPS);
+    CK(cudaMemcpy(h.data(), ctx->d_prof, h.size() * 8, cudaMemcpyDeviceToHost));
+    const double w = h[5] ? (double)h[5] : 1.0;
+    fprintf(stderr, "[fs prof] warps %llu  per warp: total %.0f cyc, phase1 %.0f, phase2 %.0f, TMA wait %.0f, idle loops %.1f (input done %.1f, ring full %.1f, other %.1f; mean lag %.2f frames), polls %.1f\n",
+            h[5], h[2] / w, h[0] / w, h[1] / w, h[6] / w, h[3] / w, h[7] / w, h[8] / w, h[9] / w, h[3] ? (double)h[10] / (double)h[3] : 0.0, h[4] / w);
+    fprintf(stderr, "[fs prof] per warp: busy iterations %.0f cyc, idle iterations %.0f cyc; section TMA issue %.0f, sections prefetch+poll issue %.0f\n", h[11] / w, h[12] / w, h[13] / w, h[14] / w);
+    double skew = 0, own = 0, peaks = 0, detect = 0, p2span = 0, period = 0;
+    int cnt = 0;
+    for(int f = 16; f + 16 < nf; f++)
+    {
+      const unsigned long long *q = &h[FS_PROF_HDR + (size_t)f * FS_PROF_PER_FRAME];
+      skew += (double)(q[5] - q[0]);
+      own += (double)q[1] - (double)q[5];
+      peaks += (double)(q[2] - q[1]);
+      detect += (double)q[3] - (double)q[2];
+      p2span += (double)(q[4] - q[3]);
+      period += (double)(q[5 + FS_PROF_PER_FRAME] - q[5]);
+      cnt++;
+    }
+    if(n_frames >= 64)
+    {
+      // per CTA: sums over its warps
+      double best_idle = 1e30, worst_idle = -1;
+      int bi = -1, wi = -1;
+      std::vector<double> ci(ctx->fs_grid, 0.0);
+      for(int c = 0; c < ctx->fs_grid; c++)
+      {
+        for(int q = 0; q < SSD_FS_WARPS; q++)
+          ci[c] += (double)h[woff + ((size_t)c * SSD_FS_WARPS + q) * 8 + 3];
+        if(ci[c] < best_idle)
+          best_idle = ci[c], bi = c;
+        if(ci[c] > worst_idle)
+          worst_idle = ci[c], wi = c;
+      }
+      for(int c : { bi, wi })
+      {
+        double s8[8] = { 0 };
+        for(int q = 0; q < SSD_FS_WARPS; q++)
+          for(int i = 0; i < 8; i++)
+            s8[i] += (double)h[woff + ((size_t)c * SSD_FS_WARPS + q) * 8 + i] / SSD_FS_WARPS;
+        fprintf(stderr, "[fs prof] CTA %d (%s idle): per warp p1 %.0f p2 %.0f tma %.0f idle loops %.0f (ring %.0f) total %.0f leave %.0f peaks %.0f\n", c,
+                c == bi ? "least" : "most", s8[0], s8[1], s8[2], s8[3], s8[5], s8[4], s8[6], s8[7]);
+      }
+      {
+        double mn = 1e30, mx = 0, sm = 0;
+        const int nw = ctx->fs_grid * SSD_FS_WARPS;
+        for(int q = 0; q < nw; q++)
+        {
+          const double v = (double)h[woff + (size_t)q * 8 + 0] + (double)h[woff + (size_t)q * 8 + 1];
+          mn = std::min(mn, v), mx = std::max(mx, v), sm += v;
+        }
+        fprintf(stderr, "[fs prof] phase1+phase2 cycles per warp: min %.0f mean %.0f max %.0f\n", mn, sm / nw, mx);
+      }
+      int n_low = 0;
+      for(int c = 0; c < ctx->fs_grid; c++)
+        n_low += ci[c] < 0.25 * worst_idle;
+      fprintf(stderr, "[fs prof] CTAs with less than a quarter of the worst CTA's idle loops: %d of %d\n", n_low, ctx->fs_grid);
+    }
+    if(cnt)
+      fprintf(stderr, "[fs prof] per frame (ns): first -> last CTA delivered %.0f, -> owner saw it complete %.0f, -> LUT published %.0f, -> first phase-2 step %.0f, phase-2 span %.0f, period %.0f\n",
+              skew / cnt, own / cnt, peaks / cnt, detect / cnt, p2span / cnt, period / cnt);
+  }
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop));
   ctx->timing.total_ms = ms;

@@ -27,9 +27,11 @@
 #pragma once
 #include "ssd_kernels_points.cuh"
 
+#ifndef SSD_FS_WARPS
 #define SSD_FS_WARPS 16
+#endif
 #define SSD_FS_THREADS (SSD_FS_WARPS * 32)
-#define SSD_FS_NB 8              // frames a CTA can have in flight (accumulator slots)
+#define SSD_FS_NB 16             // frames a CTA can have in flight (accumulator / LUT slots)
 #define SSD_FS_STEP_PX 128       // points per step: 32 lanes x 4
 #define SSD_FS_REC_BYTES 640     // record-ring slot: 32 code words + 32 x 4 records
 #define SSD_LUT_OUTLINED 0x100u  // lut16 flags: the label gets a BEV image
@@ -50,10 +52,13 @@ struct __align__(16) GroupSum
 struct FsParams
 {
   int n_frames;
-  int d_raw, d_rec;   // ring depths per warp (slots)
+  int d_raw, d_rec;   // ring depths per warp (slots): raw vertices in shared memory, records in global memory (L2)
+  unsigned char *recs; // record ring: grid x SSD_FS_WARPS x d_rec slots of SSD_FS_REC_BYTES
   int flags;          // SSD_FLAG_NO_LABELS
   unsigned *done;     // per frame: CTAs that have delivered their histogram (self-resetting)
   GroupSum *sums;     // n_frames x steps x 4
+  unsigned long long *prof; // optional cycle counters (SSD_GPU_FS_PROF=1), else nullptr
+  size_t prof_warp_off;
 };
 
 struct FsAcc // per in-flight frame (slot f % SSD_FS_NB) of one CTA
@@ -67,10 +72,16 @@ struct FsPeaks // scratch of the warp that completes a frame (one at a time per 
 {
   unsigned hist[SSD_BINS_PAD + 8]; // bin b at [4 + b]; zeros either side
   unsigned short lut[SSD_BINS_PAD];
-  unsigned P[10], BL[10];          // word r at [1 + r]; zeros either side
   int height[SSD_GPU_MAX_PLATEAUS], hmin[SSD_GPU_MAX_PLATEAUS], hmax[SSD_GPU_MAX_PLATEAUS];
   unsigned np[SSD_GPU_MAX_PLATEAUS];
   unsigned lock, pad[3];
+};
+
+struct FsLut // the CTA's copies of the frames' bin -> label LUTs (slot f % SSD_FS_NB), filled by whichever warp sees the frame ready first
+{
+  unsigned short lut[SSD_FS_NB][SSD_BINS_PAD];
+  int frame1[SSD_FS_NB];    // frame + 1 whose LUT the slot holds
+  unsigned busy[SSD_FS_NB]; // a warp of the CTA is asking global memory about this slot
 };
 
 template<class SRC>
@@ -91,7 +102,8 @@ __device__ __forceinline__ const void *fs_src_base(const SrcDepth &s) { return s
 
 __host__ __device__ inline size_t fs_smem_bytes(int step_bytes, int d_raw, int d_rec)
 {
-  return (size_t)SSD_FS_WARPS * d_raw * step_bytes + (size_t)SSD_FS_WARPS * d_rec * SSD_FS_REC_BYTES + (size_t)SSD_FS_WARPS * SSD_BINS_PAD * 2 +
+  (void)d_rec;
+  return (size_t)SSD_FS_WARPS * d_raw * step_bytes + sizeof(FsLut) +
          sizeof(FsAcc) * SSD_FS_NB + sizeof(FsPeaks) + (size_t)SSD_FS_WARPS * d_raw * 8 + 128;
 }
 
@@ -132,6 +144,28 @@ __device__ __noinline__ unsigned point_code_slow_d(const DevParams &p, float fx,
   return c;
 }
 
+// exact BEV pixel of an in-range point, packed as a record's pixel part; iy = H when it falls outside the image
+__device__ __noinline__ unsigned pixel_slow(const DevParams &p, float fx, float fy, float fz)
+{
+  double wx, wy;
+  camera_to_world_xy(p, fx, fy, fz, wx, wy);
+  int ix, iy;
+  world_to_image(p, wx, wy, ix, iy);
+  if(ix >= 0 && ix < p.W && iy >= 0 && iy < p.H)
+    return ((unsigned)iy << p.rec_bx) | (unsigned)ix;
+  return (unsigned)p.H << p.rec_bx;
+}
+
+__device__ __forceinline__ unsigned long long fs_gtime()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// per-frame time stamps (ns) when profiling: [0] first CTA arrival, [1] last, [2] LUT published, [3] first / [4] last phase-2 step
+#define FS_PROF_HDR 16
+#define FS_PROF_PER_FRAME 8
+
 __device__ __forceinline__ uint4 ld_volatile_v4(const void *ptr)
 {
   uint4 v;
@@ -149,12 +183,23 @@ __device__ __forceinline__ uint4 ld_volatile_v4(const void *ptr)
 //   band(i) = [i-1, i] if hist[i-1] > hist[i+1] else [i, i+1]; a bin claimed by two bands goes to the lower peak
 //   (peaks are at least two bins apart, so only the bands of the peaks at b-1, b, b+1 can hold bin b).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned fs_bit(const unsigned *words1, int idx) // words1[1 + r]; idx may be -2 .. 257
+// bit (32 r + lane + D) of a 256-bit string held as eight warp-uniform words (zeros outside), D in {-2, -1, 0, +1}
+template<int D>
+__device__ __forceinline__ unsigned fs_bit_at(const unsigned (&w)[8], int r, int lane)
 {
-  return (words1[1 + (idx >> 5)] >> (idx & 31)) & 1u;
+  const unsigned cur = w[r];
+  if(D == 0)
+    return (cur >> lane) & 1u;
+  if(D < 0)
+  {
+    const unsigned prev = r > 0 ? w[r - 1] : 0u;
+    return (__funnelshift_l(prev, cur, -D) >> lane) & 1u; // bit i of the result = bit (i + D) of the string
+  }
+  const unsigned next = r < 7 ? w[r + 1] : 0u;
+  return (__funnelshift_r(cur, next, D) >> lane) & 1u;
 }
 
-__device__ inline void fs_peaks(const DevParams &p, FrameDev &F, FsPeaks &K, int lane)
+__device__ inline void fs_peaks(const DevParams &p, FrameDev &F, FsPeaks &K, const uint4 h0, const uint4 h1, int lane)
 {
   if(lane == 0)
   {
@@ -169,59 +214,49 @@ __device__ inline void fs_peaks(const DevParams &p, FrameDev &F, FsPeaks &K, int
   __syncwarp();
   __threadfence_block();
   {
-    // the frame's histogram as the global atomics left it (L2)
-    const uint4 *src = reinterpret_cast<const uint4 *>(F.hist) + lane * 2;
-    const uint4 h0 = __ldcg(src), h1 = __ldcg(src + 1);
-    unsigned *dst = K.hist + 4 + lane * 8;
-    dst[0] = h0.x, dst[1] = h0.y, dst[2] = h0.z, dst[3] = h0.w;
-    dst[4] = h1.x, dst[5] = h1.y, dst[6] = h1.z, dst[7] = h1.w;
+    // the frame's complete histogram (bins 8 lane .. 8 lane + 7), as the owner's poll read it
+    uint4 *dst = reinterpret_cast<uint4 *>(K.hist + 4 + lane * 8);
+    dst[0] = h0;
+    dst[1] = h1;
     if(lane < 4)
     {
       K.hist[lane] = 0;
       K.hist[4 + SSD_BINS_PAD + lane] = 0;
     }
-    if(lane < 10)
-      K.P[lane] = K.BL[lane] = 0;
   }
   __syncwarp();
   const unsigned *H = K.hist + 4;
   const int last = p.n_bins - 1;
   const unsigned lt = (1u << lane) - 1u;
-  unsigned R[8], Fm[8];
+  unsigned R[8], Fm[8], Pw[8], BL[8], hc[8], hm[8], hp[8];
 #pragma unroll
   for(int r = 0; r < 8; r++)
   {
     const int b = 32 * r + lane;
-    const unsigned c = H[b], s = H[b + 1];
+    hc[r] = H[b];
+    hm[r] = H[b - 1];
+    hp[r] = H[b + 1];
     const bool v = b < last;
-    R[r] = __ballot_sync(0xffffffffu, v && c < s);
-    Fm[r] = __ballot_sync(0xffffffffu, v && c > s);
+    R[r] = __ballot_sync(0xffffffffu, v && hc[r] < hp[r]);
+    Fm[r] = __ballot_sync(0xffffffffu, v && hc[r] > hp[r]);
+    BL[r] = __ballot_sync(0xffffffffu, hm[r] > hp[r]);
   }
-  unsigned Pw[8];
   {
     bool carry = false; // ascending at the start of word r
 #pragma unroll
     for(int r = 0; r < 8; r++)
     {
-      const int b = 32 * r + lane;
-      const unsigned c = H[b];
+      const unsigned c = hc[r];
       const unsigned E = R[r] | Fm[r];
       const unsigned m = E & lt;
       const bool asc = m ? ((R[r] >> (31 - __clz(m))) & 1u) != 0u : carry;
       const bool fall = (Fm[r] >> lane) & 1u;
-      const bool peak = fall && asc && !(c < p.min_peak_points) && (unsigned)((c * 2u - H[b - 1] - H[b + 1]) * 2u) > c;
+      const bool peak = fall && asc && !(c < p.min_peak_points) && (unsigned)((c * 2u - hm[r] - hp[r]) * 2u) > c;
       Pw[r] = __ballot_sync(0xffffffffu, peak);
-      const unsigned bl = __ballot_sync(0xffffffffu, H[b - 1] > H[b + 1]);
-      if(lane == 0)
-      {
-        K.P[1 + r] = Pw[r];
-        K.BL[1 + r] = bl;
-      }
       if(E)
         carry = ((R[r] >> (31 - __clz(E))) & 1u) != 0u;
     }
   }
-  __syncwarp();
   int n_all = 0;
 #pragma unroll
   for(int r = 0; r < 8; r++)
@@ -230,7 +265,7 @@ __device__ inline void fs_peaks(const DevParams &p, FrameDev &F, FsPeaks &K, int
   unsigned status = n_all > SSD_GPU_MAX_PLATEAUS ? SSD_STATUS_TOO_MANY_PLATEAUS : 0u;
   // uint16 wrap of heightMin - 1 (pointcloud.cpp:324): a peak at bin 1 with band [0, 1] -- necessarily the first peak --
   // sends every point to the remainder; that plateau and all later ones stay empty
-  const bool wrapped = fs_bit(K.P, 1) && fs_bit(K.BL, 1);
+  const bool wrapped = ((Pw[0] >> 1) & 1u) && ((BL[0] >> 1) & 1u);
   if(wrapped)
     status |= SSD_STATUS_HMIN_WRAP;
   {
@@ -245,11 +280,11 @@ __device__ inline void fs_peaks(const DevParams &p, FrameDev &F, FsPeaks &K, int
       if(!wrapped)
       {
         int k = -1;
-        if(fs_bit(K.P, b - 1) && !fs_bit(K.BL, b - 1))
+        if(fs_bit_at<-1>(Pw, r, lane) && !fs_bit_at<-1>(BL, r, lane))
           k = cntlt - 1;
         else if(pk)
           k = cntlt;
-        else if(fs_bit(K.P, b + 1) && fs_bit(K.BL, b + 1))
+        else if(fs_bit_at<1>(Pw, r, lane) && fs_bit_at<1>(BL, r, lane))
           k = cntlt;
         if(k >= 0 && k < SSD_GPU_MAX_PLATEAUS)
           l = (unsigned)k;
@@ -261,12 +296,12 @@ __device__ inline void fs_peaks(const DevParams &p, FrameDev &F, FsPeaks &K, int
       K.lut[b] = (unsigned short)l;
       if(pk && cntlt < SSD_GPU_MAX_PLATEAUS)
       {
-        const bool lo = fs_bit(K.BL, b) != 0u;
-        unsigned np = H[b];
+        const bool lo = (BL[r] >> lane) & 1u;
+        unsigned np = hc[r];
         if(lo)
-          np += (fs_bit(K.P, b - 2) && !fs_bit(K.BL, b - 2)) ? 0u : H[b - 1];
+          np += (fs_bit_at<-2>(Pw, r, lane) && !fs_bit_at<-2>(BL, r, lane)) ? 0u : hm[r];
         else
-          np += H[b + 1];
+          np += hp[r];
         K.height[cntlt] = b;
         K.hmin[cntlt] = lo ? b - 1 : b;
         K.hmax[cntlt] = lo ? b : b + 1;
@@ -319,9 +354,6 @@ __device__ inline void fs_peaks(const DevParams &p, FrameDev &F, FsPeaks &K, int
     for(int c4 = 0; c4 < 4; c4++)
       P.quad_px[c4][0] = P.quad_px[c4][1] = P.quad_world[c4][0] = P.quad_world[c4][1] = 0;
   }
-  // the plateau records must be visible before the LUT that announces them
-  __threadfence();
-  __syncwarp();
   {
     unsigned w[4];
 #pragma unroll
@@ -343,16 +375,20 @@ __device__ inline void fs_peaks(const DevParams &p, FrameDev &F, FsPeaks &K, int
     }
     *(reinterpret_cast<uint4 *>(F.lut16) + lane) = make_uint4(w[0], w[1], w[2], w[3]);
   }
+  // the plateau records and the LUT must be visible before the flag that announces them
+  __threadfence();
   __syncwarp();
   if(lane == 0)
   {
+    *(volatile unsigned *)&F.ready = 1u;
     __threadfence_block();
     atomicExch(&K.lock, 0u);
   }
 }
 
-// a warp leaves phase 1 of frame f: the last warp of the CTA delivers the CTA's histogram; the last CTA evaluates the peaks
-__device__ inline void fs_leave_p1(const DevParams &p, const FsParams &a, FrameDev *frames, FsAcc *acc, FsPeaks &pk, int f, int lane)
+// a warp leaves phase 1 of frame f: the last warp of the CTA adds the CTA's histogram to the frame's (global reductions, no
+// fence, no counter: the frame's owner sees it complete when the bins add up to the frame's point count)
+__device__ inline void fs_leave_p1(FrameDev *frames, FsAcc *acc, int f, int lane, unsigned long long *prof)
 {
   FsAcc &A = acc[f & (SSD_FS_NB - 1)];
   __syncwarp();
@@ -385,19 +421,13 @@ __device__ inline void fs_leave_p1(const DevParams &p, const FsParams &a, FrameD
       A.n_exact = 0;
     }
     *(volatile unsigned *)&A.p1_left = 0u;
+    if(prof)
+    {
+      const unsigned long long t = fs_gtime();
+      atomicMin(prof + FS_PROF_HDR + (size_t)f * FS_PROF_PER_FRAME + 0, t);
+      atomicMax(prof + FS_PROF_HDR + (size_t)f * FS_PROF_PER_FRAME + 5, t);
+    }
   }
-  __threadfence();
-  __syncwarp();
-  unsigned glast = 0;
-  if(lane == 0)
-    glast = atomicAdd(&a.done[f], 1u) == gridDim.x - 1 ? 1u : 0u;
-  glast = __shfl_sync(0xffffffffu, glast, 0);
-  if(!glast)
-    return;
-  if(lane == 0)
-    a.done[f] = 0u; // self-resetting: nobody reads the counter after the last arrival
-  __threadfence();
-  fs_peaks(p, frames[f], pk, lane);
 }
 
 // a warp leaves phase 2 of frame f: the last warp of the CTA delivers the CTA's per-plateau BEV row ranges and counters
@@ -510,28 +540,43 @@ __device__ __forceinline__ void fs_phase1(const DevParams &p, const SRC &src, co
 #pragma unroll
   for(int j = 0; j < 4; j++)
     atomicAdd(A.hist + c[j], 1u);
-  reinterpret_cast<unsigned *>(rec)[lane] = cw;
+  __stcg(reinterpret_cast<unsigned *>(rec) + lane, cw);
   // records of the lane's in-range points (codes 254 / 255: out of range / invalid)
   if((cw & 0xfefefefeu) != 0xfefefefeu)
   {
-    unsigned r[4];
+    unsigned r[4], slow = 0;
 #pragma unroll
     for(int j = 0; j < 4; j++)
     {
       int ix, iy;
       const bool ok = fast_pixel2(p, vx[j], vy[j], vz[j], ix, iy);
-      r[j] = zp[j] | (ok ? (((unsigned)iy << p.rec_bx) | (unsigned)ix) : ((unsigned)p.H << p.rec_bx));
+      r[j] = zp[j] | ((unsigned)iy << p.rec_bx) | (unsigned)ix;
+      slow |= (!ok && c[j] < SSD_CODE_OUT_OF_RANGE) ? (1u << j) : 0u;
     }
-    reinterpret_cast<uint4 *>(rec + 128)[lane] = make_uint4(r[0], r[1], r[2], r[3]);
+    if(slow)
+    {
+      // The single-precision pixel of an in-range point was not certain (about one point in 200): the exact double chain
+      // decides here, where the vertex is in registers. A pixel outside the image (the x == W wrap of pointcloud.cpp:81,468)
+      // is marked iy = H: phase 2 then follows the reference's unchecked write from the vertex itself.
+      unsigned ns = 0;
+#pragma unroll
+      for(int j = 0; j < 4; j++)
+        if((slow >> j) & 1u)
+        {
+          r[j] = zp[j] | pixel_slow(p, vx[j], vy[j], vz[j]);
+          ns++;
+        }
+      atomicAdd(&A.n_def, ns);
+    }
+    __stcg(reinterpret_cast<uint4 *>(rec + 128) + lane, make_uint4(r[0], r[1], r[2], r[3]));
   }
 }
 
 // ---- phase 2 of one step: record slot -> labels, BEV bits, summaries ----
 template<class SRC>
-__device__ __forceinline__ void fs_phase2(const DevParams &p, const SRC &src, const FsParams &a, const unsigned char *rec, const unsigned short *lut,
+__device__ __forceinline__ void fs_phase2(const DevParams &p, const SRC &src, const FsParams &a, const unsigned cw, const uint4 rv, const unsigned short *lut,
                                           FsAcc &A, unsigned frame, unsigned step, unsigned char *labels, unsigned *bev, unsigned bmw, int lane)
 {
-  const unsigned cw = reinterpret_cast<const unsigned *>(rec)[lane];
   const size_t word = (size_t)frame * (size_t)(p.N >> 2) + (size_t)step * 32u + (unsigned)lane;
   GroupSum *gs = a.sums + (((size_t)frame * (size_t)p.gs_steps + step) * 4u + (unsigned)(lane >> 3));
   unsigned lab = cw, fl = 0, ol = 0;
@@ -559,7 +604,6 @@ __device__ __forceinline__ void fs_phase2(const DevParams &p, const SRC &src, co
   const unsigned l0 = (lab >> (8 * (__ffs(fl | 16u) - 1) & 31)) & 0xffu;
   if(fl)
   {
-    const uint4 rv = reinterpret_cast<const uint4 *>(rec + 128)[lane];
     const unsigned r[4] = { rv.x, rv.y, rv.z, rv.w };
     const unsigned bytes = ((fl * 0x00204081u) & 0x01010101u) * 0xffu;
     bad = ((lab ^ (l0 * 0x01010101u)) & bytes) != 0u;
@@ -590,7 +634,6 @@ __device__ __forceinline__ void fs_phase2(const DevParams &p, const SRC &src, co
             }
             else
               A.oob = 1;
-            atomicAdd(&A.n_def, 1u);
           }
           continue;
         }
@@ -607,17 +650,29 @@ __device__ __forceinline__ void fs_phase2(const DevParams &p, const SRC &src, co
         csum += (cw >> (8 * j)) & 0xffu;
       }
   }
-  // 8-lane summary: one reduction instruction per quantity (members = the lanes of the lane's group)
+  // 8-lane summary by xor butterflies over packed words (a reduction instruction with a partial member mask would be executed
+  // once per group, serialised): {ixmin, iymin} / {ixmax, iymax} as 16-bit pairs (two-lane min / max instructions),
+  // {count, sum of codes} and the sum of the height offsets as plain sums. Uniformity of the label by ballots.
   const unsigned gm = 0xffu << (lane & 24);
-  const unsigned cnt = (unsigned)__popc(fl);
-  const unsigned lmin = __reduce_min_sync(gm, bad ? 0u : (fl ? l0 : 0xffu));
-  const unsigned lmax = __reduce_max_sync(gm, bad ? 0xffu : (fl ? l0 : 0u));
-  const unsigned cc = __reduce_add_sync(gm, cnt | (csum << 8));
-  const int gxmin = __reduce_min_sync(gm, ixmin), gxmax = __reduce_max_sync(gm, ixmax);
-  const int gymin = __reduce_min_sync(gm, iymin), gymax = __reduce_max_sync(gm, iymax);
-  const int gds = __reduce_add_sync(gm, dsum);
+  const unsigned fg = __ballot_sync(0xffffffffu, fl != 0u) & gm;
+  const unsigned ll = __shfl_sync(0xffffffffu, l0, fg ? __ffs(fg) - 1 : lane); // label of the group's first flagged lane
+  const unsigned nb = __ballot_sync(0xffffffffu, bad || (fl && l0 != ll)) & gm;
+  const unsigned gol = __ballot_sync(0xffffffffu, ol != 0u) & gm;
+  unsigned gmn = (unsigned)ixmin | ((unsigned)iymin << 16), gmx = (unsigned)ixmax | ((unsigned)iymax << 16);
+  unsigned cc = (unsigned)__popc(fl) | (csum << 8);
+  int gds = dsum;
+#pragma unroll
+  for(int k = 1; k < 8; k <<= 1)
+  {
+    gmn = __vminu2(gmn, __shfl_xor_sync(0xffffffffu, gmn, k));
+    gmx = __vmaxu2(gmx, __shfl_xor_sync(0xffffffffu, gmx, k));
+    cc += __shfl_xor_sync(0xffffffffu, cc, k);
+    gds += __shfl_xor_sync(0xffffffffu, gds, k);
+  }
   const unsigned gcnt = cc & 0xffu;
-  const bool uniform = lmin == lmax;
+  const bool uniform = nb == 0u && fg != 0u;
+  const int gymin = (int)(gmn >> 16), gymax = (int)(gmx >> 16);
+  const unsigned lmin = ll;
   if((lane & 7) == 0)
   {
     uint4 o = make_uint4(0u, 0u, 0u, 0u);
@@ -625,8 +680,8 @@ __device__ __forceinline__ void fs_phase2(const DevParams &p, const SRC &src, co
     {
       if(uniform)
       {
-        o.x = (unsigned)gxmin | ((unsigned)gxmax << 16);
-        o.y = (unsigned)gymin | ((unsigned)gymax << 16);
+        o.x = (gmn & 0xffffu) | (gmx << 16);
+        o.y = (gmn >> 16) | (gmx & 0xffff0000u);
         o.z = (unsigned)gds;
         o.w = (cc >> 8) | (lmin << 16) | (gcnt << 24);
       }
@@ -637,7 +692,6 @@ __device__ __forceinline__ void fs_phase2(const DevParams &p, const SRC &src, co
   }
   // BEV rows touched, per plateau (the outline stages only that band): one pair of shared-memory reductions per group
   // (all flagged points of a uniform group share the label, so any lane's `ol` tells whether it is outlined)
-  const unsigned gol = __reduce_or_sync(gm, ol);
   if(uniform && gol)
   {
     if((lane & 7) == 0 && gymax >= gymin && gcnt)
@@ -649,7 +703,6 @@ __device__ __forceinline__ void fs_phase2(const DevParams &p, const SRC &src, co
   else if(ol && iymax >= iymin)
   {
     // mixed labels inside the group (plateau boundaries in the image): per point
-    const uint4 rv = reinterpret_cast<const uint4 *>(rec + 128)[lane];
     const unsigned r[4] = { rv.x, rv.y, rv.z, rv.w };
 #pragma unroll
     for(int j = 0; j < 4; j++)
@@ -669,10 +722,17 @@ __device__ __forceinline__ void fs_phase2(const DevParams &p, const SRC &src, co
 // ---------------------------------------------------------------------------------------------
 // k_frame_stream. grid = one CTA per SM (cooperative launch: all CTAs co-resident), block = 16 warps.
 // ---------------------------------------------------------------------------------------------
+// A warp's position in its step sequence. In frame f it takes the steps s_j = j * TW + ((warp - f * ROT + j * R) mod TW), j = 0, 1, ...
+// while s_j < steps per frame (TW = warps of the grid): every block of TW steps is a rotation of the warps, so the steps of a
+// frame are dealt out exactly once; the rotations by frame (ROT) and by block (R) move a warp across the image columns and
+// rows from step to step -- with a fixed stride a warp would stay in one column block of the image for ever, and the warps
+// looking at the staircase would do three times the work of the ones looking past it (measured).
 struct FsCur
 {
-  unsigned k, f, s;
+  unsigned k, f, s, j, base;
 };
+#define SSD_FS_ROT 5u
+#define SSD_FS_R 3u
 
 template<class SRC>
 __global__ void __launch_bounds__(SSD_FS_THREADS, 1) k_frame_stream(const __grid_constant__ DevParams p, const SRC src, const __grid_constant__ FsParams a,
@@ -684,9 +744,8 @@ __global__ void __launch_bounds__(SSD_FS_THREADS, 1) k_frame_stream(const __grid
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int d_raw = a.d_raw, d_rec = a.d_rec;
   unsigned char *raw_all = fs_smem;
-  unsigned char *rec_all = raw_all + (size_t)SSD_FS_WARPS * d_raw * RAW;
-  unsigned short *lut_all = reinterpret_cast<unsigned short *>(rec_all + (size_t)SSD_FS_WARPS * d_rec * SSD_FS_REC_BYTES);
-  FsAcc *acc = reinterpret_cast<FsAcc *>(lut_all + SSD_FS_WARPS * SSD_BINS_PAD);
+  FsLut *lutc = reinterpret_cast<FsLut *>(raw_all + (size_t)SSD_FS_WARPS * d_raw * RAW);
+  FsAcc *acc = reinterpret_cast<FsAcc *>(lutc + 1);
   FsPeaks *pk = reinterpret_cast<FsPeaks *>(acc + SSD_FS_NB);
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(pk + 1);
 
@@ -702,6 +761,11 @@ __global__ void __launch_bounds__(SSD_FS_THREADS, 1) k_frame_stream(const __grid
     }
     if(tid == 0)
       pk->lock = 0u;
+    if(tid < SSD_FS_NB)
+    {
+      lutc->frame1[tid] = 0;
+      lutc->busy[tid] = 0u;
+    }
     if(lane == 0)
     {
       for(int i = 0; i < d_raw; i++)
@@ -712,34 +776,35 @@ __global__ void __launch_bounds__(SSD_FS_THREADS, 1) k_frame_stream(const __grid
   }
 
   unsigned char *raw = raw_all + (size_t)warp * d_raw * RAW;
-  unsigned char *rec = rec_all + (size_t)warp * d_rec * SSD_FS_REC_BYTES;
-  unsigned short *lut = lut_all + warp * SSD_BINS_PAD;
+  unsigned char *rec = a.recs + ((size_t)blockIdx.x * SSD_FS_WARPS + warp) * (size_t)d_rec * SSD_FS_REC_BYTES;
   const unsigned raw_sa = (unsigned)__cvta_generic_to_shared(raw);
   const unsigned bar_sa = (unsigned)__cvta_generic_to_shared(bars + warp * d_raw);
 
   const unsigned S = (unsigned)p.gs_steps;
   const unsigned TW = gridDim.x * SSD_FS_WARPS, gw = blockIdx.x * SSD_FS_WARPS + warp;
-  const unsigned long long G = (unsigned long long)a.n_frames * S;
-  const unsigned K_total = gw < G ? (unsigned)((G - gw + TW - 1) / TW) : 0u;
-  const unsigned df = TW / S, ds = TW % S;
   const unsigned n_frames = (unsigned)a.n_frames;
   FsCur ct, c1, c2;
-  ct.k = 0, ct.f = gw / S, ct.s = gw % S;
+  ct.k = 0, ct.f = 0, ct.j = 0, ct.base = gw, ct.s = gw; // (TW <= S: the first block is complete)
   c1 = ct;
   c2 = ct;
-#define FS_ADV(c)          \
-  do                       \
-  {                        \
-    (c).k++;               \
-    (c).s += ds;           \
-    (c).f += df;           \
-    if((c).s >= S)         \
-    {                      \
-      (c).s -= S;          \
-      (c).f++;             \
-    }                      \
+#define FS_ADV(c)                                                        \
+  do                                                                     \
+  {                                                                      \
+    (c).k++;                                                             \
+    (c).j++;                                                             \
+    unsigned b_ = (c).base + (c).j * SSD_FS_R;                           \
+    b_ = b_ >= TW ? b_ - TW : b_;                                        \
+    (c).s = (c).j * TW + b_;                                             \
+    if((c).s >= S)                                                       \
+    {                                                                    \
+      (c).f++;                                                           \
+      (c).j = 0;                                                         \
+      (c).base = (c).base >= SSD_FS_ROT ? (c).base - SSD_FS_ROT : (c).base + TW - SSD_FS_ROT; \
+      (c).s = (c).base;                                                  \
+    }                                                                    \
   } while(0)
-#define FS_FRAME(c) ((c).k < K_total ? (c).f : n_frames)
+#define FS_LIVE(c) ((c).f < n_frames)
+#define FS_FRAME(c) ((c).f < n_frames ? (c).f : n_frames)
   unsigned slot_t = 0, slot_1 = 0, phase_1 = 0, rslot_1 = 0, rslot_2 = 0;
   unsigned left1 = 0, left2 = 0; // frames this warp has left (phase 1 / phase 2): [0, left)
   int lut_f = -1;                // frame whose LUT the warp's copy holds
@@ -748,15 +813,27 @@ __global__ void __launch_bounds__(SSD_FS_THREADS, 1) k_frame_stream(const __grid
 
   // frames before the warp's first step
   for(; left1 < FS_FRAME(c1); left1++)
-    fs_leave_p1(p, a, frames, acc, *pk, (int)left1, lane);
+    fs_leave_p1(frames, acc, (int)left1, lane, a.prof);
   for(; left2 < FS_FRAME(c2); left2++)
     fs_leave_p2(frames, acc, (int)left2, lane);
 
+  // frames whose peaks this warp evaluates: CTA f % grid, warp (f / grid) % 16
+  unsigned own_f = blockIdx.x + gridDim.x * (unsigned)warp;
+  const unsigned own_stride = gridDim.x * SSD_FS_WARPS;
   unsigned idle = 0;
-  while(c2.k < K_total)
+  long long t_leave = 0, t_other = 0;
+  long long t_p1 = 0, t_p2 = 0, t_wait = 0, n_idle = 0, n_poll = 0, n_i_done = 0, n_i_ring = 0, n_i_guard = 0, lag_sum = 0;
+  const long long t_begin = clock64();
+  const bool prof = a.prof != nullptr;
+  unsigned pf_k = 0xffffffffu; // step whose records sit in (cw2, rv2)
+  unsigned cw2 = 0;
+  uint4 rv2 = make_uint4(0u, 0u, 0u, 0u);
+  long long t_it_did = 0, t_it_idle = 0, t_sec_a = 0, t_sec_b = 0;
+  while(FS_LIVE(c2) || own_f < n_frames)
   {
+    const long long ti0 = prof ? clock64() : 0;
     // 1. keep the raw ring full
-    while(ct.k < K_total && ct.k - c1.k < (unsigned)d_raw)
+    while(FS_LIVE(ct) && ct.k - c1.k < (unsigned)d_raw)
     {
       if(lane == 0)
       {
@@ -767,22 +844,67 @@ __global__ void __launch_bounds__(SSD_FS_THREADS, 1) k_frame_stream(const __grid
       slot_t = slot_t + 1 == (unsigned)d_raw ? 0u : slot_t + 1;
       FS_ADV(ct);
     }
-    // 2. is the frame of the oldest pending phase-2 step ready? (asynchronous: the answer is looked at after phase 1)
+    const long long ti1 = prof ? clock64() : 0;
+    t_sec_a += ti1 - ti0;
     const bool pending = c2.k < c1.k;
+    // 2. the records of the oldest pending phase-2 step: requested now (from L2, where phase 1 left them), used after phase 1
+    if(pending && pf_k != c2.k)
+    {
+      const unsigned char *r2 = rec + (size_t)rslot_2 * SSD_FS_REC_BYTES;
+      cw2 = __ldcg(reinterpret_cast<const unsigned *>(r2) + lane);
+      rv2 = __ldcg(reinterpret_cast<const uint4 *>(r2 + 128) + lane);
+      pf_k = c2.k;
+    }
+    // 3. is that step's frame ready? The CTA keeps one copy of each frame's LUT; one warp at a time asks global memory
+    //    (a 4-byte flag: 148 pollers, not 2368), asynchronously: the answer is looked at after phase 1
+    const unsigned ls = c2.f & (SSD_FS_NB - 1);
     bool polled = false;
-    uint4 pv = make_uint4(0u, 0u, 0u, 0u);
+    unsigned pv = 0;
     if(pending && (int)c2.f != lut_f)
     {
-      pv = ld_volatile_v4(reinterpret_cast<const uint4 *>(frames[c2.f].lut16) + lane);
-      polled = true;
+      if(*(volatile int *)&lutc->frame1[ls] == (int)c2.f + 1)
+      {
+        __threadfence_block();
+        lut_f = (int)c2.f;
+      }
+      else
+      {
+        unsigned got = 0;
+        if(lane == 0)
+          got = atomicCAS(&lutc->busy[ls], 0u, 1u) == 0u ? 1u : 0u;
+        got = __shfl_sync(0xffffffffu, got, 0);
+        if(got)
+        {
+          if(lane == 0)
+            asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(pv) : "l"(&frames[c2.f].ready) : "memory");
+          polled = true;
+          n_poll++;
+        }
+      }
+    }
+    // 3b. the frame this warp owns: is its histogram complete? (asynchronous as well)
+    const bool own_poll = own_f < n_frames && own_f < left1;
+    uint4 oh0 = make_uint4(0u, 0u, 0u, 0u), oh1 = oh0;
+    if(own_poll)
+    {
+      const uint4 *hsrc = reinterpret_cast<const uint4 *>(frames[own_f].hist) + lane * 2;
+      oh0 = ld_volatile_v4(hsrc);
+      oh1 = ld_volatile_v4(hsrc + 1);
     }
     bool did = false;
-    // 3. phase 1 of the next loaded step
-    if(c1.k < K_total && c1.k - c2.k < (unsigned)d_rec && c1.f - c2.f < (unsigned)(SSD_FS_NB - 1))
+    if(prof)
+      t_sec_b += clock64() - ti1;
+    // 4. phase 1 of the next loaded step
+    if(FS_LIVE(c1) && c1.k - c2.k < (unsigned)d_rec && c1.f - c2.f < (unsigned)(SSD_FS_NB - 2))
     {
+      const long long tw0 = prof ? clock64() : 0;
       mbar_wait(bar_sa + slot_1 * 8u, phase_1);
+      const long long t0 = prof ? clock64() : 0;
+      t_wait += t0 - tw0;
       fs_phase1(p, src, raw + (size_t)slot_1 * RAW, rec + (size_t)rslot_1 * SSD_FS_REC_BYTES, acc[c1.f & (SSD_FS_NB - 1)], c1.s, lane);
       __syncwarp();
+      if(prof)
+        t_p1 += clock64() - t0;
       if(++slot_1 == (unsigned)d_raw)
       {
         slot_1 = 0;
@@ -790,44 +912,130 @@ __global__ void __launch_bounds__(SSD_FS_THREADS, 1) k_frame_stream(const __grid
       }
       rslot_1 = rslot_1 + 1 == (unsigned)d_rec ? 0u : rslot_1 + 1;
       FS_ADV(c1);
-      for(; left1 < FS_FRAME(c1); left1++)
-        fs_leave_p1(p, a, frames, acc, *pk, (int)left1, lane);
+      {
+        const long long tl = prof ? clock64() : 0;
+        for(; left1 < FS_FRAME(c1); left1++)
+          fs_leave_p1(frames, acc, (int)left1, lane, a.prof);
+        if(prof)
+          t_leave += clock64() - tl;
+      }
       did = true;
     }
-    // 4. the poll's answer
+    // 5. the poll's answer: copy the frame's LUT into the CTA's slot
     if(polled)
     {
-      const unsigned ok = (pv.x & pv.y & pv.z & pv.w & 0x80008000u) == 0x80008000u;
-      if(__all_sync(0xffffffffu, ok))
+      pv = __shfl_sync(0xffffffffu, pv, 0);
+      if(pv)
       {
         __threadfence();
-        reinterpret_cast<uint4 *>(lut)[lane] = pv;
+        const uint4 v = ld_volatile_v4(reinterpret_cast<const uint4 *>(frames[c2.f].lut16) + lane);
+        reinterpret_cast<uint4 *>(lutc->lut[ls])[lane] = v;
+        __threadfence_block();
         __syncwarp();
+        if(lane == 0)
+          *(volatile int *)&lutc->frame1[ls] = (int)c2.f + 1;
         lut_f = (int)c2.f;
       }
+      if(lane == 0)
+      {
+        __threadfence_block();
+        atomicExch(&lutc->busy[ls], 0u);
+      }
     }
-    // 5. phase 2 of every pending step of that frame
-    while(c2.k < c1.k && (int)c2.f == lut_f)
+    // 5b. the owned frame: every point counted -> peaks, plateau bands, LUT (the bins are final: each is written by
+    //     atomic additions only and the total is the frame's point count)
+    if(own_poll)
     {
-      fs_phase2(p, src, a, rec + (size_t)rslot_2 * SSD_FS_REC_BYTES, lut, acc[c2.f & (SSD_FS_NB - 1)], c2.f, c2.s, labels, bev, bmw, lane);
+      const unsigned tot = __reduce_add_sync(0xffffffffu, oh0.x + oh0.y + oh0.z + oh0.w + oh1.x + oh1.y + oh1.z + oh1.w);
+      if(tot == (unsigned)p.N)
+      {
+        if(prof && lane == 0)
+          a.prof[FS_PROF_HDR + (size_t)own_f * FS_PROF_PER_FRAME + 1] = fs_gtime();
+        const long long tk = clock64();
+        fs_peaks(p, frames[own_f], *pk, oh0, oh1, lane);
+        t_other += clock64() - tk;
+        if(prof && lane == 0)
+          a.prof[FS_PROF_HDR + (size_t)own_f * FS_PROF_PER_FRAME + 2] = fs_gtime();
+        own_f += own_stride;
+        did = true;
+      }
+    }
+    // 6. phase 2 of the oldest pending step
+    if(pending && (int)c2.f == lut_f)
+    {
+      const long long t0 = prof ? clock64() : 0;
+      fs_phase2(p, src, a, cw2, rv2, lutc->lut[ls], acc[ls], c2.f, c2.s, labels, bev, bmw, lane);
       __syncwarp();
       rslot_2 = rslot_2 + 1 == (unsigned)d_rec ? 0u : rslot_2 + 1;
+      if(prof && lane == 0)
+      {
+        const unsigned long long t = fs_gtime();
+        atomicMin(a.prof + FS_PROF_HDR + (size_t)c2.f * FS_PROF_PER_FRAME + 3, t);
+        atomicMax(a.prof + FS_PROF_HDR + (size_t)c2.f * FS_PROF_PER_FRAME + 4, t);
+      }
       FS_ADV(c2);
       for(; left2 < FS_FRAME(c2); left2++)
         fs_leave_p2(frames, acc, (int)left2, lane);
+      if(prof)
+        t_p2 += clock64() - t0;
       did = true;
     }
     if(did)
+    {
       idle = 0;
+      if(prof)
+        t_it_did += clock64() - ti0;
+    }
     else
     {
-      if(++idle > (1u << 22))
-        __trap(); // a frame barrier that never completes (a CTA not resident?) traps instead of hanging the GPU
-      __nanosleep(100);
+      // nothing to do: the ring is full behind a frame that is not ready. Back off (a spinning warp takes issue slots from
+      // the working ones); a frame barrier that never completes (a CTA not resident?) traps instead of hanging the GPU
+      n_idle++;
+      if(prof)
+      {
+        if(!FS_LIVE(c1))
+          n_i_done++;
+        else if(c1.k - c2.k >= (unsigned)d_rec)
+          n_i_ring++;
+        else
+          n_i_guard++;
+        lag_sum += (long long)(c1.f - c2.f);
+      }
+      if(++idle > (1u << 21))
+        __trap();
+      __nanosleep(idle < 4 ? 250 : 1000);
+      if(prof)
+        t_it_idle += clock64() - ti0;
     }
+  }
+  if(prof && lane == 0)
+  {
+    atomicAdd(a.prof + 0, (unsigned long long)t_p1);
+    atomicAdd(a.prof + 1, (unsigned long long)t_p2);
+    atomicAdd(a.prof + 2, (unsigned long long)(clock64() - t_begin));
+    atomicAdd(a.prof + 3, (unsigned long long)n_idle);
+    atomicAdd(a.prof + 4, (unsigned long long)n_poll);
+    atomicAdd(a.prof + 5, 1ull);
+    atomicAdd(a.prof + 6, (unsigned long long)t_wait);
+    if(a.n_frames >= 64)
+    {
+      // per-warp record behind the per-frame stamps (host: FS_PROF_HDR + FS_PROF_PER_FRAME * chunk_frames + 8 * global warp)
+      unsigned long long *w = a.prof + a.prof_warp_off + (size_t)gw * 8;
+      w[0] = (unsigned long long)t_p1, w[1] = (unsigned long long)t_p2, w[2] = (unsigned long long)t_wait, w[3] = (unsigned long long)n_idle;
+      w[4] = (unsigned long long)(clock64() - t_begin), w[5] = (unsigned long long)n_i_ring, w[6] = (unsigned long long)t_leave, w[7] = (unsigned long long)t_other;
+    }
+    atomicAdd(a.prof + 11, (unsigned long long)t_it_did);
+    atomicAdd(a.prof + 12, (unsigned long long)t_it_idle);
+    atomicAdd(a.prof + 13, (unsigned long long)t_sec_a);
+    atomicAdd(a.prof + 14, (unsigned long long)t_sec_b);
+    atomicAdd(a.prof + 7, (unsigned long long)n_i_done);
+    atomicAdd(a.prof + 8, (unsigned long long)n_i_ring);
+    atomicAdd(a.prof + 9, (unsigned long long)n_i_guard);
+    atomicAdd(a.prof + 10, (unsigned long long)lag_sum);
   }
 #undef FS_ADV
 #undef FS_FRAME
+#undef FS_LIVE
 }
 
 // ---------------------------------------------------------------------------------------------

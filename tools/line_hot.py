@@ -52,5 +52,7 @@ def src(ln):
             return src_cache[pth][n - 1].strip()[:100] if n - 1 < len(src_cache[pth]) else ""
     return ""
 print(f"total warp-instructions {tot}, samples {ts}")
-for ln, n in agg.most_common(top):
-    print(f"{n/tot:6.1%} {samp[ln]/max(1,ts):6.1%} x{mx[ln]:>9d} ({cnt[ln]:3d} sass)  {str(ln[1] if ln else ln):>5s} {src(ln)}")
+order = samp.most_common(top) if os.environ.get('BY_SAMPLES') else agg.most_common(top)
+for ln, _n in order:
+    n = agg[ln]
+    print(f"{n/tot:6.1%} {samp[ln]/max(1,ts):6.1%} x{mx[ln]:>9d} ({cnt[ln]:3d} sass)  {(ln[0][12:22] + ':' + str(ln[1])) if ln else 'None':>16s} {src(ln)}")
