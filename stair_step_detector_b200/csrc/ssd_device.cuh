@@ -58,7 +58,7 @@ struct DevParams
   unsigned long long axy2[3], bxy2, auv2[3], buv2;
   // {sa[j], sa[3+j]}, {sb[0], sb[1]}: the x and y rows of the range-scaled transform (point_code_scaled)
   unsigned long long sxy2[3], sbxy2;
-  // resident-frame path (ssd_kernels_stream.cuh). Per-point record: ix | iy << rec_bx | d << (32 - rec_zbits), d = the point's
+  // record chain / resident-frame path. Per-point record: ix | iy << rec_bx | (bin code & 1) << (rec_bx + rec_by) | d << (32 - rec_zbits), d = the point's
   // height offset from the centre of its bin in units of 2^-rec_zshift m (rec_mf = height_interval * 2^rec_zshift,
   // |d| <= rec_mf / 2 < 2^(rec_zbits - 1)); iy == H marks a pixel the f32 chain could not decide. rec_zbits == 0: the
   // frame size does not admit the path.

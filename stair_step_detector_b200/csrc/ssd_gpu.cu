@@ -4,6 +4,7 @@
 #include "ssd_kernels_points.cuh"
 #include "ssd_kernels_outline.cuh"
 #include "ssd_kernels_stream.cuh"
+#include "ssd_kernels_records.cuh"
 #include "scene_model.h"
 
 #include <algorithm>
@@ -63,6 +64,8 @@ struct ssd_gpu_ctx
   ssd_gpu_intrinsics intr{};                    // intrinsics the tables were built for
   // resident-frame path (ssd_kernels_stream.cuh): one persistent kernel per chunk instead of the three point passes
   bool resident = false;
+  bool records = false;           // record chain (ssd_kernels_records.cuh): the default where the frame size admits it
+  uint4 *d_rec4 = nullptr;        // n_streams x chunk_frames x N/4 x {4 records}
   int fs_grid = 0, fs_d_raw = 4, fs_d_rec = 0, fs_lag_frames = 8;
   GroupSum *d_sums = nullptr;     // n_streams x chunk_frames x N/32 summaries
   unsigned *d_done = nullptr;     // n_streams x chunk_frames frame counters (self-resetting)
@@ -269,7 +272,7 @@ static int derive_params(const ssd_gpu_config &c, const ssd_gpu_transform &t, De
       bx++;
     while((1 << by) < c.height + 1)
       by++;
-    const int zbits = std::min(12, 32 - bx - by);
+    const int zbits = std::min(12, 32 - bx - by - 1); // (one bit: parity of the bin code)
     d.rec_bx = bx;
     d.rec_by = by;
     d.rec_zbits = 0;
@@ -503,6 +506,46 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, const uin
   sd.unit = depth_unit;
   sd.wmagic = (((unsigned long long)1 << 40) + (unsigned long long)p.W - 1) / (unsigned long long)p.W;
 
+  if(ctx->records)
+  {
+    // ---- record chain: k_transform_rec -> k_peaks -> k_label_sum -> k_outline -> k_frame_logic -> k_quad_sum -> k_finalize ----
+    uint4 *recs = ctx->d_rec4 + (size_t)s * ctx->chunk_frames * (size_t)(p.N / 4);
+    STAGE_EV(0);
+    if(depth)
+      k_transform_rec_depth<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, 0, st>>>(p, sd, labels, recs, frames);
+    else
+      k_transform_rec<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, SSD_PT_ITERS * SSD_TB_STAGE_BYTES, st>>>(p, xyz_dev, labels, recs, frames);
+    STAGE_EV(1);
+    k_peaks<<<nf, 32, 0, st>>>(p, frames, nf);
+    STAGE_EV(2);
+    if(depth)
+      k_label_rec<SrcDepth><<<gpt2l, SSD_PT_THREADS, 0, st>>>(p, sd, labels, recs, frames, bev, ctx->bm_words);
+    else
+      k_label_rec<SrcVertices><<<gpt2l, SSD_PT_THREADS, 0, st>>>(p, sv, labels, recs, frames, bev, ctx->bm_words);
+    STAGE_EV(3);
+    if(ctx->outline_small)
+      k_outline<OutlineSharedSmall><<<dim3(ctx->outline_gridx, nf), SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, bev, ctx->bm_words, ctx->smem_cap_words);
+    else
+      k_outline<OutlineShared><<<dim3(ctx->outline_gridx, nf), OutlineShared::THREADS, ctx->ol_dyn_smem, st>>>(p, frames, bev, ctx->bm_words, ctx->smem_cap_words);
+    STAGE_EV(4);
+    k_frame_logic<<<nf, 32, 0, st>>>(p, frames, nf);
+    STAGE_EV(5);
+    if(depth)
+      k_quad_rec<SrcDepth><<<gpt2q, SSD_PT_THREADS, 0, st>>>(p, sd, labels, frames, bev, ctx->bm_words, recs);
+    else
+      k_quad_rec<SrcVertices><<<gpt2q, SSD_PT_THREADS, 0, st>>>(p, sv, labels, frames, bev, ctx->bm_words, recs);
+    STAGE_EV(6);
+    if(ctx->outline_small)
+      k_finalize<OutlineSharedSmall><<<nf, SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, ctx->d_out + frame0, bev, ctx->bm_words, ctx->smem_cap_words, ctx->ov,
+                                                                            ctx->d_ovl ? ctx->d_ovl + (size_t)frame0 * SSD_GPU_MAX_STEPS : nullptr);
+    else
+      k_finalize<OutlineShared><<<nf, SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, ctx->d_out + frame0, bev, ctx->bm_words, ctx->smem_cap_words, ctx->ov,
+                                                                            ctx->d_ovl ? ctx->d_ovl + (size_t)frame0 * SSD_GPU_MAX_STEPS : nullptr);
+    STAGE_EV(7);
+    *launches += SSD_GPU_N_STAGES;
+    CK(cudaGetLastError());
+    return SSD_OK;
+  }
   if(ctx->resident)
   {
     // ---- resident-frame chain: k_frame_stream -> k_outline -> k_frame_logic -> k_quad_sum -> k_finalize ----
@@ -554,9 +597,9 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, const uin
     k_frame_logic<<<nf, 32, 0, st>>>(p, frames, nf);
     STAGE_EV(5);
     if(depth)
-      k_quad_sum<SrcDepth><<<gpt2q, SSD_PT_THREADS, 0, st>>>(p, sd, labels, frames, bev, ctx->bm_words, a.sums);
+      k_quad_sum<SrcDepth><<<gpt2q, SSD_PT_THREADS, 0, st>>>(p, sd, labels, frames, bev, ctx->bm_words, a.sums, nullptr);
     else
-      k_quad_sum<SrcVertices><<<gpt2q, SSD_PT_THREADS, 0, st>>>(p, sv, labels, frames, bev, ctx->bm_words, a.sums);
+      k_quad_sum<SrcVertices><<<gpt2q, SSD_PT_THREADS, 0, st>>>(p, sv, labels, frames, bev, ctx->bm_words, a.sums, nullptr);
     STAGE_EV(6);
     if(ctx->outline_small)
       k_finalize<OutlineSharedSmall><<<nf, SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, ctx->d_out + frame0, bev, ctx->bm_words, ctx->smem_cap_words, ctx->ov,
@@ -657,6 +700,7 @@ void ssd_gpu_destroy(ssd_gpu_ctx *ctx)
   cudaFree(ctx->d_sums);
   cudaFree(ctx->d_done);
   cudaFree(ctx->d_recs);
+  cudaFree(ctx->d_rec4);
   cudaFree(ctx->d_prof);
   if(ctx->ev_fs)
     cudaEventDestroy(ctx->ev_fs);
@@ -852,7 +896,16 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
     // Resident-frame path: used when a frame's records fit the shared memory of the GPU with room for the frame barrier's
     // latency (every warp must hold all its steps of one frame, plus what it works ahead). SSD_GPU_PATH=classic|resident.
     const char *pe = getenv("SSD_GPU_PATH");
-    const bool want = !(pe && !strcmp(pe, "classic"));
+    const bool want = pe && !strcmp(pe, "resident"); // experimental: measured slower than the record chain
+    if(pe && !strcmp(pe, "records") && dp.rec_zbits > 0) // experimental: measured slower than the classic chain
+    {
+      ctx->records = true;
+      CKC(cudaMalloc(&ctx->d_rec4, (size_t)ctx->n_streams * ctx->chunk_frames * (size_t)(dp.N / 4) * sizeof(uint4)));
+      if(cudaFuncSetAttribute(k_transform_rec<SSD_PT_ITERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SSD_PT_ITERS * SSD_TB_STAGE_BYTES) != cudaSuccess)
+        return bail("cudaFuncSetAttribute(k_transform_rec) failed", SSD_E_CUDA);
+    }
+    if(pe && !strcmp(pe, "records") && !ctx->records)
+      return bail("SSD_GPU_PATH=records: the frame size does not admit the record chain", SSD_E_RANGE);
     int sms = 148, coop = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
@@ -863,16 +916,16 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
     int grid = sms;
     if(const char *e = getenv("SSD_GPU_FS_CTAS"))
       grid = std::max(1, std::min(sms, atoi(e)));
-    if(want && coop && dp.rec_zbits > 0 && dp.gs_steps >= SSD_FS_WARPS)
+    if(want && coop && dp.rec_zbits > 0 && dp.gs_steps % SSD_FS_SUB == 0 && dp.gs_steps / SSD_FS_SUB >= 64)
     {
-      grid = std::min(grid, dp.gs_steps / SSD_FS_WARPS); // at least one step per warp and frame
       // record ring: fs_lag_frames frames of a warp's steps (phase 2 may trail phase 1 by that much: the frame barrier's
       // latency and the skew between the CTAs disappear in it); ~3.9 MB per frame at 1024x768, re-used before L2 evicts it
       if(const char *e = getenv("SSD_GPU_FS_LAG"))
         ctx->fs_lag_frames = std::max(1, std::min(SSD_FS_NB - 3, atoi(e)));
-      const int per_warp = (dp.gs_steps + grid * SSD_FS_WARPS - 1) / (grid * SSD_FS_WARPS);
+      const long long S = dp.gs_steps / SSD_FS_SUB, TW = (long long)grid * SSD_FS_WARPS;
+      const int per_warp = (int)((S + TW - 1) / TW);
       if(!ctx->fs_d_rec)
-        ctx->fs_d_rec = (int)(((long long)ctx->fs_lag_frames * dp.gs_steps + (long long)grid * SSD_FS_WARPS - 1) / ((long long)grid * SSD_FS_WARPS)) + 1;
+        ctx->fs_d_rec = (int)((ctx->fs_lag_frames * S + TW - 1) / TW) + 2;
       ctx->fs_d_rec = std::max(ctx->fs_d_rec, per_warp + 2);
       const size_t sm_v = fs_smem_bytes(FsSrc<SrcVertices>::STEP_BYTES, ctx->fs_d_raw, ctx->fs_d_rec);
       const size_t sm_d = fs_smem_bytes(FsSrc<SrcDepth>::STEP_BYTES, ctx->fs_d_raw, ctx->fs_d_rec);
@@ -887,7 +940,7 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
         const size_t n_sums = (size_t)ctx->n_streams * ctx->chunk_frames * (size_t)(dp.N / 32);
         CKC(cudaMalloc(&ctx->d_sums, n_sums * sizeof(GroupSum)));
         CKC(cudaMalloc(&ctx->d_done, (size_t)ctx->n_streams * ctx->chunk_frames * sizeof(unsigned)));
-        CKC(cudaMalloc(&ctx->d_recs, (size_t)grid * SSD_FS_WARPS * ctx->fs_d_rec * SSD_FS_REC_BYTES));
+        CKC(cudaMalloc(&ctx->d_recs, (size_t)grid * SSD_FS_WARPS * ctx->fs_d_rec * SSD_FS_REC_BYTES * SSD_FS_SUB));
         CKC(cudaMemset(ctx->d_done, 0, (size_t)ctx->n_streams * ctx->chunk_frames * sizeof(unsigned)));
         CKC(cudaEventCreateWithFlags(&ctx->ev_fs, cudaEventDisableTiming));
         if(getenv("SSD_GPU_FS_PROF"))

@@ -212,11 +212,51 @@ __device__ __forceinline__ void point_load(const FrameD &f, unsigned pt, float &
 __device__ __forceinline__ void tb_word(const DevParams &p, const float vx[4], const float vy[4], const float vz[4], unsigned *__restrict__ dst_word,
                                         unsigned *s_hist, unsigned &exact)
 {
-  unsigned c[4];
-  bool unc[4];
+  // Two speeds. When every point of the warp's 128 is invalid or certainly outside the measuring range in x or y (the image
+  // rows that look past the staircase: about four words in ten) only the packed x/y rows of the transform are evaluated:
+  // max(|v_x|, |v_y|) - 1 > eps implies max_i |v_i| - 1 > eps, which is point_code_scaled's own "certainly out of range".
+  float eps[4], sx[4], sy[4];
+  bool skip = true;
 #pragma unroll
   for(int j = 0; j < 4; j++)
-    c[j] = point_code_scaled(p, vx[j], vy[j], vz[j], unc[j]);
+  {
+    const float m = max3abs_nan(vx[j], vy[j], vz[j]);
+    eps[j] = fmaf(p.E1s, m, p.E0s);
+    f2_unpack(f2_affine(p.sxy2, p.sbxy2, vx[j], vy[j], vz[j]), sx[j], sy[j]);
+    const bool far = fmaxf(fabsf(sx[j]), fabsf(sy[j])) - 1.0f > eps[j];
+    skip = skip && (far || !(vz[j] > 0.f));
+  }
+  unsigned c[4];
+  if(__all_sync(__activemask(), skip)) // (the lanes of a frame's last, partial warp that have no word are not here)
+  {
+#pragma unroll
+    for(int j = 0; j < 4; j++)
+    {
+      c[j] = vz[j] > 0.f ? SSD_CODE_OUT_OF_RANGE : SSD_CODE_INVALID;
+      atomicAdd(s_hist + c[j], 1u);
+    }
+    *dst_word = c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24);
+    return;
+  }
+  bool unc[4];
+  const float MAGIC = 12582912.0f;
+#pragma unroll
+  for(int j = 0; j < 4; j++)
+  {
+    // the rest of point_code_scaled (ssd_device.cuh): z row, range test on all three rows, height bin with its certainty
+    const float sz = fmaf(p.sa[8], vz[j], fmaf(p.sa[7], vy[j], fmaf(p.sa[6], vx[j], p.sb[2])));
+    const float e1 = max3abs_nan(sx[j], sy[j], sz) - 1.0f;
+    const float uf = fmaf(sz, p.Gf, p.Gm);
+    const float s = uf + MAGIC;
+    const float d = uf - (s - MAGIC);
+    const float thr = fmaf(-p.Gup, eps[j], p.thr0);
+    const bool out = e1 > eps[j];
+    const bool in_bin = e1 < -eps[j] && fabsf(d) < thr;
+    const bool valid = vz[j] > 0.f;
+    unc[j] = valid && !(out || in_bin);
+    const unsigned cc = out ? SSD_CODE_OUT_OF_RANGE : ((unsigned)__float_as_int(s) & 0xffu);
+    c[j] = valid ? cc : SSD_CODE_INVALID;
+  }
   if(unc[0] || unc[1] || unc[2] || unc[3])
   {
     // rare: one out-of-line exact evaluation per uncertain point
@@ -367,7 +407,7 @@ __global__ void __launch_bounds__(32) k_peaks(const __grid_constant__ DevParams 
   __shared__ __align__(8) unsigned char s_lut[SSD_BINS_PAD];
   __shared__ int s_height[SSD_GPU_MAX_PLATEAUS], s_hmin[SSD_GPU_MAX_PLATEAUS], s_hmax[SSD_GPU_MAX_PLATEAUS];
   __shared__ unsigned s_np[SSD_GPU_MAX_PLATEAUS];
-  __shared__ int s_K, s_first_outlined;
+  __shared__ int s_K, s_first_outlined, s_ground;
   const int f = blockIdx.x, lane = threadIdx.x;
   if(f >= n_frames)
     return;
@@ -453,6 +493,7 @@ __global__ void __launch_bounds__(32) k_peaks(const __grid_constant__ DevParams 
     }
     s_K = K;
     s_first_outlined = i;
+    s_ground = ground;
     F.n_nonzero = (unsigned)p.N - hist[SSD_CODE_INVALID];
     F.n_in_range = (unsigned)p.N - hist[SSD_CODE_INVALID] - hist[SSD_CODE_OUT_OF_RANGE];
     F.n_plateaus = K;
@@ -464,12 +505,13 @@ __global__ void __launch_bounds__(32) k_peaks(const __grid_constant__ DevParams 
   }
   __syncwarp();
   {
-    // bin code -> label | 0x100 for the labels that get a BEV image (first_outlined .. K-1)
-    const int K = s_K, fo = s_first_outlined;
+    // bin code -> label | 0x100 for the labels that get a BEV image (first_outlined .. K-1) | 0x200 for the ground plateau
+    // | 0x8000 (entry written): the flags of ssd_kernels_stream.cuh
+    const int K = s_K, fo = s_first_outlined, gr = s_ground;
     for(int b = lane; b < SSD_BINS_PAD; b += 32)
     {
       const unsigned l = s_lut[b];
-      F.lut16[b] = (unsigned short)(l | (((int)l >= fo && (int)l < K) ? 0x100u : 0u));
+      F.lut16[b] = (unsigned short)(l | (((int)l >= fo && (int)l < K) ? 0x100u : 0u) | ((int)l == gr ? 0x200u : 0u) | 0x8000u);
     }
   }
   if(lane < s_K)

@@ -32,8 +32,11 @@
 #endif
 #define SSD_FS_THREADS (SSD_FS_WARPS * 32)
 #define SSD_FS_NB 16             // frames a CTA can have in flight (accumulator / LUT slots)
-#define SSD_FS_STEP_PX 128       // points per step: 32 lanes x 4
-#define SSD_FS_REC_BYTES 640     // record-ring slot: 32 code words + 32 x 4 records
+#define SSD_FS_STEP_PX 128       // points per sub-step: 32 lanes x 4
+#ifndef SSD_FS_SUB
+#define SSD_FS_SUB 2              // sub-steps per step (one bulk copy, one ring slot, one turn of a warp's loop)
+#endif
+#define SSD_FS_REC_BYTES 640     // records of one sub-step: 32 code words + 32 x 4 records
 #define SSD_LUT_OUTLINED 0x100u  // lut16 flags: the label gets a BEV image
 #define SSD_LUT_GROUND 0x200u    //              the label is the ground plateau
 #define SSD_LUT_VALID 0x8000u    //              entry written (a zero entry means "frame not ready")
@@ -103,7 +106,7 @@ __device__ __forceinline__ const void *fs_src_base(const SrcDepth &s) { return s
 __host__ __device__ inline size_t fs_smem_bytes(int step_bytes, int d_raw, int d_rec)
 {
   (void)d_rec;
-  return (size_t)SSD_FS_WARPS * d_raw * step_bytes + sizeof(FsLut) +
+  return (size_t)SSD_FS_WARPS * d_raw * step_bytes * SSD_FS_SUB + sizeof(FsLut) +
          sizeof(FsAcc) * SSD_FS_NB + sizeof(FsPeaks) + (size_t)SSD_FS_WARPS * d_raw * 8 + 128;
 }
 
@@ -505,22 +508,63 @@ __device__ __forceinline__ void fs_unpack_raw(const SrcDepth &src, const DevPara
   word_unpack(f, w, vx, vy, vz);
 }
 
-template<class SRC>
-__device__ __forceinline__ void fs_phase1(const DevParams &p, const SRC &src, const unsigned char *raw, unsigned char *rec, FsAcc &A, unsigned step,
-                                          int lane)
+// One 128-point sub-step. Returns through `A` / `rec`. Two speeds:
+//   * every point of the warp's 128 is invalid or certainly outside the measuring range in x or y (the image rows that look
+//     past the staircase: about four sub-steps in ten): only the packed x/y rows of the transform are evaluated; codes 254 / 255,
+//     the histogram, no records;
+//   * otherwise the full decision of point_code_scaled for all four points of every lane (no divergence), the exact fallback
+//     for the uncertain ones, and the records of the in-range points.
+template<class SRC, class ACC>
+__device__ __forceinline__ void fs_phase1(const DevParams &p, const SRC &src, const unsigned char *raw, unsigned *code_slot, uint4 *rec_slot, ACC &A,
+                                          unsigned step, int lane)
 {
   float vx[4], vy[4], vz[4];
   fs_unpack_raw(src, p, raw, step, lane, vx, vy, vz);
   const float MAGIC = 12582912.0f;
   const int zsh = 32 - p.rec_zbits;
-  unsigned c[4], zp[4];
+  float eps[4], sx[4], sy[4];
+  bool skip = true;
+#pragma unroll
+  for(int j = 0; j < 4; j++)
+  {
+    const float m = max3abs_nan(vx[j], vy[j], vz[j]);
+    eps[j] = fmaf(p.E1s, m, p.E0s);
+    f2_unpack(f2_affine(p.sxy2, p.sbxy2, vx[j], vy[j], vz[j]), sx[j], sy[j]);
+    // certainly out of range in x or y (then max|v_i| - 1 > eps as well: point_code_scaled says 254), or invalid (255)
+    const bool far = fmaxf(fabsf(sx[j]), fabsf(sy[j])) - 1.0f > eps[j];
+    skip = skip && (far || !(vz[j] > 0.f));
+  }
+  unsigned c[4];
+  if(__all_sync(0xffffffffu, skip))
+  {
+#pragma unroll
+    for(int j = 0; j < 4; j++)
+    {
+      c[j] = vz[j] > 0.f ? SSD_CODE_OUT_OF_RANGE : SSD_CODE_INVALID;
+      atomicAdd(A.hist + c[j], 1u);
+    }
+    __stcg(code_slot, c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24));
+    return;
+  }
+  unsigned zp[4];
   bool unc[4];
 #pragma unroll
   for(int j = 0; j < 4; j++)
   {
-    float df;
-    c[j] = point_code_scaled_d(p, vx[j], vy[j], vz[j], unc[j], df);
-    zp[j] = (unsigned)__float_as_int(fmaf(df, p.rec_mf, MAGIC)) << zsh;
+    // the rest of point_code_scaled (ssd_device.cuh): z row, range test on all three rows, height bin with its certainty
+    const float sz = fmaf(p.sa[8], vz[j], fmaf(p.sa[7], vy[j], fmaf(p.sa[6], vx[j], p.sb[2])));
+    const float e1 = max3abs_nan(sx[j], sy[j], sz) - 1.0f;
+    const float uf = fmaf(sz, p.Gf, p.Gm);
+    const float s = uf + MAGIC;
+    const float d = uf - (s - MAGIC);
+    const float thr = fmaf(-p.Gup, eps[j], p.thr0);
+    const bool out = e1 > eps[j];
+    const bool in_bin = e1 < -eps[j] && fabsf(d) < thr;
+    const bool valid = vz[j] > 0.f;
+    unc[j] = valid && !(out || in_bin);
+    const unsigned cc = out ? SSD_CODE_OUT_OF_RANGE : ((unsigned)__float_as_int(s) & 0xffu);
+    c[j] = valid ? cc : SSD_CODE_INVALID;
+    zp[j] = (unsigned)__float_as_int(fmaf(d, p.rec_mf, MAGIC)) << zsh;
   }
   if(unc[0] || unc[1] || unc[2] || unc[3])
   {
@@ -540,7 +584,7 @@ __device__ __forceinline__ void fs_phase1(const DevParams &p, const SRC &src, co
 #pragma unroll
   for(int j = 0; j < 4; j++)
     atomicAdd(A.hist + c[j], 1u);
-  __stcg(reinterpret_cast<unsigned *>(rec) + lane, cw);
+  __stcg(code_slot, cw);
   // records of the lane's in-range points (codes 254 / 255: out of range / invalid)
   if((cw & 0xfefefefeu) != 0xfefefefeu)
   {
@@ -550,7 +594,7 @@ __device__ __forceinline__ void fs_phase1(const DevParams &p, const SRC &src, co
     {
       int ix, iy;
       const bool ok = fast_pixel2(p, vx[j], vy[j], vz[j], ix, iy);
-      r[j] = zp[j] | ((unsigned)iy << p.rec_bx) | (unsigned)ix;
+      r[j] = zp[j] | ((c[j] & 1u) << (p.rec_bx + p.rec_by)) | ((unsigned)iy << p.rec_bx) | (unsigned)ix;
       slow |= (!ok && c[j] < SSD_CODE_OUT_OF_RANGE) ? (1u << j) : 0u;
     }
     if(slow)
@@ -563,19 +607,19 @@ __device__ __forceinline__ void fs_phase1(const DevParams &p, const SRC &src, co
       for(int j = 0; j < 4; j++)
         if((slow >> j) & 1u)
         {
-          r[j] = zp[j] | pixel_slow(p, vx[j], vy[j], vz[j]);
+          r[j] = zp[j] | ((c[j] & 1u) << (p.rec_bx + p.rec_by)) | pixel_slow(p, vx[j], vy[j], vz[j]);
           ns++;
         }
       atomicAdd(&A.n_def, ns);
     }
-    __stcg(reinterpret_cast<uint4 *>(rec + 128) + lane, make_uint4(r[0], r[1], r[2], r[3]));
+    __stcg(rec_slot, make_uint4(r[0], r[1], r[2], r[3]));
   }
 }
 
 // ---- phase 2 of one step: record slot -> labels, BEV bits, summaries ----
-template<class SRC>
+template<class SRC, class ACC>
 __device__ __forceinline__ void fs_phase2(const DevParams &p, const SRC &src, const FsParams &a, const unsigned cw, const uint4 rv, const unsigned short *lut,
-                                          FsAcc &A, unsigned frame, unsigned step, unsigned char *labels, unsigned *bev, unsigned bmw, int lane)
+                                          ACC &A, unsigned frame, unsigned step, unsigned char *labels, unsigned *bev, unsigned bmw, int lane)
 {
   const size_t word = (size_t)frame * (size_t)(p.N >> 2) + (size_t)step * 32u + (unsigned)lane;
   GroupSum *gs = a.sums + (((size_t)frame * (size_t)p.gs_steps + step) * 4u + (unsigned)(lane >> 3));
@@ -740,7 +784,9 @@ __global__ void __launch_bounds__(SSD_FS_THREADS, 1) k_frame_stream(const __grid
                                                                     unsigned *__restrict__ bev, size_t bm_words)
 {
   extern __shared__ __align__(128) unsigned char fs_smem[];
-  constexpr int RAW = FsSrc<SRC>::STEP_BYTES;
+  constexpr int SUBRAW = FsSrc<SRC>::STEP_BYTES;
+  constexpr int RAW = SUBRAW * SSD_FS_SUB;
+  constexpr int REC = SSD_FS_REC_BYTES * SSD_FS_SUB;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int d_raw = a.d_raw, d_rec = a.d_rec;
   unsigned char *raw_all = fs_smem;
@@ -776,17 +822,23 @@ __global__ void __launch_bounds__(SSD_FS_THREADS, 1) k_frame_stream(const __grid
   }
 
   unsigned char *raw = raw_all + (size_t)warp * d_raw * RAW;
-  unsigned char *rec = a.recs + ((size_t)blockIdx.x * SSD_FS_WARPS + warp) * (size_t)d_rec * SSD_FS_REC_BYTES;
+  unsigned char *rec = a.recs + ((size_t)blockIdx.x * SSD_FS_WARPS + warp) * (size_t)d_rec * REC;
   const unsigned raw_sa = (unsigned)__cvta_generic_to_shared(raw);
   const unsigned bar_sa = (unsigned)__cvta_generic_to_shared(bars + warp * d_raw);
 
-  const unsigned S = (unsigned)p.gs_steps;
+  const unsigned S = (unsigned)p.gs_steps / SSD_FS_SUB; // steps per frame
   const unsigned TW = gridDim.x * SSD_FS_WARPS, gw = blockIdx.x * SSD_FS_WARPS + warp;
   const unsigned n_frames = (unsigned)a.n_frames;
   FsCur ct, c1, c2;
-  ct.k = 0, ct.f = 0, ct.j = 0, ct.base = gw, ct.s = gw; // (TW <= S: the first block is complete)
-  c1 = ct;
-  c2 = ct;
+  // (a warp whose rotated position lies past the frame's last step has no step in that frame)
+#define FS_NEXT_FRAME(c)                                                                        \
+  do                                                                                            \
+  {                                                                                             \
+    (c).f++;                                                                                    \
+    (c).j = 0;                                                                                  \
+    (c).base = (c).base >= SSD_FS_ROT ? (c).base - SSD_FS_ROT : (c).base + TW - SSD_FS_ROT;     \
+    (c).s = (c).base;                                                                           \
+  } while((c).s >= S && (c).f < n_frames)
 #define FS_ADV(c)                                                        \
   do                                                                     \
   {                                                                      \
@@ -796,13 +848,13 @@ __global__ void __launch_bounds__(SSD_FS_THREADS, 1) k_frame_stream(const __grid
     b_ = b_ >= TW ? b_ - TW : b_;                                        \
     (c).s = (c).j * TW + b_;                                             \
     if((c).s >= S)                                                       \
-    {                                                                    \
-      (c).f++;                                                           \
-      (c).j = 0;                                                         \
-      (c).base = (c).base >= SSD_FS_ROT ? (c).base - SSD_FS_ROT : (c).base + TW - SSD_FS_ROT; \
-      (c).s = (c).base;                                                  \
-    }                                                                    \
+      FS_NEXT_FRAME(c);                                                  \
   } while(0)
+  ct.k = 0, ct.f = 0, ct.j = 0, ct.base = gw, ct.s = gw;
+  if(ct.s >= S)
+    FS_NEXT_FRAME(ct);
+  c1 = ct;
+  c2 = ct;
 #define FS_LIVE(c) ((c).f < n_frames)
 #define FS_FRAME(c) ((c).f < n_frames ? (c).f : n_frames)
   unsigned slot_t = 0, slot_1 = 0, phase_1 = 0, rslot_1 = 0, rslot_2 = 0;
@@ -850,7 +902,7 @@ __global__ void __launch_bounds__(SSD_FS_THREADS, 1) k_frame_stream(const __grid
     // 2. the records of the oldest pending phase-2 step: requested now (from L2, where phase 1 left them), used after phase 1
     if(pending && pf_k != c2.k)
     {
-      const unsigned char *r2 = rec + (size_t)rslot_2 * SSD_FS_REC_BYTES;
+      const unsigned char *r2 = rec + (size_t)rslot_2 * REC;
       cw2 = __ldcg(reinterpret_cast<const unsigned *>(r2) + lane);
       rv2 = __ldcg(reinterpret_cast<const uint4 *>(r2 + 128) + lane);
       pf_k = c2.k;
@@ -901,7 +953,13 @@ __global__ void __launch_bounds__(SSD_FS_THREADS, 1) k_frame_stream(const __grid
       mbar_wait(bar_sa + slot_1 * 8u, phase_1);
       const long long t0 = prof ? clock64() : 0;
       t_wait += t0 - tw0;
-      fs_phase1(p, src, raw + (size_t)slot_1 * RAW, rec + (size_t)rslot_1 * SSD_FS_REC_BYTES, acc[c1.f & (SSD_FS_NB - 1)], c1.s, lane);
+#pragma unroll 1
+      for(int i = 0; i < SSD_FS_SUB; i++)
+      {
+        unsigned char *ro = rec + (size_t)rslot_1 * REC + i * SSD_FS_REC_BYTES;
+        fs_phase1(p, src, raw + (size_t)slot_1 * RAW + i * SUBRAW, reinterpret_cast<unsigned *>(ro) + lane, reinterpret_cast<uint4 *>(ro + 128) + lane,
+                  acc[c1.f & (SSD_FS_NB - 1)], c1.s * SSD_FS_SUB + i, lane);
+      }
       __syncwarp();
       if(prof)
         t_p1 += clock64() - t0;
@@ -964,7 +1022,22 @@ __global__ void __launch_bounds__(SSD_FS_THREADS, 1) k_frame_stream(const __grid
     if(pending && (int)c2.f == lut_f)
     {
       const long long t0 = prof ? clock64() : 0;
-      fs_phase2(p, src, a, cw2, rv2, lutc->lut[ls], acc[ls], c2.f, c2.s, labels, bev, bmw, lane);
+#pragma unroll 1
+      for(int i = 0; i < SSD_FS_SUB; i++)
+      {
+        // the next sub-step's records are requested before this one is worked on
+        unsigned cwn = 0;
+        uint4 rvn = make_uint4(0u, 0u, 0u, 0u);
+        if(i + 1 < SSD_FS_SUB)
+        {
+          const unsigned char *r2 = rec + (size_t)rslot_2 * REC + (i + 1) * SSD_FS_REC_BYTES;
+          cwn = __ldcg(reinterpret_cast<const unsigned *>(r2) + lane);
+          rvn = __ldcg(reinterpret_cast<const uint4 *>(r2 + 128) + lane);
+        }
+        fs_phase2(p, src, a, cw2, rv2, lutc->lut[ls], acc[ls], c2.f, c2.s * SSD_FS_SUB + i, labels, bev, bmw, lane);
+        cw2 = cwn;
+        rv2 = rvn;
+      }
       __syncwarp();
       rslot_2 = rslot_2 + 1 == (unsigned)d_rec ? 0u : rslot_2 + 1;
       if(prof && lane == 0)
@@ -1034,6 +1107,7 @@ __global__ void __launch_bounds__(SSD_FS_THREADS, 1) k_frame_stream(const __grid
     atomicAdd(a.prof + 10, (unsigned long long)lag_sum);
   }
 #undef FS_ADV
+#undef FS_NEXT_FRAME
 #undef FS_FRAME
 #undef FS_LIVE
 }
@@ -1056,7 +1130,8 @@ struct QuadSumShared
 template<class SRC>
 __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_QR_MINB) k_quad_sum(const __grid_constant__ DevParams p, const SRC src,
                                                                           const unsigned char *__restrict__ labels, FrameDev *__restrict__ frames,
-                                                                          unsigned *__restrict__ bev, size_t bm_words, const GroupSum *__restrict__ sums)
+                                                                          unsigned *__restrict__ bev, size_t bm_words, const GroupSum *__restrict__ sums,
+                                                                          const uint4 *__restrict__ recs)
 {
   __shared__ QuadReduceShared S;
   __shared__ QuadSumShared Q;
@@ -1103,7 +1178,7 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_QR_MINB) k_quad_sum(const 
     if(wt + wt_stride < wt_end)
       asm volatile("prefetch.global.L2 [%0];" ::"l"(gs + (size_t)(wt + wt_stride) * 32 + lane));
     const unsigned count = gv.w >> 24, l = (gv.w >> 16) & 0xffu;
-    bool per_point = count == SSD_GS_COMPLEX;
+    bool per_point = count == SSD_GS_COMPLEX, gbev_group = false;
     if(count != 0u && !per_point && ((amask >> (l & 31u)) & 1u) && l < SSD_GPU_MAX_PLATEAUS)
     {
       const int ixmin = (int)(gv.x & 0xffffu), ixmax = (int)(gv.x >> 16), iymin = (int)(gv.y & 0xffffu), iymax = (int)(gv.y >> 16);
@@ -1119,10 +1194,16 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_QR_MINB) k_quad_sum(const 
       bool whole = inside;
       if(inside && (int)l == ground)
       {
-        // ground points in the pixel columns detectFrontEdge probes need their BEV bit: point by point
+        // ground points in the pixel columns detectFrontEdge probes need their BEV bit: from the records when the chain kept
+        // them (every point of the summary is inside the quadrilateral), else point by point
         const unsigned r = (unsigned)(ixmin - c0 + 50 * 128) % 50u;
         if(r < 5u || r + (unsigned)(ixmax - ixmin) >= 50u)
-          whole = false;
+        {
+          if(recs)
+            gbev_group = true;
+          else
+            whole = false;
+        }
       }
       if(whole)
       {
@@ -1145,6 +1226,26 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_QR_MINB) k_quad_sum(const 
       }
       else if(!outside)
         per_point = true;
+    }
+    {
+      // ground summaries taken whole: the BEV bits of their points in the probed columns, one pixel per lane
+      unsigned gbm = __ballot_sync(0xffffffffu, gbev_group);
+      const unsigned rmx = (1u << p.rec_bx) - 1u, rmy = (1u << p.rec_by) - 1u;
+      while(gbm)
+      {
+        const int b = __ffs(gbm) - 1;
+        gbm &= gbm - 1u;
+        const size_t px = (size_t)(wt * 32 + b) * 32 + (unsigned)lane;
+        const unsigned lb = __ldg(labels + fbase + px);
+        const unsigned rc = __ldg(reinterpret_cast<const unsigned *>(recs + (size_t)frame * (p.N >> 2)) + px);
+        const int ix = (int)(rc & rmx), iy = (int)((rc >> p.rec_bx) & rmy);
+        if((int)lb == ground && ground_col_needed(p, ix))
+        {
+          atomicOr(gbev + (unsigned)iy * (unsigned)p.wpr + (unsigned)(ix >> 5), 1u << (ix & 31));
+          W.rmin = min(W.rmin, iy);
+          W.rmax = max(W.rmax, iy);
+        }
+      }
     }
     if(!__any_sync(0xffffffffu, per_point))
       continue;
