@@ -7,6 +7,7 @@
 #include "../stair_step_detector_b200/csrc/host/pointcloud.h"
 #include "../stair_step_detector_b200/csrc/host/transformation.h"
 #include "../stair_step_detector_b200/csrc/host/window.h"
+#include "../include/ssd_scene.h" // synthetic input source (libssd_scene.so), in place of Camera::waitForFrames
 #include <cstdlib>
 #include <iostream>
 #include <vector>

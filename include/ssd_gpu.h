@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SSD_GPU_ABI_VERSION 1
+#define SSD_GPU_ABI_VERSION 2
 
 /* ---- limits ---- */
 #define SSD_GPU_MAX_BINS 253      /* height-histogram bins; bin codes are u8, 253..255 reserved */
@@ -125,15 +125,15 @@ typedef struct ssd_gpu_frame_info
 } ssd_gpu_frame_info;
 
 typedef struct ssd_gpu_ctx ssd_gpu_ctx;
-struct ssd_scene;
 
 /* Timing of the last ssd_gpu_process_* call, CUDA events on the ctx stream (milliseconds). */
 typedef struct ssd_gpu_timing
 {
-  float total_ms;    /* first kernel to results resident in pinned host memory */
-  float h2d_ms;      /* host->device upload (process_host only) */
-  float kernels_ms;  /* all kernels of the chain */
-  float label_ms;    /* the dominant transform/histogram/label stage alone */
+  float total_ms;    /* first copy / kernel to results resident in pinned host memory */
+  float h2d_ms;      /* host-input calls: first to last host->device copy on the copy stream (the copies overlap the kernels
+                        of earlier chunks, so this is a span inside total_ms, not a share of it); 0 for device input */
+  float reserved0;
+  float label_ms;    /* the dominant transform/histogram stage alone (calls made with SSD_FLAG_STAGE_TIMING), else 0 */
   int32_t n_launches;/* kernels launched by the call */
   int32_t reserved;
 } ssd_gpu_timing;
@@ -173,11 +173,7 @@ int ssd_gpu_process_depth_host(ssd_gpu_ctx *ctx, const uint16_t *z16_host, const
 int ssd_gpu_process_depth_device(ssd_gpu_ctx *ctx, const uint16_t *z16_dev, const ssd_gpu_intrinsics *intr, int n_frames);
 /* Deprojection alone: n_frames depth frames (device) -> packed vertices (device), for parity checks. */
 int ssd_gpu_deproject_device(ssd_gpu_ctx *ctx, const uint16_t *z16_dev, const ssd_gpu_intrinsics *intr, int n_frames, float *xyz_dev);
-/* intrinsics of a synthetic scene */
-void ssd_scene_intrinsics(const struct ssd_scene *s, ssd_gpu_intrinsics *out);
 
-/* Same, but skips the per-point label store (labels are still computed; results identical). */
-#define SSD_FLAG_NO_LABELS 0x1
 /* Record CUDA events around every kernel of the chain (on the launching streams); read with ssd_gpu_get_stage_times. */
 #define SSD_FLAG_STAGE_TIMING 0x2
 /* Run every chunk on one stream (no overlap between chunks): with STAGE_TIMING the event brackets are then the kernels' own durations. */
@@ -276,46 +272,6 @@ int ssd_inverse3(const double a[9], double a_inv[9]);
 #define SSD_CAL_TRIANGLE_INVALID 2
 #define SSD_CAL_POINTS_MISSING 3
 int ssd_load_calibration(const char *directory, ssd_gpu_transform *out, double world_pts[9], double camera_pts[9]);
-
-/* ---- synthetic input source (stands in for the stubbed RealSense capture) ---- */
-typedef struct ssd_scene
-{
-  int32_t width, height;
-  float fx, fy, ppx, ppy;      /* pin-hole intrinsics */
-  float depth_unit;            /* metres per z16 count (L515: 0.00025) */
-  float cam_height;            /* camera height above the calibration plane (m) */
-  float cam_pitch_deg;         /* optical axis below horizontal */
-  float cam_roll_deg;
-  float cam_yaw_deg;
-  float cam_x, cam_y;          /* camera foot point in scene coordinates */
-  float ground_z;              /* ground plane height */
-  int32_t n_steps;
-  float riser, tread, width_m; /* step geometry (m) */
-  float first_riser_y;         /* y of the first riser */
-  float x_center;              /* lateral centre of the flight */
-  float top_landing;           /* extra depth of the top tread (m) */
-  float noise_sigma;           /* N(0,sigma) along the ray (m) */
-  float dropout;               /* probability of a zero-depth pixel */
-  int32_t n_holes;             /* rectangular zero-depth holes */
-  int32_t n_occluders;         /* boxes floating between camera and stairs */
-  int32_t rotate180;           /* camera mounted upside down (README "descending stairs") */
-  int32_t randomize_camera;    /* ssd_scene_randomize also jitters the camera pose (needs a per-frame calibration) */
-  uint64_t seed;
-} ssd_scene;
-
-void ssd_scene_default(ssd_scene *s, int32_t width, int32_t height);
-/* Randomise the geometry of frame `index` of a batch (SURVEY.md 8(d) config 3/4/5 distributions). */
-void ssd_scene_randomize(ssd_scene *s, const ssd_scene *base, uint64_t base_seed, int64_t index, int min_steps, int max_steps);
-/* Three ground points seen by the scene's camera, for ssd_make_transform / the reference ctor. */
-void ssd_scene_calibration_points(const ssd_scene *s, double world_pts[9], double camera_pts[9]);
-/* z16 depth image of one scene, host. */
-int ssd_synth_depth_host(const ssd_scene *s, uint16_t *depth_out);
-/* z16 -> vertices (the stubbed rs2::pointcloud::calculate, pointcloud.cpp:138), host. */
-int ssd_deproject_host(const ssd_scene *s, const uint16_t *depth, float *xyz_out);
-/* Device versions: generate n_frames randomised scenes straight into HBM (xyz_dev: n_frames*W*H*3 floats).
- * depth_dev may be NULL. */
-int ssd_gpu_synth_frames(ssd_gpu_ctx *ctx, const ssd_scene *base, uint64_t base_seed, int64_t first_index, int n_frames,
-                         int min_steps, int max_steps, float *xyz_dev, uint16_t *depth_dev);
 
 /* ---- raw device memory helpers for callers without a CUDA runtime binding ---- */
 int ssd_gpu_malloc(ssd_gpu_ctx *ctx, size_t bytes, void **dev_ptr);

@@ -26,6 +26,18 @@ def lib():
     return _lib
 
 
+_scene_lib = None
+
+
+def scene_lib():
+    """libssd_scene.so: the synthetic input source (include/ssd_scene.h). Not the product: generating input never needs
+    libssd_gpu.so."""
+    global _scene_lib
+    if _scene_lib is None:
+        _scene_lib = A.load_scene()
+    return _scene_lib
+
+
 class SsdError(RuntimeError):
     pass
 
@@ -68,7 +80,7 @@ def load_calibration(directory=""):
 
 def default_scene(width, height, **overrides):
     s = Scene()
-    lib().ssd_scene_default(C.byref(s), width, height)
+    scene_lib().ssd_scene_default(C.byref(s), width, height)
     for k, v in overrides.items():
         setattr(s, k, v)
     return s
@@ -77,7 +89,7 @@ def default_scene(width, height, **overrides):
 def scene_transform(scene):
     w = (C.c_double * 9)()
     c = (C.c_double * 9)()
-    lib().ssd_scene_calibration_points(C.byref(scene), w, c)
+    scene_lib().ssd_scene_calibration_points(C.byref(scene), w, c)
     xf = Transform()
     rc = lib().ssd_make_transform(w, c, C.byref(xf))
     if rc:
@@ -90,7 +102,7 @@ def scene_transform_ex(scene):
     for Detector.set_overlay."""
     w = (C.c_double * 9)()
     c = (C.c_double * 9)()
-    lib().ssd_scene_calibration_points(C.byref(scene), w, c)
+    scene_lib().ssd_scene_calibration_points(C.byref(scene), w, c)
     xf = Transform()
     a_inv = (C.c_double * 9)()
     rc = lib().ssd_make_transform_ex(w, c, C.byref(xf), a_inv)
@@ -111,13 +123,13 @@ def inverse3(a):
 
 def randomize_scene(base, base_seed, index, min_steps, max_steps):
     s = Scene()
-    lib().ssd_scene_randomize(C.byref(s), C.byref(base), base_seed, index, min_steps, max_steps)
+    scene_lib().ssd_scene_randomize(C.byref(s), C.byref(base), base_seed, index, min_steps, max_steps)
     return s
 
 
 def synth_depth_host(scene):
     d = np.empty((scene.height, scene.width), np.uint16)
-    rc = lib().ssd_synth_depth_host(C.byref(scene), _ptr(d))
+    rc = scene_lib().ssd_synth_depth_host(C.byref(scene), _ptr(d))
     if rc:
         raise SsdError(f"ssd_synth_depth_host failed ({rc})")
     return d
@@ -126,7 +138,7 @@ def synth_depth_host(scene):
 def deproject_host(scene, depth):
     depth = np.ascontiguousarray(depth, np.uint16)
     xyz = np.empty((scene.height, scene.width, 3), np.float32)
-    rc = lib().ssd_deproject_host(C.byref(scene), _ptr(depth), _ptr(xyz))
+    rc = scene_lib().ssd_deproject_host(C.byref(scene), _ptr(depth), _ptr(xyz))
     if rc:
         raise SsdError(f"ssd_deproject_host failed ({rc})")
     return xyz
@@ -135,7 +147,7 @@ def deproject_host(scene, depth):
 def scene_intrinsics(scene):
     """Pin-hole intrinsics + depth unit of a synthetic scene (what rs2 would report for the depth stream)."""
     k = A.Intrinsics()
-    lib().ssd_scene_intrinsics(C.byref(scene), C.byref(k))
+    scene_lib().ssd_scene_intrinsics(C.byref(scene), C.byref(k))
     return k
 
 
@@ -344,8 +356,11 @@ class Detector:
         self._ck(self._l.ssd_gpu_memcpy_d2h(self._h, _ptr(dst), src, dst.nbytes if nbytes is None else nbytes), "ssd_gpu_memcpy_d2h")
 
     def synth_frames(self, base_scene, base_seed, first_index, n_frames, min_steps, max_steps, xyz_dev, depth_dev=None):
-        self._ck(self._l.ssd_gpu_synth_frames(self._h, C.byref(base_scene), base_seed, first_index, n_frames, min_steps, max_steps,
-                                              xyz_dev, depth_dev), "ssd_gpu_synth_frames")
+        """fill device buffers of this context's GPU with synthetic frames (libssd_scene.so: input source, not the product)"""
+        rc = scene_lib().ssd_scene_synth_frames_device(self.device, C.byref(base_scene), base_seed, first_index, n_frames, min_steps, max_steps,
+                                                       xyz_dev, depth_dev)
+        if rc != A.OK:
+            raise SsdError(f"ssd_scene_synth_frames_device failed ({rc})")
 
 
 def pinned_empty(shape, dtype):

@@ -25,7 +25,6 @@ STATUS_TOO_MANY_PLATEAUS = 0x10
 STATUS_BEV_OOB = 0x20
 STATUS_HMIN_WRAP = 0x40
 
-FLAG_NO_LABELS = 0x1
 FLAG_STAGE_TIMING = 0x2
 FLAG_SINGLE_STREAM = 0x4
 N_STAGES = 7
@@ -73,7 +72,7 @@ class FrameInfo(C.Structure):
 
 
 class Timing(C.Structure):
-    _fields_ = [("total_ms", C.c_float), ("h2d_ms", C.c_float), ("kernels_ms", C.c_float),
+    _fields_ = [("total_ms", C.c_float), ("h2d_ms", C.c_float), ("reserved0", C.c_float),
                 ("label_ms", C.c_float), ("n_launches", C.c_int32), ("reserved", C.c_int32)]
 
 
@@ -111,7 +110,6 @@ PROTOTYPES = {
     "ssd_gpu_process_depth_host": (C.c_int, [_vp, _vp, _P(Intrinsics), C.c_int]),
     "ssd_gpu_process_depth_device": (C.c_int, [_vp, _vp, _P(Intrinsics), C.c_int]),
     "ssd_gpu_deproject_device": (C.c_int, [_vp, _vp, _P(Intrinsics), C.c_int, _vp]),
-    "ssd_scene_intrinsics": (None, [_P(Scene), _P(Intrinsics)]),
     "ssd_gpu_get_steps": (C.c_int, [_vp, C.c_int, _P(Step), C.c_int, _P(C.c_int), _P(C.c_uint32)]),
     "ssd_gpu_set_overlay": (C.c_int, [_vp, _P(C.c_double), _P(Intrinsics)]),
     "ssd_gpu_get_overlay": (C.c_int, [_vp, C.c_int, _P(Overlay), C.c_int, _P(C.c_int)]),
@@ -133,12 +131,6 @@ PROTOTYPES = {
     "ssd_make_transform": (C.c_int, [_P(C.c_double), _P(C.c_double), _P(Transform)]),
     "ssd_make_transform_ex": (C.c_int, [_P(C.c_double), _P(C.c_double), _P(Transform), _P(C.c_double)]),
     "ssd_inverse3": (C.c_int, [_P(C.c_double), _P(C.c_double)]),
-    "ssd_scene_default": (None, [_P(Scene), C.c_int32, C.c_int32]),
-    "ssd_scene_randomize": (None, [_P(Scene), _P(Scene), C.c_uint64, C.c_int64, C.c_int, C.c_int]),
-    "ssd_scene_calibration_points": (None, [_P(Scene), _P(C.c_double), _P(C.c_double)]),
-    "ssd_synth_depth_host": (C.c_int, [_P(Scene), _vp]),
-    "ssd_deproject_host": (C.c_int, [_P(Scene), _vp, _vp]),
-    "ssd_gpu_synth_frames": (C.c_int, [_vp, _P(Scene), C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "ssd_gpu_malloc": (C.c_int, [_vp, C.c_size_t, _P(_vp)]),
     "ssd_gpu_free": (C.c_int, [_vp, _vp]),
     "ssd_gpu_memcpy_h2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
@@ -147,6 +139,18 @@ PROTOTYPES = {
     "ssd_gpu_malloc_host": (C.c_int, [C.c_size_t, _P(_vp)]),
     "ssd_gpu_free_host": (C.c_int, [_vp]),
 }
+
+# every symbol include/ssd_scene.h declares (libssd_scene.so: the synthetic input source, not part of the product)
+SCENE_PROTOTYPES = {
+    "ssd_scene_default": (None, [_P(Scene), C.c_int32, C.c_int32]),
+    "ssd_scene_randomize": (None, [_P(Scene), _P(Scene), C.c_uint64, C.c_int64, C.c_int, C.c_int]),
+    "ssd_scene_calibration_points": (None, [_P(Scene), _P(C.c_double), _P(C.c_double)]),
+    "ssd_scene_intrinsics": (None, [_P(Scene), _P(Intrinsics)]),
+    "ssd_synth_depth_host": (C.c_int, [_P(Scene), _vp]),
+    "ssd_deproject_host": (C.c_int, [_P(Scene), _vp, _vp]),
+    "ssd_scene_synth_frames_device": (C.c_int, [C.c_int, _P(Scene), C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+}
+SCENE_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libssd_scene.so")
 
 # SSD_GPU_LIB: developer override (A/B builds of the same library on the GPU box); never a different implementation
 LIB_PATH = os.environ.get("SSD_GPU_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libssd_gpu.so")
@@ -158,6 +162,12 @@ def bind(lib, prototypes=PROTOTYPES):
         fn.restype = res
         fn.argtypes = args
     return lib
+
+
+def load_scene(path=SCENE_LIB_PATH):
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: build first (python -c 'import __graft_entry__ as g; g.build()')")
+    return bind(C.CDLL(path), SCENE_PROTOTYPES)
 
 
 def load(path=LIB_PATH):

@@ -13,6 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libssd_gpu.so")
+SCENE_LIB = os.path.join(LIB_DIR, "libssd_scene.so")  # synthetic input source (include/ssd_scene.h): not the product
+SCENE_SOURCES = ["scene/ssd_scene.cu"]
 
 SOURCES = [
     "ssd_gpu.cu",
@@ -22,6 +24,7 @@ SOURCES = [
     "host/pointcloud.cpp",
     "host/segmentation.cpp",
     "host/quadrilateralTest.cpp",
+    "host/defaultContext.cpp",
     "host/calibrationTriangle.cpp",
     "host/geometricCalibration.cpp",
 ]
@@ -42,24 +45,31 @@ def _stale(out, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    deps = list(srcs) + [os.path.join(HERE, "..", "include", "ssd_gpu.h"), __file__]
+def _build_one(out, sources, force, verbose, log=None):
+    srcs = [os.path.join(CSRC, s) for s in sources if os.path.exists(os.path.join(CSRC, s))]
+    deps = list(srcs) + [os.path.join(HERE, "..", "include", "ssd_gpu.h"), os.path.join(HERE, "..", "include", "ssd_scene.h"), __file__]
     for root, _, files in os.walk(CSRC):
         deps += [os.path.join(root, f) for f in files if f.endswith((".h", ".cuh"))]
-    if not force and not _stale(LIB, deps):
-        return LIB
+    if not force and not _stale(out, deps):
+        return out
     os.makedirs(LIB_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + srcs
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", out] + srcs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed building libssd_gpu.so")
-    with open(os.path.join(LIB_DIR, "ptxas.log"), "w") as f:
-        f.write(r.stderr)
-    return LIB
+        raise RuntimeError("nvcc failed building " + os.path.basename(out))
+    if log:
+        with open(os.path.join(LIB_DIR, log), "w") as f:
+            f.write(r.stderr)
+    return out
+
+
+def build(force=False, verbose=False):
+    """libssd_gpu.so (the product) and libssd_scene.so (synthetic input source for tests / bench)."""
+    _build_one(SCENE_LIB, SCENE_SOURCES, force, verbose)
+    return _build_one(LIB, SOURCES, force, verbose, log="ptxas.log")
 
 
 if __name__ == "__main__":

@@ -1,11 +1,14 @@
 // QuadrilateralTest over the C ABI (replaces reference quadrilateralTest.cpp:275-451).
 #include "quadrilateralTest.h"
+#include "defaultContext.h"
 #include "../../../include/ssd_gpu.h"
 #include <stdexcept>
 #include <string>
 
 namespace stairs
 {
+
+QuadrilateralTest::QuadrilateralTest(const Quadrilateral_t &q) : QuadrilateralTest(defaultContext(640, 480), q) {}
 
 QuadrilateralTest::QuadrilateralTest(ssd_gpu_ctx *ctx, const Quadrilateral_t &q) : _ctx(ctx)
 {

@@ -16,6 +16,7 @@ namespace stairs
 class QuadrilateralTest
 {
 public:
+  explicit QuadrilateralTest(const Quadrilateral_t &q); // quadrilateralTest.h:35 (default context, defaultContext.h)
   QuadrilateralTest(ssd_gpu_ctx *ctx, const Quadrilateral_t &q);
   bool isPointWithin(const Point2 &point) const;
   std::vector<uint8_t> arePointsWithin(const std::vector<Point2> &points) const;

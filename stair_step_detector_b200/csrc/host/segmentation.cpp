@@ -1,6 +1,7 @@
 // Segmentation over the C ABI (replaces reference segmentation.cpp:879-971).
 #include "segmentation.h"
 #include "image.h"
+#include "defaultContext.h"
 #include "../../../include/ssd_gpu.h"
 #include <stdexcept>
 #include <vector>
@@ -23,6 +24,16 @@ const uint8_t *dense(const Image &image, std::vector<uint8_t> &tmp)
 }
 
 } // namespace
+
+Segmentation::FrontEdge Segmentation::detectFrontEdge(const Image &image, const std::string &windowName)
+{
+  return detectFrontEdge(defaultContext(image.width(), image.height()), image, windowName);
+}
+
+Segmentation::Outline Segmentation::detectOutline(const Image &image, int minImgYExtent, double xyRatio, const std::string &windowName)
+{
+  return detectOutline(defaultContext(image.width(), image.height()), image, minImgYExtent, xyRatio, windowName);
+}
 
 Segmentation::FrontEdge Segmentation::detectFrontEdge(ssd_gpu_ctx *ctx, const Image &image, const std::string &)
 {

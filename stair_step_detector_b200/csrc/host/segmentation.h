@@ -1,7 +1,7 @@
 // Host mirror of the reference's 2-D outline detector interface (segmentation.h:32-58): same static
 // functions and result structs. The work runs in the k_outline / front-edge CUDA code on the plateau's
-// top-down image; the extra leading argument is the GPU context (the reference's functions are free of
-// state, ours need the device).
+// top-down image. The reference's signatures (no context argument) run on a process-wide default context for the
+// image's size (defaultContext.h); the overloads with a leading ssd_gpu_ctx* use the caller's.
 #pragma once
 #include "types.h"
 #include <string>
@@ -21,6 +21,7 @@ public:
     Point2 pointLeft, pointRight;
     bool valid = false;
   };
+  static FrontEdge detectFrontEdge(const Image &image, const std::string &windowName = ""); // segmentation.h:40
   static FrontEdge detectFrontEdge(ssd_gpu_ctx *ctx, const Image &image, const std::string &windowName = "");
 
   struct Outline
@@ -29,6 +30,7 @@ public:
     Quadrilateral_t quadrilateral;
     bool valid = false;
   };
+  static Outline detectOutline(const Image &image, int minImgYExtent, double xyRatio, const std::string &windowName = ""); // segmentation.h:57
   static Outline detectOutline(ssd_gpu_ctx *ctx, const Image &image, int minImgYExtent, double xyRatio, const std::string &windowName = "");
 };
 

@@ -11,7 +11,7 @@
 #ifndef SSD_SCENE_MODEL_H_
 #define SSD_SCENE_MODEL_H_
 
-#include "../../include/ssd_gpu.h"
+#include "../../../include/ssd_scene.h"
 #include <math.h>
 
 #ifdef __CUDACC__

@@ -5,13 +5,13 @@
 #include "ssd_kernels_outline.cuh"
 #include "ssd_kernels_stream.cuh"
 #include "ssd_kernels_records.cuh"
-#include "scene_model.h"
 
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -43,11 +43,9 @@ struct ssd_gpu_ctx
   int n_streams = 2;
   cudaStream_t stream[SSD_MAX_STREAMS]{};
   cudaStream_t copy_stream{};
-  // optional lead stream: k_transform_bin of every chunk runs here (low priority), the rest of the chain on stream[s]
-  cudaStream_t p1_stream{};
-  cudaEvent_t ev_pre[SSD_MAX_STREAMS]{}, ev_p1[SSD_MAX_STREAMS]{};
-  int split = 0;
-  size_t pad_tb = 0, pad_l = 0, pad_q = 0; // extra dynamic shared memory per block: caps the resident blocks per SM
+  // knobs, read once in ssd_gpu_create: blocks per frame of the point kernels, small-batch split, depth A/B path
+  int bpf_l_knob = 0, bpf_q_knob = 0;
+  bool no_split_small = false, depth_unfused = false;
   cudaEvent_t ev_start{}, ev_stop{}, ev_h2d0{}, ev_h2d1{};
   cudaEvent_t ev_in_ready[SSD_MAX_STREAMS]{}, ev_in_free[SSD_MAX_STREAMS]{}, ev_chunk_done[SSD_MAX_STREAMS]{};
   FrameDev *d_frames = nullptr;   // max_frames
@@ -302,40 +300,6 @@ static int derive_params(const ssd_gpu_config &c, const ssd_gpu_transform &t, De
 }
 
 // ---------------------------------------------------------------------------------------------
-// scene generation / deprojection kernels (synthetic input source)
-// ---------------------------------------------------------------------------------------------
-__global__ void k_synth_frames(ssd_scene base, uint64_t base_seed, long long first_index, int n_frames, int min_steps, int max_steps,
-                               float *__restrict__ xyz, uint16_t *__restrict__ depth)
-{
-  __shared__ ssd_scene s;
-  __shared__ ssd_scene_rt rt;
-  const int f = blockIdx.y;
-  if(threadIdx.x == 0)
-  {
-    if(min_steps > 0)
-      ssd_scene_randomize_hd(&s, &base, base_seed, first_index + f, min_steps, max_steps);
-    else
-      s = base;
-    ssd_scene_prepare(&s, &rt);
-  }
-  __syncthreads();
-  const int N = s.width * s.height;
-  for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x)
-  {
-    const int v = i / s.width, u = i - v * s.width;
-    const uint16_t d = ssd_scene_depth(&s, &rt, u, v);
-    if(depth)
-      depth[(size_t)f * N + i] = d;
-    float o[3];
-    ssd_deproject_pixel(&s, u, v, d, o);
-    float *dst = xyz + ((size_t)f * N + i) * 3;
-    dst[0] = o[0];
-    dst[1] = o[1];
-    dst[2] = o[2];
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // depth frame -> vertices: the deprojection the reference delegates to rs2::pointcloud::calculate
 // (pointcloud.cpp:138; pin-hole model of rs2_deproject_pixel_to_point / camera.h:99-116). Single-rounded f32
 // operations in the order of ssd_deproject_pixel (scene_model.h), so the vertices are bit-identical to the host's.
@@ -370,7 +334,8 @@ __global__ void __launch_bounds__(256) k_deproject(int W, int N, float depth_uni
 }
 
 // ---------------------------------------------------------------------------------------------
-// single-stage kernels (same device functions as the chain)
+// single-stage kernels behind ssd_gpu_detect_outline / _front_edge / _points_in_quad / _camera_to_world: the host classes
+// Segmentation, QuadrilateralTest and CameraToWorld call them (same device functions as the chain)
 // ---------------------------------------------------------------------------------------------
 __global__ void k_pack_bitmap(const __grid_constant__ DevParams p, const unsigned char *__restrict__ img, unsigned *__restrict__ bm)
 {
@@ -388,7 +353,7 @@ __global__ void k_pack_bitmap(const __grid_constant__ DevParams p, const unsigne
   bm[i] = v;
 }
 
-__global__ void k_test_setup_plateau(FrameDev *frames, int H)
+__global__ void k_single_setup_plateau(FrameDev *frames, int H)
 {
   FrameDev &F = frames[0];
   F.n_plateaus = 1;
@@ -403,7 +368,7 @@ __global__ void k_test_setup_plateau(FrameDev *frames, int H)
   P.row_max = H - 1;
 }
 
-__global__ void __launch_bounds__(SSD_OL_THREADS) k_test_front_edge(const __grid_constant__ DevParams p, unsigned *__restrict__ bev,
+__global__ void __launch_bounds__(SSD_OL_THREADS) k_single_front_edge(const __grid_constant__ DevParams p, unsigned *__restrict__ bev,
                                                                      size_t smem_cap_words, double *out)
 {
   extern __shared__ __align__(16) unsigned s_words[];
@@ -434,7 +399,7 @@ __global__ void __launch_bounds__(SSD_OL_THREADS) k_test_front_edge(const __grid
   }
 }
 
-__global__ void k_test_points_in_quad(const double *__restrict__ quad, const double *__restrict__ xy, int n, unsigned char *__restrict__ inside,
+__global__ void k_single_points_in_quad(const double *__restrict__ quad, const double *__restrict__ xy, int n, unsigned char *__restrict__ inside,
                                       int *ctor_status)
 {
   __shared__ QuadTestDev qt;
@@ -455,7 +420,7 @@ __global__ void k_test_points_in_quad(const double *__restrict__ quad, const dou
     inside[i] = qt.status ? 0 : (unsigned char)quadtest_within(qt, xy[i * 2], xy[i * 2 + 1]);
 }
 
-__global__ void k_test_camera_to_world(const __grid_constant__ DevParams p, const float *__restrict__ xyz, int n, double *__restrict__ world)
+__global__ void k_single_camera_to_world(const __grid_constant__ DevParams p, const float *__restrict__ xyz, int n, double *__restrict__ world)
 {
   for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
   {
@@ -473,7 +438,7 @@ __global__ void k_test_camera_to_world(const __grid_constant__ DevParams p, cons
 // xyz_dev: packed vertices of the chunk, or nullptr with z16_dev: the chunk's depth frames, deprojected inside the
 // three point kernels (SrcDepth)
 static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, const uint16_t *z16_dev, float depth_unit, int frame0, int nf, int *launches,
-                        cudaEvent_t *ev, bool single = false)
+                        cudaEvent_t *ev)
 {
 #define STAGE_EV(i)                         \
   do                                        \
@@ -490,11 +455,7 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, const uin
   // k_label_bev / k_quad_reduce: each block loops over tiles of its frame; enough blocks for ~6 waves of the GPU
   const int tiles2 = (p.N + SSD_WT_PX * SSD_PT_WARPS - 1) / (SSD_WT_PX * SSD_PT_WARPS); // at least one warp-tile per warp
   const int bpf = std::max(1, std::min(tiles2, (ctx->pt_blocks_target + nf - 1) / nf));
-  int bpf_l = bpf, bpf_q = bpf;
-  if(const char *e = getenv("SSD_GPU_L_BPF"))
-    bpf_l = std::max(1, std::min(tiles2, atoi(e)));
-  if(const char *e = getenv("SSD_GPU_Q_BPF"))
-    bpf_q = std::max(1, std::min(tiles2, atoi(e)));
+  const int bpf_l = ctx->bpf_l_knob > 0 ? std::min(tiles2, ctx->bpf_l_knob) : bpf, bpf_q = ctx->bpf_q_knob > 0 ? std::min(tiles2, ctx->bpf_q_knob) : bpf;
   const dim3 gpt2l(bpf_l, nf), gpt2q(bpf_q, nf);
   const bool depth = xyz_dev == nullptr;
   SrcVertices sv;
@@ -612,36 +573,20 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, const uin
     CK(cudaGetLastError());
     return SSD_OK;
   }
-  if(ctx->split && !single)
-  {
-    // everything already queued on stream s (input copy / deprojection, the previous chunk of this stream) first
-    cudaStream_t p1 = ctx->p1_stream;
-    CK(cudaEventRecord(ctx->ev_pre[s], st));
-    CK(cudaStreamWaitEvent(p1, ctx->ev_pre[s], 0));
-    if(ev)
-      CK(cudaEventRecord(ev[0], p1));
-    if(depth)
-      k_transform_bin_depth<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, 0, p1>>>(p, sd, labels, frames);
-    else
-      k_transform_bin<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, SSD_PT_ITERS * SSD_TB_STAGE_BYTES + ctx->pad_tb, p1>>>(p, xyz_dev, labels, frames);
-    CK(cudaEventRecord(ctx->ev_p1[s], p1));
-    CK(cudaStreamWaitEvent(st, ctx->ev_p1[s], 0));
-  }
-  else
   {
     STAGE_EV(0);
     if(depth)
       k_transform_bin_depth<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, 0, st>>>(p, sd, labels, frames);
     else
-      k_transform_bin<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, SSD_PT_ITERS * SSD_TB_STAGE_BYTES + ctx->pad_tb, st>>>(p, xyz_dev, labels, frames);
+      k_transform_bin<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, SSD_PT_ITERS * SSD_TB_STAGE_BYTES, st>>>(p, xyz_dev, labels, frames);
   }
   STAGE_EV(1);
   k_peaks<<<nf, 32, 0, st>>>(p, frames, nf);
   STAGE_EV(2);
   if(depth)
-    k_label_bev<SrcDepth><<<gpt2l, SSD_PT_THREADS, ctx->pad_l, st>>>(p, sd, labels, frames, bev, ctx->bm_words);
+    k_label_bev<SrcDepth><<<gpt2l, SSD_PT_THREADS, 0, st>>>(p, sd, labels, frames, bev, ctx->bm_words);
   else
-    k_label_bev<SrcVertices><<<gpt2l, SSD_PT_THREADS, ctx->pad_l, st>>>(p, sv, labels, frames, bev, ctx->bm_words);
+    k_label_bev<SrcVertices><<<gpt2l, SSD_PT_THREADS, 0, st>>>(p, sv, labels, frames, bev, ctx->bm_words);
   STAGE_EV(3);
   if(ctx->outline_small)
     k_outline<OutlineSharedSmall><<<dim3(ctx->outline_gridx, nf), SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, bev, ctx->bm_words, ctx->smem_cap_words);
@@ -651,9 +596,9 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, const uin
   k_frame_logic<<<nf, 32, 0, st>>>(p, frames, nf);
   STAGE_EV(5);
   if(depth)
-    k_quad_reduce<SrcDepth><<<gpt2q, SSD_PT_THREADS, ctx->pad_q, st>>>(p, sd, labels, frames, bev, ctx->bm_words);
+    k_quad_reduce<SrcDepth><<<gpt2q, SSD_PT_THREADS, 0, st>>>(p, sd, labels, frames, bev, ctx->bm_words);
   else
-    k_quad_reduce<SrcVertices><<<gpt2q, SSD_PT_THREADS, ctx->pad_q, st>>>(p, sv, labels, frames, bev, ctx->bm_words);
+    k_quad_reduce<SrcVertices><<<gpt2q, SSD_PT_THREADS, 0, st>>>(p, sv, labels, frames, bev, ctx->bm_words);
   STAGE_EV(6);
   if(ctx->outline_small)
     k_finalize<OutlineSharedSmall><<<nf, SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, ctx->d_out + frame0, bev, ctx->bm_words, ctx->smem_cap_words, ctx->ov,
@@ -719,13 +664,7 @@ void ssd_gpu_destroy(ssd_gpu_ctx *ctx)
       cudaEventDestroy(ctx->ev_in_free[i]);
     if(ctx->ev_chunk_done[i])
       cudaEventDestroy(ctx->ev_chunk_done[i]);
-    if(ctx->ev_pre[i])
-      cudaEventDestroy(ctx->ev_pre[i]);
-    if(ctx->ev_p1[i])
-      cudaEventDestroy(ctx->ev_p1[i]);
   }
-  if(ctx->p1_stream)
-    cudaStreamDestroy(ctx->p1_stream);
   if(ctx->copy_stream)
     cudaStreamDestroy(ctx->copy_stream);
   for(cudaEvent_t e : { ctx->ev_start, ctx->ev_stop, ctx->ev_h2d0, ctx->ev_h2d1 })
@@ -749,7 +688,7 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
   DevParams dp;
   const int rc = derive_params(*cfg, *xf, dp);
   if(rc)
-    return fail(nullptr, rc, "ssd_gpu_create: configuration out of range (bins <= 253, width*height % 4 == 0, width <= 4700)");
+    return fail(nullptr, rc, "ssd_gpu_create: configuration out of range (3 <= height bins <= 253, width*height % 16 == 0, width <= 4700, height <= 5100)");
 
   ssd_gpu_ctx *ctx = new ssd_gpu_ctx();
   ctx->device = device;
@@ -784,7 +723,7 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
     const size_t budget = (size_t)8 << 30;
     if((size_t)cf * per_frame > budget)
       cf = (int)(budget / per_frame);
-    cf = std::max(1, std::min(cf, max_frames));
+    cf = std::max(1, std::min({ cf, max_frames, 65535 })); // (a chunk is gridDim.y of the point kernels)
     ctx->chunk_frames = cf;
     int hc = 32; // measured on B200 (tools/e2e_sweep.py): 16..64 frames reach 54.4 GB/s of H2D, 512 only 49.5
     if(const char *e = getenv("SSD_GPU_HOST_CHUNK_FRAMES"))
@@ -808,7 +747,7 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
     return bail("cudaFuncGetAttributes(k_outline) failed: was the library built for this GPU (sm_100a)?", SSD_E_CUDA);
   cudaFuncAttributes fb{}, fc{};
   cudaFuncGetAttributes(&fb, k_finalize<OutlineShared>);
-  cudaFuncGetAttributes(&fc, k_test_front_edge);
+  cudaFuncGetAttributes(&fc, k_single_front_edge);
   const size_t stat = std::max({ fa.sharedSizeBytes, fb.sharedSizeBytes, fc.sharedSizeBytes });
   size_t dyn = (size_t)max_optin > stat + 1024 ? (size_t)max_optin - stat - 1024 : 0;
   // raw band only (the close is evaluated on the fly); no more than the full image needs, and by default
@@ -821,30 +760,23 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
   dyn &= ~(size_t)15;
   ctx->ol_dyn_smem = dyn;
   ctx->smem_cap_words = dyn / 4;
-  if(const char *e = getenv("SSD_GPU_TB_PAD_KB"))
-    ctx->pad_tb = (size_t)atoi(e) * 1024;
-  if(const char *e = getenv("SSD_GPU_L_PAD_KB"))
-    ctx->pad_l = (size_t)atoi(e) * 1024;
-  if(const char *e = getenv("SSD_GPU_Q_PAD_KB"))
-    ctx->pad_q = (size_t)atoi(e) * 1024;
-  if(ctx->pad_l)
-  {
-    cudaFuncSetAttribute(k_label_bev<SrcVertices>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->pad_l);
-    cudaFuncSetAttribute(k_label_bev<SrcDepth>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->pad_l);
-  }
-  if(ctx->pad_q)
-  {
-    cudaFuncSetAttribute(k_quad_reduce<SrcVertices>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->pad_q);
-    cudaFuncSetAttribute(k_quad_reduce<SrcDepth>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->pad_q);
-  }
-  if(cudaFuncSetAttribute(k_transform_bin<SSD_PT_ITERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SSD_PT_ITERS * SSD_TB_STAGE_BYTES + (int)ctx->pad_tb) != cudaSuccess)
+  if(cudaFuncSetAttribute(k_transform_bin<SSD_PT_ITERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SSD_PT_ITERS * SSD_TB_STAGE_BYTES) != cudaSuccess)
     return bail("cudaFuncSetAttribute(k_transform_bin) failed", SSD_E_CUDA);
-  cudaFuncSetAttribute(k_outline<OutlineShared>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-  cudaFuncSetAttribute(k_outline<OutlineSharedSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-  cudaFuncSetAttribute(k_finalize<OutlineShared>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-  cudaFuncSetAttribute(k_finalize<OutlineSharedSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-  cudaFuncSetAttribute(k_test_front_edge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-
+  {
+    // The attribute is per function and process-wide: never lower it (another context of a larger frame size may be alive).
+    static std::mutex mtx;
+    static size_t granted = 0;
+    std::lock_guard<std::mutex> lock(mtx);
+    if(dyn > granted)
+    {
+      cudaFuncSetAttribute(k_outline<OutlineShared>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+      cudaFuncSetAttribute(k_outline<OutlineSharedSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+      cudaFuncSetAttribute(k_finalize<OutlineShared>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+      cudaFuncSetAttribute(k_finalize<OutlineSharedSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+      cudaFuncSetAttribute(k_single_front_edge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+      granted = dyn;
+    }
+  }
 
 #define CKC(call)                                                            \
   do                                                                         \
@@ -856,26 +788,17 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
       return bail(#call, e_ == cudaErrorMemoryAllocation ? SSD_E_NOMEM : SSD_E_CUDA); \
     }                                                                        \
   } while(0)
-  int prio_lo = 0, prio_hi = 0;
-  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-  int use_prio = 0;
-  if(const char *e = getenv("SSD_GPU_SPLIT"))
-    ctx->split = atoi(e);
-  if(const char *e = getenv("SSD_GPU_PRIO"))
-    use_prio = atoi(e);
-  if(const char *e = getenv("SSD_GPU_TB_PAD_KB"))
-    ctx->pad_tb = (size_t)atoi(e) * 1024;
-  if(const char *e = getenv("SSD_GPU_L_PAD_KB"))
-    ctx->pad_l = (size_t)atoi(e) * 1024;
-  if(const char *e = getenv("SSD_GPU_Q_PAD_KB"))
-    ctx->pad_q = (size_t)atoi(e) * 1024;
-  if(ctx->split)
-    CKC(cudaStreamCreateWithPriority(&ctx->p1_stream, cudaStreamNonBlocking, use_prio ? prio_lo : 0));
+  if(const char *e = getenv("SSD_GPU_L_BPF"))
+    ctx->bpf_l_knob = std::max(0, atoi(e));
+  if(const char *e = getenv("SSD_GPU_Q_BPF"))
+    ctx->bpf_q_knob = std::max(0, atoi(e));
+  if(const char *e = getenv("SSD_GPU_NO_SPLIT_SMALL"))
+    ctx->no_split_small = atoi(e) != 0;
+  if(const char *e = getenv("SSD_GPU_DEPTH_UNFUSED"))
+    ctx->depth_unfused = atoi(e) != 0;
   for(int i = 0; i < ctx->n_streams; i++)
   {
-    CKC(cudaStreamCreateWithPriority(&ctx->stream[i], cudaStreamNonBlocking, (use_prio && ctx->split) ? prio_hi : 0));
-    CKC(cudaEventCreateWithFlags(&ctx->ev_pre[i], cudaEventDisableTiming));
-    CKC(cudaEventCreateWithFlags(&ctx->ev_p1[i], cudaEventDisableTiming));
+    CKC(cudaStreamCreateWithFlags(&ctx->stream[i], cudaStreamNonBlocking));
     CKC(cudaEventCreateWithFlags(&ctx->ev_in_ready[i], cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->ev_in_free[i], cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->ev_chunk_done[i], cudaEventDisableTiming));
@@ -988,13 +911,16 @@ static int ensure_deproject_tables(ssd_gpu_ctx *ctx, const ssd_gpu_intrinsics &i
 }
 
 // xyz != nullptr: packed vertices; else z16 depth frames + intrinsics (deprojected chunk by chunk into the vertex staging)
-static int process_common(ssd_gpu_ctx *ctx, const float *xyz, const uint16_t *z16, const ssd_gpu_intrinsics *intr, bool host_input, int n_frames,
-                          int flags)
+static int process_impl(ssd_gpu_ctx *ctx, const float *xyz, const uint16_t *z16, const ssd_gpu_intrinsics *intr, bool host_input, int n_frames,
+                        int flags)
 {
   if(!ctx || (!xyz && !(z16 && intr)) || n_frames <= 0)
     return fail(ctx, SSD_E_INVALID_ARG, "process: bad argument");
   if(n_frames > ctx->max_frames)
     return fail(ctx, SSD_E_RANGE, "process: n_frames exceeds max_frames of the context");
+  // the point kernels use 16-byte vector loads / bulk copies (vertices) and 8-byte loads (depth)
+  if((xyz && ((uintptr_t)xyz & 15u)) || (z16 && ((uintptr_t)z16 & 7u)))
+    return fail(ctx, SSD_E_INVALID_ARG, "process: the input buffer must be 16-byte aligned (vertices) / 8-byte aligned (depth)");
   CK(cudaSetDevice(ctx->device));
   const DevParams &p = ctx->dp;
   const size_t frame_floats = (size_t)p.N * 3;
@@ -1004,7 +930,7 @@ static int process_common(ssd_gpu_ctx *ctx, const float *xyz, const uint16_t *z1
   // a device-resident batch that fits one chunk is still split over the streams, so that one half's latency-bound
   // per-plateau kernels overlap the other half's point kernels (measured: 64 frames of 4096x3072 as 2 x 32: +5 %;
   // below ~32 frames per chain the per-frame kernels lose more parallelism than the overlap returns)
-  if(!host_input && !(flags & SSD_FLAG_SINGLE_STREAM) && ctx->n_streams > 1 && n_frames <= cf && !getenv("SSD_GPU_NO_SPLIT_SMALL"))
+  if(!host_input && !(flags & SSD_FLAG_SINGLE_STREAM) && ctx->n_streams > 1 && n_frames <= cf && !ctx->no_split_small)
   {
     const int half = (n_frames + ctx->n_streams - 1) / ctx->n_streams;
     if(half >= 32)
@@ -1018,8 +944,7 @@ static int process_common(ssd_gpu_ctx *ctx, const float *xyz, const uint16_t *z1
       return rc;
   }
   // depth frames are deprojected inside the point kernels (SrcDepth): no vertex array is ever written.
-  const char *unfused_env = getenv("SSD_GPU_DEPTH_UNFUSED"); // A/B switch, read per call
-  const bool unfused = unfused_env && atoi(unfused_env) != 0;
+  const bool unfused = ctx->depth_unfused; // A/B switch (SSD_GPU_DEPTH_UNFUSED, read in ssd_gpu_create)
   if(host_input || depth_input)
     for(int i = 0; i < ctx->n_streams; i++)
     {
@@ -1063,6 +988,8 @@ static int process_common(ssd_gpu_ctx *ctx, const float *xyz, const uint16_t *z1
   for(int i = 1; i < ctx->n_streams; i++)
     CK(cudaStreamWaitEvent(ctx->stream[i], ctx->ev_start, 0));
   CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_start, 0));
+  if(host_input)
+    CK(cudaEventRecord(ctx->ev_h2d0, ctx->copy_stream));
   // per-frame state: histogram must start at zero
   CK(cudaMemsetAsync(ctx->d_frames, 0, sizeof(FrameDev) * (size_t)n_frames, ctx->stream[0]));
   CK(cudaEventRecord(ctx->ev_chunk_done[0], ctx->stream[0]));
@@ -1106,12 +1033,14 @@ static int process_common(ssd_gpu_ctx *ctx, const float *xyz, const uint16_t *z1
     }
     const bool fused = depth_input && !unfused;
     const int rc = launch_chunk(ctx, s, fused ? nullptr : src, fused ? dsrc : nullptr, fused ? intr->depth_unit : 0.f, f0, nf, &launches,
-                                stage_timing ? &ctx->stage_ev[(size_t)chunk * (SSD_GPU_N_STAGES + 1)] : nullptr, (flags & SSD_FLAG_SINGLE_STREAM) != 0);
+                                stage_timing ? &ctx->stage_ev[(size_t)chunk * (SSD_GPU_N_STAGES + 1)] : nullptr);
     if(rc)
       return rc;
     if(host_input && (!depth_input || fused))
       CK(cudaEventRecord(ctx->ev_in_free[s], ctx->stream[s])); // all three passes have read the staging
   }
+  if(host_input)
+    CK(cudaEventRecord(ctx->ev_h2d1, ctx->copy_stream));
   // join stream 1 into stream 0, then bring the compact results home
   for(int i = 1; i < ctx->n_streams; i++)
   {
@@ -1194,8 +1123,13 @@ static int process_common(ssd_gpu_ctx *ctx, const float *xyz, const uint16_t *z1
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop));
   ctx->timing.total_ms = ms;
-  ctx->timing.kernels_ms = ms;
   ctx->timing.h2d_ms = 0;
+  if(host_input)
+  {
+    float h = 0;
+    CK(cudaEventElapsedTime(&h, ctx->ev_h2d0, ctx->ev_h2d1));
+    ctx->timing.h2d_ms = h;
+  }
   ctx->timing.label_ms = 0;
   ctx->timing.n_launches = launches;
   for(int i = 0; i < SSD_GPU_N_STAGES; i++)
@@ -1217,6 +1151,27 @@ static int process_common(ssd_gpu_ctx *ctx, const float *xyz, const uint16_t *z1
     ctx->timing.label_ms = ctx->stage_ms[0];
   }
   return SSD_OK;
+}
+
+// A failure inside the chain (launch error, bad user pointer, out of memory while growing a staging buffer) may leave streams
+// unsynchronised and BEV bitmaps half written: the bitmaps are "self-cleaning" only along a complete chain. Bring the context
+// back to a clean state so that the next call starts from zeroed bitmaps and no stale results can be read.
+static int process_common(ssd_gpu_ctx *ctx, const float *xyz, const uint16_t *z16, const ssd_gpu_intrinsics *intr, bool host_input, int n_frames,
+                          int flags)
+{
+  const int rc = process_impl(ctx, xyz, z16, intr, host_input, n_frames, flags);
+  if(rc != SSD_OK && rc != SSD_E_INVALID_ARG && rc != SSD_E_RANGE && ctx)
+  {
+    const std::string keep = ctx->err;
+    cudaDeviceSynchronize();
+    cudaGetLastError();
+    if(ctx->d_bev)
+      cudaMemset(ctx->d_bev, 0, (size_t)ctx->n_streams * ctx->chunk_frames * SSD_GPU_MAX_PLATEAUS * ctx->bm_words * 4);
+    ctx->fs_pending = false;
+    ctx->n_frames_last = 0;
+    ctx->err = keep;
+  }
+  return rc;
 }
 
 int ssd_gpu_process_host(ssd_gpu_ctx *ctx, const float *xyz_host, int n_frames)
@@ -1496,7 +1451,7 @@ int ssd_gpu_detect_outline(ssd_gpu_ctx *ctx, const uint8_t *image_host, int min_
   p.min_img_y_extent = min_img_y_extent;
   p.xy_ratio = xy_ratio;
   cudaStream_t st = ctx->stream[0];
-  k_test_setup_plateau<<<1, 1, 0, st>>>(ctx->d_frames, p.H);
+  k_single_setup_plateau<<<1, 1, 0, st>>>(ctx->d_frames, p.H);
   if(ctx->outline_small)
     k_outline<OutlineSharedSmall><<<dim3(1, 1), SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, ctx->d_frames, ctx->d_bev, ctx->bm_words, ctx->smem_cap_words);
   else
@@ -1521,7 +1476,7 @@ int ssd_gpu_detect_front_edge(ssd_gpu_ctx *ctx, const uint8_t *image_host, doubl
   cudaStream_t st = ctx->stream[0];
   double *d_out = nullptr;
   CK(cudaMalloc(&d_out, sizeof(double) * 8));
-  k_test_front_edge<<<1, SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(ctx->dp, ctx->d_bev, ctx->smem_cap_words, d_out);
+  k_single_front_edge<<<1, SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(ctx->dp, ctx->d_bev, ctx->smem_cap_words, d_out);
   double h[8];
   cudaError_t e = cudaMemcpyAsync(h, d_out, sizeof(double) * 5, cudaMemcpyDeviceToHost, st);
   if(e == cudaSuccess)
@@ -1552,7 +1507,7 @@ int ssd_gpu_points_in_quad(ssd_gpu_ctx *ctx, const double quad[8], const double 
   CK(cudaMalloc(&d_st, sizeof(int)));
   cudaMemcpyAsync(d_q, quad, sizeof(double) * 8, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(d_xy, xy_host, sizeof(double) * 2 * (size_t)n, cudaMemcpyHostToDevice, st);
-  k_test_points_in_quad<<<std::min(1024, (n + 255) / 256), 256, 0, st>>>(d_q, d_xy, n, d_in, d_st);
+  k_single_points_in_quad<<<std::min(1024, (n + 255) / 256), 256, 0, st>>>(d_q, d_xy, n, d_in, d_st);
   cudaMemcpyAsync(inside_host, d_in, (size_t)n, cudaMemcpyDeviceToHost, st);
   cudaMemcpyAsync(ctor_status, d_st, sizeof(int), cudaMemcpyDeviceToHost, st);
   const cudaError_t e = cudaStreamSynchronize(st);
@@ -1575,34 +1530,12 @@ int ssd_gpu_camera_to_world(ssd_gpu_ctx *ctx, const float *xyz_host, int n, doub
   CK(cudaMalloc(&d_in, sizeof(float) * 3 * (size_t)n));
   CK(cudaMalloc(&d_out, sizeof(double) * 3 * (size_t)n));
   cudaMemcpyAsync(d_in, xyz_host, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, st);
-  k_test_camera_to_world<<<std::min(1024, (n + 255) / 256), 256, 0, st>>>(ctx->dp, d_in, n, d_out);
+  k_single_camera_to_world<<<std::min(1024, (n + 255) / 256), 256, 0, st>>>(ctx->dp, d_in, n, d_out);
   cudaMemcpyAsync(world_host, d_out, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, st);
   const cudaError_t e = cudaStreamSynchronize(st);
   cudaFree(d_in);
   cudaFree(d_out);
   CK(e);
-  return SSD_OK;
-}
-
-// ---- synthetic frames on the device ----
-int ssd_gpu_synth_frames(ssd_gpu_ctx *ctx, const ssd_scene *base, uint64_t base_seed, int64_t first_index, int n_frames, int min_steps,
-                         int max_steps, float *xyz_dev, uint16_t *depth_dev)
-{
-  if(!ctx || !base || !xyz_dev || n_frames <= 0)
-    return SSD_E_INVALID_ARG;
-  if(base->width != ctx->dp.W || base->height != ctx->dp.H)
-    return fail(ctx, SSD_E_INVALID_ARG, "scene size differs from the context's configuration");
-  CK(cudaSetDevice(ctx->device));
-  const int N = ctx->dp.N;
-  const int bx = std::min((N + 255) / 256, 512);
-  for(int f0 = 0; f0 < n_frames; f0 += 32768)
-  {
-    const int nf = std::min(32768, n_frames - f0);
-    k_synth_frames<<<dim3(bx, nf), 256, 0, ctx->stream[0]>>>(*base, base_seed, first_index + f0, nf, min_steps, max_steps,
-                                                               xyz_dev + (size_t)f0 * N * 3, depth_dev ? depth_dev + (size_t)f0 * N : nullptr);
-  }
-  CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(ctx->stream[0]));
   return SSD_OK;
 }
 

@@ -4,7 +4,6 @@
 #include "../../include/ssd_gpu.h"
 #include "host/transformation.h"
 #include "host/geometricCalibration.h"
-#include "scene_model.h"
 #include <exception>
 
 extern "C"
@@ -130,67 +129,6 @@ int ssd_load_calibration(const char *directory, ssd_gpu_transform *out, double w
   {
     return SSD_E_INVALID_ARG;
   }
-}
-
-void ssd_scene_default(ssd_scene *s, int32_t width, int32_t height)
-{
-  ssd_scene_default_hd(s, width, height);
-}
-
-void ssd_scene_randomize(ssd_scene *s, const ssd_scene *base, uint64_t base_seed, int64_t index, int min_steps, int max_steps)
-{
-  ssd_scene_randomize_hd(s, base, base_seed, index, min_steps, max_steps);
-}
-
-// Three marks on the calibration plane (z = 0 in scene coordinates), laid out like the reference's
-// calibration-triangle file (top-left, top-right, bottom), and where the scene's camera sees them.
-void ssd_scene_calibration_points(const ssd_scene *s, double world_pts[9], double camera_pts[9])
-{
-  ssd_scene_rt rt;
-  ssd_scene_prepare(s, &rt);
-  const double marks[3][3] = { { s->cam_x - 0.45, s->cam_y + 1.25, 0.0 }, { s->cam_x + 0.45, s->cam_y + 1.25, 0.0 },
-                               { s->cam_x + 0.30, s->cam_y + 0.35, 0.0 } };
-  for(int i = 0; i < 3; i++)
-  {
-    for(int j = 0; j < 3; j++)
-      world_pts[i * 3 + j] = marks[i][j];
-    ssd_scene_to_camera(&rt, marks[i], camera_pts + i * 3);
-  }
-}
-
-void ssd_scene_intrinsics(const ssd_scene *s, ssd_gpu_intrinsics *out)
-{
-  memset(out, 0, sizeof(*out));
-  out->fx = s->fx;
-  out->fy = s->fy;
-  out->ppx = s->ppx;
-  out->ppy = s->ppy;
-  out->depth_unit = s->depth_unit;
-}
-
-int ssd_synth_depth_host(const ssd_scene *s, uint16_t *depth_out)
-{
-  if(!s || !depth_out || s->width <= 0 || s->height <= 0)
-    return SSD_E_INVALID_ARG;
-  ssd_scene_rt rt;
-  ssd_scene_prepare(s, &rt);
-  for(int v = 0; v < s->height; v++)
-    for(int u = 0; u < s->width; u++)
-      depth_out[size_t(v) * s->width + u] = ssd_scene_depth(s, &rt, u, v);
-  return SSD_OK;
-}
-
-int ssd_deproject_host(const ssd_scene *s, const uint16_t *depth, float *xyz_out)
-{
-  if(!s || !depth || !xyz_out)
-    return SSD_E_INVALID_ARG;
-  for(int v = 0; v < s->height; v++)
-    for(int u = 0; u < s->width; u++)
-    {
-      const size_t i = size_t(v) * s->width + u;
-      ssd_deproject_pixel(s, u, v, depth[i], xyz_out + i * 3);
-    }
-  return SSD_OK;
 }
 
 } // extern "C"

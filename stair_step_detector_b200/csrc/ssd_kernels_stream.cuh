@@ -57,7 +57,7 @@ struct FsParams
   int n_frames;
   int d_raw, d_rec;   // ring depths per warp (slots): raw vertices in shared memory, records in global memory (L2)
   unsigned char *recs; // record ring: grid x SSD_FS_WARPS x d_rec slots of SSD_FS_REC_BYTES
-  int flags;          // SSD_FLAG_NO_LABELS
+  int flags;          // (none defined)
   unsigned *done;     // per frame: CTAs that have delivered their histogram (self-resetting)
   GroupSum *sums;     // n_frames x steps x 4
   unsigned long long *prof; // optional cycle counters (SSD_GPU_FS_PROF=1), else nullptr
@@ -632,8 +632,7 @@ __device__ __forceinline__ void fs_phase2(const DevParams &p, const SRC &src, co
     fl = ((e0 & K) ? 1u : 0u) | ((e1 & K) ? 2u : 0u) | ((e2 & K) ? 4u : 0u) | ((e3 & K) ? 8u : 0u);
     ol = ((e0 >> 8) & 1u) | ((e1 >> 7) & 2u) | ((e2 >> 6) & 4u) | ((e3 >> 5) & 8u);
   }
-  if(!(a.flags & SSD_FLAG_NO_LABELS))
-    reinterpret_cast<unsigned *>(labels)[word] = lab;
+  reinterpret_cast<unsigned *>(labels)[word] = lab;
   if(!__any_sync(0xffffffffu, fl != 0u))
   {
     if((lane & 7) == 0)

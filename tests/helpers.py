@@ -174,38 +174,6 @@ def ref_a_inv(lib, xf):
     return np.array(out[:])
 
 
-def make_config(hostlib, width, height, **kw):
-    cfg = A.Config()
-    hostlib.ssd_gpu_default_config(C.byref(cfg), width, height)
-    for k, v in kw.items():
-        setattr(cfg, k, v)
-    return cfg
-
-
-def make_scene(hostlib, width, height, **kw):
-    s = A.Scene()
-    hostlib.ssd_scene_default(C.byref(s), width, height)
-    for k, v in kw.items():
-        setattr(s, k, v)
-    return s
-
-
-def scene_transform(hostlib, scene):
-    w = (C.c_double * 9)()
-    c = (C.c_double * 9)()
-    hostlib.ssd_scene_calibration_points(C.byref(scene), w, c)
-    xf = A.Transform()
-    rc = hostlib.ssd_make_transform(w, c, C.byref(xf))
-    assert rc == 0
-    return xf, np.array(w[:]).reshape(3, 3), np.array(c[:]).reshape(3, 3)
-
-
-def scene_depth(hostlib, scene):
-    d = np.empty((scene.height, scene.width), np.uint16)
-    assert hostlib.ssd_synth_depth_host(C.byref(scene), ptr(d)) == 0
-    return d
-
-
 def deproject_np(scene, depth):
     """numpy restatement of ssd_deproject_pixel: single f32 operations in the same order."""
     H, W = depth.shape
@@ -219,14 +187,6 @@ def deproject_np(scene, depth):
     out[..., 1] = z * yn
     out[..., 2] = z
     return out
-
-
-def scene_xyz(hostlib, scene, depth=None):
-    if depth is None:
-        depth = scene_depth(hostlib, scene)
-    xyz = np.empty((scene.height, scene.width, 3), np.float32)
-    assert hostlib.ssd_deproject_host(C.byref(scene), ptr(depth), ptr(xyz)) == 0
-    return xyz
 
 
 def compare_results(a, b, tol=1e-4, check_labels=True):

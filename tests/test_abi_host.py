@@ -13,21 +13,34 @@ from stair_step_detector_b200 import _abi as A
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_functions():
-    src = open(os.path.join(ROOT, "include", "ssd_gpu.h")).read()
+def declared_functions(header="ssd_gpu.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(ssd_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_every_declared_symbol_is_exported_and_bound(built_lib):
     names = declared_functions()
-    assert len(names) >= 35
+    assert len(names) >= 30
     out = subprocess.run(["nm", "-D", "--defined-only", A.LIB_PATH], capture_output=True, text=True, check=True).stdout
     exported = set(re.findall(r" T (ssd_[a-z0-9_]+)", out))
     missing = [n for n in names if n not in exported]
     assert not missing, missing
     unbound = [n for n in names if n not in A.PROTOTYPES]
     assert not unbound, unbound
+
+
+def test_scene_library_exports_its_header_and_nothing_of_the_product(built_lib):
+    """the synthetic input source lives in its own library (include/ssd_scene.h): a process that only generates input or
+    runs the CPU reference (bench.py --impl reference) never maps libssd_gpu.so"""
+    names = declared_functions("ssd_scene.h")
+    assert len(names) == 7
+    out = subprocess.run(["nm", "-D", "--defined-only", A.SCENE_LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (ssd_[a-z0-9_]+)", out))
+    assert sorted(exported) == names
+    assert not [n for n in names if n not in A.SCENE_PROTOTYPES]
+    prod = subprocess.run(["nm", "-D", "--defined-only", A.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert not re.findall(r" T (ssd_scene_[a-z0-9_]+|ssd_synth[a-z0-9_]*|k_synth[a-z0-9_]*)", prod)
 
 
 def test_struct_layouts_match_header():
@@ -78,7 +91,7 @@ def test_transform_is_a_rigid_map_onto_the_calibration_plane(S):
     sc = S.default_scene(640, 480, cam_roll_deg=4.0, cam_yaw_deg=-9.0, cam_pitch_deg=42.0)
     w = (C.c_double * 9)()
     c = (C.c_double * 9)()
-    S.lib().ssd_scene_calibration_points(C.byref(sc), w, c)
+    S.scene_lib().ssd_scene_calibration_points(C.byref(sc), w, c)
     xf = S.make_transform(np.array(w[:]).reshape(3, 3), np.array(c[:]).reshape(3, 3))
     a = np.array(xf.a[:]).reshape(3, 3)
     assert np.allclose(a @ a.T, np.eye(3), atol=1e-14) and abs(np.linalg.det(a) - 1) < 1e-14

@@ -489,7 +489,7 @@ def test_cpp_host_classes_main_loop(S, oracle, tmp_path):
     exe = str(tmp_path / "detect_stairs_synthetic")
     libdir = os.path.join(root, "stair_step_detector_b200", "lib")
     subprocess.run(["g++", "-std=c++17", "-O2", "-o", exe, os.path.join(root, "examples", "detect_stairs_synthetic.cpp"),
-                    "-L" + libdir, "-lssd_gpu", "-Wl,-rpath," + libdir], check=True)
+                    "-L" + libdir, "-lssd_gpu", "-lssd_scene", "-Wl,-rpath," + libdir], check=True)
     w, h, n = 640, 480, 3
     run = subprocess.run([exe, str(w), str(h), str(n), "overlay"], capture_output=True, text=True, check=True)
     out = run.stdout.strip().splitlines()
