@@ -9,6 +9,9 @@ import helpers as H
 from stair_step_detector_b200 import _abi as A
 
 NOISY = dict(noise_sigma=0.0025, dropout=0.03, n_holes=3)
+# status bits the harness around the compiled reference does not raise (it reports only NO_STEPS / DEGENERATE_QUAD; the quirks
+# themselves -- all-zero ground step, NaN mean, wrap -- are in the compared RESULTS)
+QUIRKS = A.STATUS_BEV_OOB | A.STATUS_INVALID_FRONT_EDGE | A.STATUS_EMPTY_MEAN | A.STATUS_HMIN_WRAP | A.STATUS_TOO_MANY_PLATEAUS
 
 
 def get_ref(S, w, h):
@@ -32,8 +35,33 @@ def test_frames_random_scenes(S, oracle, w, h, n):
         o = H.oracle_process(oracle, cfg, xf, xyz)
         r = H.ref_process(ref, cfg, xf, xyz)
         assert not H.compare_results(r, o, tol=1e-12), i
-        assert (o.info["status"] & ~A.STATUS_BEV_OOB) == (r.info["status"] & ~A.STATUS_BEV_OOB)
+        assert (o.info["status"] & ~QUIRKS) == (r.info["status"] & ~QUIRKS)
     assert oracle.ssd_oracle_sort_ties() == 0  # no rank tie that the reference's unstable sort could resolve differently
+
+
+HIRES = dict(n_steps=12, riser=0.17, tread=0.26, cam_height=3.2, cam_pitch_deg=48.0, first_riser_y=0.5)
+
+
+@pytest.mark.parametrize("w,h,ck,sk,n", [(2560, 1920, {}, {}, 2), (4096, 3072, dict(y_max=3.7, z_max=2.3), HIRES, 2)])
+def test_frames_hires(S, oracle, w, h, ck, sk, n):
+    """BASELINE.json configs[4] (4096x3072, extended range: 241 height bins, ~83 points per BestLine list) and 2560x1920
+    (more than 12 'smallest distances' per line fit): the restatement against the compiled reference, as pinned as the
+    small sizes."""
+    cfg = S.default_config(w, h, **ck)
+    ref = H.load_ref(cfg)
+    if ref is None:
+        pytest.skip("oracle/_ref not built and /root/reference absent")
+    base = S.default_scene(w, h, **sk, **NOISY)
+    for i in range(n):
+        sc = S.randomize_scene(base, 4141, i, sk.get("n_steps", 3), sk.get("n_steps", 8))
+        xf = S.scene_transform(base)
+        xyz = S.deproject_host(sc, S.synth_depth_host(sc))
+        o = H.oracle_process(oracle, cfg, xf, xyz)
+        r = H.ref_process(ref, cfg, xf, xyz)
+        assert not H.compare_results(r, o, tol=1e-12), i
+        assert (o.info["status"] & ~QUIRKS) == (r.info["status"] & ~QUIRKS)
+        assert o.info["n_plateaus"] >= 3
+    assert oracle.ssd_oracle_sort_ties() == 0
 
 
 @pytest.mark.parametrize("w,h,n", [(320, 240, 6), (640, 480, 4), (1024, 768, 2)])
