@@ -276,7 +276,10 @@ def parity_block(det, A, cfg, xf, ref, xyz_sample):
         o = helpers.ref_process(ref, cfg, xf, xyz_sample[f]) if ref is not None else helpers.oracle_process(orc, cfg, xf, xyz_sample[f])
         lab_bad += int((g.labels != o.labels).sum())
         hist_bad += int(not np.array_equal(g.hist, o.hist))
-        status_bad += int(g.info["status"] != o.info["status"])
+        # (the harness around the compiled reference raises only NO_STEPS / DEGENERATE_QUAD; the quirk bits' effects -- all-zero
+        #  ground step, NaN mean, wrapped plateaus -- are in the compared results themselves)
+        smask = 0x3 if ref is not None else 0xffffffff
+        status_bad += int((g.info["status"] & smask) != (o.info["status"] & smask))
         if len(g.steps) != len(o.steps):
             count_bad += 1
         else:

@@ -139,7 +139,7 @@ struct FrameDev
   unsigned short lut16[SSD_BINS_PAD]; // bin code -> segment label | 0x100 if that label gets a BEV image (k_peaks)
   unsigned quad_amask;                // labels k_quad_reduce reduces: ground + valid plateaus with a usable test (k_frame_logic)
   unsigned ready;                     // k_frame_stream: plateau records and lut16 are written (the frame barrier's flag)
-  unsigned pad_a[2];
+  unsigned tb_done, ol_done;          // fused small-batch chain: blocks of k_transform_bin / k_outline that have finished this frame
   QuadFilterDev qf[SSD_GPU_MAX_PLATEAUS]; // f32 image of each step's QuadrilateralTest (k_frame_logic)
   unsigned status;
   int n_plateaus;

@@ -20,6 +20,7 @@
 #endif
 #define SSD_TILE_POINTS (SSD_PT_THREADS * 4 * SSD_PT_ITERS)
 #define SSD_MAX_STREAMS 4
+#define SSD_FUSE_MAX_FRAMES 16 // batches up to this size take the fused (latency) variants of k_transform_bin / k_outline
 
 static thread_local std::string g_create_error;
 
@@ -573,27 +574,50 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, const uin
     CK(cudaGetLastError());
     return SSD_OK;
   }
+  // small batches (the reference's real use is one frame per call): the last block of a frame in k_transform_bin evaluates the
+  // peaks and the last block in k_outline the frame logic -- five launches instead of seven
+  const bool fused = nf <= SSD_FUSE_MAX_FRAMES && !ev;
+  STAGE_EV(0);
+  if(fused)
   {
-    STAGE_EV(0);
+    if(depth)
+      k_transform_bin_depth<SSD_PT_ITERS, true><<<gpt, SSD_PT_THREADS, 0, st>>>(p, sd, labels, frames);
+    else
+      k_transform_bin<SSD_PT_ITERS, true><<<gpt, SSD_PT_THREADS, SSD_PT_ITERS * SSD_TB_STAGE_BYTES, st>>>(p, xyz_dev, labels, frames);
+  }
+  else
+  {
     if(depth)
       k_transform_bin_depth<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, 0, st>>>(p, sd, labels, frames);
     else
       k_transform_bin<SSD_PT_ITERS><<<gpt, SSD_PT_THREADS, SSD_PT_ITERS * SSD_TB_STAGE_BYTES, st>>>(p, xyz_dev, labels, frames);
   }
   STAGE_EV(1);
-  k_peaks<<<nf, 32, 0, st>>>(p, frames, nf);
+  if(!fused)
+    k_peaks<<<nf, 32, 0, st>>>(p, frames, nf);
   STAGE_EV(2);
   if(depth)
     k_label_bev<SrcDepth><<<gpt2l, SSD_PT_THREADS, 0, st>>>(p, sd, labels, frames, bev, ctx->bm_words);
   else
     k_label_bev<SrcVertices><<<gpt2l, SSD_PT_THREADS, 0, st>>>(p, sv, labels, frames, bev, ctx->bm_words);
   STAGE_EV(3);
-  if(ctx->outline_small)
-    k_outline<OutlineSharedSmall><<<dim3(ctx->outline_gridx, nf), SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, bev, ctx->bm_words, ctx->smem_cap_words);
+  if(fused)
+  {
+    if(ctx->outline_small)
+      k_outline<OutlineSharedSmall, true><<<dim3(ctx->outline_gridx, nf), SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, bev, ctx->bm_words, ctx->smem_cap_words);
+    else
+      k_outline<OutlineShared, true><<<dim3(ctx->outline_gridx, nf), OutlineShared::THREADS, ctx->ol_dyn_smem, st>>>(p, frames, bev, ctx->bm_words, ctx->smem_cap_words);
+  }
   else
-    k_outline<OutlineShared><<<dim3(ctx->outline_gridx, nf), OutlineShared::THREADS, ctx->ol_dyn_smem, st>>>(p, frames, bev, ctx->bm_words, ctx->smem_cap_words);
+  {
+    if(ctx->outline_small)
+      k_outline<OutlineSharedSmall><<<dim3(ctx->outline_gridx, nf), SSD_OL_THREADS, ctx->ol_dyn_smem, st>>>(p, frames, bev, ctx->bm_words, ctx->smem_cap_words);
+    else
+      k_outline<OutlineShared><<<dim3(ctx->outline_gridx, nf), OutlineShared::THREADS, ctx->ol_dyn_smem, st>>>(p, frames, bev, ctx->bm_words, ctx->smem_cap_words);
+  }
   STAGE_EV(4);
-  k_frame_logic<<<nf, 32, 0, st>>>(p, frames, nf);
+  if(!fused)
+    k_frame_logic<<<nf, 32, 0, st>>>(p, frames, nf);
   STAGE_EV(5);
   if(depth)
     k_quad_reduce<SrcDepth><<<gpt2q, SSD_PT_THREADS, 0, st>>>(p, sd, labels, frames, bev, ctx->bm_words);
@@ -608,7 +632,7 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, const uin
                                                                           ctx->d_ovl ? ctx->d_ovl + (size_t)frame0 * SSD_GPU_MAX_STEPS : nullptr);
   STAGE_EV(7);
 #undef STAGE_EV
-  *launches += SSD_GPU_N_STAGES;
+  *launches += fused ? SSD_GPU_N_STAGES - 2 : SSD_GPU_N_STAGES;
   CK(cudaGetLastError());
   return SSD_OK;
 }
@@ -760,6 +784,7 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
   dyn &= ~(size_t)15;
   ctx->ol_dyn_smem = dyn;
   ctx->smem_cap_words = dyn / 4;
+  cudaFuncSetAttribute(k_transform_bin<SSD_PT_ITERS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SSD_PT_ITERS * SSD_TB_STAGE_BYTES);
   if(cudaFuncSetAttribute(k_transform_bin<SSD_PT_ITERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SSD_PT_ITERS * SSD_TB_STAGE_BYTES) != cudaSuccess)
     return bail("cudaFuncSetAttribute(k_transform_bin) failed", SSD_E_CUDA);
   {
@@ -771,6 +796,8 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
     {
       cudaFuncSetAttribute(k_outline<OutlineShared>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
       cudaFuncSetAttribute(k_outline<OutlineSharedSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+      cudaFuncSetAttribute(k_outline<OutlineShared, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+      cudaFuncSetAttribute(k_outline<OutlineSharedSmall, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
       cudaFuncSetAttribute(k_finalize<OutlineShared>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
       cudaFuncSetAttribute(k_finalize<OutlineSharedSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
       cudaFuncSetAttribute(k_single_front_edge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);

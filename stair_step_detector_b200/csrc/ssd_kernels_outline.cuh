@@ -252,6 +252,9 @@ __device__ inline double pair_residual(const P2id *pts, int n, int pi, int qi, L
     // smallest T with count(d <= T) >= cnt; sum = sum(d < T) + (cnt - count(d < T)) * T. The distances are computed once
     // into a per-thread array (local memory: interleaved per thread, so a warp's accesses coalesce and stay in L1) and
     // each of the ~22 bisection passes is a load, a compare and an add per point.
+    // (measured, r2: recomputing the distances from the list in shared memory in every pass instead of keeping them in this
+    //  local-memory array is 2.8x slower for k_outline at 4096x3072 -- 3.43 against 1.21 ms per 64 frames -- although the
+    //  array's L1 hit rate is poor)
     int d[MAXPTS]; // the list capacity of the frame-size class
     int k = 0, hi = 0, lo = 0;
     for(int i = 0; i < n; i++)
@@ -916,82 +919,18 @@ __device__ inline void band_clear_global(const DevParams &p, const Band &bd, uns
     base[i] = 0u;
 }
 
-// ---------------------------------------------------------------------------------------------
-// k_outline: grid = (SSD_GPU_MAX_PLATEAUS, frames); one block per outlined plateau
-// (loop B of detectStairSteps, pointcloud.cpp:419-429, incl. imgPointsToWorld :476-487)
-// ---------------------------------------------------------------------------------------------
-#ifndef SSD_OL_MINB
-#define SSD_OL_MINB 6
-#endif
-template<class OutlineShared>
-__global__ void __launch_bounds__(OutlineShared::THREADS, OutlineShared::MINB ? OutlineShared::MINB : SSD_OL_MINB) k_outline(const __grid_constant__ DevParams p, FrameDev *__restrict__ frames,
-                                                             unsigned *__restrict__ bev, size_t bm_words, size_t smem_cap_words)
+// the rest of detectStairSteps after the outlines (k_frame_logic below; also the tail of k_outline's fused variant)
+struct FrameLogicScratch
 {
-  extern __shared__ __align__(16) unsigned s_words[];
-  __shared__ OutlineShared S;
-  __shared__ Band bd;
-  __shared__ int s_smem_path;
-  const int frame = blockIdx.y, tid = threadIdx.x;
-  FrameDev &F = frames[frame];
-  // grid.x blocks per frame walk the frame's outlined plateaus (first_outlined .. n_plateaus-1, k_peaks); grid.x is
-  // smaller than SSD_GPU_MAX_PLATEAUS because a frame rarely has more than a handful (ssd_gpu.cu, launch_chain)
-  const int n_plat = F.n_plateaus;
-  for(int k = max(F.first_outlined, 0) + (int)blockIdx.x; k < n_plat; k += (int)gridDim.x)
-  {
-  if(!F.plat[k].outlined)
-    continue;
-  PlateauDev &P = F.plat[k];
-  P2d quad[4];
-  int valid = 0;
-  if(P.row_max >= 0)
-  {
-    unsigned *gb = bev + ((size_t)frame * SSD_GPU_MAX_PLATEAUS + k) * bm_words;
-    if(tid == 0)
-      s_smem_path = band_setup(p, bd, P.row_min, P.row_max, s_words, smem_cap_words, gb);
-    __syncthreads();
-    if(s_smem_path)
-      band_stage(p, s_words, bd, gb, tid, OutlineShared::THREADS);
-    detect_outline_block(p, bd, S, p.min_img_y_extent, p.xy_ratio, quad, valid, tid, OutlineShared::THREADS);
-    if(!s_smem_path)
-    {
-      __syncthreads();
-      band_clear_global(p, bd, gb, tid, OutlineShared::THREADS);
-    }
-  }
-  else if(tid == 0)
-  {
-    for(int i = 0; i < 4; i++)
-      quad[i].x = quad[i].y = 0;
-  }
-  if(tid == 0)
-  {
-    for(int c = 0; c < 4; c++)
-    {
-      P.quad_px[c][0] = quad[c].x;
-      P.quad_px[c][1] = quad[c].y;
-      const P2d w = image_to_world(p, quad[c]);
-      P.quad_world[c][0] = w.x;
-      P.quad_world[c][1] = w.y;
-    }
-    P.valid = valid;
-  }
-  __syncthreads(); // the shared band / work area is reused by the next plateau of this block
-  }
-}
+  QuadTestDev qt[SSD_GPU_MAX_PLATEAUS];
+  double gq[4][2];
+};
 
-// ---------------------------------------------------------------------------------------------
-// k_frame_logic: the rest of detectStairSteps (pointcloud.cpp:427-443): first valid plateau, the ground
-// quadrilateral (calcGroundQuadrilateral, :489-512) and one QuadrilateralTest per emitted step.
-// One warp per frame, one lane per plateau.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) k_frame_logic(const __grid_constant__ DevParams p, FrameDev *__restrict__ frames, int n_frames)
+// one warp, one lane per plateau; Sc: the warp's scratch in shared memory
+__device__ inline void frame_logic_warp(const DevParams &p, FrameDev &F, FrameLogicScratch &Sc, int lane)
 {
-  __shared__ QuadTestDev s_qt[SSD_GPU_MAX_PLATEAUS];
-  __shared__ double s_gq[4][2];
-  const int f = blockIdx.x, lane = threadIdx.x;
-  if(f >= n_frames)
-    return;
-  FrameDev &F = frames[f];
+  QuadTestDev *s_qt = Sc.qt;
+  double(*s_gq)[2] = Sc.gq;
   const int K = F.n_plateaus, ground = F.ground_index;
   const bool myValid = lane < K && lane >= F.first_outlined && F.plat[lane].valid;
   const unsigned vm = __ballot_sync(0xffffffffu, myValid);
@@ -1064,6 +1003,100 @@ __global__ void __launch_bounds__(32) k_frame_logic(const __grid_constant__ DevP
     }
   if(lane == 0 && bad)
     F.status |= SSD_STATUS_DEGENERATE_QUAD;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_outline: grid = (SSD_GPU_MAX_PLATEAUS, frames); one block per outlined plateau
+// (loop B of detectStairSteps, pointcloud.cpp:419-429, incl. imgPointsToWorld :476-487)
+// ---------------------------------------------------------------------------------------------
+#ifndef SSD_OL_MINB
+#define SSD_OL_MINB 6
+#endif
+// FUSE_LOGIC (small batches: latency matters, not occupancy): the last block of a frame to finish runs the frame logic
+// (k_frame_logic) itself -- one launch and one kernel boundary less on the single-frame path.
+template<class OutlineShared, bool FUSE_LOGIC = false>
+__global__ void __launch_bounds__(OutlineShared::THREADS, FUSE_LOGIC ? 1 : (OutlineShared::MINB ? OutlineShared::MINB : SSD_OL_MINB)) k_outline(const __grid_constant__ DevParams p, FrameDev *__restrict__ frames,
+                                                             unsigned *__restrict__ bev, size_t bm_words, size_t smem_cap_words)
+{
+  extern __shared__ __align__(16) unsigned s_words[];
+  __shared__ OutlineShared S;
+  __shared__ Band bd;
+  __shared__ int s_smem_path;
+  const int frame = blockIdx.y, tid = threadIdx.x;
+  FrameDev &F = frames[frame];
+  // grid.x blocks per frame walk the frame's outlined plateaus (first_outlined .. n_plateaus-1, k_peaks); grid.x is
+  // smaller than SSD_GPU_MAX_PLATEAUS because a frame rarely has more than a handful (ssd_gpu.cu, launch_chain)
+  const int n_plat = F.n_plateaus;
+  for(int k = max(F.first_outlined, 0) + (int)blockIdx.x; k < n_plat; k += (int)gridDim.x)
+  {
+  if(!F.plat[k].outlined)
+    continue;
+  PlateauDev &P = F.plat[k];
+  P2d quad[4];
+  int valid = 0;
+  if(P.row_max >= 0)
+  {
+    unsigned *gb = bev + ((size_t)frame * SSD_GPU_MAX_PLATEAUS + k) * bm_words;
+    if(tid == 0)
+      s_smem_path = band_setup(p, bd, P.row_min, P.row_max, s_words, smem_cap_words, gb);
+    __syncthreads();
+    if(s_smem_path)
+      band_stage(p, s_words, bd, gb, tid, OutlineShared::THREADS);
+    detect_outline_block(p, bd, S, p.min_img_y_extent, p.xy_ratio, quad, valid, tid, OutlineShared::THREADS);
+    if(!s_smem_path)
+    {
+      __syncthreads();
+      band_clear_global(p, bd, gb, tid, OutlineShared::THREADS);
+    }
+  }
+  else if(tid == 0)
+  {
+    for(int i = 0; i < 4; i++)
+      quad[i].x = quad[i].y = 0;
+  }
+  if(tid == 0)
+  {
+    for(int c = 0; c < 4; c++)
+    {
+      P.quad_px[c][0] = quad[c].x;
+      P.quad_px[c][1] = quad[c].y;
+      const P2d w = image_to_world(p, quad[c]);
+      P.quad_world[c][0] = w.x;
+      P.quad_world[c][1] = w.y;
+    }
+    P.valid = valid;
+  }
+  __syncthreads(); // the shared band / work area is reused by the next plateau of this block
+  }
+  if(FUSE_LOGIC)
+  {
+    __shared__ FrameLogicScratch Sc;
+    __shared__ unsigned s_last;
+    __threadfence();
+    __syncthreads();
+    if(tid == 0)
+      s_last = atomicAdd(&F.ol_done, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if(s_last && tid < 32)
+    {
+      __threadfence();
+      frame_logic_warp(p, F, Sc, tid);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_frame_logic: the rest of detectStairSteps (pointcloud.cpp:427-443): first valid plateau, the ground
+// quadrilateral (calcGroundQuadrilateral, :489-512) and one QuadrilateralTest per emitted step.
+// One warp per frame, one lane per plateau.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_frame_logic(const __grid_constant__ DevParams p, FrameDev *__restrict__ frames, int n_frames)
+{
+  __shared__ FrameLogicScratch Sc;
+  const int f = blockIdx.x;
+  if(f >= n_frames)
+    return;
+  frame_logic_warp(p, frames[f], Sc, threadIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -198,6 +198,211 @@ __device__ __forceinline__ void point_load(const FrameD &f, unsigned pt, float &
 }
 
 // ---------------------------------------------------------------------------------------------
+// Peaks of one frame, one warp: HeightsHistogram::findPeaks / filterPeaks (pointcloud.cpp:214-256), the plateau bands of
+// extractPlateauPoints (:300-335) as a bin -> label LUT, ground / first-outlined bookkeeping (:402-418). Evaluated bin-parallel:
+//   rise(i) = hist[i] < hist[i+1], fall(i) = hist[i] > hist[i+1]   (i < n_bins - 1)
+//   ascending before i  <=>  the nearest j < i with rise(j) or fall(j) is a rise      (equal neighbours keep the flag)
+//   peak(i) = fall(i) && ascending && hist[i] >= min_peak_points && (2 hist[i] - hist[i-1] - hist[i+1]) * 2 > hist[i]
+//   band(i) = [i-1, i] if hist[i-1] > hist[i+1] else [i, i+1]; a bin claimed by two bands goes to the lower peak
+//   (peaks are at least two bins apart, so only the bands of the peaks at b-1, b, b+1 can hold bin b).
+// ---------------------------------------------------------------------------------------------
+struct __align__(16) PeaksScratch // per-warp scratch of peaks_warp (16-byte vector stores into hist)
+{
+  unsigned hist[SSD_BINS_PAD + 8]; // bin b at [4 + b]; zeros either side
+  unsigned short lut[SSD_BINS_PAD];
+  int height[SSD_GPU_MAX_PLATEAUS], hmin[SSD_GPU_MAX_PLATEAUS], hmax[SSD_GPU_MAX_PLATEAUS];
+  unsigned np[SSD_GPU_MAX_PLATEAUS];
+};
+
+#define SSD_LUT_OUTLINED 0x100u  // lut16 flags: the label gets a BEV image
+#define SSD_LUT_GROUND 0x200u    //              the label is the ground plateau
+#define SSD_LUT_VALID 0x8000u    //              entry written (a zero entry means "frame not ready")
+
+// bit (32 r + lane + D) of a 256-bit string held as eight warp-uniform words (zeros outside), D in {-2, -1, 0, +1}
+template<int D>
+__device__ __forceinline__ unsigned peaks_bit_at(const unsigned (&w)[8], int r, int lane)
+{
+  const unsigned cur = w[r];
+  if(D == 0)
+    return (cur >> lane) & 1u;
+  if(D < 0)
+  {
+    const unsigned prev = r > 0 ? w[r - 1] : 0u;
+    return (__funnelshift_l(prev, cur, -D) >> lane) & 1u; // bit i of the result = bit (i + D) of the string
+  }
+  const unsigned next = r < 7 ? w[r + 1] : 0u;
+  return (__funnelshift_r(cur, next, D) >> lane) & 1u;
+}
+
+// K: scratch in shared memory, private to the calling warp for the duration of the call. h0, h1: bins 8 lane .. 8 lane + 7.
+// lut_flags: OR-ed into every lut16 entry (SSD_LUT_VALID for the resident-frame path's polling).
+__device__ inline void peaks_warp(const DevParams &p, FrameDev &F, PeaksScratch &K, const uint4 h0, const uint4 h1, int lane)
+{
+  {
+    // the frame's complete histogram (bins 8 lane .. 8 lane + 7), as the owner's poll read it
+    uint4 *dst = reinterpret_cast<uint4 *>(K.hist + 4 + lane * 8);
+    dst[0] = h0;
+    dst[1] = h1;
+    if(lane < 4)
+    {
+      K.hist[lane] = 0;
+      K.hist[4 + SSD_BINS_PAD + lane] = 0;
+    }
+  }
+  __syncwarp();
+  const unsigned *H = K.hist + 4;
+  const int last = p.n_bins - 1;
+  const unsigned lt = (1u << lane) - 1u;
+  unsigned R[8], Fm[8], Pw[8], BL[8], hc[8], hm[8], hp[8];
+#pragma unroll
+  for(int r = 0; r < 8; r++)
+  {
+    const int b = 32 * r + lane;
+    hc[r] = H[b];
+    hm[r] = H[b - 1];
+    hp[r] = H[b + 1];
+    const bool v = b < last;
+    R[r] = __ballot_sync(0xffffffffu, v && hc[r] < hp[r]);
+    Fm[r] = __ballot_sync(0xffffffffu, v && hc[r] > hp[r]);
+    BL[r] = __ballot_sync(0xffffffffu, hm[r] > hp[r]);
+  }
+  {
+    bool carry = false; // ascending at the start of word r
+#pragma unroll
+    for(int r = 0; r < 8; r++)
+    {
+      const unsigned c = hc[r];
+      const unsigned E = R[r] | Fm[r];
+      const unsigned m = E & lt;
+      const bool asc = m ? ((R[r] >> (31 - __clz(m))) & 1u) != 0u : carry;
+      const bool fall = (Fm[r] >> lane) & 1u;
+      const bool peak = fall && asc && !(c < p.min_peak_points) && (unsigned)((c * 2u - hm[r] - hp[r]) * 2u) > c;
+      Pw[r] = __ballot_sync(0xffffffffu, peak);
+      if(E)
+        carry = ((R[r] >> (31 - __clz(E))) & 1u) != 0u;
+    }
+  }
+  int n_all = 0;
+#pragma unroll
+  for(int r = 0; r < 8; r++)
+    n_all += __popc(Pw[r]);
+  const int Kn = min(n_all, SSD_GPU_MAX_PLATEAUS);
+  unsigned status = n_all > SSD_GPU_MAX_PLATEAUS ? SSD_STATUS_TOO_MANY_PLATEAUS : 0u;
+  // uint16 wrap of heightMin - 1 (pointcloud.cpp:324): a peak at bin 1 with band [0, 1] -- necessarily the first peak --
+  // sends every point to the remainder; that plateau and all later ones stay empty
+  const bool wrapped = ((Pw[0] >> 1) & 1u) && ((BL[0] >> 1) & 1u);
+  if(wrapped)
+    status |= SSD_STATUS_HMIN_WRAP;
+  {
+    int base = 0;
+#pragma unroll
+    for(int r = 0; r < 8; r++)
+    {
+      const int b = 32 * r + lane;
+      const int cntlt = base + __popc(Pw[r] & lt); // peaks at bins < b
+      const bool pk = (Pw[r] >> lane) & 1u;
+      unsigned l = SSD_LABEL_REMAINDER;
+      if(!wrapped)
+      {
+        int k = -1;
+        if(peaks_bit_at<-1>(Pw, r, lane) && !peaks_bit_at<-1>(BL, r, lane))
+          k = cntlt - 1;
+        else if(pk)
+          k = cntlt;
+        else if(peaks_bit_at<1>(Pw, r, lane) && peaks_bit_at<1>(BL, r, lane))
+          k = cntlt;
+        if(k >= 0 && k < SSD_GPU_MAX_PLATEAUS)
+          l = (unsigned)k;
+      }
+      if(b == (int)SSD_CODE_OUT_OF_RANGE)
+        l = SSD_LABEL_OUT_OF_RANGE;
+      if(b == (int)SSD_CODE_INVALID)
+        l = SSD_LABEL_INVALID;
+      K.lut[b] = (unsigned short)l;
+      if(pk && cntlt < SSD_GPU_MAX_PLATEAUS)
+      {
+        const bool lo = (BL[r] >> lane) & 1u;
+        unsigned np = hc[r];
+        if(lo)
+          np += (peaks_bit_at<-2>(Pw, r, lane) && !peaks_bit_at<-2>(BL, r, lane)) ? 0u : hm[r];
+        else
+          np += hp[r];
+        K.height[cntlt] = b;
+        K.hmin[cntlt] = lo ? b - 1 : b;
+        K.hmax[cntlt] = lo ? b : b + 1;
+        K.np[cntlt] = wrapped ? 0u : np;
+      }
+      base += __popc(Pw[r]);
+    }
+  }
+  __syncwarp();
+  // ground = the largest of the leading plateaus below minHeight (first maximum), outlines from the first plateau at or above it
+  const bool mine = lane < Kn;
+  const int height = mine ? K.height[lane] : 0;
+  const unsigned np = mine ? K.np[lane] : 0u;
+  const unsigned hi = __ballot_sync(0xffffffffu, mine && height >= p.min_height);
+  const int fo = hi ? __ffs(hi) - 1 : Kn;
+  const unsigned gnp = (mine && lane < fo) ? np : 0u;
+  const unsigned gmax = __reduce_max_sync(0xffffffffu, gnp);
+  const unsigned gb = __ballot_sync(0xffffffffu, lane < fo && mine && gnp == gmax);
+  const int ground = gmax > 0u ? __ffs(gb) - 1 : -1;
+  if(lane == 0)
+  {
+    F.n_nonzero = (unsigned)p.N - H[SSD_CODE_INVALID];
+    F.n_in_range = (unsigned)p.N - H[SSD_CODE_INVALID] - H[SSD_CODE_OUT_OF_RANGE];
+    F.n_plateaus = Kn;
+    F.ground_index = ground;
+    F.first_outlined = fo;
+    F.first_valid = -1;
+    F.n_steps = 0;
+    F.status = status;
+  }
+  if(mine)
+  {
+    PlateauDev &P = F.plat[lane];
+    P.height = height;
+    P.hmin = K.hmin[lane];
+    P.hmax = K.hmax[lane];
+    P.n_points = np;
+    P.valid = 0;
+    P.outlined = lane >= fo;
+    P.n_in_quad = 0;
+    P.quad_status = -1;
+    P.mean_z = 0;
+    P.sum_fix = 0;
+    P.sum_d = 0;
+    P.sum_c = 0;
+    P.n_sum = 0;
+    P.row_min = 0x7fffffff;
+    P.row_max = -1;
+    P.front_valid = 0;
+    for(int c4 = 0; c4 < 4; c4++)
+      P.quad_px[c4][0] = P.quad_px[c4][1] = P.quad_world[c4][0] = P.quad_world[c4][1] = 0;
+  }
+  {
+    unsigned w[4];
+#pragma unroll
+    for(int i = 0; i < 4; i++)
+    {
+      unsigned e2[2];
+#pragma unroll
+      for(int h = 0; h < 2; h++)
+      {
+        const unsigned l = K.lut[lane * 8 + i * 2 + h];
+        unsigned e = l | SSD_LUT_VALID;
+        if((int)l >= fo && (int)l < Kn)
+          e |= SSD_LUT_OUTLINED;
+        if((int)l == ground)
+          e |= SSD_LUT_GROUND;
+        e2[h] = e;
+      }
+      w[i] = e2[0] | (e2[1] << 16);
+    }
+    *(reinterpret_cast<uint4 *>(F.lut16) + lane) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_transform_bin: PointsExtraction::extract + HeightsHistogram::calcHist
 // (pointcloud.cpp:122-178, 194-204). grid = (tiles_per_frame, frames), block = 256.
 // Each thread handles 4 consecutive points per iteration: three 16 B loads, one 4 B store.
@@ -280,7 +485,24 @@ __device__ __forceinline__ void tb_word(const DevParams &p, const float vx[4], c
 }
 
 #define SSD_TB_STAGE_BYTES (SSD_PT_THREADS * 48) // one iteration of the block: 256 threads x 4 vertices x 12 B
-template<int ITERS>
+// FUSE_PEAKS (small batches): the last block of a frame to deliver its histogram evaluates the peaks (k_peaks) itself.
+__device__ __forceinline__ void tb_fused_peaks(const DevParams &p, FrameDev &F, PeaksScratch &K, unsigned &s_last, int tid)
+{
+  __threadfence();
+  __syncthreads();
+  if(tid == 0)
+    s_last = atomicAdd(&F.tb_done, 1u) == gridDim.x - 1 ? 1u : 0u;
+  __syncthreads();
+  if(s_last && tid < 32)
+  {
+    __threadfence();
+    const uint4 *src = reinterpret_cast<const uint4 *>(F.hist) + tid * 2;
+    const uint4 h0 = __ldcg(src), h1 = __ldcg(src + 1);
+    peaks_warp(p, F, K, h0, h1, tid);
+  }
+}
+
+template<int ITERS, bool FUSE_PEAKS = false>
 __global__ void __launch_bounds__(SSD_PT_THREADS) k_transform_bin(const __grid_constant__ DevParams p, const float *__restrict__ xyz,
                                                                    unsigned char *__restrict__ codes, FrameDev *__restrict__ frames)
 {
@@ -343,6 +565,12 @@ __global__ void __launch_bounds__(SSD_PT_THREADS) k_transform_bin(const __grid_c
     atomicAdd(&frames[frame].hist[tid], sum);
   if(tid == 0 && s_exact)
     atomicAdd(&frames[frame].n_exact_bin, s_exact);
+  if(FUSE_PEAKS)
+  {
+    __shared__ PeaksScratch K;
+    __shared__ unsigned s_last;
+    tb_fused_peaks(p, frames[frame], K, s_last, tid);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -350,7 +578,7 @@ __global__ void __launch_bounds__(SSD_PT_THREADS) k_transform_bin(const __grid_c
 // deprojected vertices live in registers only. No staging: the loads are 8 bytes per lane (256 B per warp, coalesced) and
 // all ITERS words of a thread are requested before the first is consumed. Not HBM-bound (3 B/point): issue-bound.
 // ---------------------------------------------------------------------------------------------
-template<int ITERS>
+template<int ITERS, bool FUSE_PEAKS = false>
 __global__ void __launch_bounds__(SSD_PT_THREADS) k_transform_bin_depth(const __grid_constant__ DevParams p, const SrcDepth src,
                                                                          unsigned char *__restrict__ codes, FrameDev *__restrict__ frames)
 {
@@ -392,150 +620,29 @@ __global__ void __launch_bounds__(SSD_PT_THREADS) k_transform_bin_depth(const __
     atomicAdd(&frames[frame].hist[tid], sum);
   if(tid == 0 && s_exact)
     atomicAdd(&frames[frame].n_exact_bin, s_exact);
+  if(FUSE_PEAKS)
+  {
+    __shared__ PeaksScratch K;
+    __shared__ unsigned s_last;
+    tb_fused_peaks(p, frames[frame], K, s_last, tid);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
 // k_peaks: HeightsHistogram::findPeaks/filterPeaks (pointcloud.cpp:214-256), the plateau bands of
 // PlateausExtraction::extractPlateauPoints (:300-335) folded into a bin->label LUT, and the ground /
 // first-outlined bookkeeping of StairsDetector::detectStairSteps (:402-418).
-// One warp per frame: the histogram and the LUT live in shared memory, lane 0 walks the <= 253 bins,
-// the lanes write the LUT and the plateau records back in parallel.
+// One warp per frame (peaks_warp above: bin-parallel).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) k_peaks(const __grid_constant__ DevParams p, FrameDev *__restrict__ frames, int n_frames)
 {
-  __shared__ unsigned s_hist[SSD_BINS_PAD];
-  __shared__ __align__(8) unsigned char s_lut[SSD_BINS_PAD];
-  __shared__ int s_height[SSD_GPU_MAX_PLATEAUS], s_hmin[SSD_GPU_MAX_PLATEAUS], s_hmax[SSD_GPU_MAX_PLATEAUS];
-  __shared__ unsigned s_np[SSD_GPU_MAX_PLATEAUS];
-  __shared__ int s_K, s_first_outlined, s_ground;
+  __shared__ PeaksScratch K;
   const int f = blockIdx.x, lane = threadIdx.x;
   if(f >= n_frames)
     return;
-  FrameDev &F = frames[f];
-  for(int b = lane; b < SSD_BINS_PAD; b += 32)
-  {
-    s_hist[b] = F.hist[b];
-    s_lut[b] = (unsigned char)SSD_LABEL_REMAINDER;
-  }
-  __syncwarp();
-  if(lane == 0)
-  {
-    const unsigned *hist = s_hist;
-    unsigned status = 0;
-    s_lut[SSD_CODE_OUT_OF_RANGE] = (unsigned char)SSD_LABEL_OUT_OF_RANGE;
-    s_lut[SSD_CODE_INVALID] = (unsigned char)SSD_LABEL_INVALID;
-    int K = 0;
-    bool ascending = false, wrapped = false;
-    const int last = p.n_bins - 1;
-    for(int i = 0; i < last; i++)
-    {
-      const unsigned c = hist[i], s = hist[i + 1];
-      if(c < s)
-      {
-        ascending = true;
-        continue;
-      }
-      if(c > s)
-      {
-        if(ascending && !(c < p.min_peak_points) && (unsigned)((c * 2u - hist[i - 1] - hist[i + 1]) * 2u) > c)
-        {
-          if(K >= SSD_GPU_MAX_PLATEAUS)
-            status |= SSD_STATUS_TOO_MANY_PLATEAUS;
-          else
-          {
-            int hmin, hmax;
-            if(hist[i - 1] > hist[i + 1]) // :307-316
-            {
-              hmin = i - 1;
-              hmax = i;
-            }
-            else
-            {
-              hmin = i;
-              hmax = i + 1;
-            }
-            unsigned np = 0;
-            if(hmin == 0)
-            {
-              // uint16 wrap of heightMin - 1 (:324): everything left goes to the remainder, this plateau
-              // and all later ones stay empty
-              wrapped = true;
-              status |= SSD_STATUS_HMIN_WRAP;
-            }
-            if(!wrapped)
-              for(int b = hmin; b <= hmax; b++)
-                if(s_lut[b] == SSD_LABEL_REMAINDER)
-                {
-                  s_lut[b] = (unsigned char)K;
-                  np += hist[b];
-                }
-            s_height[K] = i;
-            s_hmin[K] = hmin;
-            s_hmax[K] = hmax;
-            s_np[K] = np;
-            K++;
-          }
-        }
-        ascending = false;
-      }
-    }
-    int ground = -1, i = 0;
-    unsigned maxGround = 0;
-    for(; i < K; i++)
-    {
-      if(s_height[i] >= p.min_height)
-        break;
-      if(maxGround < s_np[i])
-      {
-        maxGround = s_np[i];
-        ground = i;
-      }
-    }
-    s_K = K;
-    s_first_outlined = i;
-    s_ground = ground;
-    F.n_nonzero = (unsigned)p.N - hist[SSD_CODE_INVALID];
-    F.n_in_range = (unsigned)p.N - hist[SSD_CODE_INVALID] - hist[SSD_CODE_OUT_OF_RANGE];
-    F.n_plateaus = K;
-    F.ground_index = ground;
-    F.first_outlined = i;
-    F.first_valid = -1;
-    F.n_steps = 0;
-    F.status = status;
-  }
-  __syncwarp();
-  {
-    // bin code -> label | 0x100 for the labels that get a BEV image (first_outlined .. K-1) | 0x200 for the ground plateau
-    // | 0x8000 (entry written): the flags of ssd_kernels_stream.cuh
-    const int K = s_K, fo = s_first_outlined, gr = s_ground;
-    for(int b = lane; b < SSD_BINS_PAD; b += 32)
-    {
-      const unsigned l = s_lut[b];
-      F.lut16[b] = (unsigned short)(l | (((int)l >= fo && (int)l < K) ? 0x100u : 0u) | ((int)l == gr ? 0x200u : 0u) | 0x8000u);
-    }
-  }
-  if(lane < s_K)
-  {
-    PlateauDev &P = F.plat[lane];
-    P.height = s_height[lane];
-    P.hmin = s_hmin[lane];
-    P.hmax = s_hmax[lane];
-    P.n_points = s_np[lane];
-    P.valid = 0;
-    P.outlined = lane >= s_first_outlined;
-    P.n_in_quad = 0;
-    P.quad_status = -1;
-    P.mean_z = 0;
-    P.sum_fix = 0;
-    P.sum_d = 0;
-    P.sum_c = 0;
-    P.n_sum = 0;
-    P.row_min = 0x7fffffff;
-    P.row_max = -1;
-    P.front_valid = 0;
-    for(int c4 = 0; c4 < 4; c4++)
-      P.quad_px[c4][0] = P.quad_px[c4][1] = P.quad_world[c4][0] = P.quad_world[c4][1] = 0;
-  }
+  const uint4 *src = reinterpret_cast<const uint4 *>(frames[f].hist) + lane * 2;
+  const uint4 h0 = src[0], h1 = src[1];
+  peaks_warp(p, frames[f], K, h0, h1, lane);
 }
 
 // ---------------------------------------------------------------------------------------------

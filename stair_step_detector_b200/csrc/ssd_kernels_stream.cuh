@@ -37,9 +37,6 @@
 #define SSD_FS_SUB 2              // sub-steps per step (one bulk copy, one ring slot, one turn of a warp's loop)
 #endif
 #define SSD_FS_REC_BYTES 640     // records of one sub-step: 32 code words + 32 x 4 records
-#define SSD_LUT_OUTLINED 0x100u  // lut16 flags: the label gets a BEV image
-#define SSD_LUT_GROUND 0x200u    //              the label is the ground plateau
-#define SSD_LUT_VALID 0x8000u    //              entry written (a zero entry means "frame not ready")
 
 // One summary per 32 consecutive pixels (8 lanes x 4): the points of the ground / outlined plateaus among them.
 struct __align__(16) GroupSum
@@ -71,12 +68,9 @@ struct FsAcc // per in-flight frame (slot f % SSD_FS_NB) of one CTA
   unsigned p1_left, p2_left, n_exact, oob, n_def, pad[3];
 };
 
-struct FsPeaks // scratch of the warp that completes a frame (one at a time per CTA: lock)
+struct FsPeaks // scratch of the warp that evaluates a frame's peaks (one at a time per CTA: lock)
 {
-  unsigned hist[SSD_BINS_PAD + 8]; // bin b at [4 + b]; zeros either side
-  unsigned short lut[SSD_BINS_PAD];
-  int height[SSD_GPU_MAX_PLATEAUS], hmin[SSD_GPU_MAX_PLATEAUS], hmax[SSD_GPU_MAX_PLATEAUS];
-  unsigned np[SSD_GPU_MAX_PLATEAUS];
+  PeaksScratch K;
   unsigned lock, pad[3];
 };
 
@@ -176,32 +170,7 @@ __device__ __forceinline__ uint4 ld_volatile_v4(const void *ptr)
   return v;
 }
 
-// ---------------------------------------------------------------------------------------------
-// Peaks of one frame, one warp: HeightsHistogram::findPeaks / filterPeaks (pointcloud.cpp:214-256), the plateau bands of
-// extractPlateauPoints (:300-335) as a bin -> label LUT, ground / first-outlined bookkeeping (:402-418). Same results as
-// k_peaks (which walks the bins serially), evaluated bin-parallel:
-//   rise(i) = hist[i] < hist[i+1], fall(i) = hist[i] > hist[i+1]   (i < n_bins - 1)
-//   ascending before i  <=>  the nearest j < i with rise(j) or fall(j) is a rise      (equal neighbours keep the flag)
-//   peak(i) = fall(i) && ascending && hist[i] >= min_peak_points && (2 hist[i] - hist[i-1] - hist[i+1]) * 2 > hist[i]
-//   band(i) = [i-1, i] if hist[i-1] > hist[i+1] else [i, i+1]; a bin claimed by two bands goes to the lower peak
-//   (peaks are at least two bins apart, so only the bands of the peaks at b-1, b, b+1 can hold bin b).
-// ---------------------------------------------------------------------------------------------
-// bit (32 r + lane + D) of a 256-bit string held as eight warp-uniform words (zeros outside), D in {-2, -1, 0, +1}
-template<int D>
-__device__ __forceinline__ unsigned fs_bit_at(const unsigned (&w)[8], int r, int lane)
-{
-  const unsigned cur = w[r];
-  if(D == 0)
-    return (cur >> lane) & 1u;
-  if(D < 0)
-  {
-    const unsigned prev = r > 0 ? w[r - 1] : 0u;
-    return (__funnelshift_l(prev, cur, -D) >> lane) & 1u; // bit i of the result = bit (i + D) of the string
-  }
-  const unsigned next = r < 7 ? w[r + 1] : 0u;
-  return (__funnelshift_r(cur, next, D) >> lane) & 1u;
-}
-
+// peaks of a frame inside k_frame_stream: the CTA's scratch under its lock, then the flag the other warps poll
 __device__ inline void fs_peaks(const DevParams &p, FrameDev &F, FsPeaks &K, const uint4 h0, const uint4 h1, int lane)
 {
   if(lane == 0)
@@ -216,168 +185,7 @@ __device__ inline void fs_peaks(const DevParams &p, FrameDev &F, FsPeaks &K, con
   }
   __syncwarp();
   __threadfence_block();
-  {
-    // the frame's complete histogram (bins 8 lane .. 8 lane + 7), as the owner's poll read it
-    uint4 *dst = reinterpret_cast<uint4 *>(K.hist + 4 + lane * 8);
-    dst[0] = h0;
-    dst[1] = h1;
-    if(lane < 4)
-    {
-      K.hist[lane] = 0;
-      K.hist[4 + SSD_BINS_PAD + lane] = 0;
-    }
-  }
-  __syncwarp();
-  const unsigned *H = K.hist + 4;
-  const int last = p.n_bins - 1;
-  const unsigned lt = (1u << lane) - 1u;
-  unsigned R[8], Fm[8], Pw[8], BL[8], hc[8], hm[8], hp[8];
-#pragma unroll
-  for(int r = 0; r < 8; r++)
-  {
-    const int b = 32 * r + lane;
-    hc[r] = H[b];
-    hm[r] = H[b - 1];
-    hp[r] = H[b + 1];
-    const bool v = b < last;
-    R[r] = __ballot_sync(0xffffffffu, v && hc[r] < hp[r]);
-    Fm[r] = __ballot_sync(0xffffffffu, v && hc[r] > hp[r]);
-    BL[r] = __ballot_sync(0xffffffffu, hm[r] > hp[r]);
-  }
-  {
-    bool carry = false; // ascending at the start of word r
-#pragma unroll
-    for(int r = 0; r < 8; r++)
-    {
-      const unsigned c = hc[r];
-      const unsigned E = R[r] | Fm[r];
-      const unsigned m = E & lt;
-      const bool asc = m ? ((R[r] >> (31 - __clz(m))) & 1u) != 0u : carry;
-      const bool fall = (Fm[r] >> lane) & 1u;
-      const bool peak = fall && asc && !(c < p.min_peak_points) && (unsigned)((c * 2u - hm[r] - hp[r]) * 2u) > c;
-      Pw[r] = __ballot_sync(0xffffffffu, peak);
-      if(E)
-        carry = ((R[r] >> (31 - __clz(E))) & 1u) != 0u;
-    }
-  }
-  int n_all = 0;
-#pragma unroll
-  for(int r = 0; r < 8; r++)
-    n_all += __popc(Pw[r]);
-  const int Kn = min(n_all, SSD_GPU_MAX_PLATEAUS);
-  unsigned status = n_all > SSD_GPU_MAX_PLATEAUS ? SSD_STATUS_TOO_MANY_PLATEAUS : 0u;
-  // uint16 wrap of heightMin - 1 (pointcloud.cpp:324): a peak at bin 1 with band [0, 1] -- necessarily the first peak --
-  // sends every point to the remainder; that plateau and all later ones stay empty
-  const bool wrapped = ((Pw[0] >> 1) & 1u) && ((BL[0] >> 1) & 1u);
-  if(wrapped)
-    status |= SSD_STATUS_HMIN_WRAP;
-  {
-    int base = 0;
-#pragma unroll
-    for(int r = 0; r < 8; r++)
-    {
-      const int b = 32 * r + lane;
-      const int cntlt = base + __popc(Pw[r] & lt); // peaks at bins < b
-      const bool pk = (Pw[r] >> lane) & 1u;
-      unsigned l = SSD_LABEL_REMAINDER;
-      if(!wrapped)
-      {
-        int k = -1;
-        if(fs_bit_at<-1>(Pw, r, lane) && !fs_bit_at<-1>(BL, r, lane))
-          k = cntlt - 1;
-        else if(pk)
-          k = cntlt;
-        else if(fs_bit_at<1>(Pw, r, lane) && fs_bit_at<1>(BL, r, lane))
-          k = cntlt;
-        if(k >= 0 && k < SSD_GPU_MAX_PLATEAUS)
-          l = (unsigned)k;
-      }
-      if(b == (int)SSD_CODE_OUT_OF_RANGE)
-        l = SSD_LABEL_OUT_OF_RANGE;
-      if(b == (int)SSD_CODE_INVALID)
-        l = SSD_LABEL_INVALID;
-      K.lut[b] = (unsigned short)l;
-      if(pk && cntlt < SSD_GPU_MAX_PLATEAUS)
-      {
-        const bool lo = (BL[r] >> lane) & 1u;
-        unsigned np = hc[r];
-        if(lo)
-          np += (fs_bit_at<-2>(Pw, r, lane) && !fs_bit_at<-2>(BL, r, lane)) ? 0u : hm[r];
-        else
-          np += hp[r];
-        K.height[cntlt] = b;
-        K.hmin[cntlt] = lo ? b - 1 : b;
-        K.hmax[cntlt] = lo ? b : b + 1;
-        K.np[cntlt] = wrapped ? 0u : np;
-      }
-      base += __popc(Pw[r]);
-    }
-  }
-  __syncwarp();
-  // ground = the largest of the leading plateaus below minHeight (first maximum), outlines from the first plateau at or above it
-  const bool mine = lane < Kn;
-  const int height = mine ? K.height[lane] : 0;
-  const unsigned np = mine ? K.np[lane] : 0u;
-  const unsigned hi = __ballot_sync(0xffffffffu, mine && height >= p.min_height);
-  const int fo = hi ? __ffs(hi) - 1 : Kn;
-  const unsigned gnp = (mine && lane < fo) ? np : 0u;
-  const unsigned gmax = __reduce_max_sync(0xffffffffu, gnp);
-  const unsigned gb = __ballot_sync(0xffffffffu, lane < fo && mine && gnp == gmax);
-  const int ground = gmax > 0u ? __ffs(gb) - 1 : -1;
-  if(lane == 0)
-  {
-    F.n_nonzero = (unsigned)p.N - H[SSD_CODE_INVALID];
-    F.n_in_range = (unsigned)p.N - H[SSD_CODE_INVALID] - H[SSD_CODE_OUT_OF_RANGE];
-    F.n_plateaus = Kn;
-    F.ground_index = ground;
-    F.first_outlined = fo;
-    F.first_valid = -1;
-    F.n_steps = 0;
-    F.status = status;
-  }
-  if(mine)
-  {
-    PlateauDev &P = F.plat[lane];
-    P.height = height;
-    P.hmin = K.hmin[lane];
-    P.hmax = K.hmax[lane];
-    P.n_points = np;
-    P.valid = 0;
-    P.outlined = lane >= fo;
-    P.n_in_quad = 0;
-    P.quad_status = -1;
-    P.mean_z = 0;
-    P.sum_fix = 0;
-    P.sum_d = 0;
-    P.sum_c = 0;
-    P.n_sum = 0;
-    P.row_min = 0x7fffffff;
-    P.row_max = -1;
-    P.front_valid = 0;
-    for(int c4 = 0; c4 < 4; c4++)
-      P.quad_px[c4][0] = P.quad_px[c4][1] = P.quad_world[c4][0] = P.quad_world[c4][1] = 0;
-  }
-  {
-    unsigned w[4];
-#pragma unroll
-    for(int i = 0; i < 4; i++)
-    {
-      unsigned e2[2];
-#pragma unroll
-      for(int h = 0; h < 2; h++)
-      {
-        const unsigned l = K.lut[lane * 8 + i * 2 + h];
-        unsigned e = l | SSD_LUT_VALID;
-        if((int)l >= fo && (int)l < Kn)
-          e |= SSD_LUT_OUTLINED;
-        if((int)l == ground)
-          e |= SSD_LUT_GROUND;
-        e2[h] = e;
-      }
-      w[i] = e2[0] | (e2[1] << 16);
-    }
-    *(reinterpret_cast<uint4 *>(F.lut16) + lane) = make_uint4(w[0], w[1], w[2], w[3]);
-  }
+  peaks_warp(p, F, K.K, h0, h1, lane);
   // the plateau records and the LUT must be visible before the flag that announces them
   __threadfence();
   __syncwarp();
