@@ -1,16 +1,17 @@
-// ssd_kernels_records.cuh -- the record chain: the three point passes of the classic chain (ssd_kernels_points.cuh) with the
-// vertices read ONCE.
+// ssd_kernels_records.cuh -- the record chain (EXPERIMENTAL, SSD_GPU_PATH=records): the three point passes of the classic chain
+// (ssd_kernels_points.cuh) with the vertices read ONCE. Parity-tested like the default chain; measured SLOWER (166 k frames/s
+// against 268 k: more instructions per point than the classic passes, DESIGN.md section 6 "Round 2").
 //   k_transform_rec : k_transform_bin (z>0, CameraToWorld, range filter, height bin, histogram; pointcloud.cpp:122-178,
-//                     194-204) that also leaves a 4-byte record per in-range point {BEV pixel (pointcloud.cpp:79-83), height
-//                     offset inside the bin} -- the phase-1 body of the resident-frame path (fs_phase1)
+//                     194-204) that also leaves a 4-byte record per in-range point {BEV pixel (pointcloud.cpp:79-83), parity of
+//                     the bin, height offset inside the bin} -- the phase-1 body of the resident-frame chain (fs_phase1)
 //   k_peaks         : unchanged
-//   k_label_sum     : per-point segment labels, BEV bitmaps of the outlined plateaus (pointcloud.cpp:280-343, 458-471) and one
-//                     16-byte summary per 32 pixels, from the 1-byte codes and the records alone (fs_phase2): no vertex, no
-//                     transform, 5 bytes per in-range point instead of 12
-//   k_quad_sum      : (ssd_kernels_stream.cuh) the per-step sums from the summaries; only the points of the summaries an edge of
-//                     a quadrilateral crosses are read again as vertices
-// DRAM traffic per point: 12 B + 1 B code + ~2.2 B records written | 1 B + ~2.2 B read, 1 B label + 0.5 B summaries written |
-// 0.5 B + the crossed summaries' points: ~21 B against the classic chain's 24, and no second / third evaluation of the transform.
+//   k_label_rec     : per-point segment labels and BEV bitmaps of the outlined plateaus (pointcloud.cpp:280-343, 458-471) from
+//                     the 1-byte codes and the records alone: no vertex, no transform
+//   k_quad_rec      : getPointsInQuadrilateral + calcAverageZ (pointcloud.cpp:560-581) from labels and records: a point whose
+//                     BEV pixel lies in a pixel box inside the verified inner box of its step's QuadrilateralTest is inside
+//                     (two integer comparisons); only the fringe along the quadrilateral's edges is re-read as vertices
+//   (k_label_sum / k_quad_sum: the summary-based variants shared with the resident-frame chain)
+// DRAM traffic per point (ncu, profiles/r02_records_ncu_full.csv): 15.0 | 2.6 | 3.3 = 21 B against the classic chain's 24.
 #pragma once
 #include "ssd_kernels_stream.cuh"
 

@@ -1,29 +1,31 @@
-// ssd_kernels_stream.cuh -- the resident-frame path: ONE persistent kernel reads every vertex exactly once.
+// ssd_kernels_stream.cuh -- the resident-frame chain (EXPERIMENTAL, SSD_GPU_PATH=resident): ONE persistent kernel reads every
+// vertex exactly once. Parity-tested like the default chain; measured SLOWER (83 k frames/s against 268 k, DESIGN.md section 6,
+// "Round 2"): it is kept as the record of that experiment and because k_quad_sum / the phase bodies are shared with the record chain.
 //
 // Why: labels depend on the whole-frame height histogram (pointcloud.cpp:184-256 before :280-343), so the classic chain
 // (ssd_kernels_points.cuh) reads the plateau points of a frame three times from HBM (24 B/point of DRAM traffic against
 // 13 algorithmic). A 1024x768 frame is 9.4 MB of vertices -- the shared memory of the 148 SMs together holds three of them.
-// k_frame_stream keeps a frame on chip between the two phases that the histogram separates:
+// k_frame_stream keeps what the later phases need across the barrier the histogram imposes:
 //
-//   phase 1 (per 128-point step, one warp): TMA bulk copy of the step's 1536 B of vertices into the warp's raw ring ->
-//            z>0 / CameraToWorld / range filter / height bin (point_code_scaled, exact fallback: the same decisions as
+//   phase 1 (per 128-point sub-step, one warp): TMA bulk copy of the step's vertices into the warp's raw ring in shared memory
+//            -> z>0 / CameraToWorld / range filter / height bin (the decisions of point_code_scaled, exact fallback: the same as
 //            k_transform_bin, pointcloud.cpp:122-178) -> block histogram in shared memory (pointcloud.cpp:194-204) ->
-//            a 4-byte record per point {BEV pixel (pointcloud.cpp:79-83), height offset inside its bin} + the 1-byte bin
-//            code into the warp's record ring (5 B/point stay on chip instead of 12).
-//   frame barrier: the last warp of a CTA to leave a frame adds the CTA's histogram to the frame's (global atomics) and
-//            arrives on the frame's counter; the last CTA to arrive evaluates the peaks / plateau bands / bin->label LUT
-//            (pointcloud.cpp:214-256, 300-335, 402-418; warp-parallel) and publishes the LUT -- the LUT's valid bits are
-//            the "frame ready" flag the other warps poll.
-//   phase 2 (same warp, same step, from the record ring): bin code -> segment label (1 B/point, the only per-point
+//            a 4-byte record per in-range point {BEV pixel (pointcloud.cpp:79-83), parity of the bin, height offset inside the
+//            bin} + the 1-byte bin code into the warp's record ring (global memory, re-used every SSD_GPU_FS_LAG frames).
+//   frame barrier: the last warp of a CTA to leave a frame adds the CTA's histogram to the frame's (global reductions, no
+//            fence, no counter); the frame's OWNER warp (by frame index) polls the frame's histogram, sees it complete when the
+//            bins add up to the frame's point count, evaluates peaks / plateau bands / bin->label LUT (peaks_warp,
+//            pointcloud.cpp:214-256, 300-335, 402-418) and raises the frame's flag; one warp per CTA polls it and copies the
+//            LUT into the CTA's shared memory.
+//   phase 2 (same warp, same step, from its record ring): bin code -> segment label (1 B/point, the only per-point
 //            output), BEV occupancy bit of every point of an outlined plateau (projectToBinaryImage, pointcloud.cpp:458-471),
-//            and one 16-byte summary per 32 points {label, count, sum of height offsets, BEV pixel box} for the per-step
-//            mean (calcAverageZ, pointcloud.cpp:574-581): k_quad_sum adds whole summaries whose pixel box lies inside the
-//            quadrilateral and re-reads only the points of the summaries an edge crosses.
+//            and one 16-byte summary per 32 points {label, count, sums of bin codes and height offsets, BEV pixel box} for the
+//            per-step mean (calcAverageZ, pointcloud.cpp:574-581): k_quad_sum adds whole summaries whose pixel box lies inside
+//            the quadrilateral and re-reads only the points of the summaries an edge crosses.
 //
-// Every warp is its own little pipeline (TMA issue -> phase 1 -> phase 2 on its steps g = warp + k * total_warps of the
-// chunk's step stream); the only block-level state are the per-frame accumulators; the only grid-level synchronisation is
-// the per-frame counter. All CTAs must be co-resident (cooperative launch, one CTA per SM).
-// DRAM traffic: 12 B read + 1 B label + 0.5 B summaries per point.
+// Every warp is its own little pipeline (TMA issue -> phase 1 -> phase 2, phase 2 trailing by up to SSD_GPU_FS_LAG frames); the
+// steps of a frame are dealt to the warps by a rotation that changes with the frame (FsCur); the only block-level state are
+// the per-frame accumulators; there is no grid-wide barrier. All CTAs must be co-resident (cooperative launch, one CTA per SM).
 #pragma once
 #include "ssd_kernels_points.cuh"
 
