@@ -65,6 +65,10 @@ struct ssd_gpu_ctx
   bool resident = false;
   bool records = false;           // record chain (ssd_kernels_records.cuh): the default where the frame size admits it
   uint4 *d_rec4 = nullptr;        // n_streams x chunk_frames x N/4 x {4 records}
+  // word-record chain (SSD_GPU_PATH=wordrec, experimental): k_label_bev<SRC, true> leaves 8 bytes per 4-pixel word of the
+  // outlined plateaus, k_quad_reduce_rec takes the words that lie inside their step's quadrilateral from those
+  bool wordrec = false;
+  uint2 *d_wrec = nullptr;        // n_streams x chunk_frames x N/4
   int fs_grid = 0, fs_d_raw = 4, fs_d_rec = 0, fs_lag_frames = 8;
   GroupSum *d_sums = nullptr;     // n_streams x chunk_frames x N/32 summaries
   unsigned *d_done = nullptr;     // n_streams x chunk_frames frame counters (self-resetting)
@@ -596,7 +600,15 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, const uin
   if(!fused)
     k_peaks<<<nf, 32, 0, st>>>(p, frames, nf);
   STAGE_EV(2);
-  if(depth)
+  uint2 *wrec = ctx->wordrec ? ctx->d_wrec + (size_t)s * ctx->chunk_frames * (size_t)(p.N / 4) : nullptr;
+  if(wrec)
+  {
+    if(depth)
+      k_label_bev<SrcDepth, true><<<gpt2l, SSD_PT_THREADS, 0, st>>>(p, sd, labels, frames, bev, ctx->bm_words, wrec);
+    else
+      k_label_bev<SrcVertices, true><<<gpt2l, SSD_PT_THREADS, 0, st>>>(p, sv, labels, frames, bev, ctx->bm_words, wrec);
+  }
+  else if(depth)
     k_label_bev<SrcDepth><<<gpt2l, SSD_PT_THREADS, 0, st>>>(p, sd, labels, frames, bev, ctx->bm_words);
   else
     k_label_bev<SrcVertices><<<gpt2l, SSD_PT_THREADS, 0, st>>>(p, sv, labels, frames, bev, ctx->bm_words);
@@ -619,7 +631,14 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, const uin
   if(!fused)
     k_frame_logic<<<nf, 32, 0, st>>>(p, frames, nf);
   STAGE_EV(5);
-  if(depth)
+  if(wrec)
+  {
+    if(depth)
+      k_quad_reduce_rec<SrcDepth><<<gpt2q, SSD_PT_THREADS, 0, st>>>(p, sd, labels, frames, bev, ctx->bm_words, wrec);
+    else
+      k_quad_reduce_rec<SrcVertices><<<gpt2q, SSD_PT_THREADS, 0, st>>>(p, sv, labels, frames, bev, ctx->bm_words, wrec);
+  }
+  else if(depth)
     k_quad_reduce<SrcDepth><<<gpt2q, SSD_PT_THREADS, 0, st>>>(p, sd, labels, frames, bev, ctx->bm_words);
   else
     k_quad_reduce<SrcVertices><<<gpt2q, SSD_PT_THREADS, 0, st>>>(p, sv, labels, frames, bev, ctx->bm_words);
@@ -670,6 +689,7 @@ void ssd_gpu_destroy(ssd_gpu_ctx *ctx)
   cudaFree(ctx->d_done);
   cudaFree(ctx->d_recs);
   cudaFree(ctx->d_rec4);
+  cudaFree(ctx->d_wrec);
   cudaFree(ctx->d_prof);
   if(ctx->ev_fs)
     cudaEventDestroy(ctx->ev_fs);
@@ -847,6 +867,14 @@ int ssd_gpu_create(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, int d
     // latency (every warp must hold all its steps of one frame, plus what it works ahead). SSD_GPU_PATH=classic|resident.
     const char *pe = getenv("SSD_GPU_PATH");
     const bool want = pe && !strcmp(pe, "resident"); // experimental: measured slower than the record chain
+    // word-record chain (experimental: measured slower than the classic chain): box coordinates are 12 bits each
+    if(pe && !strcmp(pe, "wordrec") && dp.W <= 4096 && dp.H <= 4096)
+    {
+      ctx->wordrec = true;
+      CKC(cudaMalloc(&ctx->d_wrec, (size_t)ctx->n_streams * ctx->chunk_frames * (size_t)(dp.N / 4) * sizeof(uint2)));
+    }
+    if(pe && !strcmp(pe, "wordrec") && !ctx->wordrec)
+      return bail("SSD_GPU_PATH=wordrec: the frame size does not admit the word-record chain", SSD_E_RANGE);
     if(pe && !strcmp(pe, "records") && dp.rec_zbits > 0) // experimental: measured slower than the classic chain
     {
       ctx->records = true;

@@ -735,10 +735,20 @@ __device__ __forceinline__ void label_bev_exact_point(const DevParams &p, float 
 #ifndef SSD_LB_MINB
 #define SSD_LB_MINB 4
 #endif
-template<class SRC>
+// REC: every 4-pixel word with points of outlined plateaus also leaves an 8-byte word record for k_quad_reduce_rec (word_rec_*):
+// the box of its BEV pixels and the fixed-point z sum of those points, so that pass 3 takes a word that lies inside its step's
+// quadrilateral without reading its vertices again.
+#define SSD_WREC_ELIGIBLE 0x40000000u // one label, every pixel certain, box at most 8 x 8 pixels
+__device__ __forceinline__ uint2 word_rec_pack(bool eligible, int xlo, int ylo, int xhi, int yhi, unsigned zsum, unsigned count)
+{
+  const unsigned lo = eligible ? ((unsigned)xlo | ((unsigned)ylo << 12) | ((unsigned)(xhi - xlo) << 24) | ((unsigned)(yhi - ylo) << 27) | SSD_WREC_ELIGIBLE) : 0u;
+  return make_uint2(lo, zsum | (count << 25));
+}
+
+template<class SRC, bool REC = false>
 __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_LB_MINB) k_label_bev(const __grid_constant__ DevParams p, const SRC src,
                                                                unsigned char *__restrict__ labels, FrameDev *__restrict__ frames,
-                                                               unsigned *__restrict__ bev, size_t bm_words)
+                                                               unsigned *__restrict__ bev, size_t bm_words, uint2 *__restrict__ wrec = nullptr)
 {
   __shared__ LabelBevShared S;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -840,13 +850,14 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_LB_MINB) k_label_bev(const
       // (image rows are iso-height: almost every word is)
       const unsigned l0 = (lab >> (8 * (__ffs(m4 | 16u) - 1) & 31)) & 0xffu;
       const unsigned bytes = ((m4 * 0x00204081u) & 0x01010101u) * 0xffu;
-      if(((lab ^ (l0 * 0x01010101u)) & bytes) == 0u)
+      const bool uniform = ((lab ^ (l0 * 0x01010101u)) & bytes) == 0u;
+      int ylo = 0x7fffffff, yhi = -1, xlo = 0x7fffffff, xhi = -1;
+      if(uniform)
       {
         // word index of the plateau's bitmap within the stream's BEV buffer: 32-bit (the buffer holds < 2^32 words, see
         // ssd_gpu_create), so a reduction's address is one widening multiply-add on the kernel's base pointer
         unsigned lidx = ((unsigned)frame * SSD_GPU_MAX_PLATEAUS + l0) * bmw;
         asm volatile("" : "+r"(lidx)); // keep it in a register: the compiler otherwise recomputes it inside every predicated reduction
-        int ylo = 0x7fffffff, yhi = -1;
 #pragma unroll
         for(int j = 0; j < 4; j++)
           if((good >> j) & 1u)
@@ -854,6 +865,11 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_LB_MINB) k_label_bev(const
             atomicOr(bev + (lidx + (unsigned)iy[j] * wpr + ((unsigned)ix[j] >> 5)), 1u << (ix[j] & 31));
             ylo = min(ylo, iy[j]);
             yhi = max(yhi, iy[j]);
+            if(REC)
+            {
+              xlo = min(xlo, ix[j]);
+              xhi = max(xhi, ix[j]);
+            }
           }
         if(yhi >= 0)
         {
@@ -891,6 +907,15 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_LB_MINB) k_label_bev(const
         for(int j = 0; j < 4; j++)
           if((bad >> j) & 1u)
             defer_push(S.L, warp, ((e >> 4) << 2) | (unsigned)j);
+      }
+      if(REC && e)
+      {
+        unsigned zs = 0;
+#pragma unroll
+        for(int j = 0; j < 4; j++)
+          zs += z_fix_u(p, vx[j], vy[j], vz[j]) & (0u - ((m4 >> j) & 1u));
+        const bool eligible = uniform && bad == 0u && yhi >= 0 && xhi - xlo < 8 && yhi - ylo < 8;
+        wrec[(size_t)frame * (size_t)nquads + wbase + (e >> 4)] = word_rec_pack(eligible, xlo, ylo, xhi, yhi, zs, (unsigned)__popc(m4));
       }
       e = e1;
       wc = wn;
@@ -1022,6 +1047,22 @@ struct QrWarp
   unsigned long long seg_sum;
   int rmin, rmax;
 };
+
+// end of a warp-tile: combine the warp's 32 open segments (single-pass segmented reduce: lanes grouped by label, 64-bit sums
+// as 21 low bits + the rest), one set of shared-memory adds per distinct label
+__device__ __forceinline__ void qr_seg_combine(QuadReduceShared &S, QrWarp &W, int lane)
+{
+  const unsigned key = W.seg_n ? W.seg_l : 0xffu;
+  const unsigned grp = __match_any_sync(0xffffffffu, key);
+  const unsigned lo = __reduce_add_sync(grp, (unsigned)W.seg_sum & 0x1fffffu);
+  const unsigned hi = __reduce_add_sync(grp, (unsigned)(W.seg_sum >> 21)); // a lane's sum < 2^23 * 2^10 points per tile
+  const unsigned cn = __reduce_add_sync(grp, W.seg_n);
+  if(key != 0xffu && lane == __ffs(grp) - 1)
+    seg_flush(S, key, ((unsigned long long)hi << 21) + (unsigned long long)lo, cn);
+  W.seg_l = 0xffu;
+  W.seg_sum = 0;
+  W.seg_n = 0;
+}
 
 // The dense part of one warp-tile: phase B over the n compacted words of the warp's list (S.L.act / S.L.lab), the exact
 // pass over the deferred points, the queued ground BEV pixels, and the warp's segmented reduce. wbase: first 4-point word
@@ -1221,20 +1262,7 @@ __device__ __forceinline__ void qr_dense(const DevParams &p, const FRAME &FR, Qu
         S.L.ngb[warp] = 0;
     }
   }
-  {
-    // end of the warp-tile: combine the warp's 32 open segments (single-pass segmented reduce: lanes grouped by
-    // label, 64-bit sums as 21 low bits + the rest), one set of shared-memory adds per distinct label
-    const unsigned key = seg_n ? seg_l : 0xffu;
-    const unsigned grp = __match_any_sync(0xffffffffu, key);
-    const unsigned lo = __reduce_add_sync(grp, (unsigned)seg_sum & 0x1fffffu);
-    const unsigned hi = __reduce_add_sync(grp, (unsigned)(seg_sum >> 21)); // a lane's sum < 2^23 * 2^10 points per tile
-    const unsigned cn = __reduce_add_sync(grp, seg_n);
-    if(key != 0xffu && lane == __ffs(grp) - 1)
-      seg_flush(S, key, ((unsigned long long)hi << 21) + (unsigned long long)lo, cn);
-    seg_l = 0xffu;
-    seg_sum = 0;
-    seg_n = 0;
-  }
+  qr_seg_combine(S, W, lane);
 }
 
 // the frame's filter tables and the block's accumulators (k_quad_reduce / k_quad_sum)
@@ -1375,5 +1403,162 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_QR_MINB) k_quad_reduce(con
     qr_dense<SRC>(p, FR, S, W, F, amask, ground, gbev, wbase, n, warp, lane);
     __syncwarp();
   }
+  qr_epilogue(S, W, F, ground, tid, lane);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// k_quad_reduce_rec: k_quad_reduce for the chain whose k_label_bev<SRC, true> left word records. A 4-pixel word whose plateau
+// points share one label of a valid (non-ground) step and whose record is eligible is decided as a whole: the world
+// rectangle that every point with a BEV pixel in the record's box lies in -- centre (cx, cy), half extents widened by the
+// rounding margins -- goes through the step's verified inner box and, failing that, through the f32 image of the reference's
+// test (quadfilter_eval with the half extent as the position uncertainty: "certainly inside" then holds for every point of the
+// rectangle). Such a word adds the record's z sum and count; its 48 bytes of vertices are not read. Everything else -- ground
+// words (they also feed the ground's BEV image), words with mixed labels or an uncertain pixel, words the quadrilateral's
+// edges come near -- is re-compacted and takes the dense pass of k_quad_reduce (qr_dense) unchanged, so both chains produce
+// the same integer sums and counts.
+// ---------------------------------------------------------------------------------------------
+template<class SRC>
+__global__ void __launch_bounds__(SSD_PT_THREADS, SSD_QR_MINB) k_quad_reduce_rec(const __grid_constant__ DevParams p, const SRC src,
+                                                                     const unsigned char *__restrict__ labels, FrameDev *__restrict__ frames,
+                                                                     unsigned *__restrict__ bev, size_t bm_words, const uint2 *__restrict__ wrec)
+{
+  __shared__ QuadReduceShared S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int frame = blockIdx.y;
+  FrameDev &F = frames[frame];
+  const unsigned amask = F.quad_amask;
+  if(amask == 0u)
+    return; // no valid plateau: nothing is emitted (pointcloud.cpp:434)
+  const int ground = F.ground_index;
+  const unsigned wmask = ground >= 0 ? amask & ~(1u << ground) : amask; // steps whose words can be taken whole
+  const size_t fbase = (size_t)frame * p.N;
+  const unsigned *lab32 = reinterpret_cast<const unsigned *>(labels + fbase);
+  unsigned *gbev = ground >= 0 ? bev + ((size_t)frame * SSD_GPU_MAX_PLATEAUS + ground) * bm_words : nullptr;
+  const int nquads = p.N >> 2;
+  const uint2 *frec = wrec + (size_t)frame * (size_t)nquads;
+  int wt, wt_end, wt_stride;
+  warp_tile_range((p.N + SSD_WT_PX - 1) / SSD_WT_PX, warp, wt, wt_end, wt_stride);
+
+  qr_init(S, F, amask, tid);
+  __syncthreads();
+
+  unsigned short *act = S.L.act[warp];
+  unsigned *labs = S.L.lab[warp];
+  QrWarp W = { 0xffu, 0u, 0u, 0u, 0ull, 0x7fffffff, -1 };
+  const typename SrcTraits<SRC>::Frame FR = src_frame(src, p, fbase);
+  const unsigned lt = (1u << lane) - 1u;
+
+  for(; wt < wt_end; wt += wt_stride)
+  {
+    const unsigned wbase = (unsigned)wt * (SSD_WT_PX / 4); // first word of the warp-tile within the frame
+    // ---- phase A: compaction of the words holding plateau labels (bit 7 of a label byte clear <=> label < 128) ----
+    unsigned n = 0;
+    unsigned labw[SSD_WT_WORDS];
+#pragma unroll
+    for(int it = 0; it < SSD_WT_WORDS; it++)
+    {
+      const int q = wt * (SSD_WT_PX / 4) + it * 32 + lane;
+      labw[it] = q < nquads ? __ldg(lab32 + q) : 0xffffffffu;
+    }
+    if(wt + wt_stride < wt_end)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(lab32 + (size_t)(wt + wt_stride) * (SSD_WT_PX / 4) + lane * 8));
+#pragma unroll
+    for(int it = 0; it < SSD_WT_WORDS; it++)
+    {
+      const unsigned lw = labw[it];
+      const unsigned am4 = (((~lw >> 7) & 0x01010101u) * 0x10204080u) >> 28; // bit j <-> byte j < 128
+      if(__any_sync(0xffffffffu, am4 != 0u))
+      {
+        if(am4)
+          labs[it * 32 + lane] = lw;
+        n = compact_append(act, n, am4, it, lane);
+      }
+    }
+    if(n == 0)
+      continue;
+    __syncwarp();
+
+    // ---- phase B': whole words from their records; the rest is re-compacted in place (writes trail the reads) ----
+    unsigned n2 = 0;
+    for(unsigned s0 = 0; s0 < n; s0 += 32)
+    {
+      const unsigned i0 = s0 + lane;
+      const unsigned e = i0 < n ? act[i0] : 0u;
+      bool dense = false;
+      if(e)
+      {
+        const unsigned m4 = e & 15u;
+        const unsigned lw = labs[e >> 4];
+        const unsigned l0 = (lw >> (8 * (__ffs(m4) - 1))) & 0xffu;
+        const unsigned bytes = ((m4 * 0x00204081u) & 0x01010101u) * 0xffu;
+        const bool uniform = ((lw ^ (l0 * 0x01010101u)) & bytes) == 0u;
+        if(!uniform)
+          dense = true;
+        else if(l0 < SSD_GPU_MAX_PLATEAUS && ((amask >> l0) & 1u))
+        {
+          dense = true;
+          if((wmask >> l0) & 1u)
+          {
+            const uint2 r = __ldg(frec + wbase + (e >> 4));
+            if(r.x & SSD_WREC_ELIGIBLE)
+            {
+              // centre and half extents of the pixel box [x0, x0 + w] x [y0, y0 + h] in pixels, then in metres
+              const float hw = 0.5f * (float)(((r.x >> 24) & 7u) + 1u), hh = 0.5f * (float)(((r.x >> 27) & 7u) + 1u);
+              const float cx = fmaf((float)(r.x & 0xfffu) + hw, p.gs_xw, p.gs_x0);
+              const float cy = fmaf(-((float)((r.x >> 12) & 0xfffu) + hh), p.gs_yw, p.gs_y0);
+              const float eb = fmaxf(hw * p.gs_xw, hh * p.gs_yw) + p.gs_margin;
+              const float4 ib = S.fast[l0].ibe;
+              bool whole = fabsf(cx - ib.x) < ib.z - eb && fabsf(cy - ib.y) < ib.w - eb;
+              if(!whole)
+              {
+                bool unc;
+                const bool in = quadfilter_eval(S.qf[l0], cx, cy, eb + p.epsc, unc);
+                whole = in && !unc;
+              }
+              if(whole)
+              {
+                dense = false;
+                if(l0 != W.seg_l)
+                {
+                  if(W.seg_n)
+                    seg_flush(S, W.seg_l, W.seg_sum, W.seg_n);
+                  W.seg_l = l0;
+                  W.seg_sum = 0;
+                  W.seg_n = 0;
+                }
+                W.seg_sum += r.y & 0x1ffffffu;
+                W.seg_n += r.y >> 25;
+              }
+            }
+          }
+        }
+      }
+      const unsigned b = __ballot_sync(0xffffffffu, dense);
+      __syncwarp();
+#ifdef SSD_WREC_DEBUG
+      {
+        // debug build: words taken whole / words sent to the dense pass, in the counters the stats call reports as n_bev_exact / n_quad_exact
+        const unsigned bw = __ballot_sync(0xffffffffu, e != 0u && !dense);
+        if(lane == 0)
+        {
+          atomicAdd(&F.n_def_bev, (unsigned)__popc(bw));
+          atomicAdd(&F.n_def_quad, (unsigned)__popc(b));
+        }
+      }
+#endif
+      if(dense)
+      {
+        act[n2 + __popc(b & lt)] = (unsigned short)e;
+        word_prefetch_l2(FR, wbase + (e >> 4));
+      }
+      n2 += __popc(b);
+    }
+    __syncwarp();
+    if(n2)
+      qr_dense<SRC>(p, FR, S, W, F, amask, ground, gbev, wbase, n2, warp, lane);
+    __syncwarp();
+  }
+  qr_seg_combine(S, W, lane);
   qr_epilogue(S, W, F, ground, tid, lane);
 }

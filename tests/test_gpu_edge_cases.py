@@ -165,9 +165,9 @@ def test_two_contexts_of_different_sizes_alternate(S, oracle):
                 assert not H.compare_results(H.oracle_process(oracle, small_cfg, small_xf, small_xyz), T.gpu_result(S, small, 0), tol=TOL)
 
 
-@pytest.mark.parametrize("path", ["records", "resident"])
+@pytest.mark.parametrize("path", ["wordrec", "records", "resident"])
 def test_experimental_chains_match_the_oracle(S, oracle, monkeypatch, path):
-    """the record chain and the resident-frame chain (SSD_GPU_PATH): same results as the oracle on a random batch"""
+    """the word-record chain, the record chain and the resident-frame chain (SSD_GPU_PATH): same results as the oracle on a random batch"""
     monkeypatch.setenv("SSD_GPU_PATH", path)
     import test_gpu_parity as T
     cfg = S.default_config(1024, 768)
