@@ -371,11 +371,17 @@ __device__ __forceinline__ P2d image_to_world(const DevParams &p, P2d px)
 
 // Correctly rounded hypot for the magnitudes that occur here (no overflow/underflow handling needed):
 // x^2+y^2 in double-double via exact FMA residuals, one Newton correction of the square root.
-// Stands in for std::hypot (segmentation.cpp:346-349); tests/test_hypot.py checks it against glibc.
-__device__ __forceinline__ double hypot_cr(double x, double y)
+// Stands in for std::hypot (segmentation.cpp:346-349); tests/test_hypot.py compiles this very function for the host and
+// checks it against glibc's hypot on the operand ranges of the path (integer line coefficients, normalised lines).
+#ifdef __CUDA_ARCH__
+#define SSD_FMA_RN(a, b, c) __fma_rn(a, b, c)
+#else
+#define SSD_FMA_RN(a, b, c) fma(a, b, c)
+#endif
+__host__ __device__ __forceinline__ double hypot_cr(double x, double y)
 {
   const double xx = x * x, yy = y * y;
-  const double ex = __fma_rn(x, x, -xx), ey = __fma_rn(y, y, -yy);
+  const double ex = SSD_FMA_RN(x, x, -xx), ey = SSD_FMA_RN(y, y, -yy);
   const double s = xx + yy;
   const double bb = s - xx;
   const double es = (xx - (s - bb)) + (yy - bb); // TwoSum error
@@ -383,7 +389,7 @@ __device__ __forceinline__ double hypot_cr(double x, double y)
   if(s == 0.0)
     return 0.0;
   const double h = sqrt(s);
-  const double r = __fma_rn(-h, h, s) + lo;
+  const double r = SSD_FMA_RN(-h, h, s) + lo;
   return h + r / (2.0 * h);
 }
 
