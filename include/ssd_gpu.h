@@ -206,6 +206,34 @@ typedef struct ssd_gpu_overlay
 int ssd_gpu_set_overlay(ssd_gpu_ctx *ctx, const double a_inv[9], const ssd_gpu_intrinsics *intr);
 /* out[0..min(*n, cap)): one projected quadrilateral per step of ssd_gpu_get_steps, same order. */
 int ssd_gpu_get_overlay(ssd_gpu_ctx *ctx, int frame, ssd_gpu_overlay *out, int cap, int *n);
+/*
+ * Vertical faces (risers) from the remainder. PlateausExtraction::extractPlateaus (pointcloud.cpp:280-297) collects the
+ * remainder -- the in-range points that fall in no plateau band -- and then drops it: "TODO use remainder to detect vertical
+ * faces" (:293). The reference therefore defines the point set but no result; this library's definition (restated in
+ * oracle/ssd_oracle.c: ssd_oracle_vertical_faces, the checker of the parity tests) is:
+ *   riser k (0 <= k < n_plateaus - 1) joins plateau k and plateau k + 1 (plateaus ascend in height). Its points are the
+ *   remainder points (label SSD_LABEL_REMAINDER) whose height index h = (uint16)((z - z_min) * heightIntervalReciprocal)
+ *   (calcHeights, pointcloud.cpp:175) lies strictly between the two bands: hmax[k] < h < hmin[k + 1].
+ *   Footprint: with X = (int64)((x - x_min) * 65536), Y = (int64)((y - y_min) * 65536) of the exact double-precision world
+ *   coordinates (CameraToWorld, transformation.h:59-64), x_min/x_max/y_min/y_max are the extremes of X, Y and x_mean/y_mean
+ *   their integer sums divided by n_points, mapped back to metres (x = x_min_cfg + X / 65536). Integer sums: the result does
+ *   not depend on the order the points are visited in. z_bottom / z_top: the top of the lower band and the bottom of the
+ *   upper band, z_min + (hmax[k] + 1) * height_interval and z_min + hmin[k + 1] * height_interval.
+ * A riser without points has n_points == 0 and a zero footprint. Off until enabled (one more pass over the remainder points,
+ * about an eighth of a frame); enable != 0 switches it on for the following ssd_gpu_process_* calls.
+ */
+typedef struct ssd_gpu_riser
+{
+  int32_t lower_plateau, upper_plateau; /* k, k + 1 */
+  uint32_t n_points;
+  uint32_t pad;
+  double x_min, x_max, y_min, y_max;    /* metres, world frame */
+  double x_mean, y_mean;
+  double z_bottom, z_top;
+} ssd_gpu_riser;
+int ssd_gpu_set_vertical_faces(ssd_gpu_ctx *ctx, int enable);
+/* out[0..min(*n, cap)): *n = max(0, n_plateaus - 1) risers of the frame, ascending. */
+int ssd_gpu_get_vertical_faces(ssd_gpu_ctx *ctx, int frame, ssd_gpu_riser *out, int cap, int *n);
 /* Per-pixel segment labels (device -> host copy of width*height bytes). */
 int ssd_gpu_get_labels(ssd_gpu_ctx *ctx, int frame, uint8_t *out_host);
 /* Height histogram, HeightsHistogram::calcHist (pointcloud.cpp:194-204). */

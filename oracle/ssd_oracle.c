@@ -1057,6 +1057,81 @@ int ssd_oracle_points_in_quad(const double quad[8], const double *xy, int n, uin
 }
 
 /* ---------------------------------------------------------------------------------------------
+ * Vertical faces from the remainder. The reference stops at "TODO use remainder to detect vertical faces"
+ * (pointcloud.cpp:293) after collecting the remainder (:283-291): there is no reference behaviour to restate, so this is the
+ * restatement of the DEFINITION in include/ssd_gpu.h (ssd_gpu_riser) -- parity for this row is unpinned by construction.
+ * labels / plateaus: as ssd_oracle_process (or the compiled reference, whose remainder vector holds exactly the points with
+ * label SSD_LABEL_REMAINDER) produced them for the same vertices.
+ * ------------------------------------------------------------------------------------------- */
+int ssd_oracle_vertical_faces(const ssd_gpu_config *cfg, const ssd_gpu_transform *xf, const float *xyz, const uint8_t *labels,
+                              const ssd_gpu_plateau *plateaus, int n_plateaus, ssd_gpu_riser *out, int cap, int *n)
+{
+  ssd_oracle_derived d;
+  const int rc = ssd_oracle_derive(cfg, &d);
+  if(rc)
+    return rc;
+  const int R = n_plateaus > 1 ? n_plateaus - 1 : 0;
+  if(n)
+    *n = R;
+  if(R > SSD_GPU_MAX_PLATEAUS)
+    return SSD_E_RANGE;
+  uint32_t cnt[SSD_GPU_MAX_PLATEAUS];
+  long long sx[SSD_GPU_MAX_PLATEAUS], sy[SSD_GPU_MAX_PLATEAUS], xmin[SSD_GPU_MAX_PLATEAUS], xmax[SSD_GPU_MAX_PLATEAUS], ymin[SSD_GPU_MAX_PLATEAUS],
+    ymax[SSD_GPU_MAX_PLATEAUS];
+  for(int k = 0; k < SSD_GPU_MAX_PLATEAUS; k++)
+  {
+    cnt[k] = 0;
+    sx[k] = sy[k] = 0;
+    xmin[k] = ymin[k] = 0x7fffffff;
+    xmax[k] = ymax[k] = -1;
+  }
+  const size_t N = (size_t)cfg->width * cfg->height;
+  for(size_t i = 0; i < N; i++)
+  {
+    if(labels[i] != SSD_LABEL_REMAINDER)
+      continue;
+    double w[3];
+    camera_to_world(xf, xyz + i * 3, w);
+    const int h = (uint16_t)((w[2] - cfg->z_min) * d.height_interval_reciprocal); /* calcHeights (pointcloud.cpp:175) */
+    int r = -1;
+    for(int k = 0; k + 1 < n_plateaus; k++)
+      if(h > plateaus[k].hmax && h < plateaus[k + 1].hmin)
+        r = k;
+    if(r < 0)
+      continue;
+    const long long X = (long long)((w[0] - cfg->x_min) * 65536.0), Y = (long long)((w[1] - cfg->y_min) * 65536.0);
+    cnt[r]++;
+    sx[r] += X;
+    sy[r] += Y;
+    if(X < xmin[r]) xmin[r] = X;
+    if(X > xmax[r]) xmax[r] = X;
+    if(Y < ymin[r]) ymin[r] = Y;
+    if(Y > ymax[r]) ymax[r] = Y;
+  }
+  for(int k = 0; k < R && k < cap && out; k++)
+  {
+    ssd_gpu_riser o;
+    memset(&o, 0, sizeof o);
+    o.lower_plateau = k;
+    o.upper_plateau = k + 1;
+    o.n_points = cnt[k];
+    o.z_bottom = cfg->z_min + (double)(plateaus[k].hmax + 1) * cfg->height_interval;
+    o.z_top = cfg->z_min + (double)plateaus[k + 1].hmin * cfg->height_interval;
+    if(cnt[k])
+    {
+      o.x_min = cfg->x_min + (double)xmin[k] / 65536.0;
+      o.x_max = cfg->x_min + (double)xmax[k] / 65536.0;
+      o.y_min = cfg->y_min + (double)ymin[k] / 65536.0;
+      o.y_max = cfg->y_min + (double)ymax[k] / 65536.0;
+      o.x_mean = cfg->x_min + (double)(unsigned long long)sx[k] / (double)cnt[k] / 65536.0;
+      o.y_mean = cfg->y_min + (double)(unsigned long long)sy[k] / (double)cnt[k] / 65536.0;
+    }
+    out[k] = o;
+  }
+  return SSD_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------
  * The frame pipeline (pointcloud.cpp:108-626)
  * ------------------------------------------------------------------------------------------- */
 typedef struct

@@ -250,6 +250,17 @@ class Detector:
         self._ck(self._l.ssd_gpu_get_overlay(self._h, frame, out, A.MAX_STEPS, C.byref(n)), "ssd_gpu_get_overlay")
         return np.array([[[o.px[c][0], o.px[c][1]] for c in range(4)] for o in out[:n.value]], np.float32).reshape(n.value, 4, 2)
 
+    def set_vertical_faces(self, enable=True):
+        """Vertical faces (risers) from the remainder points (include/ssd_gpu.h: ssd_gpu_riser); one more pass over the points."""
+        self._ck(self._l.ssd_gpu_set_vertical_faces(self._h, 1 if enable else 0), "ssd_gpu_set_vertical_faces")
+
+    def vertical_faces(self, frame):
+        """list of dicts, one per pair of consecutive plateaus (riser k joins plateau k and k + 1)"""
+        out = (A.Riser * A.MAX_PLATEAUS)()
+        n = C.c_int()
+        self._ck(self._l.ssd_gpu_get_vertical_faces(self._h, frame, out, A.MAX_PLATEAUS, C.byref(n)), "ssd_gpu_get_vertical_faces")
+        return [{f: getattr(r, f) for f, _ in A.Riser._fields_ if f != "pad"} for r in out[:n.value]]
+
     def n_steps_all(self, n_frames):
         out = np.empty(n_frames, np.int32)
         n = C.c_int()

@@ -54,6 +54,12 @@ class Overlay(C.Structure):
     _fields_ = [("px", (C.c_float * 2) * 4)]
 
 
+class Riser(C.Structure):
+    _fields_ = [("lower_plateau", C.c_int32), ("upper_plateau", C.c_int32), ("n_points", C.c_uint32), ("pad", C.c_uint32),
+                ("x_min", C.c_double), ("x_max", C.c_double), ("y_min", C.c_double), ("y_max", C.c_double),
+                ("x_mean", C.c_double), ("y_mean", C.c_double), ("z_bottom", C.c_double), ("z_top", C.c_double)]
+
+
 class Step(C.Structure):
     _fields_ = [("height", C.c_double), ("quad", (C.c_double * 2) * 4)]
 
@@ -113,6 +119,8 @@ PROTOTYPES = {
     "ssd_gpu_get_steps": (C.c_int, [_vp, C.c_int, _P(Step), C.c_int, _P(C.c_int), _P(C.c_uint32)]),
     "ssd_gpu_set_overlay": (C.c_int, [_vp, _P(C.c_double), _P(Intrinsics)]),
     "ssd_gpu_get_overlay": (C.c_int, [_vp, C.c_int, _P(Overlay), C.c_int, _P(C.c_int)]),
+    "ssd_gpu_set_vertical_faces": (C.c_int, [_vp, C.c_int]),
+    "ssd_gpu_get_vertical_faces": (C.c_int, [_vp, C.c_int, _P(Riser), C.c_int, _P(C.c_int)]),
     "ssd_gpu_get_frame_info": (C.c_int, [_vp, C.c_int, _P(FrameInfo)]),
     "ssd_gpu_get_plateaus": (C.c_int, [_vp, C.c_int, _P(Plateau), C.c_int, _P(C.c_int)]),
     "ssd_gpu_get_labels": (C.c_int, [_vp, C.c_int, _vp]),

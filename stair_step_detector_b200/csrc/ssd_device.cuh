@@ -133,6 +133,15 @@ struct PlateauDev
   QuadTestDev qt;
 };
 
+// accumulators of one riser (ssd_gpu_riser, include/ssd_gpu.h): X = (int64)((x - x_min) * 65536), Y likewise
+struct RiserDev
+{
+  unsigned cnt;
+  int xmin, xmax, ymin, ymax;
+  int pad;
+  unsigned long long sx, sy;
+};
+
 struct FrameDev
 {
   unsigned hist[SSD_BINS_PAD];
@@ -152,6 +161,7 @@ struct FrameDev
   unsigned n_def_quad;   // ... of which went to the compacted exact pass
   unsigned n_def_bev;    // k_label_bev: BEV pixels computed by the exact double chain
   PlateauDev plat[SSD_GPU_MAX_PLATEAUS];
+  RiserDev ris[SSD_GPU_MAX_PLATEAUS]; // k_riser_reduce (only when vertical faces are enabled); zeroed by k_peaks
 };
 
 // compact per-frame result copied to the host after every call

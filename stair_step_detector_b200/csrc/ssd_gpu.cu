@@ -68,6 +68,7 @@ struct ssd_gpu_ctx
   // word-record chain (SSD_GPU_PATH=wordrec, experimental): k_label_bev<SRC, true> leaves 8 bytes per 4-pixel word of the
   // outlined plateaus, k_quad_reduce_rec takes the words that lie inside their step's quadrilateral from those
   bool wordrec = false;
+  bool risers = false;            // ssd_gpu_set_vertical_faces: k_riser_reduce after the chain
   uint2 *d_wrec = nullptr;        // n_streams x chunk_frames x N/4
   int fs_grid = 0, fs_d_raw = 4, fs_d_rec = 0, fs_lag_frames = 8;
   GroupSum *d_sums = nullptr;     // n_streams x chunk_frames x N/32 summaries
@@ -471,6 +472,17 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, const uin
   sd.yn = ctx->d_yn;
   sd.unit = depth_unit;
   sd.wmagic = (((unsigned long long)1 << 40) + (unsigned long long)p.W - 1) / (unsigned long long)p.W;
+  // optional fourth pass: vertical faces from the remainder (labels are final once the chain's label kernel has run)
+  auto launch_risers = [&]()
+  {
+    if(!ctx->risers)
+      return;
+    if(depth)
+      k_riser_reduce<SrcDepth><<<gpt2q, SSD_PT_THREADS, 0, st>>>(p, sd, labels, frames);
+    else
+      k_riser_reduce<SrcVertices><<<gpt2q, SSD_PT_THREADS, 0, st>>>(p, sv, labels, frames);
+    *launches += 1;
+  };
 
   if(ctx->records)
   {
@@ -509,6 +521,7 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, const uin
                                                                             ctx->d_ovl ? ctx->d_ovl + (size_t)frame0 * SSD_GPU_MAX_STEPS : nullptr);
     STAGE_EV(7);
     *launches += SSD_GPU_N_STAGES;
+    launch_risers();
     CK(cudaGetLastError());
     return SSD_OK;
   }
@@ -575,6 +588,7 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, const uin
                                                                             ctx->d_ovl ? ctx->d_ovl + (size_t)frame0 * SSD_GPU_MAX_STEPS : nullptr);
     STAGE_EV(7);
     *launches += 5;
+    launch_risers();
     CK(cudaGetLastError());
     return SSD_OK;
   }
@@ -652,6 +666,7 @@ static int launch_chunk(ssd_gpu_ctx *ctx, int s, const float *xyz_dev, const uin
   STAGE_EV(7);
 #undef STAGE_EV
   *launches += fused ? SSD_GPU_N_STAGES - 2 : SSD_GPU_N_STAGES;
+  launch_risers();
   CK(cudaGetLastError());
   return SSD_OK;
 }
@@ -1349,6 +1364,54 @@ int ssd_gpu_get_overlay(ssd_gpu_ctx *ctx, int frame, ssd_gpu_overlay *out, int c
   if(out)
     for(int i = 0; i < ns && i < cap; i++)
       out[i] = ctx->h_ovl[(size_t)frame * SSD_GPU_MAX_STEPS + i];
+  return SSD_OK;
+}
+
+int ssd_gpu_set_vertical_faces(ssd_gpu_ctx *ctx, int enable)
+{
+  if(!ctx)
+    return SSD_E_INVALID_ARG;
+  ctx->risers = enable != 0;
+  ctx->n_frames_last = 0; // results of an earlier call carry no risers
+  return SSD_OK;
+}
+
+int ssd_gpu_get_vertical_faces(ssd_gpu_ctx *ctx, int frame, ssd_gpu_riser *out, int cap, int *n)
+{
+  const int rc = check_frame(ctx, frame);
+  if(rc)
+    return rc;
+  if(!ctx->risers)
+    return fail(ctx, SSD_E_STATE, "ssd_gpu_get_vertical_faces: not enabled (ssd_gpu_set_vertical_faces)");
+  CK(cudaSetDevice(ctx->device));
+  std::vector<PlateauDev> pl(SSD_GPU_MAX_PLATEAUS);
+  std::vector<RiserDev> rs(SSD_GPU_MAX_PLATEAUS);
+  CK(cudaMemcpy(pl.data(), ctx->d_frames[frame].plat, sizeof(PlateauDev) * SSD_GPU_MAX_PLATEAUS, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(rs.data(), ctx->d_frames[frame].ris, sizeof(RiserDev) * SSD_GPU_MAX_PLATEAUS, cudaMemcpyDeviceToHost));
+  const int K = ctx->h_out[frame].info.n_plateaus;
+  const int R = K > 1 ? K - 1 : 0;
+  if(n)
+    *n = R;
+  const ssd_gpu_config &c = ctx->cfg;
+  for(int k = 0; k < R && k < cap && out; k++)
+  {
+    ssd_gpu_riser o{};
+    o.lower_plateau = k;
+    o.upper_plateau = k + 1;
+    o.n_points = rs[k].cnt;
+    o.z_bottom = c.z_min + (double)(pl[k].hmax + 1) * c.height_interval;
+    o.z_top = c.z_min + (double)pl[k + 1].hmin * c.height_interval;
+    if(rs[k].cnt)
+    {
+      o.x_min = c.x_min + (double)rs[k].xmin / 65536.0;
+      o.x_max = c.x_min + (double)rs[k].xmax / 65536.0;
+      o.y_min = c.y_min + (double)rs[k].ymin / 65536.0;
+      o.y_max = c.y_min + (double)rs[k].ymax / 65536.0;
+      o.x_mean = c.x_min + (double)rs[k].sx / (double)rs[k].cnt / 65536.0;
+      o.y_mean = c.y_min + (double)rs[k].sy / (double)rs[k].cnt / 65536.0;
+    }
+    out[k] = o;
+  }
   return SSD_OK;
 }
 

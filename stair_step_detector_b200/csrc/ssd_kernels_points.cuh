@@ -357,6 +357,13 @@ __device__ inline void peaks_warp(const DevParams &p, FrameDev &F, PeaksScratch 
     F.n_steps = 0;
     F.status = status;
   }
+  {
+    RiserDev &R = F.ris[lane]; // SSD_GPU_MAX_PLATEAUS == 32: one per lane
+    R.cnt = 0;
+    R.xmin = R.ymin = 0x7fffffff;
+    R.xmax = R.ymax = -1;
+    R.sx = R.sy = 0;
+  }
   if(mine)
   {
     PlateauDev &P = F.plat[lane];
@@ -1561,4 +1568,164 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_QR_MINB) k_quad_reduce_rec
   }
   qr_seg_combine(S, W, lane);
   qr_epilogue(S, W, F, ground, tid, lane);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// k_riser_reduce: vertical faces from the remainder (include/ssd_gpu.h: ssd_gpu_riser; the reference only leaves
+// "TODO use remainder to detect vertical faces", pointcloud.cpp:293). Optional fourth pass over the points, launched only
+// when ssd_gpu_set_vertical_faces is on: the words that hold remainder labels are compacted like in the other passes, their
+// vertices re-read, and every remainder point goes through the exact double-precision CameraToWorld (these are an eighth of
+// the points and the footprint wants the exact coordinates): height index -> riser through a per-frame bin table, footprint
+// as integer extremes and sums (order independent). Per-lane running segment, shared-memory accumulators per block, one set
+// of global atomics per riser and block.
+// ---------------------------------------------------------------------------------------------
+struct RiserShared
+{
+  signed char riser_of_bin[SSD_BINS_PAD];
+  unsigned cnt[SSD_GPU_MAX_PLATEAUS];
+  int xmin[SSD_GPU_MAX_PLATEAUS], xmax[SSD_GPU_MAX_PLATEAUS], ymin[SSD_GPU_MAX_PLATEAUS], ymax[SSD_GPU_MAX_PLATEAUS];
+  unsigned long long sx[SSD_GPU_MAX_PLATEAUS], sy[SSD_GPU_MAX_PLATEAUS];
+  unsigned short act[SSD_PT_WARPS][SSD_WT_PX / 4];
+};
+
+struct RiserSeg
+{
+  int r;
+  unsigned cnt;
+  int xmin, xmax, ymin, ymax;
+  unsigned long long sx, sy;
+};
+
+__device__ __forceinline__ void riser_flush(RiserShared &S, RiserSeg &g)
+{
+  if(g.cnt)
+  {
+    atomicAdd(&S.cnt[g.r], g.cnt);
+    atomicAdd(&S.sx[g.r], g.sx);
+    atomicAdd(&S.sy[g.r], g.sy);
+    atomicMin(&S.xmin[g.r], g.xmin);
+    atomicMax(&S.xmax[g.r], g.xmax);
+    atomicMin(&S.ymin[g.r], g.ymin);
+    atomicMax(&S.ymax[g.r], g.ymax);
+  }
+  g.cnt = 0;
+  g.sx = g.sy = 0;
+  g.xmin = g.ymin = 0x7fffffff;
+  g.xmax = g.ymax = -1;
+}
+
+template<class SRC>
+__global__ void __launch_bounds__(SSD_PT_THREADS) k_riser_reduce(const __grid_constant__ DevParams p, const SRC src,
+                                                                 const unsigned char *__restrict__ labels, FrameDev *__restrict__ frames)
+{
+  __shared__ RiserShared S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int frame = blockIdx.y;
+  FrameDev &F = frames[frame];
+  const int K = F.n_plateaus;
+  if(K < 2)
+    return;
+  const size_t fbase = (size_t)frame * p.N;
+  const unsigned *lab32 = reinterpret_cast<const unsigned *>(labels + fbase);
+  const int nquads = p.N >> 2;
+  int wt, wt_end, wt_stride;
+  warp_tile_range((p.N + SSD_WT_PX - 1) / SSD_WT_PX, warp, wt, wt_end, wt_stride);
+  {
+    // bin -> riser: k where hmax[k] < bin < hmin[k + 1], else -1 (SSD_PT_THREADS == SSD_BINS_PAD: one bin per thread)
+    int r = -1;
+    for(int k = 0; k + 1 < K; k++)
+      if(tid > F.plat[k].hmax && tid < F.plat[k + 1].hmin)
+        r = k;
+    S.riser_of_bin[tid] = (signed char)r;
+    if(tid < SSD_GPU_MAX_PLATEAUS)
+    {
+      S.cnt[tid] = 0;
+      S.sx[tid] = S.sy[tid] = 0;
+      S.xmin[tid] = S.ymin[tid] = 0x7fffffff;
+      S.xmax[tid] = S.ymax[tid] = -1;
+    }
+  }
+  __syncthreads();
+  unsigned short *act = S.act[warp];
+  const typename SrcTraits<SRC>::Frame FR = src_frame(src, p, fbase);
+  RiserSeg g;
+  g.r = 0;
+  g.cnt = 0;
+  g.sx = g.sy = 0;
+  g.xmin = g.ymin = 0x7fffffff;
+  g.xmax = g.ymax = -1;
+
+  for(; wt < wt_end; wt += wt_stride)
+  {
+    const unsigned wbase = (unsigned)wt * (SSD_WT_PX / 4);
+    // ---- phase A: words with remainder labels ----
+    unsigned n = 0;
+#pragma unroll
+    for(int it = 0; it < SSD_WT_WORDS; it++)
+    {
+      const int q = wt * (SSD_WT_PX / 4) + it * 32 + lane;
+      const unsigned lw = q < nquads ? __ldg(lab32 + q) : 0xffffffffu;
+      const unsigned x = lw ^ (SSD_LABEL_REMAINDER * 0x01010101u);                 // zero byte <=> remainder label
+      const unsigned z = ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;     // bit 7 of every zero byte (exact, no borrow)
+      const unsigned am4 = ((z >> 7) * 0x10204080u) >> 28;
+      if(__any_sync(0xffffffffu, am4 != 0u))
+        n = compact_append(act, n, am4, it, lane);
+    }
+    if(n == 0)
+      continue;
+    __syncwarp();
+    // ---- phase B: the remainder points of the compacted words ----
+    for(unsigned s0 = 0; s0 < n; s0 += 32)
+    {
+      const unsigned i0 = s0 + lane;
+      const unsigned e = i0 < n ? act[i0] : 0u;
+      if(e)
+      {
+        typename SrcTraits<SRC>::Word w;
+        word_load(FR, wbase + (e >> 4), w);
+        float vx[4], vy[4], vz[4];
+        word_unpack(FR, w, vx, vy, vz);
+#pragma unroll
+        for(int j = 0; j < 4; j++)
+          if((e >> j) & 1u)
+          {
+            double wx, wy, wz;
+            camera_to_world(p, vx[j], vy[j], vz[j], wx, wy, wz);
+            const unsigned h = (unsigned)(unsigned short)((wz - p.z_min) * p.hir); // calcHeights (pointcloud.cpp:175)
+            const int r = h < SSD_BINS_PAD ? (int)S.riser_of_bin[h] : -1;
+            if(r >= 0)
+            {
+              const long long X = (long long)((wx - p.x_min) * 65536.0), Y = (long long)((wy - p.y_min) * 65536.0);
+              if(r != g.r)
+              {
+                riser_flush(S, g);
+                g.r = r;
+              }
+              g.cnt++;
+              g.sx += (unsigned long long)X;
+              g.sy += (unsigned long long)Y;
+              g.xmin = min(g.xmin, (int)X);
+              g.xmax = max(g.xmax, (int)X);
+              g.ymin = min(g.ymin, (int)Y);
+              g.ymax = max(g.ymax, (int)Y);
+            }
+          }
+      }
+    }
+    __syncwarp();
+  }
+  riser_flush(S, g);
+  __syncthreads();
+  if(tid < SSD_GPU_MAX_PLATEAUS && S.cnt[tid])
+  {
+    RiserDev &R = F.ris[tid];
+    atomicAdd(&R.cnt, S.cnt[tid]);
+    atomicAdd(&R.sx, S.sx[tid]);
+    atomicAdd(&R.sy, S.sy[tid]);
+    atomicMin(&R.xmin, S.xmin[tid]);
+    atomicMax(&R.xmax, S.xmax[tid]);
+    atomicMin(&R.ymin, S.ymin[tid]);
+    atomicMax(&R.ymax, S.ymax[tid]);
+  }
 }

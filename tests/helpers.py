@@ -45,6 +45,7 @@ def load_oracle():
     lib.ssd_oracle_make_transform.argtypes = [_P(C.c_double), _P(C.c_double), _P(A.Transform)]
     lib.ssd_oracle_serialize.argtypes = [_P(A.Step), C.c_int, C.c_char_p, C.c_size_t]
     lib.ssd_oracle_inverse3.argtypes = [_P(C.c_double), _P(C.c_double)]
+    lib.ssd_oracle_vertical_faces.argtypes = [_P(A.Config), _P(A.Transform), _vp, _vp, _P(A.Plateau), C.c_int, _P(A.Riser), C.c_int, _P(C.c_int)]
     lib.ssd_oracle_last_overlay.argtypes = [_P(A.Transform), _P(C.c_double), _P(A.Intrinsics), _P(A.Overlay), C.c_int, _P(C.c_int)]
     return lib
 
@@ -145,6 +146,32 @@ def ref_process(lib, cfg, xf, xyz):
     rc = lib.ssd_ref_process(C.byref(xf), ptr(xyz), ptr(labels), ptr(hist), A.MAX_BINS, C.byref(info), plats, steps, line, len(line))
     assert rc == 0, (rc, lib.ssd_ref_last_error())
     return _collect(labels, hist, info, plats, steps, line.value.decode())
+
+
+def oracle_vertical_faces(lib, cfg, xf, xyz, labels=None, plats=None):
+    """ssd_gpu_riser records of one frame by the oracle's restatement of the definition (include/ssd_gpu.h). labels / plats: a
+    FrameResult-independent way to feed the labels and plateau bands of another implementation (e.g. the compiled reference)."""
+    xyz = np.ascontiguousarray(xyz, np.float32)
+    N = cfg.width * cfg.height
+    if labels is None:
+        labels = np.empty(N, np.uint8)
+        hist = np.zeros(A.MAX_BINS, np.uint32)
+        info = A.FrameInfo()
+        plats = (A.Plateau * A.MAX_PLATEAUS)()
+        steps = (A.Step * A.MAX_STEPS)()
+        assert lib.ssd_oracle_process(C.byref(cfg), C.byref(xf), ptr(xyz), ptr(labels), ptr(hist), A.MAX_BINS, C.byref(info), plats, steps) == 0
+        K = info.n_plateaus
+    else:
+        K = len(plats)
+        arr = (A.Plateau * A.MAX_PLATEAUS)()
+        for k, pl in enumerate(plats):
+            arr[k].hmin, arr[k].hmax = pl["hmin"], pl["hmax"]
+        plats = arr
+        labels = np.ascontiguousarray(labels, np.uint8)
+    out = (A.Riser * A.MAX_PLATEAUS)()
+    n = C.c_int()
+    assert lib.ssd_oracle_vertical_faces(C.byref(cfg), C.byref(xf), ptr(xyz), ptr(labels), plats, K, out, A.MAX_PLATEAUS, C.byref(n)) == 0
+    return [{f: getattr(r, f) for f, _ in A.Riser._fields_ if f != "pad"} for r in out[:n.value]]
 
 
 def oracle_overlay(lib, xf, a_inv, intr):
