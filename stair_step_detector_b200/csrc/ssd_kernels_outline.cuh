@@ -8,8 +8,16 @@
 // the global bitmap is zeroed behind the read so it is clean for the next batch.
 #pragma once
 #include "ssd_device.cuh"
+#ifdef SSD_OL_PROF
+#include <cstdio>
+#endif
 
 #define SSD_OL_THREADS 256
+// columns a warp probes at once (probe_columns). Measured on B200 (r2): 1 -> k_outline 0.49 ms per 2048 frames, 35 us for one
+// frame; 2 -> 0.55 ms / 37 us; 3 -> 0.57 ms / 40 us: the kernel lives under a 40-register cap and the extra chains spill
+#ifndef SSD_OL_PROBE_G
+#define SSD_OL_PROBE_G 1
+#endif
 
 // Band of a raw BEV bitmap: rows [b0, b0+nb) with row stride rs words, staged in shared memory (or left
 // in global memory for images too large); rows outside the band are all zero. The 3x3 close is evaluated
@@ -83,18 +91,35 @@ __device__ inline unsigned closed_word(const DevParams &p, const Band &bd, int y
   return out;
 }
 
-// stage the raw rows of a band into shared memory (coalesced) and clear the global bitmap behind the read
+// stage the raw rows of a band into shared memory (coalesced) and clear the global bitmap behind the read. The band is one
+// contiguous run of words in the bitmap; eight independent loads per thread are in flight before the first is consumed (the
+// plain loop -- load, conditional store to the same array, next load -- ran as a chain of dependent L2 round trips).
 __device__ inline void band_stage(const DevParams &p, unsigned *sm, const Band &bd, unsigned *__restrict__ g, int tid, int nthreads)
 {
-  const int wpr = p.wpr;
-  for(int i = tid; i < bd.nb * wpr; i += nthreads)
+  const unsigned wpr = (unsigned)p.wpr;
+  const unsigned total = (unsigned)bd.nb * wpr;
+  const unsigned magic = 0xffffffffu / wpr + 1u; // row = (i * magic) >> 32, exact for i * wpr < 2^32
+  unsigned *src = g + (size_t)bd.b0 * wpr;
+  for(unsigned base = (unsigned)tid; base < total; base += (unsigned)nthreads * 8u)
   {
-    const int r = i / wpr, w = i - r * wpr;
-    const size_t gi = (size_t)(bd.b0 + r) * wpr + w;
-    const unsigned v = g[gi];
-    if(v)
-      g[gi] = 0u;
-    sm[(size_t)r * bd.rs + w] = v;
+    unsigned v[8];
+#pragma unroll
+    for(int k = 0; k < 8; k++)
+    {
+      const unsigned i = base + (unsigned)(k * nthreads);
+      v[k] = i < total ? __ldcg(src + i) : 0u;
+    }
+#pragma unroll
+    for(int k = 0; k < 8; k++)
+    {
+      const unsigned i = base + (unsigned)(k * nthreads);
+      if(i < total)
+      {
+        if(v[k])
+          src[i] = 0u;
+        sm[i + __umulhi(i, magic) * (unsigned)(bd.rs - (int)wpr)] = v[k]; // row stride rs: r * rs + (i - r * wpr)
+      }
+    }
   }
   __syncthreads();
 }
@@ -108,41 +133,43 @@ __device__ inline void band_stage(const DevParams &p, unsigned *sm, const Band &
 //   E   = D with out-of-image columns forced to 1; rows outside the image count as all ones (erosion ignores them)
 //   closed(x, y) = E(y-1) == E(y) == E(y+1) == 111b
 // A warp pass covers 28 rows (lanes 2..29) plus a two-row halo on either side.
+// rows base .. base + 27 of column x as a ballot mask (bit = lane = row base - 2 + lane), restricted to rows [lo, hi]
+__device__ __forceinline__ unsigned probe_chunk(const DevParams &p, const Band &bd, int x, int base, int lo, int hi, int lane)
+{
+  const int xl = x - 2;
+  const int wA = xl >> 5, sh = xl & 31; // arithmetic shift: xl < 0 -> word -1 (reads as 0)
+  // columns x-1, x, x+1 that lie outside the image
+  const unsigned colout = (x - 1 < 0 ? 1u : 0u) | (x + 1 >= p.W ? 4u : 0u);
+  const int y = base - 2 + lane;
+  const int r = y - bd.b0;
+  unsigned hd = 0;
+  if(r >= 0 && r < bd.nb) // (band rows are image rows)
+  {
+    const unsigned w0 = raw_word(bd, r, wA, p.wpr), w1 = raw_word(bd, r, wA + 1, p.wpr);
+    const unsigned f = __funnelshift_r(w0, w1, sh) & 31u;
+    hd = (f | (f >> 1) | (f >> 2)) & 7u;
+  }
+  const unsigned up = __shfl_up_sync(0xffffffffu, hd, 1), dn = __shfl_down_sync(0xffffffffu, hd, 1);
+  const bool inimg = y >= 0 && y < p.H;
+  // lanes 0 and 31 lack one neighbour: their E is never used for a reported row (lanes 2..29 read lanes 1..30)
+  const unsigned E = inimg ? (hd | up | dn | colout) : 7u;
+  const unsigned full = E == 7u ? 1u : 0u;
+  const unsigned fu = __shfl_up_sync(0xffffffffu, full, 1), fd = __shfl_down_sync(0xffffffffu, full, 1);
+  const bool set = (full & fu & fd) != 0u && lane >= 2 && lane < 30 && y >= lo && y <= hi;
+  return __ballot_sync(0xffffffffu, set);
+}
+
 __device__ __forceinline__ bool probe_column(const DevParams &p, const Band &bd, int x, int ylo, int yhi, int lane, int &yFirst, int &ySecond)
 {
   int first = 0x7fffffff, last = -1;
   // the closed image can only be set within one row of the raw band
   const int lo = max(ylo, bd.b0), hi = min(yhi, bd.b0 + bd.nb - 1);
-  const int xl = x - 2;
-  const int wA = xl >> 5, sh = xl & 31; // arithmetic shift: xl < 0 -> word -1 (reads as 0)
-  // columns x-1, x, x+1 that lie outside the image
-  const unsigned colout = (x - 1 < 0 ? 1u : 0u) | (x + 1 >= p.W ? 4u : 0u);
-  // rows base .. base + 27 of the column as a ballot mask (bit = lane = row base - 2 + lane)
-  auto chunk = [&](int base) -> unsigned {
-    const int y = base - 2 + lane;
-    const int r = y - bd.b0;
-    unsigned hd = 0;
-    if(r >= 0 && r < bd.nb) // (band rows are image rows)
-    {
-      const unsigned w0 = raw_word(bd, r, wA, p.wpr), w1 = raw_word(bd, r, wA + 1, p.wpr);
-      const unsigned f = __funnelshift_r(w0, w1, sh) & 31u;
-      hd = (f | (f >> 1) | (f >> 2)) & 7u;
-    }
-    const unsigned up = __shfl_up_sync(0xffffffffu, hd, 1), dn = __shfl_down_sync(0xffffffffu, hd, 1);
-    const bool inimg = y >= 0 && y < p.H;
-    // lanes 0 and 31 lack one neighbour: their E is never used for a reported row (lanes 2..29 read lanes 1..30)
-    const unsigned E = inimg ? (hd | up | dn | colout) : 7u;
-    const unsigned full = E == 7u ? 1u : 0u;
-    const unsigned fu = __shfl_up_sync(0xffffffffu, full, 1), fd = __shfl_down_sync(0xffffffffu, full, 1);
-    const bool set = (full & fu & fd) != 0u && lane >= 2 && lane < 30 && y >= lo && y <= hi;
-    return __ballot_sync(0xffffffffu, set);
-  };
   // top-down to the first set row, then bottom-up to the last one: a plateau's column is set near both ends of its band,
   // so two passes usually do where a full scan of the band took nine
   int bf = lo;
   for(; bf <= hi; bf += 28)
   {
-    const unsigned m = chunk(bf);
+    const unsigned m = probe_chunk(p, bd, x, bf, lo, hi, lane);
     if(m)
     {
       first = bf - 2 + __ffs(m) - 1;
@@ -153,7 +180,7 @@ __device__ __forceinline__ bool probe_column(const DevParams &p, const Band &bd,
   if(last >= 0)
     for(int b2 = hi - 27; b2 > bf; b2 -= 28)
     {
-      const unsigned m = chunk(b2);
+      const unsigned m = probe_chunk(p, bd, x, b2, lo, hi, lane);
       if(m)
       {
         last = max(last, b2 - 2 + 31 - __clz(m));
@@ -163,6 +190,41 @@ __device__ __forceinline__ bool probe_column(const DevParams &p, const Band &bd,
   yFirst = first;
   ySecond = last;
   return last >= 0;
+}
+
+// G columns at once (one warp): the top and the bottom chunk of every column are evaluated first -- independent chains of
+// shared-memory loads and shuffles that overlap -- and decide the column when both hold a set row (they nearly always do: the
+// band hugs the plateau); any other column takes probe_column. Same result: first / last set row of the column in [ylo, yhi].
+template<int G>
+__device__ __forceinline__ void probe_columns(const DevParams &p, const Band &bd, const int (&x)[G], int nvalid, int ylo, int yhi, int lane,
+                                              int (&yFirst)[G], int (&ySecond)[G], bool (&found)[G])
+{
+  const int lo = max(ylo, bd.b0), hi = min(yhi, bd.b0 + bd.nb - 1);
+  const bool two = hi - 27 > lo;
+  unsigned mt[G], mb[G];
+#pragma unroll
+  for(int g = 0; g < G; g++)
+    mt[g] = (g < nvalid && lo <= hi) ? probe_chunk(p, bd, x[g], lo, lo, hi, lane) : 0u;
+#pragma unroll
+  for(int g = 0; g < G; g++)
+    mb[g] = (g < nvalid && two) ? probe_chunk(p, bd, x[g], hi - 27, lo, hi, lane) : 0u;
+#pragma unroll
+  for(int g = 0; g < G; g++)
+  {
+    if(g >= nvalid)
+      continue;
+    if(mt[g] && (!two || mb[g]))
+    {
+      yFirst[g] = lo - 2 + __ffs(mt[g]) - 1;
+      int last = lo - 2 + 31 - __clz(mt[g]);
+      if(two)
+        last = max(last, hi - 27 - 2 + 31 - __clz(mb[g]));
+      ySecond[g] = last;
+      found[g] = true;
+    }
+    else
+      found[g] = probe_column(p, bd, x[g], ylo, yhi, lane, yFirst[g], ySecond[g]);
+  }
 }
 
 // ---- BestLine (segmentation.cpp:409-487): every pair (p,q), residual = mean of the n smallest integer
@@ -387,13 +449,16 @@ __device__ inline void best_lines_block(const P2id *const lists[4], const int n[
     while(t >= off[e + 1])
       e++;
     const int local = t - off[e], ne = n[e];
-    // local = pI*ne - pI*(pI+1)/2 + (qI - pI - 1), pairs in (p,q) lexicographic order
-    int pI = 0, rowStart = 0;
-    while(rowStart + (ne - 1 - pI) <= local)
-    {
-      rowStart += ne - 1 - pI;
+    // local = pI*ne - pI*(pI+1)/2 + (qI - pI - 1), pairs in (p,q) lexicographic order: pI is the largest p whose row starts at
+    // or before local, from the root of the quadratic (single precision: exact to within one, then corrected)
+    const int bq = 2 * ne - 1;
+    int pI = (int)(((float)bq - sqrtf((float)(bq * bq - 8 * local))) * 0.5f);
+    pI = max(0, min(pI, ne - 2));
+    while(pI + 1 <= ne - 2 && (pI + 1) * ne - (pI + 1) * (pI + 2) / 2 <= local)
       pI++;
-    }
+    while(pI * ne - pI * (pI + 1) / 2 > local)
+      pI--;
+    const int rowStart = pI * ne - pI * (pI + 1) / 2;
     const int qI = local - rowStart + pI + 1;
     const P2id *pts = lists[e];
     const LineId l = linei_from(pts[pI], pts[qI]);
@@ -531,6 +596,7 @@ struct OutlineSharedT
   int vn;
   int ve_left, ve_right, ve_ystart, ve_yend, ve_go;
   LineDd base;
+  LineDd nl[4], nl2[2]; // base line: the four normalised edge lines, then the two normalised bisectors (one thread each)
   P2d outer[4];
   int best_pt;
 };
@@ -542,80 +608,127 @@ typedef OutlineSharedT<64, 32, 112> OutlineSharedSmall;                         
 
 // Segmentation::detectOutline after the close (segmentation.cpp:930-946). Block-cooperative.
 // Thread 0 ends up with the quadrilateral (image pixels) and the valid flag.
+#ifdef SSD_OL_PROF
+// debug variant: cycle stamps of thread 0 at the phase boundaries of one plateau (printed by k_outline for frame 0)
+__device__ long long g_olp[16];
+#define OLP(i)                     \
+  do                               \
+  {                                \
+    if(tid == 0 && blockIdx.y == 0 && blockIdx.x == 0) \
+      g_olp[i] = clock64();        \
+  } while(0)
+#else
+#define OLP(i)
+#endif
 template<class OutlineShared>
 __device__ inline void detect_outline_block(const DevParams &p, const Band &bd, OutlineShared &S, int min_img_y_extent, double xy_ratio,
                                             P2d quad[4], int &valid, int tid, int nthreads)
 {
+  OLP(1);
   const int W = p.W, H = p.H;
   const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
   const int xStep = 25, xCenter = W / 2; // HorizontalEdgesDetector (segmentation.cpp:605-611)
   // candidate columns: right = xCenter + j*25 (< W); left = xCenter - 25 - j*25 (>= 0)
   const int nRc = (W - 1 - xCenter) / xStep + 1;
   const int nLc = xCenter - xStep >= 0 ? (xCenter - xStep) / xStep + 1 : 0;
-  for(int c = warp; c < nRc + nLc; c += nwarps)
   {
-    const int x = c < nRc ? xCenter + c * xStep : xCenter - xStep - (c - nRc) * xStep;
-    int yf, ys;
-    const bool f = probe_column(p, bd, x, 0, H - 1, lane, yf, ys);
-    if(lane == 0)
+    constexpr int G = SSD_OL_PROBE_G; // columns a warp probes at once
+    for(int c0 = warp * G; c0 < nRc + nLc; c0 += nwarps * G)
     {
-      S.scan_found[c] = f;
-      S.scan_yf[c] = yf;
-      S.scan_ys[c] = ys;
+      int x[G], yf[G], ys[G];
+      bool f[G];
+      const int nv = min(G, nRc + nLc - c0);
+#pragma unroll
+      for(int g = 0; g < G; g++)
+      {
+        const int c = c0 + g;
+        x[g] = c < nRc ? xCenter + c * xStep : xCenter - xStep - (c - nRc) * xStep;
+      }
+      probe_columns<G>(p, bd, x, nv, 0, H - 1, lane, yf, ys, f);
+      if(lane < nv)
+      {
+#pragma unroll
+        for(int g = 0; g < G; g++)
+          if(lane == g)
+          {
+            S.scan_found[c0 + g] = f[g];
+            S.scan_yf[c0 + g] = yf[g];
+            S.scan_ys[c0 + g] = ys[g];
+          }
+      }
     }
   }
   __syncthreads();
-  if(tid == 0)
+  OLP(2);
   {
-    // Scanner::scan stop rule (segmentation.cpp:68-80): stop at the first empty or too short column
+    // Scanner::scan stop rule (segmentation.cpp:68-80): stop at the first empty or too short column. Every warp counts the
+    // leading good columns itself (ballots over the scan results), then all threads fill the four point lists.
+    auto good = [&](int c) { return S.scan_found[c] && S.scan_ys[c] - S.scan_yf[c] >= min_img_y_extent; };
     int nr = 0, nl = 0;
-    while(nr < nRc && S.scan_found[nr] && S.scan_ys[nr] - S.scan_yf[nr] >= min_img_y_extent)
-      nr++;
-    if(nr > 0)
-      while(nl < nLc && S.scan_found[nRc + nl] && S.scan_ys[nRc + nl] - S.scan_yf[nRc + nl] >= min_img_y_extent)
-        nl++;
-    S.ok = nr > 0 && nl + nr >= 3; // :612-616
-    S.nLeft = S.nRight = 0;
-    if(S.ok)
+    for(int b = 0; b < nRc; b += 32)
     {
-      // Scanner::obtainLinePoints (:129-156); scansRight[i] = column i, scansLeft[i] = column nRc+i
-      const int total = nl + nr, half = total / 2 + 1;
-      int indLeft = 0, indRight = 0;
-      auto pushL = [&](int c)
+      const int c = b + lane;
+      const unsigned bad = ~__ballot_sync(0xffffffffu, c < nRc && good(c));
+      if(bad)
       {
-        const int x = c < nRc ? xCenter + c * xStep : xCenter - xStep - (c - nRc) * xStep;
-        S.frontLeft[S.nLeft].x = x;
-        S.frontLeft[S.nLeft].y = S.scan_ys[c];
-        S.backLeft[S.nLeft].x = x;
-        S.backLeft[S.nLeft].y = S.scan_yf[c];
-        S.nLeft++;
-      };
-      auto pushR = [&](int c)
-      {
-        const int x = c < nRc ? xCenter + c * xStep : xCenter - xStep - (c - nRc) * xStep;
-        S.frontRight[S.nRight].x = x;
-        S.frontRight[S.nRight].y = S.scan_ys[c];
-        S.backRight[S.nRight].x = x;
-        S.backRight[S.nRight].y = S.scan_yf[c];
-        S.nRight++;
-      };
-      if(nl >= half)
-      {
-        indLeft = nl - half;
-        for(int i = indLeft; i >= 0; i--)
-          pushR(nRc + i);
+        nr = b + __ffs(bad) - 1;
+        break;
       }
-      else
+      nr = b + 32;
+    }
+    if(nr > 0)
+      for(int b = 0; b < nLc; b += 32)
       {
-        if(nr > half)
-          indRight = nr - half;
-        for(int i = indRight; i >= 0; i--)
-          pushL(i);
+        const int c = b + lane;
+        const unsigned bad = ~__ballot_sync(0xffffffffu, c < nLc && good(nRc + c));
+        if(bad)
+        {
+          nl = b + __ffs(bad) - 1;
+          break;
+        }
+        nl = b + 32;
       }
-      for(; indRight < nr; indRight++)
-        pushR(indRight);
-      for(; indLeft < nl; indLeft++)
-        pushL(nRc + indLeft);
+    const bool ok = nr > 0 && nl + nr >= 3; // :612-616
+    // Scanner::obtainLinePoints (:129-156) in closed form; scansRight[i] = column i, scansLeft[i] = column nRc+i.
+    //   half = total / 2 + 1
+    //   nl >= half:  right list = left columns iL .. 0 (iL = nl - half), then right columns 0 .. nr-1;  left list = left columns iL .. nl-1
+    //   else:        left list = right columns iR .. 0 (iR = nr - half if nr > half, else 0), then left columns 0 .. nl-1;
+    //                right list = right columns iR .. nr-1
+    int nLeft = 0, nRight = 0;
+    if(ok)
+    {
+      const int half = (nl + nr) / 2 + 1;
+      const bool caseA = nl >= half;
+      const int iL = caseA ? nl - half : 0, iR = (!caseA && nr > half) ? nr - half : 0;
+      nLeft = caseA ? nl - iL : iR + 1 + nl;
+      nRight = caseA ? iL + 1 + nr : nr - iR;
+      for(int j = tid; j < nLeft || j < nRight; j += nthreads)
+      {
+        if(j < nLeft)
+        {
+          const int c = caseA ? nRc + iL + j : (j <= iR ? iR - j : nRc + (j - iR - 1));
+          const int x = c < nRc ? xCenter + c * xStep : xCenter - xStep - (c - nRc) * xStep;
+          S.frontLeft[j].x = x;
+          S.frontLeft[j].y = S.scan_ys[c];
+          S.backLeft[j].x = x;
+          S.backLeft[j].y = S.scan_yf[c];
+        }
+        if(j < nRight)
+        {
+          const int c = caseA ? (j <= iL ? nRc + (iL - j) : j - iL - 1) : iR + j;
+          const int x = c < nRc ? xCenter + c * xStep : xCenter - xStep - (c - nRc) * xStep;
+          S.frontRight[j].x = x;
+          S.frontRight[j].y = S.scan_ys[c];
+          S.backRight[j].x = x;
+          S.backRight[j].y = S.scan_yf[c];
+        }
+      }
+    }
+    if(tid == 0)
+    {
+      S.ok = ok;
+      S.nLeft = nLeft;
+      S.nRight = nRight;
     }
   }
   __syncthreads();
@@ -626,30 +739,50 @@ __device__ inline void detect_outline_block(const DevParams &p, const Band &bd, 
   if(!S.ok)
     return;
 
+  OLP(3);
   // HorizontalEdges (:592-599): four best lines
   {
     const P2id *const lists[4] = { S.frontLeft, S.frontRight, S.backLeft, S.backRight };
     const int ns[4] = { S.nLeft, S.nRight, S.nLeft, S.nRight };
     best_lines_block<OutlineShared::MAX_LPTS>(lists, ns, S.wk, S.line, tid, nthreads);
   }
+  OLP(4);
 
+  // The boundary points of the four edges and the base line (VerticalEdgesDetector::calcBaseLine, :672-679) are chains of
+  // double-precision divisions and square roots; the independent ones run on one thread each (first lanes of eight warps),
+  // the same operations on the same operands as the serial order.
+  if((tid & 31) == 0 && tid < 256)
+  {
+    const int j = tid >> 5;
+    if(j < 4)
+    {
+      const P2id *lst = j == 0 ? S.frontLeft : (j == 1 ? S.frontRight : (j == 2 ? S.backLeft : S.backRight));
+      S.outer[j] = boundary_outer(lst, (j & 1) ? S.nRight : S.nLeft, flat_from(S.line[j]));
+    }
+    else
+    {
+      // nl[0] = normalised reversed front-left, nl[1] = front-right, nl[2] = reversed back-left, nl[3] = back-right
+      const int e = j - 4;
+      LineId l = S.line[e];
+      if(!(e & 1))
+      {
+        l.a = -l.a;
+        l.b = -l.b;
+        l.c = -l.c;
+      }
+      S.nl[e] = lined_normalized(lined_from_i(l));
+    }
+  }
+  __syncthreads();
+  if(tid == 0 || tid == 32)
+  {
+    const int h = tid >> 5; // 0: front, 1: back
+    S.nl2[h] = lined_normalized(bisector(S.nl[2 * h], S.nl[2 * h + 1]));
+  }
+  __syncthreads();
   if(tid == 0)
   {
-    S.outer[0] = boundary_outer(S.frontLeft, S.nLeft, flat_from(S.line[0]));
-    S.outer[1] = boundary_outer(S.frontRight, S.nRight, flat_from(S.line[1]));
-    S.outer[2] = boundary_outer(S.backLeft, S.nLeft, flat_from(S.line[2]));
-    S.outer[3] = boundary_outer(S.backRight, S.nRight, flat_from(S.line[3]));
-    // VerticalEdgesDetector::calcBaseLine (:672-679)
-    LineId rfl, rbl;
-    rfl.a = -S.line[0].a;
-    rfl.b = -S.line[0].b;
-    rfl.c = -S.line[0].c;
-    rbl.a = -S.line[2].a;
-    rbl.b = -S.line[2].b;
-    rbl.c = -S.line[2].c;
-    const LineDd front = bisector(lined_normalized(lined_from_i(rfl)), lined_normalized(lined_from_i(S.line[1])));
-    const LineDd back = bisector(lined_normalized(lined_from_i(rbl)), lined_normalized(lined_from_i(S.line[3])));
-    const LineDd center = bisector(lined_normalized(front), lined_normalized(back));
+    const LineDd center = bisector(S.nl2[0], S.nl2[1]);
     const double cf = xy_ratio * xy_ratio;
     LineDd corr;
     corr.a = center.a * cf; // slopeCorrection (:377-380)
@@ -667,6 +800,7 @@ __device__ inline void detect_outline_block(const DevParams &p, const Band &bd, 
   // VerticalEdgesDetector::detect (:653-669): left edge (probe to the right), right edge (probe to the left)
   for(int e = 0; e < 2; e++)
   {
+    OLP(5 + 4 * e);
     if(tid == 0)
     {
       const P2d front = S.outer[e], back = S.outer[2 + e];
@@ -749,6 +883,7 @@ __device__ inline void detect_outline_block(const DevParams &p, const Band &bd, 
         }
       }
       __syncthreads();
+      OLP(6 + 4 * e);
       if(tid == 0)
       {
         // compact in probing order (top of the list = yStart)
@@ -766,6 +901,7 @@ __device__ inline void detect_outline_block(const DevParams &p, const Band &bd, 
         S.best_pt = -1;
       }
       __syncthreads();
+      OLP(7 + 4 * e);
       // findBestPoint (:708-728): element of rank 2n/3 by distance (ties: list order)
       const int n = S.vn;
       if(n > 0)
@@ -785,6 +921,7 @@ __device__ inline void detect_outline_block(const DevParams &p, const Band &bd, 
         }
       }
       __syncthreads();
+      OLP(8 + 4 * e);
       if(tid == 0 && S.vn > 0 && S.best_pt >= 0)
       {
         const P2id bp = S.vpts[S.best_pt];
@@ -802,6 +939,7 @@ __device__ inline void detect_outline_block(const DevParams &p, const Band &bd, 
     }
     __syncthreads();
   }
+  OLP(13);
   if(tid == 0)
     valid = quad_is_convex(quad);
 }
@@ -818,16 +956,28 @@ __device__ inline void detect_front_edge_block(const DevParams &p, const Band &b
   // all candidate columns x = xCenter + j*50 for j in [-jl, jr]
   const int jr = (W - 1 - xCenter) / xStep, jl = xCenter / xStep;
   const int ncols = jl + jr + 1;
-  for(int c = warp; c < ncols; c += nwarps)
   {
-    const int x = xCenter + (c - jl) * xStep;
-    int yf, ys;
-    // probeBottomUp (:225-240): lowest set pixel with y > H/2
-    const bool f = probe_column(p, bd, x, H / 2 + 1, H - 1, lane, yf, ys);
-    if(lane == 0)
+    constexpr int G = SSD_OL_PROBE_G; // columns a warp probes at once
+    for(int c0 = warp * G; c0 < ncols; c0 += nwarps * G)
     {
-      S.scan_found[c] = f;
-      S.scan_ys[c] = ys;
+      int x[G], yf[G], ys[G];
+      bool f[G];
+      const int nv = min(G, ncols - c0);
+#pragma unroll
+      for(int g = 0; g < G; g++)
+        x[g] = xCenter + (c0 + g - jl) * xStep;
+      // probeBottomUp (:225-240): lowest set pixel with y > H/2
+      probe_columns<G>(p, bd, x, nv, H / 2 + 1, H - 1, lane, yf, ys, f);
+      if(lane < nv)
+      {
+#pragma unroll
+        for(int g = 0; g < G; g++)
+          if(lane == g)
+          {
+            S.scan_found[c0 + g] = f[g];
+            S.scan_ys[c0 + g] = ys[g];
+          }
+      }
     }
   }
   __syncthreads();
@@ -1037,6 +1187,7 @@ __global__ void __launch_bounds__(OutlineShared::THREADS, FUSE_LOGIC ? 1 : (Outl
   if(P.row_max >= 0)
   {
     unsigned *gb = bev + ((size_t)frame * SSD_GPU_MAX_PLATEAUS + k) * bm_words;
+    OLP(0);
     if(tid == 0)
       s_smem_path = band_setup(p, bd, P.row_min, P.row_max, s_words, smem_cap_words, gb);
     __syncthreads();
@@ -1066,6 +1217,16 @@ __global__ void __launch_bounds__(OutlineShared::THREADS, FUSE_LOGIC ? 1 : (Outl
     }
     P.valid = valid;
   }
+#ifdef SSD_OL_PROF
+  if(tid == 0 && blockIdx.y == 0 && blockIdx.x == 0)
+  {
+    g_olp[14] = clock64();
+    printf("[ol prof] plateau %d band rows %d:", k, bd.nb);
+    for(int i = 1; i <= 14; i++)
+      printf(" %lld", g_olp[i] - g_olp[i - 1]);
+    printf("\n");
+  }
+#endif
   __syncthreads(); // the shared band / work area is reused by the next plateau of this block
   }
   if(FUSE_LOGIC)
