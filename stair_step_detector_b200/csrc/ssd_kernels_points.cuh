@@ -717,7 +717,10 @@ __device__ __forceinline__ void warp_tile_range(int n_wt, int warp, int &first, 
 // ---------------------------------------------------------------------------------------------
 struct LabelBevShared
 {
-  unsigned short lut[SSD_BINS_PAD]; // label | 0x100 if the label gets a BEV image
+  // bin code -> {label << 8 j, (label gets a BEV image) << j}, one table per byte position j of a 4-pixel code word: the label
+  // word and the pixel mask of a code word are the OR of four 8-byte lookups, no shifting / masking of the looked-up values
+  // (measured against one 16-bit table: k_label_bev 2.03 -> 1.96 ms per 2048 frames)
+  uint2 lut64[4][SSD_BINS_PAD];
   int rmin[SSD_GPU_MAX_PLATEAUS], rmax[SSD_GPU_MAX_PLATEAUS];
   unsigned oob, n_def;
   WarpLists L;
@@ -769,7 +772,12 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_LB_MINB) k_label_bev(const
   int wt, wt_end, wt_stride;
   warp_tile_range((p.N + SSD_WT_PX - 1) / SSD_WT_PX, warp, wt, wt_end, wt_stride);
 
-  S.lut[tid] = F.lut16[tid]; // SSD_PT_THREADS == SSD_BINS_PAD
+  {
+    const unsigned e = F.lut16[tid]; // SSD_PT_THREADS == SSD_BINS_PAD
+#pragma unroll
+    for(int j = 0; j < 4; j++)
+      S.lut64[j][tid] = make_uint2((e & 0xffu) << (8 * j), ((e >> 8) & 1u) << j);
+  }
   if(tid < SSD_GPU_MAX_PLATEAUS)
   {
     S.rmin[tid] = 0x7fffffff;
@@ -814,9 +822,9 @@ __global__ void __launch_bounds__(SSD_PT_THREADS, SSD_LB_MINB) k_label_bev(const
       // codes 254 / 255 (out of range / invalid) are their own labels and never matter: skip such words outright
       if((cw & 0xfefefefeu) != 0xfefefefeu)
       {
-        const unsigned e0 = S.lut[cw & 0xffu], e1 = S.lut[(cw >> 8) & 0xffu], e2 = S.lut[(cw >> 16) & 0xffu], e3 = S.lut[cw >> 24];
-        const unsigned lab = (e0 & 0xffu) | ((e1 & 0xffu) << 8) | ((e2 & 0xffu) << 16) | (e3 << 24);
-        am4 = ((e0 >> 8) & 1u) | ((e1 >> 7) & 2u) | ((e2 >> 6) & 4u) | ((e3 >> 5) & 8u);
+        const uint2 a0 = S.lut64[0][cw & 0xffu], a1 = S.lut64[1][(cw >> 8) & 0xffu], a2 = S.lut64[2][(cw >> 16) & 0xffu], a3 = S.lut64[3][cw >> 24];
+        const unsigned lab = a0.x | a1.x | a2.x | a3.x;
+        am4 = a0.y | a1.y | a2.y | a3.y;
         lab32[wt * (SSD_WT_PX / 4) + it * 32 + lane] = lab; // (cw is never the all-ones padding here)
         labs[it * 32 + lane] = lab;
       }
