@@ -231,12 +231,17 @@ __device__ __forceinline__ void probe_columns(const DevParams &p, const Band &bd
 // distances of the other points / hypot(a,b); winner = first minimal residual in (p,q) order.
 // Up to four point lists are fitted in one pass: one (list, pair) task per thread, warp-shuffle arg-min on
 // (residual, pair index) per list, one shared-memory round across the warps.
+#define SSD_BL_CHUNK 2048 // line-fit candidates probed per round (large frame-size class)
 template<int NWARPS>
 struct BestLineWorkT
 {
   double res[NWARPS][4];
   int idx[NWARPS][4];
   unsigned long long best[4]; // large frame-size class: bits of the smallest residual any thread has computed so far, per list
+  // ... and the queue of the candidates that survive the pruning probe (best_lines_block): the few survivors are evaluated
+  // densely, one per thread, instead of dragging the 31 pruned lanes of their warps through the bisection
+  int nq;
+  int queue[NWARPS > 8 ? SSD_BL_CHUNK : 1];
 };
 
 // Sum of the cnt (<= S) smallest distances of the other points to line l: insertion into a sorted register array
@@ -266,6 +271,36 @@ __device__ __forceinline__ long long sum_smallest(const P2id *pts, int n, int pi
   for(int k = 0; k < S; k++)
     sum += k < cnt ? a[k] : 0;
   return sum;
+}
+
+// The pruning probe of pair_residual alone (large frame-size class): true when the line through points pi, qi is certainly worse
+// than `bound` (see pair_residual for the argument). No per-thread array: one pass over the list.
+__device__ inline bool pair_abandoned(const P2id *pts, int n, int pi, int qi, LineId l, double bound)
+{
+  if(n <= 2 || !(bound < 1e300))
+    return false;
+  const int m = n - 2;
+  const int cnt = m > 4 ? (m - 1) / 2 : 1;
+  const double Bf = bound * ((double)(size_t)cnt * sqrt((double)((long long)l.a * l.a + (long long)l.b * l.b))) * (1.0 + 1e-12);
+  if(!(Bf < 4e18))
+    return false;
+  const long long B = (long long)Bf + 1;
+  const long long th = 2 * B / cnt;
+  const int mid = th < 0x7fffffffll ? (int)th : 0x7fffffff;
+  int c = 0, mx = 0;
+  long long sb = 0;
+  for(int i = 0; i < n; i++)
+    if(i != pi && i != qi)
+    {
+      const int v = abs(pts[i].x * l.a + pts[i].y * l.b + l.c);
+      mx = max(mx, v);
+      if(v <= mid)
+      {
+        c++;
+        sb += v;
+      }
+    }
+  return (long long)cnt * mx < (1ll << 31) && th < mx && c < cnt && sb + (long long)(cnt - c) * ((long long)mid + 1) >= B;
 }
 
 // bound: a residual some line of this list is already known to reach (+inf: none). Only the large frame-size class
@@ -317,39 +352,38 @@ __device__ inline double pair_residual(const P2id *pts, int n, int pi, int qi, L
     // (measured, r2: recomputing the distances from the list in shared memory in every pass instead of keeping them in this
     //  local-memory array is 2.8x slower for k_outline at 4096x3072 -- 3.43 against 1.21 ms per 64 frames -- although the
     //  array's L1 hit rate is poor)
-    int d[MAXPTS]; // the list capacity of the frame-size class
-    int k = 0, hi = 0, lo = 0;
-    for(int i = 0; i < n; i++)
-      if(i != pi && i != qi)
-      {
-        const int v = abs(pts[i].x * l.a + pts[i].y * l.b + l.c);
-        d[k++] = v;
-        hi = max(hi, v);
-      }
-    // Pruning probe. residual = isum / D with D = cnt * hypot (below). If isum >= B := floor(bound * D * (1 + 1e-12)) + 1 then
-    // isum / D exceeds bound by a relative 0.9e-12 >> 1 ulp, so the rounded residual is strictly larger than bound. With
-    // c = count(d <= mid) < cnt every one of the cnt smallest beyond those c is >= mid + 1, so
-    // sum >= sum(d <= mid) + (cnt - c) * (mid + 1): at mid = 2 B / cnt (twice the admissible mean) a line with fewer than
-    // cnt / 2 points that close is out after this single pass; otherwise the probe narrows the bisection interval.
+    // Pruning probe FIRST, without the array (r2: the array made every candidate write and re-read 81 values of local memory, ~9 MB
+    // per plateau through L2; all but a few candidates end here). residual = isum / D with D = cnt * hypot (below). If
+    // isum >= B := floor(bound * D * (1 + 1e-12)) + 1 then isum / D exceeds bound by a relative 0.9e-12 >> 1 ulp, so the rounded
+    // residual is strictly larger than bound. With c = count(d <= mid) < cnt every one of the cnt smallest beyond those c is
+    // >= mid + 1, so sum >= sum(d <= mid) + (cnt - c) * (mid + 1): at mid = 2 B / cnt (twice the admissible mean) a line with
+    // fewer than cnt / 2 points that close is out after this single pass; otherwise the probe narrows the bisection interval.
     // Only when the reference's int sum cannot wrap (cnt * hi < 2^31), so that isum == sum.
-    if(bound < 1e300 && (long long)cnt * hi < (1ll << 31))
+    int hi = -1, lo = 0;
+    if(bound < 1e300)
     {
       const double Bf = bound * ((double)(size_t)cnt * sqrt((double)((long long)l.a * l.a + (long long)l.b * l.b))) * (1.0 + 1e-12);
       if(Bf < 4e18)
       {
         const long long B = (long long)Bf + 1;
         const long long th = 2 * B / cnt;
-        if(th < hi)
-        {
-          const int mid = (int)th;
-          int c = 0;
-          long long sb = 0;
-          for(int i = 0; i < k; i++)
-            if(d[i] <= mid)
+        const int mid = th < 0x7fffffffll ? (int)th : 0x7fffffff;
+        int c = 0, mx = 0;
+        long long sb = 0;
+        for(int i = 0; i < n; i++)
+          if(i != pi && i != qi)
+          {
+            const int v = abs(pts[i].x * l.a + pts[i].y * l.b + l.c);
+            mx = max(mx, v);
+            if(v <= mid)
             {
               c++;
-              sb += d[i];
+              sb += v;
             }
+          }
+        hi = mx;
+        if((long long)cnt * mx < (1ll << 31) && th < mx)
+        {
           if(c >= cnt)
             hi = mid;
           else
@@ -361,6 +395,19 @@ __device__ inline double pair_residual(const P2id *pts, int n, int pi, int qi, L
         }
       }
     }
+    // survivors (and the first candidates, which have no bound yet): value bisection on the distances, computed once into a
+    // per-thread array (local memory: interleaved per thread, so a warp's accesses coalesce)
+    int d[MAXPTS]; // the list capacity of the frame-size class
+    int k = 0, mx2 = 0;
+    for(int i = 0; i < n; i++)
+      if(i != pi && i != qi)
+      {
+        const int v = abs(pts[i].x * l.a + pts[i].y * l.b + l.c);
+        d[k++] = v;
+        mx2 = max(mx2, v);
+      }
+    if(hi < 0)
+      hi = mx2;
     while(lo < hi)
     {
       const int mid = lo + ((hi - lo) >> 1);
@@ -443,38 +490,93 @@ __device__ inline void best_lines_block(const P2id *const lists[4], const int n[
       wk.best[tid] = 0x7ff0000000000000ull; // +inf
     __syncthreads();
   }
-  for(int t = tid; t < off[4]; t += nthreads)
+  // one candidate: task index -> (list, pair), residual (with the list's current bound), the thread's running minimum
+  auto decode = [&](int t, int &e, int &local, int &pI, int &qI)
   {
-    int e = 0;
+    e = 0;
     while(t >= off[e + 1])
       e++;
-    const int local = t - off[e], ne = n[e];
+    local = t - off[e];
+    const int ne = n[e];
     // local = pI*ne - pI*(pI+1)/2 + (qI - pI - 1), pairs in (p,q) lexicographic order: pI is the largest p whose row starts at
     // or before local, from the root of the quadratic (single precision: exact to within one, then corrected)
     const int bq = 2 * ne - 1;
-    int pI = (int)(((float)bq - sqrtf((float)(bq * bq - 8 * local))) * 0.5f);
+    pI = (int)(((float)bq - sqrtf((float)(bq * bq - 8 * local))) * 0.5f);
     pI = max(0, min(pI, ne - 2));
     while(pI + 1 <= ne - 2 && (pI + 1) * ne - (pI + 1) * (pI + 2) / 2 <= local)
       pI++;
     while(pI * ne - pI * (pI + 1) / 2 > local)
       pI--;
     const int rowStart = pI * ne - pI * (pI + 1) / 2;
-    const int qI = local - rowStart + pI + 1;
+    qI = local - rowStart + pI + 1;
+  };
+  auto evaluate = [&](int t)
+  {
+    int e, local, pI, qI;
+    decode(t, e, local, pI, qI);
     const P2id *pts = lists[e];
     const LineId l = linei_from(pts[pI], pts[qI]);
     double bound = __longlong_as_double(0x7ff0000000000000ll);
     if(MAXPTS > 64)
       bound = __longlong_as_double((long long)atomicMin(&wk.best[e], ~0ull)); // atomic read (other threads lower it concurrently)
-    const double r = pair_residual<MAXPTS>(pts, ne, pI, qI, l, bound);
+    const double r = pair_residual<MAXPTS>(pts, n[e], pI, qI, l, bound);
     if(MAXPTS > 64 && r >= 0.0 && r < bound) // (false for NaN; non-negative doubles order like their bit patterns)
       atomicMin(&wk.best[e], (unsigned long long)__double_as_longlong(r));
 #pragma unroll
     for(int k = 0; k < 4; k++)
-      if(k == e && (bidx[k] == 0x7fffffff || r < bres[k])) // local ascends per thread: first of equals kept
+      if(k == e && (bidx[k] == 0x7fffffff || r < bres[k] || (r == bres[k] && local < bidx[k]))) // first of equals in pair order
       {
         bres[k] = r;
         bidx[k] = local;
       }
+  };
+  if(MAXPTS > 64 && sizeof(wk.queue) >= sizeof(int) * SSD_BL_CHUNK)
+  {
+    // Large frame-size class (n ~ 40-80 points per list, thousands of candidate lines): almost every candidate is pruned by
+    // one probe against the best residual known so far, but a warp that holds one survivor used to take all its lanes through
+    // the array fill and ~25 bisection passes (a third of the warps did: 32 % of the kernel's instructions). Instead:
+    //   seeds   one candidate per thread evaluated in full: the first pairs (0, q) of each list give every list a bound
+    //   rounds  SSD_BL_CHUNK candidates at a time: every thread probes its share (no array), survivors go to a queue in shared
+    //           memory; then the queue is evaluated densely, one survivor per thread (the probe is repeated there against the
+    //           bound as it stands then). Abandoned candidates are provably worse than a residual that some line reaches, so
+    //           the minimum and its first index are unchanged.
+    const int seeds = nthreads >> 2; // per list
+    {
+      const int e = tid & 3, local = tid >> 2;
+      if(local < off[e + 1] - off[e])
+        evaluate(off[e] + local);
+    }
+    if(tid == 0)
+      wk.nq = 0;
+    __syncthreads();
+    for(int base = 0; base < off[4]; base += SSD_BL_CHUNK)
+    {
+      const int end = min(off[4], base + SSD_BL_CHUNK);
+      for(int t = base + tid; t < end; t += nthreads)
+      {
+        int e, local, pI, qI;
+        decode(t, e, local, pI, qI);
+        if(local < seeds)
+          continue; // evaluated as a seed
+        const P2id *pts = lists[e];
+        const double bound = __longlong_as_double((long long)atomicMin(&wk.best[e], ~0ull));
+        if(!pair_abandoned(pts, n[e], pI, qI, linei_from(pts[pI], pts[qI]), bound))
+          wk.queue[atomicAdd(&wk.nq, 1)] = t;
+      }
+      __syncthreads();
+      const int nq = wk.nq;
+      for(int i = tid; i < nq; i += nthreads)
+        evaluate(wk.queue[i]);
+      __syncthreads();
+      if(tid == 0)
+        wk.nq = 0;
+      __syncthreads();
+    }
+  }
+  else
+  {
+    for(int t = tid; t < off[4]; t += nthreads)
+      evaluate(t);
   }
   const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
 #pragma unroll
