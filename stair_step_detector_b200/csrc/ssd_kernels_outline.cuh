@@ -535,16 +535,16 @@ __device__ inline void best_lines_block(const P2id *const lists[4], const int n[
     // Large frame-size class (n ~ 40-80 points per list, thousands of candidate lines): almost every candidate is pruned by
     // one probe against the best residual known so far, but a warp that holds one survivor used to take all its lanes through
     // the array fill and ~25 bisection passes (a third of the warps did: 32 % of the kernel's instructions). Instead:
-    //   seeds   one candidate per thread evaluated in full: the first pairs (0, q) of each list give every list a bound
+    //   seeds   one candidate per thread evaluated in full: the pairs (i, i + n/2) of each list give every list a tight bound
     //   rounds  SSD_BL_CHUNK candidates at a time: every thread probes its share (no array), survivors go to a queue in shared
     //           memory; then the queue is evaluated densely, one survivor per thread (the probe is repeated there against the
     //           bound as it stands then). Abandoned candidates are provably worse than a residual that some line reaches, so
     //           the minimum and its first index are unchanged.
-    const int seeds = nthreads >> 2; // per list
+    // seeds: the pairs (i, i + n/2) of every list -- long baselines, i.e. lines close to the best -- one per thread
     {
-      const int e = tid & 3, local = tid >> 2;
-      if(local < off[e + 1] - off[e])
-        evaluate(off[e] + local);
+      const int e = tid & 3, i = tid >> 2, ne = n[e], h = ne >> 1;
+      if(ne >= 2 && i < ne - h)
+        evaluate(off[e] + i * ne - i * (i + 1) / 2 + (h - 1)); // local index of the pair (i, i + h)
     }
     if(tid == 0)
       wk.nq = 0;
@@ -556,7 +556,7 @@ __device__ inline void best_lines_block(const P2id *const lists[4], const int n[
       {
         int e, local, pI, qI;
         decode(t, e, local, pI, qI);
-        if(local < seeds)
+        if(qI - pI == (n[e] >> 1) && pI < (nthreads >> 2))
           continue; // evaluated as a seed
         const P2id *pts = lists[e];
         const double bound = __longlong_as_double((long long)atomicMin(&wk.best[e], ~0ull));
