@@ -387,5 +387,18 @@ def pinned_empty(shape, dtype):
     return arr, p
 
 
+def register_host(array):
+    """Page-lock a numpy array the caller owns (ssd_gpu_register_host); pair with unregister_host(array)."""
+    rc = lib().ssd_gpu_register_host(_ptr(array), array.nbytes)
+    if rc != 0:
+        raise SsdError(f"ssd_gpu_register_host failed ({rc})")
+
+
+def unregister_host(array):
+    rc = lib().ssd_gpu_unregister_host(_ptr(array))
+    if rc != 0:
+        raise SsdError(f"ssd_gpu_unregister_host failed ({rc})")
+
+
 def free_pinned(p):
     lib().ssd_gpu_free_host(p)

@@ -146,6 +146,8 @@ PROTOTYPES = {
     "ssd_load_calibration": (C.c_int, [C.c_char_p, _P(Transform), _P(C.c_double), _P(C.c_double)]),
     "ssd_gpu_malloc_host": (C.c_int, [C.c_size_t, _P(_vp)]),
     "ssd_gpu_free_host": (C.c_int, [_vp]),
+    "ssd_gpu_register_host": (C.c_int, [_vp, C.c_size_t]),
+    "ssd_gpu_unregister_host": (C.c_int, [_vp]),
 }
 
 # every symbol include/ssd_scene.h declares (libssd_scene.so: the synthetic input source, not part of the product)

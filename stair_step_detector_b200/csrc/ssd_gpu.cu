@@ -1712,4 +1712,24 @@ int ssd_gpu_free_host(void *host_ptr)
   return cudaFreeHost(host_ptr) == cudaSuccess ? SSD_OK : SSD_E_CUDA;
 }
 
+int ssd_gpu_register_host(void *host_ptr, size_t bytes)
+{
+  if(!host_ptr || !bytes)
+    return SSD_E_INVALID_ARG;
+  const cudaError_t e = cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable);
+  if(e != cudaSuccess)
+    cudaGetLastError(); // (not sticky: clear it for the next call)
+  return e == cudaSuccess ? SSD_OK : (e == cudaErrorMemoryAllocation ? SSD_E_NOMEM : SSD_E_CUDA);
+}
+
+int ssd_gpu_unregister_host(void *host_ptr)
+{
+  if(!host_ptr)
+    return SSD_E_INVALID_ARG;
+  const cudaError_t e = cudaHostUnregister(host_ptr);
+  if(e != cudaSuccess)
+    cudaGetLastError();
+  return e == cudaSuccess ? SSD_OK : SSD_E_CUDA;
+}
+
 } // extern "C"

@@ -187,3 +187,26 @@ def test_misaligned_device_input_is_refused(S):
         with pytest.raises(S.SsdError, match="aligned"):
             det.process_device(C.c_void_p(d.value + 4), 1)
         det.free(d)
+
+
+def test_registered_host_buffer(S, oracle):
+    """ssd_gpu_register_host: a caller-owned (pageable) frame buffer, page-locked in place, gives the same results"""
+    cfg = S.default_config(640, 480)
+    sc = S.default_scene(640, 480, noise_sigma=0.0025, dropout=0.03, n_holes=2)
+    xf = S.scene_transform(sc)
+    intr = S.scene_intrinsics(sc)
+    depth = np.ascontiguousarray(S.synth_depth_host(sc)[None])
+    with S.Detector(cfg, xf, max_frames=1) as det:
+        det.process_depth_host(depth, intr)
+        a = det.steps(0)
+        S.register_host(depth)
+        try:
+            det.process_depth_host(depth, intr)
+            b = det.steps(0)
+        finally:
+            S.unregister_host(depth)
+        assert a[1] == b[1] and len(a[0]) == len(b[0]) >= 3
+        for (h0, q0), (h1, q1) in zip(a[0], b[0]):
+            assert h0 == h1 and np.array_equal(q0, q1)
+    with pytest.raises(S.SsdError):
+        S.unregister_host(depth)  # not registered any more
