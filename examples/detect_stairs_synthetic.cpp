@@ -3,7 +3,8 @@
 //   Window app; GeometricTransformation trans(world, camera); Pointcloud pointcloud(app, trans);
 //   for each frame: pointcloud.process(frame)   -> one result line per frame on stdout
 // Usage: detect_stairs_synthetic [width height n_frames [overlay]]   (overlay: the step quadrilaterals projected into the
-//        camera image, what the reference draws over the depth view, one line per step on stderr)
+//        camera image, what the reference draws over the depth view, one line per step on stderr; with it also the vertical
+//        faces from the remainder points, one "riser" line each)
 #include "../stair_step_detector_b200/csrc/host/pointcloud.h"
 #include "../stair_step_detector_b200/csrc/host/transformation.h"
 #include "../stair_step_detector_b200/csrc/host/window.h"
@@ -41,7 +42,10 @@ int main(int argc, char **argv)
   ssd_gpu_intrinsics intr;
   ssd_scene_intrinsics(&base, &intr);
   if(argc > 4)
+  {
     pointcloud.enableOverlay(intr);
+    pointcloud.enableVerticalFaces();
+  }
   for(int f = 0; f < nFrames && app; f++)
   {
     ssd_scene sc;
@@ -56,6 +60,9 @@ int main(int argc, char **argv)
           std::cerr << ' ' << p.x << ' ' << p.y;
         std::cerr << std::endl;
       }
+    if(argc > 4)
+      for(const ssd_gpu_riser &r : pointcloud.verticalFaces())
+        std::cerr << "riser " << f << ' ' << r.lower_plateau << ' ' << r.n_points << ' ' << r.y_mean << ' ' << r.z_bottom << ' ' << r.z_top << std::endl;
   }
   return 0;
 }

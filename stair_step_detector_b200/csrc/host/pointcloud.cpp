@@ -44,6 +44,7 @@ void Pointcloud::enableOverlay(const ssd_gpu_intrinsics &intrinsics) const
   _overlayIntrinsics = intrinsics;
   _overlay = true;
   _overlayApplied = false;
+  _risersApplied = false;
 }
 
 std::vector<Quadrilateralf_t> Pointcloud::overlay(int frame) const
@@ -71,6 +72,12 @@ std::vector<Stairs> Pointcloud::processBatch(const Camera::DepthFrame &frames, i
     if(ssd_gpu_set_overlay(_ctx, aInv, &_overlayIntrinsics) != SSD_OK)
       throw std::runtime_error(std::string("ssd_gpu_set_overlay: ") + ssd_gpu_last_error(_ctx));
     _overlayApplied = true;
+  }
+  if(_risers != _risersApplied)
+  {
+    if(ssd_gpu_set_vertical_faces(_ctx, _risers ? 1 : 0) != SSD_OK)
+      throw std::runtime_error(std::string("ssd_gpu_set_vertical_faces: ") + ssd_gpu_last_error(_ctx));
+    _risersApplied = _risers;
   }
   int rc;
   if(frames.z16)
@@ -114,6 +121,22 @@ void Pointcloud::process(const Camera::DepthFrame &frame) const
   const Stairs stairs = detect(frame);
   _window.setViewport(viewportId::infrared);
   std::cout << stairs.serialize() << std::endl;
+}
+
+void Pointcloud::enableVerticalFaces(bool enable) const
+{
+  _risers = enable;
+}
+
+std::vector<ssd_gpu_riser> Pointcloud::verticalFaces(int frame) const
+{
+  if(!_ctx)
+    throw std::logic_error("Pointcloud::verticalFaces before any frame was processed");
+  ssd_gpu_riser r[SSD_GPU_MAX_PLATEAUS];
+  int n = 0;
+  if(ssd_gpu_get_vertical_faces(_ctx, frame, r, SSD_GPU_MAX_PLATEAUS, &n) != SSD_OK)
+    throw std::runtime_error(std::string("ssd_gpu_get_vertical_faces: ") + ssd_gpu_last_error(_ctx));
+  return std::vector<ssd_gpu_riser>(r, r + n);
 }
 
 std::vector<uint8_t> Pointcloud::labels(int frame) const

@@ -40,6 +40,10 @@ public:
   // hands to drawQuadrilateral are then available per frame after process()/processBatch().
   void enableOverlay(const ssd_gpu_intrinsics &intrinsics) const;
   std::vector<Quadrilateralf_t> overlay(int frame = 0) const;
+  // vertical faces (risers) from the remainder points -- the reference stops at "TODO use remainder to detect vertical faces"
+  // (pointcloud.cpp:293); definition: include/ssd_gpu.h, ssd_gpu_riser. One more pass over the points when enabled.
+  void enableVerticalFaces(bool enable = true) const;
+  std::vector<ssd_gpu_riser> verticalFaces(int frame = 0) const;
   ssd_gpu_ctx *context() const { return _ctx; }
 
 private:
@@ -51,6 +55,7 @@ private:
   mutable ssd_gpu_ctx *_ctx = nullptr;
   mutable bool _explicitConfig = false;
   mutable bool _overlay = false, _overlayApplied = false;
+  mutable bool _risers = false, _risersApplied = false;
   mutable ssd_gpu_intrinsics _overlayIntrinsics{};
 };
 

@@ -537,6 +537,13 @@ def test_cpp_host_classes_main_loop(S, oracle, tmp_path):
         mine = np.array([d[1:] for d in drawn if d[0] == f]).reshape(-1, 4, 2)
         assert mine.shape == want.shape and len(want) == len(o.steps)
         assert np.abs(mine - want).max() < 2e-3
+        # Pointcloud::verticalFaces(): one line per riser (printed with 6 digits)
+        ris = [[float(v) for v in l.split()[1:]] for l in run.stderr.splitlines() if l.startswith("riser ")]
+        want_r = H.oracle_vertical_faces(oracle, cfg, xf, S.deproject_host(sc, S.synth_depth_host(sc)).reshape(-1, 3))
+        mine_r = [r for r in ris if r[0] == f]
+        assert len(mine_r) == len(want_r)
+        for m, r in zip(mine_r, want_r):
+            assert m[1] == r["lower_plateau"] and m[2] == r["n_points"] and abs(m[3] - r["y_mean"]) < 1e-4 * max(1.0, abs(r["y_mean"]))
         got = json.loads(out[f])
         assert got[0] == "stairs" and got[1] == ["stairSteps", len(o.steps)]
         for s, g in zip(o.steps, got[2] if len(o.steps) else []):
